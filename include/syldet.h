@@ -1,0 +1,187 @@
+/*
+ * syldet.h — C-ABI of libsyldet_cuda.so, the B200 (sm_100a) syllable-detection engine.
+ *
+ * The reference (gardner-lab/syllable-detector-swift) has no FFI boundary for this path: the Swift classes in
+ * Common/ are compiled straight into the app and the CLI, and the only C boundary is the bridging header for
+ * TPCircularBuffer (Common/Common-Bridging-Header.h:5).  This header therefore defines the boundary a Swift-on-Linux
+ * shim binds through a module map (include/module.modulemap); each entry point names the reference interface it
+ * replaces.  Paths are relative to the reference root.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every function returns a syldet_status (0 = ok) unless it is a pure getter;
+ *   - syldet_last_error() returns a thread-local, human-readable description of the last failure on this thread;
+ *   - invariant violations that are fatalError() upstream are reported as SYLDET_ERR_CONFIG / SYLDET_ERR_OVERFLOW, the
+ *     Swift shim re-raises them as fatalError to keep upstream behaviour;
+ *   - audio is IEEE float32 at the configuration's sampling rate (upstream asks AVFoundation for exactly that:
+ *     Common/SyllableDetector.swift:19-23);
+ *   - there is NO CPU fallback: every compute entry point fails with SYLDET_ERR_CUDA when no sm_100 device is usable.
+ *   - calls on one handle must be serialised by the caller; distinct handles are independent; a syldet_config is
+ *     immutable and may be shared (stronger than upstream, where NeuralNet scratch is shared: NeuralNet.swift:241).
+ */
+#ifndef SYLDET_H
+#define SYLDET_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum syldet_status {
+    SYLDET_OK = 0,
+    SYLDET_ERR_OPEN = 1,        /* ParseError.unableToOpenPath  (Common/SyllableDetectorConfig.swift:51) */
+    SYLDET_ERR_MISSING = 2,     /* ParseError.missingValue      (:52) */
+    SYLDET_ERR_INVALID = 3,     /* ParseError.invalidValue      (:53) */
+    SYLDET_ERR_MISMATCH = 4,    /* ParseError.mismatchedLength  (:54) */
+    SYLDET_ERR_CONFIG = 5,      /* fatalError invariants: SyllableDetector.swift:46-60, CSTFT.swift:76-91, NeuralNet.swift:245-255,340-348 */
+    SYLDET_ERR_ARG = 6,         /* bad argument to this API */
+    SYLDET_ERR_CUDA = 7,        /* CUDA failure or no usable sm_100 device (there is no CPU fallback) */
+    SYLDET_ERR_NOMEM = 8,
+    SYLDET_ERR_OVERFLOW = 9,    /* "Insufficient space on buffer." fatalError (CSTFT.swift:199, SyllableDetector.swift:146) */
+    SYLDET_ERR_UNSUPPORTED = 10
+} syldet_status;
+
+enum { SYLDET_SCALING_LINEAR = 0, SYLDET_SCALING_LOG = 1, SYLDET_SCALING_DB = 2 };         /* SyllableDetectorConfig.Scaling :13-30 */
+enum { SYLDET_TF_TANSIG = 0, SYLDET_TF_LOGSIG = 1, SYLDET_TF_PURELIN = 2, SYLDET_TF_SATLIN = 3 }; /* NeuralNet.swift:189-228 */
+enum { SYLDET_PROC_MAPMINMAX = 0, SYLDET_PROC_MAPSTD = 1, SYLDET_PROC_L2NORMALIZE = 2,
+       SYLDET_PROC_NORMALIZE = 3, SYLDET_PROC_NORMALIZESTD = 4 };                          /* NeuralNet.swift:41-182 */
+enum { SYLDET_LAYOUT_PLANAR = 0, SYLDET_LAYOUT_INTERLEAVED = 1 };
+enum { SYLDET_DETECT_ANY_OUTPUT = 0,   /* TrackDetector.swift:71-77 (CLI rule)  */
+       SYLDET_DETECT_FIRST_OUTPUT = 1  /* SyllableDetector.lastDetected :27-31 (live rule) */ };
+enum { SYLDET_PCM_F32 = 0, SYLDET_PCM_S16 = 1 };
+enum { SYLDET_KERNEL_AUTO = 0, SYLDET_KERNEL_GENERIC = 1, SYLDET_KERNEL_FUSED = 2 };
+
+typedef struct syldet_config syldet_config;     /* SyllableDetectorConfig + NeuralNet                    */
+typedef struct syldet_batch syldet_batch;       /* TrackDetector + main.swift loop, many channels at once */
+typedef struct syldet_detector syldet_detector; /* SyllableDetector (one stream)                          */
+typedef struct syldet_stream syldet_stream;     /* Processor.swift: many live channels, small buffers     */
+typedef struct syldet_resampler syldet_resampler; /* ResamplerLinear                                       */
+typedef struct syldet_events syldet_events;
+
+/* One CSV row of the CLI: "channel,sample,seconds,out0[,out1...]" (TrackDetector.swift:92-96); seconds = sample / fs. */
+typedef struct syldet_event {
+    int32_t channel;
+    int32_t reserved;
+    int64_t sample; /* S_j = gap + W + stride*(T-1) + stride*j (TrackDetector.swift:39-42,67-68) */
+} syldet_event;
+
+const char *syldet_last_error(void);
+const char *syldet_version(void);
+/* Number of usable CUDA devices with compute capability 10.x; 0 when none. */
+int syldet_device_count(void);
+
+/* ---- configuration: SyllableDetectorConfig.init(fromTextFile:) (SyllableDetectorConfig.swift:170-277) ------------ */
+syldet_status syldet_config_load_text(const char *path, syldet_config **out);
+syldet_status syldet_config_parse_text(const char *text, size_t len, syldet_config **out);
+void syldet_config_free(syldet_config *cfg);
+/* name of the key the last parse error on this thread refers to (the String payload of ParseError) */
+const char *syldet_config_error_key(void);
+
+double syldet_config_sampling_rate(const syldet_config *cfg);
+int syldet_config_fourier_length(const syldet_config *cfg);
+int syldet_config_window_length(const syldet_config *cfg);
+int syldet_config_window_overlap(const syldet_config *cfg); /* raw value; negative = gap (CSTFT.swift:66-73) */
+int syldet_config_time_range(const syldet_config *cfg);
+int syldet_config_scaling(const syldet_config *cfg);
+syldet_status syldet_config_freq_range(const syldet_config *cfg, double *lo, double *hi);
+int syldet_config_threshold_count(const syldet_config *cfg);
+syldet_status syldet_config_thresholds(const syldet_config *cfg, double *out, int cap);
+int syldet_config_net_inputs(const syldet_config *cfg);  /* NeuralNet.inputs  (NeuralNet.swift:235) */
+int syldet_config_net_outputs(const syldet_config *cfg); /* NeuralNet.outputs (:236) */
+int syldet_config_layer_count(const syldet_config *cfg);
+syldet_status syldet_config_layer_info(const syldet_config *cfg, int layer, int *inputs, int *outputs, int *transfer);
+syldet_status syldet_config_layer_weights(const syldet_config *cfg, int layer, float *w, size_t cap); /* row-major [out][in] */
+syldet_status syldet_config_layer_biases(const syldet_config *cfg, int layer, float *b, size_t cap);
+int syldet_config_input_processing_count(const syldet_config *cfg);
+int syldet_config_output_processing_count(const syldet_config *cfg);
+/* which: 0 = input chain, 1 = output chain. xoff/gain may be NULL; they receive `n` values for mapminmax/mapstd. */
+syldet_status syldet_config_processing(const syldet_config *cfg, int which, int index, int *function, float *y,
+                                       float *xoff, float *gain, size_t cap);
+
+/* The checks SyllableDetector.init performs (SyllableDetector.swift:37-60, CSTFT.swift:61-129). Also run by every *_create. */
+syldet_status syldet_config_validate(const syldet_config *cfg);
+/* frequencyIndexRange (CSTFT.swift:166-191) of the configured band. */
+syldet_status syldet_config_freq_index_range(const syldet_config *cfg, int *start, int *end);
+int syldet_config_gap(const syldet_config *cfg);
+int syldet_config_hop(const syldet_config *cfg);                               /* gap + W - overlap */
+int64_t syldet_config_first_output_sample(const syldet_config *cfg);           /* TrackDetector.swift:39-42 */
+int64_t syldet_config_num_columns(const syldet_config *cfg, int64_t n_samples);
+int64_t syldet_config_num_evals(const syldet_config *cfg, int64_t n_samples);
+/* Int(seconds * samplingRate) (TrackDetector.swift:23-25) */
+int64_t syldet_config_debounce_frames(const syldet_config *cfg, double seconds);
+
+/* ---- batch: what TrackDetector.process + main.swift do, for n_channels independent channels ---------------------- */
+syldet_status syldet_batch_create(const syldet_config *cfg, int device, syldet_batch **out);
+void syldet_batch_destroy(syldet_batch *b);
+/* SYLDET_KERNEL_AUTO picks the fused kernel when the configuration qualifies, else the generic path. */
+syldet_status syldet_batch_set_kernel(syldet_batch *b, int kernel);
+int syldet_batch_active_kernel(const syldet_batch *b);
+
+/*
+ * Host buffers in, events out (H2D copy, kernels, D2H of the sparse events, host-side debounce).
+ *   pcm            planar: channel c starts at pcm + c*channel_stride; interleaved: sample i of channel c at pcm[i*n_channels + c]
+ *   pcm_format     SYLDET_PCM_F32 (float) or SYLDET_PCM_S16 (int16, converted on the device as x/32768)
+ *   debounce_frames  TrackDetector.debounceFrames; 0 = every detected evaluation is an event
+ *   all_outputs    optional host buffer [n_channels][E][O] receiving every network output (E = num_evals)
+ *   events         receives a new syldet_events (sorted by channel, then sample); free with syldet_events_free
+ */
+syldet_status syldet_batch_run_host(syldet_batch *b, const void *pcm, int pcm_format, int n_channels, int64_t n_samples,
+                                    int64_t channel_stride, int layout, int64_t debounce_frames, int detect_rule,
+                                    float *all_outputs, syldet_events **events);
+/*
+ * Device-resident variant: d_pcm is a device pointer (float32), d_all_outputs an optional device buffer.
+ * `stream` is a cudaStream_t (NULL = legacy default stream).  Launches are asynchronous; nothing is copied to the host.
+ * Call syldet_batch_collect afterwards to synchronise and fetch the events.
+ */
+syldet_status syldet_batch_launch_device(syldet_batch *b, const float *d_pcm, int n_channels, int64_t n_samples,
+                                         int64_t channel_stride, int layout, int detect_rule, float *d_all_outputs,
+                                         void *stream);
+syldet_status syldet_batch_collect(syldet_batch *b, int64_t debounce_frames, syldet_events **events);
+/* Kernels launched by this handle since creation (for bench.py's gpu_launches). */
+int64_t syldet_batch_launch_count(const syldet_batch *b);
+/* Raw detection count of the last launch before debounce (synchronises). */
+syldet_status syldet_batch_last_detection_count(syldet_batch *b, int64_t *count);
+
+int64_t syldet_events_count(const syldet_events *ev);
+int syldet_events_outputs_per_event(const syldet_events *ev);
+const syldet_event *syldet_events_data(const syldet_events *ev);
+const float *syldet_events_outputs(const syldet_events *ev); /* [count][O] */
+void syldet_events_free(syldet_events *ev);
+
+/* ---- one stream: class SyllableDetector (Common/SyllableDetector.swift:13-231) ------------------------------------ */
+syldet_status syldet_detector_create(const syldet_config *cfg, int device, syldet_detector **out);
+void syldet_detector_destroy(syldet_detector *d);
+/* appendAudioData(_:withSamples:) (:129-132). SYLDET_ERR_OVERFLOW mirrors the 409 600-byte ring (CSTFT.swift:61,199). */
+syldet_status syldet_detector_append(syldet_detector *d, const float *samples, int64_t n);
+/* processNewValue() (:153-217): 1 = a new evaluation was produced (see last_outputs), 0 = not enough data, <0 = -status */
+int syldet_detector_process_new_value(syldet_detector *d);
+syldet_status syldet_detector_last_outputs(const syldet_detector *d, float *out, int cap); /* lastOutputs (:26) */
+int syldet_detector_last_detected(const syldet_detector *d);                               /* lastDetected (:27-31) */
+int syldet_detector_seen_syllable(syldet_detector *d);                                     /* seenSyllable() (:220-230) */
+
+/* ---- live group: Processor.swift (one detector per channel, small buffers per tick) -------------------------------- */
+syldet_status syldet_stream_create(const syldet_config *cfg, int n_channels, int max_buffer, int device, syldet_stream **out);
+void syldet_stream_destroy(syldet_stream *s);
+/*
+ * One tick: bufs[c] points at n float32 samples for channel c (receiveAudioFrom(...) for every channel, Processor.swift:102-149).
+ * On return seen[c] = 1 iff any evaluation completed by this tick had output 0 >= threshold 0 (the `seen` flag of :131-147),
+ * n_new[c] = evaluations completed, last_out[c*O..] = outputs of the newest evaluation (unchanged if none). Arrays may be NULL.
+ */
+syldet_status syldet_stream_submit(syldet_stream *s, const float *const *bufs, int n, uint8_t *seen, int32_t *n_new,
+                                   float *last_out);
+int64_t syldet_stream_launch_count(const syldet_stream *s);
+
+/* ---- ResamplerLinear (Common/Resampler.swift:20-70), bit-faithful including per-buffer state ------------------------ */
+syldet_status syldet_resampler_linear_create(double rate_in, double rate_out, syldet_resampler **out);
+void syldet_resampler_destroy(syldet_resampler *r);
+/* resampleVector(_:ofLength:) (:35-70). *n_out receives the produced count; SYLDET_ERR_ARG if cap is too small. */
+syldet_status syldet_resampler_process(syldet_resampler *r, const float *in, int64_t n_in, float *out, int64_t cap,
+                                       int64_t *n_out);
+/* Upper bound of samples one call can produce for n_in inputs. */
+int64_t syldet_resampler_max_output(const syldet_resampler *r, int64_t n_in);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SYLDET_H */

@@ -1,0 +1,303 @@
+// extern "C" surface of libsyldet_cuda.so (include/syldet.h). Thin forwarding only.
+#include <cstring>
+#include <new>
+
+#include "engine.hpp"
+#include "stream.hpp"
+
+using namespace syldet;
+
+namespace {
+template <typename F>
+syldet_status guarded(F &&f) {
+    try {
+        return f();
+    } catch (const std::bad_alloc &) {
+        return set_error(SYLDET_ERR_NOMEM, "out of host memory");
+    } catch (const std::exception &e) {
+        return set_error(SYLDET_ERR_ARG, std::string("unexpected exception: ") + e.what());
+    }
+}
+const Config *valid_or_null(const syldet_config *cfg) { return cfg ? &cfg->c : nullptr; }
+}  // namespace
+
+extern "C" {
+
+const char *syldet_last_error(void) { return last_error_message().c_str(); }
+const char *syldet_config_error_key(void) { return last_error_key().c_str(); }
+const char *syldet_version(void) { return "syldet-b200 0.1.0 (sm_100a)"; }
+int syldet_device_count(void) { return usable_device_count(); }
+
+syldet_status syldet_config_load_text(const char *path, syldet_config **out) {
+    if (!path || !out) return set_error(SYLDET_ERR_ARG, "null argument");
+    *out = nullptr;
+    return guarded([&] {
+        auto *cfg = new syldet_config();
+        syldet_status st = load_config_file(path, cfg->c);
+        if (st != SYLDET_OK) { delete cfg; return st; }
+        *out = cfg;
+        return SYLDET_OK;
+    });
+}
+
+syldet_status syldet_config_parse_text(const char *text, size_t len, syldet_config **out) {
+    if (!text || !out) return set_error(SYLDET_ERR_ARG, "null argument");
+    *out = nullptr;
+    return guarded([&] {
+        auto *cfg = new syldet_config();
+        syldet_status st = parse_config_text(text, len, cfg->c);
+        if (st != SYLDET_OK) { delete cfg; return st; }
+        *out = cfg;
+        return SYLDET_OK;
+    });
+}
+
+void syldet_config_free(syldet_config *cfg) { delete cfg; }
+
+double syldet_config_sampling_rate(const syldet_config *cfg) { return cfg->c.sampling_rate; }
+int syldet_config_fourier_length(const syldet_config *cfg) { return cfg->c.fourier_length; }
+int syldet_config_window_length(const syldet_config *cfg) { return cfg->c.window_length; }
+int syldet_config_window_overlap(const syldet_config *cfg) { return cfg->c.window_overlap; }
+int syldet_config_time_range(const syldet_config *cfg) { return cfg->c.time_range; }
+int syldet_config_scaling(const syldet_config *cfg) { return cfg->c.scaling; }
+syldet_status syldet_config_freq_range(const syldet_config *cfg, double *lo, double *hi) {
+    if (!cfg || !lo || !hi) return set_error(SYLDET_ERR_ARG, "null argument");
+    *lo = cfg->c.freq_lo;
+    *hi = cfg->c.freq_hi;
+    return SYLDET_OK;
+}
+int syldet_config_threshold_count(const syldet_config *cfg) { return (int)cfg->c.thresholds.size(); }
+syldet_status syldet_config_thresholds(const syldet_config *cfg, double *out, int cap) {
+    if (!cfg || !out) return set_error(SYLDET_ERR_ARG, "null argument");
+    if (cap < (int)cfg->c.thresholds.size()) return set_error(SYLDET_ERR_ARG, "capacity too small");
+    std::memcpy(out, cfg->c.thresholds.data(), cfg->c.thresholds.size() * sizeof(double));
+    return SYLDET_OK;
+}
+int syldet_config_net_inputs(const syldet_config *cfg) { return cfg->c.layers.empty() ? 0 : cfg->c.layers.front().inputs; }
+int syldet_config_net_outputs(const syldet_config *cfg) { return cfg->c.layers.empty() ? 0 : cfg->c.layers.back().outputs; }
+int syldet_config_layer_count(const syldet_config *cfg) { return (int)cfg->c.layers.size(); }
+syldet_status syldet_config_layer_info(const syldet_config *cfg, int layer, int *inputs, int *outputs, int *transfer) {
+    if (!cfg || layer < 0 || layer >= (int)cfg->c.layers.size()) return set_error(SYLDET_ERR_ARG, "layer index out of range");
+    if (inputs) *inputs = cfg->c.layers[layer].inputs;
+    if (outputs) *outputs = cfg->c.layers[layer].outputs;
+    if (transfer) *transfer = cfg->c.layers[layer].transfer;
+    return SYLDET_OK;
+}
+syldet_status syldet_config_layer_weights(const syldet_config *cfg, int layer, float *w, size_t cap) {
+    if (!cfg || !w || layer < 0 || layer >= (int)cfg->c.layers.size()) return set_error(SYLDET_ERR_ARG, "layer index out of range");
+    const auto &v = cfg->c.layers[layer].weights;
+    if (cap < v.size()) return set_error(SYLDET_ERR_ARG, "capacity too small");
+    std::memcpy(w, v.data(), v.size() * sizeof(float));
+    return SYLDET_OK;
+}
+syldet_status syldet_config_layer_biases(const syldet_config *cfg, int layer, float *b, size_t cap) {
+    if (!cfg || !b || layer < 0 || layer >= (int)cfg->c.layers.size()) return set_error(SYLDET_ERR_ARG, "layer index out of range");
+    const auto &v = cfg->c.layers[layer].biases;
+    if (cap < v.size()) return set_error(SYLDET_ERR_ARG, "capacity too small");
+    std::memcpy(b, v.data(), v.size() * sizeof(float));
+    return SYLDET_OK;
+}
+int syldet_config_input_processing_count(const syldet_config *cfg) { return (int)cfg->c.input_processing.size(); }
+int syldet_config_output_processing_count(const syldet_config *cfg) { return (int)cfg->c.output_processing.size(); }
+syldet_status syldet_config_processing(const syldet_config *cfg, int which, int index, int *function, float *y, float *xoff,
+                                       float *gain, size_t cap) {
+    if (!cfg || (which != 0 && which != 1)) return set_error(SYLDET_ERR_ARG, "bad chain selector");
+    const auto &chain = which == 0 ? cfg->c.input_processing : cfg->c.output_processing;
+    if (index < 0 || index >= (int)chain.size()) return set_error(SYLDET_ERR_ARG, "processing index out of range");
+    const Processing &p = chain[index];
+    if (function) *function = p.function;
+    if (y) *y = p.y;
+    if (xoff) {
+        if (cap < p.x_offsets.size()) return set_error(SYLDET_ERR_ARG, "capacity too small");
+        std::memcpy(xoff, p.x_offsets.data(), p.x_offsets.size() * sizeof(float));
+    }
+    if (gain) {
+        if (cap < p.gains.size()) return set_error(SYLDET_ERR_ARG, "capacity too small");
+        std::memcpy(gain, p.gains.data(), p.gains.size() * sizeof(float));
+    }
+    return SYLDET_OK;
+}
+
+syldet_status syldet_config_validate(const syldet_config *cfg) {
+    if (!cfg) return set_error(SYLDET_ERR_ARG, "null argument");
+    return guarded([&] { return validate_config(const_cast<syldet_config *>(cfg)->c); });
+}
+static bool ensure_valid(const syldet_config *cfg) {
+    return cfg && (cfg->c.valid || validate_config(const_cast<syldet_config *>(cfg)->c) == SYLDET_OK);
+}
+syldet_status syldet_config_freq_index_range(const syldet_config *cfg, int *start, int *end) {
+    if (!cfg || !start || !end) return set_error(SYLDET_ERR_ARG, "null argument");
+    if (!frequency_index_range(cfg->c.fourier_length, cfg->c.freq_lo, cfg->c.freq_hi, cfg->c.sampling_rate, *start, *end))
+        return set_error(SYLDET_ERR_CONFIG, "The frequency range is invalid.", "freqRange");
+    return SYLDET_OK;
+}
+int syldet_config_gap(const syldet_config *cfg) { return ensure_valid(cfg) ? cfg->c.gap : -1; }
+int syldet_config_hop(const syldet_config *cfg) { return ensure_valid(cfg) ? cfg->c.hop : -1; }
+int64_t syldet_config_first_output_sample(const syldet_config *cfg) { return ensure_valid(cfg) ? cfg->c.first_output_sample() : -1; }
+int64_t syldet_config_num_columns(const syldet_config *cfg, int64_t n) { return ensure_valid(cfg) ? cfg->c.num_columns(n) : -1; }
+int64_t syldet_config_num_evals(const syldet_config *cfg, int64_t n) { return ensure_valid(cfg) ? cfg->c.num_evals(n) : -1; }
+int64_t syldet_config_debounce_frames(const syldet_config *cfg, double seconds) {
+    return (int64_t)(seconds * cfg->c.sampling_rate);  // Int(newValue * samplingRate), TrackDetector.swift:23-25
+}
+
+// ---- batch ---------------------------------------------------------------------------------------------------------
+syldet_status syldet_batch_create(const syldet_config *cfg, int device, syldet_batch **out) {
+    if (!valid_or_null(cfg) || !out) return set_error(SYLDET_ERR_ARG, "null argument");
+    *out = nullptr;
+    return guarded([&] {
+        auto *b = new syldet_batch();
+        syldet_status st = b->b.init(cfg->c, device);
+        if (st != SYLDET_OK) { delete b; return st; }
+        *out = b;
+        return SYLDET_OK;
+    });
+}
+void syldet_batch_destroy(syldet_batch *b) { delete b; }
+syldet_status syldet_batch_set_kernel(syldet_batch *b, int kernel) {
+    if (!b) return set_error(SYLDET_ERR_ARG, "null argument");
+    return b->b.set_kernel(kernel);
+}
+int syldet_batch_active_kernel(const syldet_batch *b) { return b ? b->b.active_kernel() : -1; }
+
+syldet_status syldet_batch_run_host(syldet_batch *b, const void *pcm, int pcm_format, int n_channels, int64_t n_samples,
+                                    int64_t channel_stride, int layout, int64_t debounce_frames, int detect_rule,
+                                    float *all_outputs, syldet_events **events) {
+    if (!b || !events) return set_error(SYLDET_ERR_ARG, "null argument");
+    *events = nullptr;
+    return guarded([&] {
+        auto *ev = new syldet_events();
+        syldet_status st = b->b.run_host(pcm, pcm_format, n_channels, n_samples, channel_stride, layout, debounce_frames,
+                                         detect_rule, all_outputs, ev->e);
+        if (st != SYLDET_OK) { delete ev; return st; }
+        *events = ev;
+        return SYLDET_OK;
+    });
+}
+syldet_status syldet_batch_launch_device(syldet_batch *b, const float *d_pcm, int n_channels, int64_t n_samples,
+                                         int64_t channel_stride, int layout, int detect_rule, float *d_all_outputs, void *stream) {
+    if (!b) return set_error(SYLDET_ERR_ARG, "null argument");
+    return guarded([&] {
+        return b->b.launch_device(d_pcm, n_channels, n_samples, channel_stride, layout, detect_rule, d_all_outputs,
+                                  static_cast<cudaStream_t>(stream));
+    });
+}
+syldet_status syldet_batch_collect(syldet_batch *b, int64_t debounce_frames, syldet_events **events) {
+    if (!b || !events) return set_error(SYLDET_ERR_ARG, "null argument");
+    *events = nullptr;
+    return guarded([&] {
+        auto *ev = new syldet_events();
+        syldet_status st = b->b.collect(debounce_frames, ev->e);
+        if (st != SYLDET_OK) { delete ev; return st; }
+        *events = ev;
+        return SYLDET_OK;
+    });
+}
+int64_t syldet_batch_launch_count(const syldet_batch *b) { return b ? b->b.launch_count() : 0; }
+syldet_status syldet_batch_last_detection_count(syldet_batch *b, int64_t *count) {
+    if (!b || !count) return set_error(SYLDET_ERR_ARG, "null argument");
+    return b->b.last_detection_count(count);
+}
+
+int64_t syldet_events_count(const syldet_events *ev) { return ev ? (int64_t)ev->e.rows.size() : 0; }
+int syldet_events_outputs_per_event(const syldet_events *ev) { return ev ? ev->e.outputs_per_event : 0; }
+const syldet_event *syldet_events_data(const syldet_events *ev) { return ev ? ev->e.rows.data() : nullptr; }
+const float *syldet_events_outputs(const syldet_events *ev) { return ev ? ev->e.outputs.data() : nullptr; }
+void syldet_events_free(syldet_events *ev) { delete ev; }
+
+// ---- single stream ---------------------------------------------------------------------------------------------------
+syldet_status syldet_detector_create(const syldet_config *cfg, int device, syldet_detector **out) {
+    if (!valid_or_null(cfg) || !out) return set_error(SYLDET_ERR_ARG, "null argument");
+    *out = nullptr;
+    return guarded([&] {
+        auto *d = new syldet_detector();
+        syldet_status st = d->d.init(cfg->c, device);
+        if (st != SYLDET_OK) { delete d; return st; }
+        *out = d;
+        return SYLDET_OK;
+    });
+}
+void syldet_detector_destroy(syldet_detector *d) { delete d; }
+syldet_status syldet_detector_append(syldet_detector *d, const float *samples, int64_t n) {
+    if (!d) return set_error(SYLDET_ERR_ARG, "null argument");
+    return guarded([&] { return d->d.append(samples, n); });
+}
+int syldet_detector_process_new_value(syldet_detector *d) {
+    if (!d) return -(int)set_error(SYLDET_ERR_ARG, "null argument");
+    try {
+        return d->d.process_new_value();
+    } catch (const std::exception &e) {
+        return -(int)set_error(SYLDET_ERR_NOMEM, e.what());
+    }
+}
+syldet_status syldet_detector_last_outputs(const syldet_detector *d, float *out, int cap) {
+    if (!d || !out) return set_error(SYLDET_ERR_ARG, "null argument");
+    const auto &v = d->d.last_outputs();
+    if (cap < (int)v.size()) return set_error(SYLDET_ERR_ARG, "capacity too small");
+    std::memcpy(out, v.data(), v.size() * sizeof(float));
+    return SYLDET_OK;
+}
+int syldet_detector_last_detected(const syldet_detector *d) { return d && d->d.last_detected() ? 1 : 0; }
+int syldet_detector_seen_syllable(syldet_detector *d) {
+    if (!d) return -(int)set_error(SYLDET_ERR_ARG, "null argument");
+    try {
+        return d->d.seen_syllable();
+    } catch (const std::exception &e) {
+        return -(int)set_error(SYLDET_ERR_NOMEM, e.what());
+    }
+}
+
+// ---- live group ------------------------------------------------------------------------------------------------------
+syldet_status syldet_stream_create(const syldet_config *cfg, int n_channels, int max_buffer, int device, syldet_stream **out) {
+    if (!valid_or_null(cfg) || !out) return set_error(SYLDET_ERR_ARG, "null argument");
+    *out = nullptr;
+    return guarded([&] {
+        auto *s = new syldet_stream();
+        syldet_status st = s->g.init(cfg->c, n_channels, max_buffer, device);
+        if (st != SYLDET_OK) { delete s; return st; }
+        *out = s;
+        return SYLDET_OK;
+    });
+}
+void syldet_stream_destroy(syldet_stream *s) { delete s; }
+syldet_status syldet_stream_submit(syldet_stream *s, const float *const *bufs, int n, uint8_t *seen, int32_t *n_new, float *last_out) {
+    if (!s || !bufs) return set_error(SYLDET_ERR_ARG, "null argument");
+    return guarded([&] {
+        const float *outs = nullptr;
+        int64_t fresh = 0;
+        syldet_status st = s->g.submit(bufs, n, &outs, &fresh);
+        if (st != SYLDET_OK) return st;
+        const Config &c = s->g.config();
+        const int O = c.outputs, nch = s->g.n_channels();
+        for (int ch = 0; ch < nch; ++ch) {
+            bool any = false;
+            for (int64_t j = 0; j < fresh; ++j)  // lastDetected for every new value (Processor.swift:136-144)
+                if ((double)outs[((size_t)ch * fresh + j) * O] >= c.thresholds[0]) any = true;
+            if (seen) seen[ch] = any ? 1 : 0;
+            if (n_new) n_new[ch] = (int32_t)fresh;
+            if (last_out && fresh > 0) std::memcpy(last_out + (size_t)ch * O, outs + ((size_t)ch * fresh + fresh - 1) * O, O * sizeof(float));
+        }
+        return SYLDET_OK;
+    });
+}
+int64_t syldet_stream_launch_count(const syldet_stream *s) { return s ? s->g.launch_count() : 0; }
+
+// ---- resampler -------------------------------------------------------------------------------------------------------
+syldet_status syldet_resampler_linear_create(double rate_in, double rate_out, syldet_resampler **out) {
+    if (!out) return set_error(SYLDET_ERR_ARG, "null argument");
+    *out = nullptr;
+    return guarded([&] {
+        auto *r = new syldet_resampler();
+        syldet_status st = r->r.init(rate_in, rate_out, 0);
+        if (st != SYLDET_OK) { delete r; return st; }
+        *out = r;
+        return SYLDET_OK;
+    });
+}
+void syldet_resampler_destroy(syldet_resampler *r) { delete r; }
+syldet_status syldet_resampler_process(syldet_resampler *r, const float *in, int64_t n_in, float *out, int64_t cap, int64_t *n_out) {
+    if (!r || !out || !n_out) return set_error(SYLDET_ERR_ARG, "null argument");
+    return guarded([&] { return r->r.process(in, n_in, out, cap, n_out); });
+}
+int64_t syldet_resampler_max_output(const syldet_resampler *r, int64_t n_in) { return r ? r->r.max_output(n_in) : 0; }
+
+}  // extern "C"

@@ -1,0 +1,511 @@
+#include "engine.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+
+namespace syldet {
+
+syldet_status cuda_fail(cudaError_t e, const char *what) {
+    return set_error(SYLDET_ERR_CUDA, std::string("CUDA error '") + cudaGetErrorString(e) + "' in " + what);
+}
+
+int usable_device_count() {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int d = 0; d < n; ++d) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ++ok;
+    }
+    return ok;
+}
+
+syldet_status use_device(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return set_error(SYLDET_ERR_CUDA, "no CUDA device is visible; libsyldet_cuda has no CPU fallback");
+    }
+    if (device < 0 || device >= n) return set_error(SYLDET_ERR_ARG, "device index out of range");
+    int major = 0;
+    SYLDET_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    if (major != 10) return set_error(SYLDET_ERR_CUDA, "device is not compute capability 10.x; the kernels are built for sm_100a only");
+    SYLDET_CUDA(cudaSetDevice(device));
+    return SYLDET_OK;
+}
+
+DeviceBuffer::~DeviceBuffer() {
+    if (ptr_) cudaFree(ptr_);
+}
+
+syldet_status DeviceBuffer::reserve(size_t bytes) {
+    if (bytes <= size_) return SYLDET_OK;
+    if (ptr_) { cudaFree(ptr_); ptr_ = nullptr; size_ = 0; }
+    cudaError_t e = cudaMalloc(&ptr_, bytes);
+    if (e != cudaSuccess) {
+        ptr_ = nullptr;
+        cudaGetLastError();
+        return set_error(SYLDET_ERR_NOMEM, "cudaMalloc of " + std::to_string(bytes) + " bytes failed: " + cudaGetErrorString(e));
+    }
+    size_ = bytes;
+    return SYLDET_OK;
+}
+
+// -----------------------------------------------------------------------------------------------------------------
+FusedPlan plan_fused(const Config &c) {
+    FusedPlan plan;
+    auto no = [&](const std::string &why) { plan.ok = false; plan.why = why; return plan; };
+    const int N = c.fourier_length;
+    if (!fused_supports_fft(N)) return no("fourierLength not in {64,128,256,512}");
+    if (c.band > kFusedMaxBand) return no("band wider than 128 bins");
+    if ((int)c.layers.size() > kFusedMaxLayers) return no("more than 4 layers");
+    if (c.outputs > kFusedMaxOut) return no("more than 8 outputs");
+    if ((int)c.output_processing.size() > kMaxProcessing) return no("too many output processing functions");
+    for (size_t l = 0; l < c.layers.size(); ++l)
+        if (c.layers[l].outputs > kFusedMaxHidden) return no("a layer is wider than 8 units");
+    const int H = c.layers[0].outputs, I = c.inputs;
+    const int hp = H <= 4 ? 4 : 8;
+    if ((long)I * hp > kFusedMaxW0) return no("layer 0 does not fit the kernel parameter space");
+
+    // input chain: [one per-window statistic]? followed by per-position affine maps
+    FusedParams &p = plan.params;
+    std::memset(&p, 0, sizeof p);
+    p.window_stat = FUSED_STAT_NONE;
+    std::vector<double> A(I, 1.0), C(I, 0.0);  // y_i = A_i * (alpha x_i + beta) + C_i
+    for (size_t k = 0; k < c.input_processing.size(); ++k) {
+        const Processing &pr = c.input_processing[k];
+        if (pr.function == SYLDET_PROC_MAPMINMAX || pr.function == SYLDET_PROC_MAPSTD) {
+            for (int i = 0; i < I; ++i) {
+                A[i] = A[i] * (double)pr.gains[i];
+                C[i] = (C[i] - (double)pr.x_offsets[i]) * (double)pr.gains[i] + (double)pr.y;
+            }
+        } else {
+            if (k != 0) return no("a per-window normaliser after another processing function");
+            p.window_stat = pr.function == SYLDET_PROC_L2NORMALIZE ? FUSED_STAT_L2
+                          : pr.function == SYLDET_PROC_NORMALIZE ? FUSED_STAT_MINMAX : FUSED_STAT_STD;
+        }
+    }
+    const Layer &l0 = c.layers[0];
+    for (int h = 0; h < H; ++h) {
+        double v = 0.0, b = (double)l0.biases[h];
+        for (int i = 0; i < I; ++i) {
+            const double w = (double)l0.weights[(size_t)h * I + i];
+            p.w0[(size_t)i * hp + h] = (float)(w * A[i]);
+            v += w * A[i];
+            b += w * C[i];
+        }
+        p.v[h] = (float)v;
+        p.bprime[h] = (float)b;
+    }
+    p.n_layers = (int)c.layers.size();
+    for (int l = 0; l < p.n_layers; ++l) p.tf[l] = c.layers[l].transfer;
+    for (int l = 1; l < p.n_layers; ++l) {
+        const Layer &ly = c.layers[l];
+        for (int o = 0; o < ly.outputs; ++o) {
+            for (int i = 0; i < ly.inputs; ++i)
+                p.rest_w[((l - 1) * kFusedMaxHidden + o) * kFusedMaxHidden + i] = ly.weights[(size_t)o * ly.inputs + i];
+            p.rest_b[(l - 1) * kFusedMaxHidden + o] = ly.biases[o];
+        }
+    }
+    p.n_out = c.outputs;
+    p.n_op = (int)c.output_processing.size();
+    for (int k = 0; k < p.n_op; ++k) {
+        const Processing &pr = c.output_processing[k];
+        p.op_y[k] = pr.y;
+        for (int o = 0; o < c.outputs; ++o) {
+            p.op_gain[k * kFusedMaxOut + o] = pr.gains[o];
+            p.op_xoff[k * kFusedMaxOut + o] = pr.x_offsets[o];
+        }
+    }
+    for (int o = 0; o < c.outputs; ++o) p.thr[o] = c.thresholds[o];
+
+    p.win_len = c.window_length;
+    p.gap = c.gap;
+    p.hop = c.hop;
+    p.k0 = c.k0;
+    p.band = c.band;
+    p.time_range = c.time_range;
+    p.scaling = c.scaling;
+    p.band_pitch = c.band | 1;
+    const int rc = fused_round_cols(N);
+    p.nn_tile = std::max(2 * rc, kFusedThreads - rc);
+    p.ring_cols = p.nn_tile + 2 * rc + c.time_range;
+    const long span = (long)(rc - 1) * c.hop + c.window_length + 3;
+    if (span > (1L << 16)) return no("hop too large for shared-memory staging");
+    p.abuf_floats = (int)((span + 3) & ~3L) + 4;
+    plan.launch.fft_len = N;
+    plan.launch.hp = hp;
+    plan.launch.smem = fused_smem_bytes(N, p);
+    if (plan.launch.smem > 200 * 1024) return no("shared-memory working set too large");
+    plan.ok = true;
+    return plan;
+}
+
+// -----------------------------------------------------------------------------------------------------------------
+syldet_status DeviceModel::init(const Config &cfg, int device) {
+    cfg_ = cfg;
+    if (!cfg_.valid) {
+        syldet_status st = validate_config(cfg_);
+        if (st != SYLDET_OK) return st;
+    }
+    if ((int)cfg_.input_processing.size() > kMaxProcessing || (int)cfg_.output_processing.size() > kMaxProcessing)
+        return set_error(SYLDET_ERR_UNSUPPORTED, "more than 8 processing functions in a chain");
+    if ((int)cfg_.layers.size() > kMaxLayers) return set_error(SYLDET_ERR_UNSUPPORTED, "more than 8 layers");
+    if (cfg_.fourier_length > 16384) return set_error(SYLDET_ERR_UNSUPPORTED, "fourierLength above 16384");
+    max_width_ = cfg_.inputs;
+    for (const Layer &l : cfg_.layers) max_width_ = std::max(max_width_, l.outputs);
+    if (max_width_ > 12288) return set_error(SYLDET_ERR_UNSUPPORTED, "a layer wider than 12288 units");
+    syldet_status st = use_device(device);
+    if (st != SYLDET_OK) return st;
+    device_ = device;
+    SYLDET_CUDA(cudaDeviceGetAttribute(&sm_count_, cudaDevAttrMultiProcessorCount, device));
+
+    // one blob: [thresholds (double)] [window] [twiddle] [per-layer w,b] [per-processing xoff,gain]
+    std::vector<unsigned char> blob;
+    auto put = [&](const void *src, size_t bytes) {
+        size_t off = (blob.size() + 15) & ~(size_t)15;
+        blob.resize(off + bytes);
+        std::memcpy(blob.data() + off, src, bytes);
+        return off;
+    };
+    const int N = cfg_.fourier_length, W = cfg_.window_length;
+    std::vector<float> window(W);
+    for (int n = 0; n < W; ++n)  // vDSP_hamm_window, N-denominator (CSTFT.swift:24, forced at SyllableDetector.swift:43)
+        window[n] = (float)(0.54 - 0.46 * std::cos(2.0 * M_PI * (double)n / (double)W));
+    std::vector<float2> tw(std::max(1, N / 2));
+    for (int k = 0; k < N / 2; ++k) {
+        const double a = -2.0 * M_PI * (double)k / (double)N;
+        tw[k] = make_float2((float)std::cos(a), (float)std::sin(a));
+    }
+    const size_t off_thr = put(cfg_.thresholds.data(), cfg_.thresholds.size() * sizeof(double));
+    const size_t off_win = put(window.data(), window.size() * sizeof(float));
+    const size_t off_tw = put(tw.data(), tw.size() * sizeof(float2));
+    std::vector<size_t> off_w, off_b;
+    for (const Layer &l : cfg_.layers) {
+        off_w.push_back(put(l.weights.data(), l.weights.size() * sizeof(float)));
+        off_b.push_back(put(l.biases.data(), l.biases.size() * sizeof(float)));
+    }
+    auto put_proc = [&](const std::vector<Processing> &ps, std::vector<size_t> &xo, std::vector<size_t> &g) {
+        for (const Processing &p : ps) {
+            xo.push_back(p.x_offsets.empty() ? 0 : put(p.x_offsets.data(), p.x_offsets.size() * sizeof(float)));
+            g.push_back(p.gains.empty() ? 0 : put(p.gains.data(), p.gains.size() * sizeof(float)));
+        }
+    };
+    std::vector<size_t> ixo, ig, oxo, og;
+    put_proc(cfg_.input_processing, ixo, ig);
+    put_proc(cfg_.output_processing, oxo, og);
+
+    st = d_blob_.reserve(blob.size());
+    if (st != SYLDET_OK) return st;
+    SYLDET_CUDA(cudaMemcpy(d_blob_.get(), blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    const unsigned char *base = d_blob_.as<unsigned char>();
+    d_window_ = reinterpret_cast<const float *>(base + off_win);
+    d_twiddle_ = reinterpret_cast<const float2 *>(base + off_tw);
+
+    DevNet net{};
+    net.fft_len = N;
+    net.win_len = W;
+    net.gap = cfg_.gap;
+    net.hop = cfg_.hop;
+    net.k0 = cfg_.k0;
+    net.band = cfg_.band;
+    net.time_range = cfg_.time_range;
+    net.inputs = cfg_.inputs;
+    net.outputs = cfg_.outputs;
+    net.scaling = cfg_.scaling;
+    net.n_ip = (int)cfg_.input_processing.size();
+    net.n_op = (int)cfg_.output_processing.size();
+    net.n_layers = (int)cfg_.layers.size();
+    net.max_width = max_width_;
+    auto fill_proc = [&](const std::vector<Processing> &ps, const std::vector<size_t> &xo, const std::vector<size_t> &g, DevProcessing *dst) {
+        for (size_t i = 0; i < ps.size(); ++i) {
+            dst[i].function = ps[i].function;
+            dst[i].y = ps[i].y;
+            dst[i].xoff = ps[i].x_offsets.empty() ? nullptr : reinterpret_cast<const float *>(base + xo[i]);
+            dst[i].gain = ps[i].gains.empty() ? nullptr : reinterpret_cast<const float *>(base + g[i]);
+        }
+    };
+    fill_proc(cfg_.input_processing, ixo, ig, net.ip);
+    fill_proc(cfg_.output_processing, oxo, og, net.op);
+    for (size_t i = 0; i < cfg_.layers.size(); ++i) {
+        net.layers[i].inputs = cfg_.layers[i].inputs;
+        net.layers[i].outputs = cfg_.layers[i].outputs;
+        net.layers[i].transfer = cfg_.layers[i].transfer;
+        net.layers[i].w = reinterpret_cast<const float *>(base + off_w[i]);
+        net.layers[i].b = reinterpret_cast<const float *>(base + off_b[i]);
+    }
+    net.thresholds = reinterpret_cast<const double *>(base + off_thr);
+    net.window = d_window_;
+    net.twiddle = d_twiddle_;
+    st = d_net_.reserve(sizeof(DevNet));
+    if (st != SYLDET_OK) return st;
+    SYLDET_CUDA(cudaMemcpy(d_net_.get(), &net, sizeof net, cudaMemcpyHostToDevice));
+
+    fused_ = plan_fused(cfg_);
+    if (fused_.ok) {
+        int blocks = 0;
+        cudaError_t e = fused_max_blocks_per_sm(fused_.launch.fft_len, fused_.launch.hp, fused_.launch.smem, &blocks);
+        if (e != cudaSuccess || blocks < 1) {
+            cudaGetLastError();
+            fused_.ok = false;
+            fused_.why = std::string("fused kernel cannot be resident: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "0 blocks per SM");
+        } else {
+            fused_.blocks_per_sm = blocks;
+        }
+    }
+    return SYLDET_OK;
+}
+
+// -----------------------------------------------------------------------------------------------------------------
+void debounce_sorted(const Config &cfg, std::vector<syldet_event> &rows, std::vector<float> &outputs, int n_out,
+                     int64_t debounce_frames) {
+    // rows sorted by (channel, sample). emit iff debounceUntil < S; then debounceUntil = S + D  (TrackDetector.swift:80,99)
+    (void)cfg;
+    size_t w = 0;
+    int32_t cur_ch = INT32_MIN;
+    int64_t until = -1;
+    for (size_t r = 0; r < rows.size(); ++r) {
+        if (rows[r].channel != cur_ch) { cur_ch = rows[r].channel; until = -1; }
+        if (until < rows[r].sample) {
+            until = rows[r].sample + debounce_frames;
+            if (w != r) {
+                rows[w] = rows[r];
+                std::copy(outputs.begin() + r * n_out, outputs.begin() + (r + 1) * n_out, outputs.begin() + w * n_out);
+            }
+            ++w;
+        }
+    }
+    rows.resize(w);
+    outputs.resize(w * n_out);
+}
+
+syldet_status Batch::init(const Config &cfg, int device) {
+    syldet_status st = model_.init(cfg, device);
+    if (st != SYLDET_OK) return st;
+    SYLDET_CUDA(cudaStreamCreateWithFlags(&own_stream_, cudaStreamNonBlocking));
+    st = sink_count_.reserve(sizeof(unsigned long long));
+    return st;
+}
+
+Batch::~Batch() {
+    if (own_stream_) {
+        cudaSetDevice(model_.device());
+        cudaStreamDestroy(own_stream_);
+    }
+}
+
+syldet_status Batch::set_kernel(int kernel) {
+    if (kernel != SYLDET_KERNEL_AUTO && kernel != SYLDET_KERNEL_GENERIC && kernel != SYLDET_KERNEL_FUSED)
+        return set_error(SYLDET_ERR_ARG, "unknown kernel selector");
+    if (kernel == SYLDET_KERNEL_FUSED && !model_.fused().ok)
+        return set_error(SYLDET_ERR_UNSUPPORTED, "fused kernel not available for this configuration: " + model_.fused().why);
+    kernel_ = kernel;
+    return SYLDET_OK;
+}
+
+int Batch::active_kernel() const {
+    if (kernel_ == SYLDET_KERNEL_AUTO) return model_.fused().ok ? SYLDET_KERNEL_FUSED : SYLDET_KERNEL_GENERIC;
+    return kernel_;
+}
+
+syldet_status Batch::ensure_sink(unsigned long long capacity) {
+    if (capacity <= sink_capacity_) return SYLDET_OK;
+    syldet_status st = sink_events_.reserve(capacity * sizeof(DevEvent));
+    if (st != SYLDET_OK) return st;
+    st = sink_outputs_.reserve(capacity * sizeof(float) * model_.config().outputs);
+    if (st != SYLDET_OK) return st;
+    sink_capacity_ = capacity;
+    return SYLDET_OK;
+}
+
+syldet_status Batch::launch_planar(const float *d_planar, int n_channels, int64_t n_samples, int64_t ch_stride,
+                                   const float *valid_begin, const float *valid_end, int detect_rule, float *d_all_outputs,
+                                   cudaStream_t stream) {
+    const Config &c = model_.config();
+    const int64_t E = c.num_evals(n_samples);
+    SYLDET_CUDA(cudaMemsetAsync(sink_count_.get(), 0, sizeof(unsigned long long), stream));
+    if (E <= 0) return SYLDET_OK;
+    EventSink sink{sink_count_.as<unsigned long long>(), sink_events_.as<DevEvent>(), sink_outputs_.as<float>(), sink_capacity_};
+
+    if (active_kernel() == SYLDET_KERNEL_FUSED) {
+        const FusedPlan &fp = model_.fused();
+        FusedWork w{};
+        w.pcm = d_planar;
+        w.pcm_begin = valid_begin;
+        w.pcm_end = valid_end;
+        w.ch_stride = ch_stride;
+        w.n_channels = n_channels;
+        w.evals_per_channel = E;
+        const int resident = model_.sm_count() * fp.blocks_per_sm;
+        // chunk: a multiple of nn_tile, long enough that the T-1 warm-up columns are noise, short enough for >= 8 waves
+        const int64_t tile = fp.params.nn_tile;
+        int64_t chunk = ((E + tile - 1) / tile) * tile;
+        const int64_t want_units = (int64_t)resident * 8;
+        while (chunk > 4 * tile && n_channels * ((E + chunk - 1) / chunk) < want_units) chunk = ((chunk / 2 + tile - 1) / tile) * tile;
+        if (chunk > 64 * tile) chunk = 64 * tile;
+        w.chunk_evals = chunk;
+        w.chunks_per_channel = (int)((E + chunk - 1) / chunk);
+        w.all_out = d_all_outputs;
+        w.sink = sink;
+        w.window = model_.window();
+        w.twiddle = model_.twiddle();
+        FusedLaunch l = fp.launch;
+        const int64_t units = (int64_t)n_channels * w.chunks_per_channel;
+        l.grid = (int)std::min<int64_t>(units, resident);
+        SYLDET_CUDA(launch_fused(l, fp.params, w, stream));
+        launches_ += 1;
+        return SYLDET_OK;
+    }
+
+    // generic two-kernel path, segmented in time so the band-feature buffer stays bounded
+    const int L = c.band, T = c.time_range;
+    const int64_t budget_cols = std::max<int64_t>(T + 1, (int64_t)(512ll << 20) / ((int64_t)n_channels * L * 4));
+    const int64_t seg = std::max<int64_t>(1, budget_cols - (T - 1));
+    for (int64_t e0 = 0; e0 < E; e0 += seg) {
+        const int64_t ne = std::min(seg, E - e0), ncols = ne + T - 1;
+        syldet_status st = feat_.reserve((size_t)n_channels * ncols * L * sizeof(float));
+        if (st != SYLDET_OK) return st;
+        SYLDET_CUDA(launch_stft_band_generic(model_.dev_net(), c.fourier_length, d_planar, ch_stride, n_channels, e0, ncols,
+                                             feat_.as<float>(), stream));
+        SYLDET_CUDA(launch_nn_generic(model_.dev_net(), model_.max_width(), feat_.as<float>(), n_channels, ncols, ne, e0, E,
+                                      detect_rule, d_all_outputs, sink, stream));
+        launches_ += 2;
+    }
+    return SYLDET_OK;
+}
+
+syldet_status Batch::launch_device(const float *d_pcm, int n_channels, int64_t n_samples, int64_t ch_stride, int layout,
+                                   int detect_rule, float *d_all_outputs, cudaStream_t stream) {
+    if (!d_pcm || n_channels <= 0 || n_samples < 0) return set_error(SYLDET_ERR_ARG, "bad pcm arguments");
+    if (n_channels > 65535) return set_error(SYLDET_ERR_ARG, "more than 65535 channels in one call");
+    if (layout == SYLDET_LAYOUT_PLANAR && n_channels > 1 && ch_stride < n_samples) return set_error(SYLDET_ERR_ARG, "channel_stride < n_samples");
+    syldet_status st = use_device(model_.device());
+    if (st != SYLDET_OK) return st;
+    const Config &c = model_.config();
+    const int64_t E = c.num_evals(n_samples);
+    const unsigned long long total = (unsigned long long)std::max<int64_t>(E, 0) * n_channels;
+    if (sink_capacity_ == 0 || !last_.valid || last_.n_channels != n_channels || last_.n_samples != n_samples) {
+        st = ensure_sink(std::max<unsigned long long>(1, std::min<unsigned long long>(total, std::max<unsigned long long>(1ull << 20, total / 8))));
+        if (st != SYLDET_OK) return st;
+    }
+    last_ = Last{true, d_pcm, n_channels, n_samples, ch_stride, layout, detect_rule, d_all_outputs, stream};
+    if (layout == SYLDET_LAYOUT_INTERLEAVED && n_channels > 1) {
+        const int64_t pitch = (n_samples + 3) & ~(int64_t)3;
+        st = planar_.reserve((size_t)n_channels * pitch * sizeof(float));
+        if (st != SYLDET_OK) return st;
+        SYLDET_CUDA(launch_ingest(d_pcm, SYLDET_PCM_F32, 1, n_channels, n_samples, 0, planar_.as<float>(), pitch, stream));
+        launches_ += 1;
+        return launch_planar(planar_.as<float>(), n_channels, n_samples, pitch, planar_.as<float>(),
+                             planar_.as<float>() + (size_t)n_channels * pitch, detect_rule, d_all_outputs, stream);
+    }
+    const int64_t stride = n_channels > 1 ? ch_stride : n_samples;
+    return launch_planar(d_pcm, n_channels, n_samples, stride, d_pcm, d_pcm + (size_t)(n_channels - 1) * stride + n_samples,
+                         detect_rule, d_all_outputs, stream);
+}
+
+syldet_status Batch::last_detection_count(int64_t *count) {
+    if (!last_.valid) return set_error(SYLDET_ERR_ARG, "no launch to inspect");
+    syldet_status st = use_device(model_.device());
+    if (st != SYLDET_OK) return st;
+    SYLDET_CUDA(cudaStreamSynchronize(last_.stream));
+    unsigned long long n = 0;
+    SYLDET_CUDA(cudaMemcpy(&n, sink_count_.get(), sizeof n, cudaMemcpyDeviceToHost));
+    *count = (int64_t)n;
+    return SYLDET_OK;
+}
+
+syldet_status Batch::collect(int64_t debounce_frames, Events &out) {
+    if (!last_.valid) return set_error(SYLDET_ERR_ARG, "collect without a launch");
+    if (debounce_frames < 0) return set_error(SYLDET_ERR_ARG, "negative debounce");
+    syldet_status st = use_device(model_.device());
+    if (st != SYLDET_OK) return st;
+    const Config &c = model_.config();
+    const int O = c.outputs;
+    SYLDET_CUDA(cudaStreamSynchronize(last_.stream));
+    unsigned long long n = 0;
+    SYLDET_CUDA(cudaMemcpy(&n, sink_count_.get(), sizeof n, cudaMemcpyDeviceToHost));
+    if (n > sink_capacity_) {  // more detections than the event buffer holds: grow to the worst case and replay
+        const unsigned long long total = (unsigned long long)c.num_evals(last_.n_samples) * last_.n_channels;
+        st = ensure_sink(total);
+        if (st != SYLDET_OK) return st;
+        Last l = last_;
+        st = launch_device(l.d_pcm, l.n_channels, l.n_samples, l.ch_stride, l.layout, l.detect_rule, l.d_all_outputs, l.stream);
+        if (st != SYLDET_OK) return st;
+        SYLDET_CUDA(cudaStreamSynchronize(last_.stream));
+        SYLDET_CUDA(cudaMemcpy(&n, sink_count_.get(), sizeof n, cudaMemcpyDeviceToHost));
+        if (n > sink_capacity_) return set_error(SYLDET_ERR_OVERFLOW, "event buffer overflow after replay");
+    }
+    std::vector<DevEvent> ev(n);
+    std::vector<float> outs((size_t)n * O);
+    if (n) {
+        SYLDET_CUDA(cudaMemcpy(ev.data(), sink_events_.get(), n * sizeof(DevEvent), cudaMemcpyDeviceToHost));
+        SYLDET_CUDA(cudaMemcpy(outs.data(), sink_outputs_.get(), outs.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+    std::vector<size_t> order(n);
+    std::iota(order.begin(), order.end(), (size_t)0);
+    std::sort(order.begin(), order.end(), [&](size_t a, size_t b) {
+        return ev[a].channel != ev[b].channel ? ev[a].channel < ev[b].channel : ev[a].eval < ev[b].eval;
+    });
+    out.outputs_per_event = O;
+    out.rows.resize(n);
+    out.outputs.resize((size_t)n * O);
+    const int64_t first = c.first_output_sample();
+    for (size_t r = 0; r < n; ++r) {
+        const DevEvent &e = ev[order[r]];
+        out.rows[r] = syldet_event{e.channel, 0, first + (int64_t)c.hop * e.eval};  // TrackDetector.swift:39-42,67-68
+        std::copy(outs.begin() + order[r] * O, outs.begin() + (order[r] + 1) * O, out.outputs.begin() + r * O);
+    }
+    debounce_sorted(c, out.rows, out.outputs, O, debounce_frames);
+    return SYLDET_OK;
+}
+
+syldet_status Batch::run_host(const void *pcm, int fmt, int n_channels, int64_t n_samples, int64_t ch_stride, int layout,
+                              int64_t debounce_frames, int detect_rule, float *all_outputs, Events &out) {
+    if (!pcm || n_channels <= 0 || n_samples < 0) return set_error(SYLDET_ERR_ARG, "bad pcm arguments");
+    if (n_channels > 65535) return set_error(SYLDET_ERR_ARG, "more than 65535 channels in one call");
+    if (fmt != SYLDET_PCM_F32 && fmt != SYLDET_PCM_S16) return set_error(SYLDET_ERR_ARG, "unknown pcm format");
+    if (layout != SYLDET_LAYOUT_PLANAR && layout != SYLDET_LAYOUT_INTERLEAVED) return set_error(SYLDET_ERR_ARG, "unknown layout");
+    if (layout == SYLDET_LAYOUT_PLANAR && n_channels > 1 && ch_stride < n_samples) return set_error(SYLDET_ERR_ARG, "channel_stride < n_samples");
+    syldet_status st = use_device(model_.device());
+    if (st != SYLDET_OK) return st;
+    const Config &c = model_.config();
+    const int64_t E = c.num_evals(n_samples);
+    const int64_t pitch = (n_samples + 3) & ~(int64_t)3;
+    st = planar_.reserve(std::max<size_t>(16, (size_t)n_channels * pitch * sizeof(float)));
+    if (st != SYLDET_OK) return st;
+    const size_t esz = fmt == SYLDET_PCM_S16 ? 2 : 4;
+    cudaStream_t s = own_stream_;
+    if (n_samples > 0) {
+        if (fmt == SYLDET_PCM_F32 && layout == SYLDET_LAYOUT_PLANAR) {
+            SYLDET_CUDA(cudaMemcpy2DAsync(planar_.get(), pitch * 4, pcm, (n_channels > 1 ? ch_stride : n_samples) * 4, n_samples * 4,
+                                          n_channels, cudaMemcpyHostToDevice, s));
+        } else {
+            const bool inter = layout == SYLDET_LAYOUT_INTERLEAVED;
+            const int64_t src_stride = inter ? 0 : (n_channels > 1 ? ch_stride : n_samples);
+            const size_t src_elems = inter ? (size_t)n_channels * n_samples : (size_t)(n_channels - 1) * src_stride + n_samples;
+            st = staging_.reserve(src_elems * esz);
+            if (st != SYLDET_OK) return st;
+            SYLDET_CUDA(cudaMemcpyAsync(staging_.get(), pcm, src_elems * esz, cudaMemcpyHostToDevice, s));
+            SYLDET_CUDA(launch_ingest(staging_.get(), fmt, inter ? 1 : 0, n_channels, n_samples, src_stride, planar_.as<float>(), pitch, s));
+            launches_ += 1;
+        }
+    }
+    DeviceBuffer d_outs;
+    if (all_outputs && E > 0) {
+        st = d_outs.reserve((size_t)n_channels * E * c.outputs * sizeof(float));
+        if (st != SYLDET_OK) return st;
+    }
+    st = launch_device(planar_.as<float>(), n_channels, n_samples, pitch, SYLDET_LAYOUT_PLANAR, detect_rule,
+                       all_outputs && E > 0 ? d_outs.as<float>() : nullptr, s);
+    if (st != SYLDET_OK) return st;
+    st = collect(debounce_frames, out);
+    if (st != SYLDET_OK) return st;
+    if (all_outputs && E > 0)
+        SYLDET_CUDA(cudaMemcpy(all_outputs, d_outs.get(), (size_t)n_channels * E * c.outputs * sizeof(float), cudaMemcpyDeviceToHost));
+    return SYLDET_OK;
+}
+
+}  // namespace syldet

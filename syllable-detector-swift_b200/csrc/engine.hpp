@@ -1,0 +1,136 @@
+// Host-side engine: device copies of a configuration, kernel planning, and the batch runner that stands in for
+// TrackDetector.process + the main.swift loop (SyllableDetectorCLI/TrackDetector.swift:45-105, main.swift:126-130).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "config.hpp"
+#include "kernels.hpp"
+
+namespace syldet {
+
+syldet_status cuda_fail(cudaError_t e, const char *what);
+#define SYLDET_CUDA(expr)                                                 \
+    do {                                                                  \
+        cudaError_t _e = (expr);                                          \
+        if (_e != cudaSuccess) return ::syldet::cuda_fail(_e, #expr);     \
+    } while (0)
+
+// Selects `device` after checking it is a compute-capability 10.x part; there is no CPU fallback.
+syldet_status use_device(int device);
+int usable_device_count();
+
+// RAII device allocation that grows on demand.
+class DeviceBuffer {
+public:
+    DeviceBuffer() = default;
+    DeviceBuffer(const DeviceBuffer &) = delete;
+    DeviceBuffer &operator=(const DeviceBuffer &) = delete;
+    ~DeviceBuffer();
+    syldet_status reserve(size_t bytes);
+    void *get() const { return ptr_; }
+    template <typename T>
+    T *as() const { return static_cast<T *>(ptr_); }
+    size_t size() const { return size_; }
+
+private:
+    void *ptr_ = nullptr;
+    size_t size_ = 0;
+};
+
+struct FusedPlan {
+    bool ok = false;
+    std::string why;  // why the fused kernel does not apply
+    FusedParams params{};
+    FusedLaunch launch{};
+    int blocks_per_sm = 0;
+};
+
+// Folds the input-processing chain into layer 0 and packs everything the fused kernel reads from parameter space.
+FusedPlan plan_fused(const Config &cfg);
+
+// Device-resident copy of one configuration (weights, window, twiddles, DevNet record).
+class DeviceModel {
+public:
+    DeviceModel() = default;
+    DeviceModel(const DeviceModel &) = delete;
+    DeviceModel &operator=(const DeviceModel &) = delete;
+    syldet_status init(const Config &cfg, int device);
+    const Config &config() const { return cfg_; }
+    int device() const { return device_; }
+    const DevNet *dev_net() const { return d_net_.as<DevNet>(); }
+    const float *window() const { return d_window_; }
+    const float2 *twiddle() const { return d_twiddle_; }
+    int max_width() const { return max_width_; }
+    const FusedPlan &fused() const { return fused_; }
+    int sm_count() const { return sm_count_; }
+
+private:
+    Config cfg_;
+    int device_ = -1, max_width_ = 0, sm_count_ = 148;
+    DeviceBuffer d_blob_, d_net_;
+    const float *d_window_ = nullptr;
+    const float2 *d_twiddle_ = nullptr;
+    FusedPlan fused_;
+};
+
+struct Events {
+    int outputs_per_event = 0;
+    std::vector<syldet_event> rows;
+    std::vector<float> outputs;
+};
+
+class Batch {
+public:
+    syldet_status init(const Config &cfg, int device);
+    ~Batch();
+    syldet_status set_kernel(int kernel);
+    int active_kernel() const;
+    syldet_status run_host(const void *pcm, int fmt, int n_channels, int64_t n_samples, int64_t ch_stride, int layout,
+                           int64_t debounce_frames, int detect_rule, float *all_outputs, Events &out);
+    syldet_status launch_device(const float *d_pcm, int n_channels, int64_t n_samples, int64_t ch_stride, int layout,
+                                int detect_rule, float *d_all_outputs, cudaStream_t stream);
+    syldet_status collect(int64_t debounce_frames, Events &out);
+    syldet_status last_detection_count(int64_t *count);
+    int64_t launch_count() const { return launches_; }
+    const DeviceModel &model() const { return model_; }
+
+private:
+    syldet_status launch_planar(const float *d_planar, int n_channels, int64_t n_samples, int64_t ch_stride,
+                                const float *valid_begin, const float *valid_end, int detect_rule, float *d_all_outputs,
+                                cudaStream_t stream);
+    syldet_status ensure_sink(unsigned long long capacity);
+
+    DeviceModel model_;
+    int kernel_ = SYLDET_KERNEL_AUTO;
+    cudaStream_t own_stream_ = nullptr;
+    DeviceBuffer planar_, feat_, sink_count_, sink_events_, sink_outputs_, staging_;
+    unsigned long long sink_capacity_ = 0;
+    int64_t launches_ = 0;
+    // last launch, kept so that an event-buffer overflow can be replayed with a larger buffer
+    struct Last {
+        bool valid = false;
+        const float *d_pcm = nullptr;
+        int n_channels = 0;
+        int64_t n_samples = 0, ch_stride = 0;
+        int layout = 0, detect_rule = 0;
+        float *d_all_outputs = nullptr;
+        cudaStream_t stream = nullptr;
+    } last_;
+};
+
+// Greedy debounce over ascending sample numbers of one channel (TrackDetector.swift:80,99).
+void debounce_sorted(const Config &cfg, std::vector<syldet_event> &rows, std::vector<float> &outputs, int n_out,
+                     int64_t debounce_frames);
+
+}  // namespace syldet
+
+struct syldet_batch {
+    syldet::Batch b;
+};
+struct syldet_events {
+    syldet::Events e;
+};

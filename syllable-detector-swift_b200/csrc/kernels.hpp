@@ -1,0 +1,82 @@
+// Launch wrappers for the CUDA kernels of the detection path.
+#pragma once
+#include <algorithm>
+
+#include "device_types.cuh"
+#include "../../include/syldet.h"
+
+namespace syldet {
+
+// ---- generic (reference-order) path: kernels_generic.cu ----------------------------------------------------------
+cudaError_t launch_ingest(const void *src, int format, int interleaved, int n_channels, int64_t n_samples, int64_t src_stride,
+                          float *dst, int64_t dst_stride, cudaStream_t stream);
+cudaError_t launch_stft_band_generic(const DevNet *d_net, int fft_len, const float *pcm, int64_t ch_stride, int n_channels,
+                                     int64_t col0, int64_t n_cols, float *feat, cudaStream_t stream);
+cudaError_t launch_nn_generic(const DevNet *d_net, int max_width, const float *feat, int n_channels, int64_t n_cols,
+                              int64_t n_evals, int64_t eval0, int64_t evals_total, int detect_rule, float *all_out,
+                              EventSink sink, cudaStream_t stream);
+
+// ---- fused fast path: kernels_fused.cu ---------------------------------------------------------------------------
+constexpr int kFusedMaxW0 = 6144;     // folded layer-0 weights, floats ([inputs][HP])
+constexpr int kFusedMaxHidden = 8;    // widest layer the register epilogue handles
+constexpr int kFusedMaxLayers = 4;
+constexpr int kFusedMaxOut = 8;
+constexpr int kFusedThreads = 256;
+constexpr int kFusedMaxBand = 128;    // band bins per column (4 per lane)
+
+enum { FUSED_STAT_NONE = 0, FUSED_STAT_L2 = 1, FUSED_STAT_MINMAX = 2, FUSED_STAT_STD = 3 };
+
+// Passed by value in kernel parameter space (constant bank): the weights are warp-uniform operands of the FFMAs.
+struct alignas(16) FusedParams {
+    int win_len, gap, hop, k0, band, time_range, scaling;
+    int band_pitch;   // floats between ring columns (odd => conflict-free column reads)
+    int ring_cols;    // ring capacity in columns
+    int nn_tile;      // evaluations that trigger an epilogue pass
+    int abuf_floats;  // one audio staging buffer, floats (multiple of 4)
+    int window_stat;  // FUSED_STAT_*
+    int n_layers, n_out, n_op, detect_rule;
+    int tf[kFusedMaxLayers];
+    float v[kFusedMaxHidden];       // V_h  = sum_i W_hi A_i
+    float bprime[kFusedMaxHidden];  // B'_h = b_h + sum_i W_hi C_i
+    float rest_w[(kFusedMaxLayers - 1) * kFusedMaxHidden * kFusedMaxHidden];  // layers >= 1, [out][in] padded to 8x8
+    float rest_b[(kFusedMaxLayers - 1) * kFusedMaxHidden];
+    float op_y[kMaxProcessing];
+    float op_gain[kMaxProcessing * kFusedMaxOut];
+    float op_xoff[kMaxProcessing * kFusedMaxOut];
+    double thr[kFusedMaxOut];
+    alignas(16) float w0[kFusedMaxW0];  // [inputs][HP]: W_hi * A_i, hidden index fastest
+};
+
+struct FusedWork {
+    const float *pcm;      // planar float32
+    const float *pcm_begin, *pcm_end;  // valid range of the whole buffer (bounds for 16-byte bulk copies)
+    int64_t ch_stride;
+    int n_channels;
+    int64_t evals_per_channel;
+    int64_t chunk_evals;
+    int chunks_per_channel;
+    float *all_out;        // optional [n_channels][evals_per_channel][n_out]
+    EventSink sink;
+    const float *window;   // [win_len]
+    const float2 *twiddle; // [fft_len/2]
+};
+
+struct FusedLaunch {
+    int fft_len = 0, hp = 0;
+    int grid = 0;
+    size_t smem = 0;
+};
+
+// Geometry helpers shared by host planning and the kernel.
+__host__ __device__ constexpr int fused_r1(int fft_len) { return fft_len >= 256 ? 16 : 8; }
+__host__ __device__ constexpr int fused_r2(int fft_len) { return (fft_len / 2) / fused_r1(fft_len); }
+__host__ __device__ constexpr int fused_group(int fft_len) { return 32 * fused_r1(fft_len) / (fft_len / 2); }  // frames per warp pass
+__host__ __device__ constexpr int fused_round_cols(int fft_len) { return (kFusedThreads / 32) * fused_group(fft_len); }
+__host__ __device__ constexpr int fused_frame_pitch(int fft_len) { return fft_len / 2 + (fft_len / 2) / fused_r1(fft_len); }  // float2 per frame
+
+bool fused_supports_fft(int fft_len);
+size_t fused_smem_bytes(int fft_len, const FusedParams &p);
+cudaError_t launch_fused(const FusedLaunch &cfg, const FusedParams &p, const FusedWork &w, cudaStream_t stream);
+cudaError_t fused_max_blocks_per_sm(int fft_len, int hp, size_t smem, int *blocks);
+
+}  // namespace syldet

@@ -1,0 +1,560 @@
+// Fused sm_100a kernel: audio tile -> Hamming window -> real FFT -> band magnitude -> sliding feature window ->
+// input normalisation -> small MLP -> threshold decision, with spectra and features kept in shared memory.
+//
+// Replaces, for all channels and all hops of a recording at once, the per-column loop
+//   CircularShortTimeFourierTransform.extractPower   (Common/CircularShortTimeFourierTransform.swift:280-337)
+//   SyllableDetector.processFourierData/processNewValue (Common/SyllableDetector.swift:134-217)
+//   NeuralNet.apply / NeuralNetLayer.apply             (Common/NeuralNet.swift:294-326, 366-377)
+//   the threshold test of TrackDetector.process        (SyllableDetectorCLI/TrackDetector.swift:71-77)
+//
+// Work decomposition (B200: 148 SMs, 2 CTAs of 256 threads per SM):
+//   unit   = (channel, chunk of consecutive evaluations); CTAs walk units grid-stride.
+//   round  = 8 warps x G frames; the audio span of a round is staged in shared memory by a 1-D TMA bulk copy
+//            (cp.async.bulk + mbarrier), double buffered against the FFT of the previous round.
+//   FFT    = real N-point transform as an N/2-point complex Stockham transform in two register passes
+//            (radix R1 then R2, one padded shared-memory exchange, warp-private, __syncwarp only).
+//   ring   = band magnitudes of the last nn_tile + T columns (shared memory, odd pitch).
+//   epilogue = one thread per evaluation: gathers its T columns from the ring, layer-0 dot products against folded
+//            weights that sit in kernel-parameter constant memory (warp-uniform FFMA operands), window statistic,
+//            transfer functions, remaining layers, reverse output map, double-precision threshold compare,
+//            warp-aggregated event append.
+#include <cstdio>
+
+#include "kernels.hpp"
+
+namespace syldet {
+
+namespace {
+
+// ---- constexpr roots of unity: w_R^k = exp(-2 pi i k / R), R | 16 --------------------------------------------------
+__host__ __device__ constexpr double cos16(int i) {  // cos(2 pi i / 16)
+    i = ((i % 16) + 16) % 16;
+    switch (i) {
+        case 0: return 1.0;
+        case 1: case 15: return 0.92387953251128673848;
+        case 2: case 14: return 0.70710678118654752440;
+        case 3: case 13: return 0.38268343236508977173;
+        case 4: case 12: return 0.0;
+        case 5: case 11: return -0.38268343236508977173;
+        case 6: case 10: return -0.70710678118654752440;
+        case 7: case 9: return -0.92387953251128673848;
+        default: return -1.0;
+    }
+}
+__host__ __device__ constexpr double sin16(int i) { return cos16(i - 4); }
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+// a * w_R^K with the trivial cases folded
+template <int R, int K>
+__device__ __forceinline__ float2 mul_root(float2 a) {
+    constexpr int i = K * (16 / R);  // sixteenths of a turn
+    if constexpr (i == 0) return a;
+    else if constexpr (i == 4) return make_float2(a.y, -a.x);  // * (-i)
+    else if constexpr (i == 2) {
+        constexpr float c = (float)0.70710678118654752440;
+        return make_float2((a.x + a.y) * c, (a.y - a.x) * c);
+    } else if constexpr (i == 6) {
+        constexpr float c = (float)0.70710678118654752440;
+        return make_float2((a.y - a.x) * c, -(a.x + a.y) * c);
+    } else {
+        constexpr float cr = (float)cos16(i), ci = (float)(-sin16(i));
+        return make_float2(a.x * cr - a.y * ci, a.x * ci + a.y * cr);
+    }
+}
+
+// In-register DFT, natural order in and out: v[k] <- sum_n v[n] exp(-2 pi i n k / R)
+template <int R>
+struct Dft {
+    template <int K>
+    static __device__ __forceinline__ void combine(float2 *v, const float2 *e, const float2 *o) {
+        if constexpr (K < R / 2) {
+            const float2 t = mul_root<R, K>(o[K]);
+            v[K] = cadd(e[K], t);
+            v[K + R / 2] = csub(e[K], t);
+            combine<K + 1>(v, e, o);
+        }
+    }
+    static __device__ __forceinline__ void run(float2 *v) {
+        float2 e[R / 2], o[R / 2];
+#pragma unroll
+        for (int i = 0; i < R / 2; ++i) { e[i] = v[2 * i]; o[i] = v[2 * i + 1]; }
+        Dft<R / 2>::run(e);
+        Dft<R / 2>::run(o);
+        combine<0>(v, e, o);
+    }
+};
+template <>
+struct Dft<2> {
+    static __device__ __forceinline__ void run(float2 *v) {
+        const float2 a = v[0], b = v[1];
+        v[0] = cadd(a, b);
+        v[1] = csub(a, b);
+    }
+};
+template <>
+struct Dft<1> {
+    static __device__ __forceinline__ void run(float2 *) {}
+};
+
+// ---- mbarrier / bulk copy (TMA 1-D) ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_addr(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ float scale_value(float v, int scaling) {
+    if (scaling == SYLDET_SCALING_DB) return 20.0f * log10f(v);
+    if (scaling == SYLDET_SCALING_LOG) return logf(v);
+    return v;
+}
+
+__device__ __forceinline__ float transfer(int tf, float v) {
+    switch (tf) {
+        case SYLDET_TF_TANSIG: return tanhf(v);
+        case SYLDET_TF_LOGSIG: return 1.0f / (1.0f + expf(-v));
+        case SYLDET_TF_SATLIN: return fminf(fmaxf(v, 0.0f), 1.0f);
+        default: return v;
+    }
+}
+
+// Where the audio of one round sits in global memory and in the staging buffer.
+struct RoundSpan {
+    const float *src;     // first sample of the round's first frame
+    const char *aligned;  // 16-byte aligned start of the bulk copy
+    int off;              // floats between `aligned` and `src` (0..3)
+    uint32_t bytes;       // bulk copy size (multiple of 16)
+    int n_floats;         // samples the round's frames touch
+    bool bulk_ok;         // the aligned span lies inside the caller's buffer
+};
+
+__device__ __forceinline__ RoundSpan round_span(const FusedParams &p, const FusedWork &w, const float *x_ch, int64_t first_col,
+                                                int cols) {
+    RoundSpan s;
+    s.src = x_ch + first_col * p.hop + p.gap;
+    s.n_floats = (cols - 1) * p.hop + p.win_len;
+    const uintptr_t a = (uintptr_t)s.src;
+    s.aligned = (const char *)(a & ~(uintptr_t)15);
+    s.off = (int)((a & 15) >> 2);
+    s.bytes = (uint32_t)(((s.off + s.n_floats) * 4 + 15) & ~15);
+    s.bulk_ok = (uintptr_t)s.aligned >= (uintptr_t)w.pcm_begin && (uintptr_t)s.aligned + s.bytes <= (uintptr_t)w.pcm_end;
+    return s;
+}
+
+// ---- epilogue: one thread = one evaluation -----------------------------------------------------------------------
+template <int HP, int STAT>
+__device__ __forceinline__ void gather_layer0(const FusedParams &p, const float *ring, int slot, float (&acc)[HP], float &s0,
+                                              float &s1) {
+    // s0/s1: STAT_L2 -> (sum x^2, -) ; STAT_MINMAX -> (min, max) ; STAT_STD -> (sum x, -)
+    const int L = p.band, T = p.time_range;
+    int widx = 0;
+    for (int t = 0; t < T; ++t) {
+        const float *row = ring + slot * p.band_pitch;
+#pragma unroll 4
+        for (int f = 0; f < L; ++f) {
+            const float x = row[f];
+            if constexpr (STAT == FUSED_STAT_L2) s0 = fmaf(x, x, s0);
+            if constexpr (STAT == FUSED_STAT_MINMAX) { s0 = fminf(s0, x); s1 = fmaxf(s1, x); }
+            if constexpr (STAT == FUSED_STAT_STD) s0 += x;
+            const float4 wa = *reinterpret_cast<const float4 *>(&p.w0[widx]);
+            acc[0] = fmaf(x, wa.x, acc[0]);
+            acc[1] = fmaf(x, wa.y, acc[1]);
+            acc[2] = fmaf(x, wa.z, acc[2]);
+            acc[3] = fmaf(x, wa.w, acc[3]);
+            if constexpr (HP == 8) {
+                const float4 wb = *reinterpret_cast<const float4 *>(&p.w0[widx + 4]);
+                acc[4] = fmaf(x, wb.x, acc[4]);
+                acc[5] = fmaf(x, wb.y, acc[5]);
+                acc[6] = fmaf(x, wb.z, acc[6]);
+                acc[7] = fmaf(x, wb.w, acc[7]);
+            }
+            widx += HP;
+        }
+        if (++slot == p.ring_cols) slot = 0;
+    }
+}
+
+template <int HP>
+__device__ __forceinline__ bool evaluate(const FusedParams &p, const float *ring, int slot, float (&out)[kFusedMaxOut]) {
+    float acc[HP];
+#pragma unroll
+    for (int h = 0; h < HP; ++h) acc[h] = 0.0f;
+    float alpha_div = 1.0f, beta = 0.0f;  // z = acc / alpha_div + beta * V + B'
+    bool constant_input = false;          // `normalize` of a flat window: every input becomes -1 (NeuralNet.swift:84-88)
+    switch (p.window_stat) {
+        case FUSED_STAT_L2: {  // x / sqrt(sum x^2)  (NeuralNet.swift:47-59)
+            float ss = 0.0f, unused = 0.0f;
+            gather_layer0<HP, FUSED_STAT_L2>(p, ring, slot, acc, ss, unused);
+            alpha_div = sqrtf(ss);
+            break;
+        }
+        case FUSED_STAT_MINMAX: {  // x * 2/range + (-mn-mx)/range  (NeuralNet.swift:69-96)
+            float mn = INFINITY, mx = -INFINITY;
+            gather_layer0<HP, FUSED_STAT_MINMAX>(p, ring, slot, acc, mn, mx);
+            const float range = mx - mn;
+            if (0 == range) { constant_input = true; beta = -1.0f; }
+            else { alpha_div = range * 0.5f; beta = (0 - mn - mx) / range; }
+            break;
+        }
+        case FUSED_STAT_STD: {  // (x - mean) / std_pop  (NeuralNet.swift:105-108)
+            float sum = 0.0f, unused = 0.0f;
+            gather_layer0<HP, FUSED_STAT_STD>(p, ring, slot, acc, sum, unused);
+            const int n = p.band * p.time_range;
+            const float mean = sum / (float)n;
+            float var = 0.0f;
+            int s = slot;
+            for (int t = 0; t < p.time_range; ++t) {
+                const float *row = ring + s * p.band_pitch;
+                for (int f = 0; f < p.band; ++f) { const float d = row[f] - mean; var = fmaf(d, d, var); }
+                if (++s == p.ring_cols) s = 0;
+            }
+            alpha_div = sqrtf(var / (float)n);
+            beta = -mean / alpha_div;
+            break;
+        }
+        default: {
+            float a = 0.0f, b = 0.0f;
+            gather_layer0<HP, FUSED_STAT_NONE>(p, ring, slot, acc, a, b);
+        }
+    }
+    float a[kFusedMaxHidden], b[kFusedMaxHidden];
+#pragma unroll
+    for (int h = 0; h < kFusedMaxHidden; ++h) {
+        float z = 0.0f;
+        if (h < HP) {
+            const float u = constant_input ? 0.0f : acc[h] / alpha_div;
+            z = u + fmaf(beta, p.v[h], p.bprime[h]);
+            z = transfer(p.tf[0], z);
+        }
+        a[h] = z;
+    }
+    for (int l = 1; l < p.n_layers; ++l) {
+        const float *w = &p.rest_w[(l - 1) * kFusedMaxHidden * kFusedMaxHidden];
+        const float *bias = &p.rest_b[(l - 1) * kFusedMaxHidden];
+#pragma unroll
+        for (int o = 0; o < kFusedMaxHidden; ++o) {
+            float s = 0.0f;
+#pragma unroll
+            for (int i = 0; i < kFusedMaxHidden; ++i) s = fmaf(w[o * kFusedMaxHidden + i], a[i], s);
+            b[o] = transfer(p.tf[l], s + bias[o]);
+        }
+#pragma unroll
+        for (int o = 0; o < kFusedMaxHidden; ++o) a[o] = b[o];
+    }
+    bool hit = false;
+#pragma unroll
+    for (int o = 0; o < kFusedMaxOut; ++o) {
+        float v = a[o];
+        if (o < p.n_out) {
+            for (int k = 0; k < p.n_op; ++k) {  // reverse maps in index order (NeuralNet.swift:316-323)
+                v = (v + (0 - p.op_y[k])) / p.op_gain[k * kFusedMaxOut + o] + p.op_xoff[k * kFusedMaxOut + o];
+            }
+            const bool over = (double)v >= p.thr[o];  // TrackDetector.swift:72; NaN -> false
+            if (over && (p.detect_rule == SYLDET_DETECT_ANY_OUTPUT || o == 0)) hit = true;
+        }
+        out[o] = v;
+    }
+    return hit;
+}
+
+// ---- the kernel --------------------------------------------------------------------------------------------------
+template <int NFFT, int HP>
+__global__ void __launch_bounds__(kFusedThreads, 2) fused_detect_kernel(const __grid_constant__ FusedParams p, const FusedWork w) {
+    constexpr int M = NFFT / 2;
+    constexpr int R1 = fused_r1(NFFT), R2 = fused_r2(NFFT);
+    constexpr int G = fused_group(NFFT);             // frames per warp per round
+    constexpr int RC = fused_round_cols(NFFT);       // columns per round (CTA)
+    constexpr int FP = fused_frame_pitch(NFFT);      // float2 per frame in the exchange buffer
+    constexpr int U2 = (G * R1) / 32;                // pass-2 items per lane
+    constexpr int PF = kFusedMaxBand / 32;           // band slots per lane
+    static_assert(R1 * R2 == M && (G * M) / R1 == 32 && U2 >= 1, "plan");
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw);
+    float *abuf0 = reinterpret_cast<float *>(smem_raw + 16);
+    float *abuf1 = abuf0 + p.abuf_floats;
+    float2 *scratch = reinterpret_cast<float2 *>(abuf1 + p.abuf_floats);
+    float *ring = reinterpret_cast<float *>(scratch + (kFusedThreads / 32) * G * FP);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int L = p.band, T = p.time_range, W = p.win_len;
+    const bool full_window = (W == NFFT);
+
+    // per-lane constants -----------------------------------------------------------------------------------------
+    const int fs1 = lane / R2, j1 = lane % R2;  // pass 1: frame in group, butterfly index (M/R1 == R2 items per frame)
+    float2 wreg[R1];                            // window taps of this lane's samples
+#pragma unroll
+    for (int r = 0; r < R1; ++r) {
+        const int m0 = 2 * (j1 + r * R2);
+        wreg[r].x = m0 < W ? __ldg(w.window + m0) : 0.0f;
+        wreg[r].y = m0 + 1 < W ? __ldg(w.window + m0 + 1) : 0.0f;
+    }
+    const int j2 = lane % R1;                   // pass 2
+    float2 tw[R2];                              // w_M^{r j2} = w_N^{2 r j2}
+#pragma unroll
+    for (int r = 1; r < R2; ++r) {
+        const int q = 2 * r * j2;  // < N; the table holds k < N/2 and w_N^{k + N/2} = -w_N^k
+        const float2 t = __ldg(w.twiddle + (q >= M ? q - M : q));
+        tw[r] = q >= M ? make_float2(-t.x, -t.y) : t;
+    }
+    tw[0] = make_float2(1.0f, 0.0f);
+    float2 utw[PF];                             // untangle twiddles w_N^k of this lane's band bins
+#pragma unroll
+    for (int q = 0; q < PF; ++q) {
+        const int f = lane + 32 * q;
+        utw[q] = f < L ? __ldg(w.twiddle + p.k0 + f) : make_float2(0.0f, 0.0f);
+    }
+
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint32_t phase0 = 0, phase1 = 0;
+
+    float2 *zw = scratch + warp * G * FP;  // this warp's exchange buffer
+    const int64_t n_units = (int64_t)w.n_channels * w.chunks_per_channel;
+
+    for (int64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const int ch = (int)(unit / w.chunks_per_channel);
+        const int64_t e0 = (unit % w.chunks_per_channel) * w.chunk_evals;
+        const int64_t ne = min(w.chunk_evals, w.evals_per_channel - e0);
+        const int64_t ncols = ne + T - 1;  // column index == evaluation index of the window it opens
+        const int nrounds = (int)((ncols + RC - 1) / RC);
+        const float *x_ch = w.pcm + (int64_t)ch * w.ch_stride;
+
+        if (tid == 0) {
+            const RoundSpan s = round_span(p, w, x_ch, e0, (int)min((int64_t)RC, ncols));
+            if (s.bulk_ok) {
+                mbar_expect_tx(&mbar[0], s.bytes);
+                bulk_copy_g2s(abuf0, s.aligned, s.bytes, &mbar[0]);
+            }
+        }
+        int64_t cols_done = 0, evals_done = 0;
+        int col_slot = 0, eval_slot = 0;  // ring slots of column `cols_done` and evaluation `evals_done`
+
+        for (int r = 0; r < nrounds; ++r) {
+            const int cols = (int)min((int64_t)RC, ncols - (int64_t)r * RC);
+            float *abuf = (r & 1) ? abuf1 : abuf0;
+            if (tid == 0 && r + 1 < nrounds) {  // prefetch next round into the other buffer (free since the last sync)
+                const int ncols_next = (int)min((int64_t)RC, ncols - (int64_t)(r + 1) * RC);
+                const RoundSpan s = round_span(p, w, x_ch, e0 + (int64_t)(r + 1) * RC, ncols_next);
+                if (s.bulk_ok) {
+                    uint64_t *bar = &mbar[(r + 1) & 1];
+                    mbar_expect_tx(bar, s.bytes);
+                    bulk_copy_g2s((r & 1) ? abuf0 : abuf1, s.aligned, s.bytes, bar);
+                }
+            }
+            const RoundSpan span = round_span(p, w, x_ch, e0 + (int64_t)r * RC, cols);
+            if (span.bulk_ok) {
+                if (r & 1) { mbar_wait(&mbar[1], phase1); phase1 ^= 1; }
+                else { mbar_wait(&mbar[0], phase0); phase0 ^= 1; }
+            } else {  // edge of the caller's buffer: guarded cooperative copy
+                for (int i = tid; i < span.n_floats; i += kFusedThreads) abuf[span.off + i] = span.src[i];
+                __syncthreads();
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            }
+
+            // ---- pass 1: window + radix-R1 on strided samples -------------------------------------------------
+            {
+                const int c = warp * G + fs1;
+                float2 v[R1];
+                if (c < cols) {
+                    const float *fr = abuf + span.off + c * p.hop;
+                    const bool vec_ok = ((span.off + c * p.hop) & 1) == 0;
+#pragma unroll
+                    for (int r1 = 0; r1 < R1; ++r1) {
+                        const int m0 = 2 * (j1 + r1 * R2);
+                        float2 x;
+                        if (full_window) {
+                            if (vec_ok) x = *reinterpret_cast<const float2 *>(fr + m0);
+                            else { x.x = fr[m0]; x.y = fr[m0 + 1]; }
+                        } else {
+                            x.x = m0 < W ? fr[m0] : 0.0f;
+                            x.y = m0 + 1 < W ? fr[m0 + 1] : 0.0f;
+                        }
+                        v[r1] = make_float2(x.x * wreg[r1].x, x.y * wreg[r1].y);
+                    }
+                    Dft<R1>::run(v);
+                    float2 *zb = zw + fs1 * FP + j1 * (R1 + 1);  // padded: element e lives at e + e / R1
+#pragma unroll
+                    for (int q = 0; q < R1; ++q) zb[q] = v[q];
+                }
+            }
+            __syncwarp();
+            // ---- pass 2: twiddle + radix-R2, in place ---------------------------------------------------------
+#pragma unroll
+            for (int u = 0; u < U2; ++u) {
+                const int fs2 = lane / R1 + u * (32 / R1);
+                if (warp * G + fs2 < cols) {
+                    float2 *zb = zw + fs2 * FP + j2;
+                    float2 v[R2];
+#pragma unroll
+                    for (int r2 = 0; r2 < R2; ++r2) {
+                        const float2 z = zb[r2 * (R1 + 1)];
+                        v[r2] = r2 == 0 ? z : cmul(z, tw[r2]);
+                    }
+                    Dft<R2>::run(v);
+#pragma unroll
+                    for (int r2 = 0; r2 < R2; ++r2) zb[r2 * (R1 + 1)] = v[r2];
+                }
+            }
+            __syncwarp();
+            // ---- untangle the packed real transform, magnitude, band slice -> ring -------------------------------
+            for (int g = 0; g < G; ++g) {
+                const int c = warp * G + g;
+                if (c >= cols) break;
+                int slot = col_slot + c;
+                if (slot >= p.ring_cols) slot -= p.ring_cols;
+                const float2 *zb = zw + g * FP;
+                float *dst = ring + slot * p.band_pitch;
+#pragma unroll
+                for (int q = 0; q < PF; ++q) {
+                    const int f = lane + 32 * q;
+                    if (f < L) {
+                        const int k = p.k0 + f;
+                        float mag;
+                        if (k == 0) {
+                            const float2 z0 = zb[0];
+                            mag = fabsf(z0.x + z0.y);  // X[0]; the Nyquist term is dropped (CSTFT.swift:323)
+                        } else {
+                            const int km = M - k;
+                            const float2 za = zb[k + k / R1];
+                            const float2 zc = zb[km + km / R1];
+                            const float sr = za.x + zc.x, si = za.y - zc.y;  // Z[k] + conj Z[M-k]
+                            const float dr = za.x - zc.x, di = za.y + zc.y;  // Z[k] - conj Z[M-k]
+                            const float re = sr + (utw[q].x * di + utw[q].y * dr);
+                            const float im = si - (utw[q].x * dr - utw[q].y * di);
+                            mag = sqrtf(re * re + im * im) * 0.5f;
+                        }
+                        dst[f] = scale_value(mag, p.scaling);
+                    }
+                }
+            }
+            __syncthreads();
+            cols_done += cols;
+            col_slot += cols;
+            if (col_slot >= p.ring_cols) col_slot -= p.ring_cols;
+
+            // ---- epilogue over the evaluations whose T columns are complete ---------------------------------------
+            const int64_t ready = cols_done - (T - 1) - evals_done;
+            if (ready >= p.nn_tile || (r == nrounds - 1 && ready > 0)) {
+                const int n_ready = (int)ready;
+                for (int qb = warp * 32; qb < n_ready; qb += kFusedThreads) {
+                    const int q = qb + lane;
+                    const bool active = q < n_ready;
+                    float out[kFusedMaxOut];
+                    bool hit = false;
+                    if (active) {
+                        int slot = eval_slot + q;
+                        if (slot >= p.ring_cols) slot -= p.ring_cols;
+                        hit = evaluate<HP>(p, ring, slot, out);
+                        if (w.all_out) {
+                            float *o = w.all_out + ((int64_t)ch * w.evals_per_channel + e0 + evals_done + q) * p.n_out;
+#pragma unroll
+                            for (int i = 0; i < kFusedMaxOut; ++i)
+                                if (i < p.n_out) o[i] = out[i];
+                        }
+                    }
+                    const unsigned hits = __ballot_sync(0xffffffffu, hit);
+                    if (hits) {
+                        unsigned long long base = 0;
+                        if (lane == 0) base = atomicAdd(w.sink.count, (unsigned long long)__popc(hits));
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        if (hit) {
+                            const unsigned long long idx = base + __popc(hits & ((1u << lane) - 1));
+                            if (idx < w.sink.capacity) {
+                                w.sink.events[idx] = DevEvent{ch, 0, e0 + evals_done + q};
+#pragma unroll
+                                for (int i = 0; i < kFusedMaxOut; ++i)
+                                    if (i < p.n_out) w.sink.outputs[idx * p.n_out + i] = out[i];
+                            }
+                        }
+                    }
+                }
+                evals_done += n_ready;
+                eval_slot += n_ready;
+                while (eval_slot >= p.ring_cols) eval_slot -= p.ring_cols;
+            }
+        }
+        __syncthreads();  // ring and staging buffers are reused by the next unit
+    }
+}
+
+template <int NFFT, int HP>
+cudaError_t launch_one(const FusedLaunch &cfg, const FusedParams &p, const FusedWork &w, cudaStream_t stream) {
+    auto kern = fused_detect_kernel<NFFT, HP>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem);
+    if (e != cudaSuccess) return e;
+    kern<<<cfg.grid, kFusedThreads, cfg.smem, stream>>>(p, w);
+    return cudaGetLastError();
+}
+
+template <int NFFT, int HP>
+cudaError_t occupancy_one(size_t smem, int *blocks) {
+    auto kern = fused_detect_kernel<NFFT, HP>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, kern, kFusedThreads, smem);
+}
+
+}  // namespace
+
+bool fused_supports_fft(int fft_len) { return fft_len == 64 || fft_len == 128 || fft_len == 256 || fft_len == 512; }
+
+size_t fused_smem_bytes(int fft_len, const FusedParams &p) {
+    const size_t scratch = (size_t)(kFusedThreads / 32) * fused_group(fft_len) * fused_frame_pitch(fft_len) * sizeof(float2);
+    return 16 + 2 * (size_t)p.abuf_floats * sizeof(float) + scratch + (size_t)p.ring_cols * p.band_pitch * sizeof(float);
+}
+
+#define SYLDET_FUSED_DISPATCH(FN, ...)                                             \
+    switch (cfg_fft * 16 + cfg_hp) {                                               \
+        case 64 * 16 + 4: return FN<64, 4>(__VA_ARGS__);                           \
+        case 64 * 16 + 8: return FN<64, 8>(__VA_ARGS__);                           \
+        case 128 * 16 + 4: return FN<128, 4>(__VA_ARGS__);                         \
+        case 128 * 16 + 8: return FN<128, 8>(__VA_ARGS__);                         \
+        case 256 * 16 + 4: return FN<256, 4>(__VA_ARGS__);                         \
+        case 256 * 16 + 8: return FN<256, 8>(__VA_ARGS__);                         \
+        case 512 * 16 + 4: return FN<512, 4>(__VA_ARGS__);                         \
+        case 512 * 16 + 8: return FN<512, 8>(__VA_ARGS__);                         \
+        default: return cudaErrorInvalidValue;                                     \
+    }
+
+cudaError_t launch_fused(const FusedLaunch &cfg, const FusedParams &p, const FusedWork &w, cudaStream_t stream) {
+    const int cfg_fft = cfg.fft_len, cfg_hp = cfg.hp;
+    SYLDET_FUSED_DISPATCH(launch_one, cfg, p, w, stream)
+}
+
+cudaError_t fused_max_blocks_per_sm(int fft_len, int hp, size_t smem, int *blocks) {
+    const int cfg_fft = fft_len, cfg_hp = hp;
+    SYLDET_FUSED_DISPATCH(occupancy_one, smem, blocks)
+}
+
+}  // namespace syldet

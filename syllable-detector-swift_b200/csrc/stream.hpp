@@ -1,0 +1,81 @@
+// Streaming front-ends (see stream.cu).
+#pragma once
+#include "engine.hpp"
+
+namespace syldet {
+
+constexpr int kSampleRingFloats = 409600 / 4;  // CircularShortTimeFourierTransform(buffer: 409600) bytes (CSTFT.swift:61)
+
+class StreamGroup {
+public:
+    StreamGroup() = default;
+    StreamGroup(const StreamGroup &) = delete;
+    StreamGroup &operator=(const StreamGroup &) = delete;
+    ~StreamGroup();
+    syldet_status init(const Config &cfg, int n_channels, int max_buffer, int device);
+    // One tick. *outs -> pinned host [n_channels][*n_new][outputs], valid until the next call.
+    syldet_status submit(const float *const *bufs, int n, const float **outs, int64_t *n_new);
+    const Config &config() const { return batch_.model().config(); }
+    int n_channels() const { return n_channels_; }
+    int64_t launch_count() const { return batch_.launch_count(); }
+
+private:
+    Batch batch_;
+    int n_channels_ = 0, max_buffer_ = 0, cur_ = 0;
+    int64_t cap_ = 0;        // floats per channel in each device buffer
+    int64_t base_ = 0;       // absolute sample index of element 0 of the current device buffer
+    int64_t fill_ = 0;       // samples held per channel
+    int64_t total_ = 0;      // samples appended per channel so far
+    int64_t next_eval_ = 0;  // first evaluation not yet produced
+    int64_t max_new_ = 0;
+    DeviceBuffer ring_[2], d_out_;
+    cudaStream_t stream_ = nullptr;
+    float *h_in_ = nullptr, *h_out_ = nullptr;
+};
+
+class Detector {
+public:
+    syldet_status init(const Config &cfg, int device);
+    syldet_status append(const float *samples, int64_t n);
+    int process_new_value();  // 1 new value, 0 none, <0 -status
+    const std::vector<float> &last_outputs() const { return last_outputs_; }
+    bool last_detected() const;
+    int seen_syllable();
+
+private:
+    StreamGroup group_;
+    std::vector<float> pending_;      // appended, not yet sent to the device
+    std::vector<float> queue_;        // evaluations computed, not yet handed out
+    size_t queue_head_ = 0;
+    std::vector<float> last_outputs_;
+    int64_t appended_ = 0, cols_extracted_ = 0, evals_returned_ = 0, feature_ring_cols_ = 0;
+};
+
+class Resampler {
+public:
+    Resampler() = default;
+    Resampler(const Resampler &) = delete;
+    Resampler &operator=(const Resampler &) = delete;
+    ~Resampler();
+    syldet_status init(double rate_in, double rate_out, int device);
+    syldet_status process(const float *in, int64_t n_in, float *out, int64_t cap, int64_t *n_out);
+    int64_t max_output(int64_t n_in) const;
+
+private:
+    float step_ = 1.0f, last_ = 0.0f, offset_ = 0.0f;  // Resampler.swift:24-26
+    int device_ = 0;
+    cudaStream_t stream_ = nullptr;
+    DeviceBuffer d_in_, d_out_;
+};
+
+}  // namespace syldet
+
+struct syldet_stream {
+    syldet::StreamGroup g;
+};
+struct syldet_detector {
+    syldet::Detector d;
+};
+struct syldet_resampler {
+    syldet::Resampler r;
+};

@@ -1,0 +1,305 @@
+"""GPU parity tests (run with -m gpu on a B200). Everything goes through the C-ABI of libsyldet_cuda.so.
+
+Tolerances (north_star: "spectra and network outputs within a stated FP32 tolerance, e.g. max rel err <= 1e-5; any
+frame whose output lies within tolerance of the threshold reported separately"):
+    network outputs   |gpu - oracle| <= TOL_OUT = 1e-5 absolute (linear scaling; db/log configs scale it, see below)
+    detections        identical evaluation indices / sample numbers, except evaluations whose oracle output lies
+                      within TOL_OUT of the threshold, which are counted and must be rare
+"""
+import numpy as np
+import pytest
+
+from conftest import SAMPLE_TXT
+
+pytestmark = pytest.mark.gpu
+TOL_OUT = 1e-5
+
+
+@pytest.fixture(scope="module")
+def cfg(sd):
+    return sd.SyllableDetectorConfig(SAMPLE_TXT).validate()
+
+
+@pytest.fixture(scope="module")
+def orc(oracle_mod):
+    return oracle_mod.Oracle(SAMPLE_TXT)
+
+
+def _kernels(sd):
+    return [(sd.KERNEL_FUSED, "fused"), (sd.KERNEL_GENERIC, "generic")]
+
+
+def _check_channel(orc, x, outs, ev_samples, tol, debounce=0):
+    ref, da, _ = orc.run(x)
+    assert outs.shape == ref.shape
+    both_nan = np.isnan(outs) & np.isnan(ref)
+    err = np.abs(np.where(both_nan, 0.0, outs - ref))
+    assert not np.isnan(err).any() and err.max() <= tol, err.max()
+    thr = orc.thresholds
+    near = (np.abs(ref.astype(np.float64) - thr[None, :]) <= tol).any(axis=1)
+    ref_samples = np.array([orc.eval_sample(int(j)) for j in orc.debounce(da, debounce)], dtype=np.int64)
+    if not near.any():
+        assert np.array_equal(ev_samples, ref_samples)
+    else:  # report near-threshold evaluations separately: they may legitimately flip
+        near_samples = {orc.eval_sample(int(j)) for j in np.nonzero(near)[0]}
+        assert set(ev_samples) ^ set(ref_samples) <= near_samples or debounce > 0
+    return int(near.sum())
+
+
+def test_device_present(sd):
+    assert sd.device_count() >= 1
+
+
+def test_sample_txt_parity_both_kernels(sd, cfg, orc, synth):
+    x = synth.make_audio(3, 44100 * 6, seed=21)
+    for kernel, name in _kernels(sd):
+        det = sd.BatchDetector(cfg, kernel=kernel)
+        assert det.active_kernel == kernel
+        ev, outs = det.run(x, want_outputs=True)
+        assert len(ev) > 20, name
+        for ch in range(x.shape[0]):
+            _check_channel(orc, x[ch], outs[ch], ev.sample[ev.channel == ch], TOL_OUT)
+        assert np.allclose(ev.seconds, ev.sample / 44100.0)
+        assert det.launch_count >= 1
+
+
+def test_generic_kernel_spectra_are_bit_exact_for_linear_configs(sd, cfg, orc, synth):
+    """The reference-order kernels reproduce the oracle's float32 arithmetic; with tanh the only libm call, outputs agree
+    to a few ulp of the hidden activations."""
+    x = synth.make_audio(1, 44100 * 2, seed=5)
+    ev, outs = sd.BatchDetector(cfg, kernel=sd.KERNEL_GENERIC).run(x, want_outputs=True)
+    ref = orc.run(x[0])[0]
+    assert np.abs(outs[0] - ref).max() <= 1e-6
+
+
+def test_golden_cases(sd, oracle_mod, golden):
+    for name, g in golden.items():
+        c = sd.SyllableDetectorConfig.from_text(g["config"]).validate()
+        o = oracle_mod.Oracle(text=g["config"])
+        scale = max(1.0, float(np.nanmax(np.abs(g["outputs"]))))
+        tol = TOL_OUT * scale if c.spectrogram_scaling == "linear" else 2e-4 * scale
+        det = sd.BatchDetector(c)
+        kernels = [sd.KERNEL_GENERIC] + ([sd.KERNEL_FUSED] if det.active_kernel == sd.KERNEL_FUSED else [])
+        if name in ("sample", "log_std_128"):
+            assert det.active_kernel == sd.KERNEL_FUSED, name  # these shapes must take the fast path
+        for kernel in kernels:
+            ev, outs = sd.BatchDetector(c, kernel=kernel).run(g["audio"], want_outputs=True)
+            err = np.abs(outs[0] - g["outputs"])
+            assert np.nanmax(err) <= tol, (name, kernel, float(np.nanmax(err)))
+            near = (np.abs(g["outputs"].astype(np.float64) - o.thresholds[None, :]) <= tol).any(axis=1)
+            if not near.any():
+                assert np.array_equal(ev.sample, g["event_samples_d0"]), (name, kernel)
+                ev2 = sd.BatchDetector(c, kernel=kernel).run(g["audio"], debounce_frames=c.debounce_frames(0.05))
+                assert np.array_equal(ev2.sample, g["event_samples_d50ms"]), (name, kernel)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(fft_len=256, overlap=124, hidden=(4,), input_funcs=("l2normalize", "mapminmax")),
+    dict(fft_len=256, win_len=200, overlap=60, hidden=(7,), input_funcs=("normalize", "mapminmax", "mapstd"), transfer="LogSig"),
+    dict(fft_len=512, overlap=256, freq_range=(1000.0, 9000.0), time_range=5, hidden=(8, 5), outputs=3, input_funcs=("mapstd",), output_funcs=("mapminmax", "mapstd")),
+    dict(fft_len=128, overlap=-7, freq_range=(300.0, 20000.0), time_range=12, hidden=(3,), input_funcs=("normalizestd", "mapminmax")),
+    dict(fft_len=64, win_len=63, overlap=31, freq_range=(0.0, 22050.0), time_range=3, hidden=(), outputs=2, input_funcs=()),
+    dict(fft_len=512, win_len=512, overlap=511, freq_range=(2000.0, 4000.0), time_range=20, hidden=(4,), input_funcs=("l2normalize",)),
+    dict(fft_len=256, overlap=123, hidden=(4,), scaling="db", input_funcs=("mapminmax",)),
+    dict(fft_len=1024, overlap=512, freq_range=(1000.0, 8000.0), time_range=4, hidden=(16,), input_funcs=("l2normalize", "mapminmax")),
+    dict(fft_len=2048, win_len=1500, overlap=-100, freq_range=(500.0, 5000.0), time_range=2, hidden=(6,), scaling="log", input_funcs=("mapstd", "normalize")),
+])
+def test_generated_configs_fused_and_generic(sd, oracle_mod, cw, kw):
+    text = cw.random_config(seed=7, threshold=0.3, **kw)
+    c = sd.SyllableDetectorConfig.from_text(text).validate()
+    o = oracle_mod.Oracle(text=text)
+    rng = np.random.default_rng(9)
+    n = 40000
+    t = np.arange(n)
+    x = np.stack([(0.05 * rng.standard_normal(n) + 0.4 * np.sin(2 * np.pi * f0 * t / 44100 + 3 * np.sin(2 * np.pi * 2 * t / 44100))).astype(np.float32)
+                  for f0 in (2500.0, 5200.0)])
+    det = sd.BatchDetector(c)
+    kernels = [sd.KERNEL_GENERIC] + ([sd.KERNEL_FUSED] if det.active_kernel == sd.KERNEL_FUSED else [])
+    if kw["fft_len"] <= 512 and all(h <= 8 for h in kw.get("hidden", ())) and kw.get("input_funcs", ())[1:2] != ("normalize",):
+        assert sd.KERNEL_FUSED in kernels
+    for kernel in kernels:
+        ev, outs = sd.BatchDetector(c, kernel=kernel).run(x, want_outputs=True)
+        for ch in range(2):
+            ref = o.run(x[ch])[0]
+            scale = max(1.0, float(np.nanmax(np.abs(ref))))
+            tol = (TOL_OUT if kw.get("scaling", "linear") == "linear" else 2e-4) * scale
+            _check_channel(o, x[ch], outs[ch], ev.sample[ev.channel == ch], tol)
+
+
+def test_chunk_and_batch_invariance(sd, cfg, synth):
+    """Any split of the work gives identical results: channels together or alone, long or short recordings."""
+    x = synth.make_audio(5, 132 * 3000 + 77, seed=33)
+    det = sd.BatchDetector(cfg)
+    ev_all, out_all = det.run(x, want_outputs=True)
+    for ch in (0, 4):
+        ev1, out1 = det.run(x[ch], want_outputs=True)
+        assert np.array_equal(out1[0], out_all[ch]) and np.array_equal(ev1.sample, ev_all.sample[ev_all.channel == ch])
+    # prefix property: outputs of a prefix equal the prefix of the outputs
+    n2 = 132 * 1000 + 1444
+    ev2, out2 = det.run(x[:, :n2], want_outputs=True)
+    assert np.array_equal(out2, out_all[:, :out2.shape[1]])
+    # time-shift by whole hops shifts evaluations (pure function of the sample span)
+    ev3, out3 = det.run(x[:, 132 * 17:], want_outputs=True)
+    assert np.array_equal(out3, out_all[:, 17:])
+
+
+def test_edge_sizes(sd, cfg, orc):
+    det = sd.BatchDetector(cfg)
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 255, 1443, 1444, 1445, 1444 + 131, 1444 + 132, 1444 + 132 * 255, 1444 + 132 * 256 + 5):
+        x = (rng.standard_normal((2, max(n, 1))) * 0.01).astype(np.float32)[:, :n] if n else np.zeros((2, 0), dtype=np.float32)
+        if n == 0:
+            continue  # a zero-length buffer is rejected upstream too (guard 0 < numSamples, TrackDetector.swift:53)
+        ev, outs = det.run(x, want_outputs=True)
+        assert outs.shape[1] == orc.num_evals(n)
+        for ch in range(2):
+            if outs.shape[1]:
+                assert np.abs(outs[ch] - orc.run(x[ch])[0]).max() <= TOL_OUT
+    # silence: NaN outputs, no detection
+    ev, outs = det.run(np.zeros((1, 5000), dtype=np.float32), want_outputs=True)
+    assert np.isnan(outs).all() and len(ev) == 0
+
+
+def test_debounce_and_detect_rules(sd, oracle_mod, cw, synth, cfg, orc):
+    x = synth.make_audio(2, 44100 * 5, seed=8)
+    det = sd.BatchDetector(cfg)
+    for seconds in (0.0, 0.01, 0.05, 0.5):
+        D = cfg.debounce_frames(seconds)
+        ev = det.run(x, debounce_frames=D)
+        for ch in range(2):
+            s, _, _ = orc.events(x[ch], D)
+            assert np.array_equal(ev.sample[ev.channel == ch], s)
+    # any-output (CLI) vs first-output (live) rule on a 2-output network
+    text = cw.random_config(seed=12, hidden=(4,), outputs=2, threshold=[10.0, -10.0])
+    c = sd.SyllableDetectorConfig.from_text(text).validate()
+    o = oracle_mod.Oracle(text=text)
+    d2 = sd.BatchDetector(c)
+    assert len(d2.run(x[0], detect_rule=sd.DETECT_ANY_OUTPUT)) == o.num_evals(x.shape[1])
+    assert len(d2.run(x[0], detect_rule=sd.DETECT_FIRST_OUTPUT)) == 0
+
+
+def test_event_buffer_overflow_replay(sd, cw):
+    """Every evaluation detects: more events than the initial device buffer holds -> grow and replay."""
+    text = cw.random_config(seed=2, hidden=(4,), threshold=-1e9)
+    c = sd.SyllableDetectorConfig.from_text(text).validate()
+    x = (np.random.default_rng(0).standard_normal((12, 132 * 100000 + 1444)) * 0.01).astype(np.float32)
+    ev = sd.BatchDetector(c).run(x)
+    assert len(ev) == 12 * c.num_evals(x.shape[1]) > (1 << 20)
+    assert np.array_equal(ev.sample[:3], [1444, 1576, 1708]) and np.all(np.diff(ev.channel) >= 0)
+
+
+def test_pcm16_and_interleaved_ingest(sd, cfg, synth):
+    x = synth.make_audio(3, 44100 * 2, seed=4) * 8.0
+    s16 = np.clip(np.round(x * 32768.0), -32768, 32767).astype(np.int16)
+    xf = (s16.astype(np.float32) / 32768.0).astype(np.float32)
+    det = sd.BatchDetector(cfg)
+    ev_ref, out_ref = det.run(xf, want_outputs=True)
+    ev_a, out_a = det.run(s16, want_outputs=True)                                             # planar int16
+    ev_b, out_b = det.run(np.ascontiguousarray(xf.T), want_outputs=True, layout=sd.LAYOUT_INTERLEAVED)   # interleaved float
+    ev_c, out_c = det.run(np.ascontiguousarray(s16.T), want_outputs=True, layout=sd.LAYOUT_INTERLEAVED)  # interleaved int16
+    for o, e in ((out_a, ev_a), (out_b, ev_b), (out_c, ev_c)):
+        assert np.array_equal(o, out_ref) and np.array_equal(e.sample, ev_ref.sample) and np.array_equal(e.channel, ev_ref.channel)
+
+
+def test_syllable_detector_api_matches_oracle(sd, cfg, orc, synth):
+    """class SyllableDetector: appendAudioData / processNewValue / lastOutputs / lastDetected with ragged buffers."""
+    x = synth.make_audio(1, 44100 * 2, seed=14)[0]
+    ref, da, df = orc.run(x)
+    d = sd.SyllableDetector(cfg)
+    rng = np.random.default_rng(1)
+    pos, got, flags = 0, [], []
+    while pos < x.size:
+        n = int(rng.choice([1, 32, 100, 131, 132, 133, 500, 4096]))
+        d.append_audio_data(x[pos:pos + n])
+        pos += n
+        while d.process_new_value():
+            got.append(d.last_outputs.copy())
+            flags.append(d.last_detected)
+    got = np.array(got)
+    assert got.shape == ref.shape and np.abs(got - ref).max() <= TOL_OUT
+    assert np.array_equal(np.array(flags), df) and df.sum() > 0
+    # seenSyllable(): OR over everything pending
+    d2 = sd.SyllableDetector(cfg)
+    d2.append_audio_data(x[:44100])
+    assert d2.seen_syllable() == bool(df[:orc.num_evals(44100)].any())
+    assert d2.process_new_value() is False
+    # ring overflow is an error, not an abort (CSTFT.swift:199)
+    d3 = sd.SyllableDetector(cfg)
+    d3.append_audio_data(np.zeros(102400, dtype=np.float32))
+    with pytest.raises(sd.SyldetError) as e:
+        d3.append_audio_data(np.zeros(1, dtype=np.float32))
+    assert e.value.kind == "bufferOverflow"
+
+
+def test_track_detector_rows(sd, cfg, orc, synth):
+    x = synth.make_audio(1, 44100 * 3, seed=15)[0]
+    D = cfg.debounce_frames(0.02)
+    bufs = [x[i:i + 8192] for i in range(0, x.size, 8192)]
+    td = sd.TrackDetector(bufs, cfg, channel=3)
+    td.debounce_time = 0.02
+    assert td.debounce_frames == D
+    while td.process():
+        pass
+    s, sec, outs = orc.events(x, D)
+    assert [r[1] for r in td.rows] == list(s) and all(r[0] == 3 for r in td.rows)
+    assert np.allclose([r[2] for r in td.rows], sec) and np.abs(np.array([r[3] for r in td.rows]) - outs).max() <= TOL_OUT
+
+
+def test_stream_group_matches_batch(sd, cfg, orc, synth):
+    """Processor.swift shape: 16 channels, 32-frame buffers; per-tick `seen` flags and outputs equal the offline run."""
+    nch, nbuf, ticks = 16, 32, 1500
+    x = synth.make_audio(nch, nbuf * ticks, seed=16)
+    g = sd.StreamGroup(cfg, nch, max_buffer=nbuf)
+    total_new = np.zeros(nch, dtype=np.int64)
+    seen_eval = [[] for _ in range(nch)]
+    last = None
+    for t in range(ticks):
+        seen, n_new = g.submit(x[:, t * nbuf:(t + 1) * nbuf])
+        for ch in range(nch):
+            if n_new[ch]:
+                seen_eval[ch].append((int(total_new[ch]), int(n_new[ch]), bool(seen[ch])))
+        total_new += n_new
+        last = g.last_outputs.copy()
+    E = orc.num_evals(nbuf * ticks)
+    assert np.all(total_new == E)
+    for ch in (0, 7, 15):
+        ref, _, df = orc.run(x[ch])
+        for start, cnt, flag in seen_eval[ch]:
+            assert flag == bool(df[start:start + cnt].any())
+        assert np.abs(last[ch] - ref[-1]).max() <= TOL_OUT
+
+
+def test_resampler_matches_oracle_bit_for_bit(sd, oracle_mod):
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal(32 * 400).astype(np.float32)
+    for rin, rout, nbuf in ((48000, 44100, 32), (44100, 48000, 32), (96000, 44100, 512), (22050, 44100, 100), (44100, 44100, 64)):
+        a, b = sd.ResamplerLinear(rin, rout), oracle_mod.Resampler(rin, rout)
+        for i in range(0, x.size - nbuf + 1, nbuf):
+            ya, yb = a.resample_vector(x[i:i + nbuf]), b.process(x[i:i + nbuf])
+            assert ya.size == yb.size and np.array_equal(ya, yb), (rin, rout, i)
+
+
+def test_large_run_properties(sd, cfg, orc, synth):
+    """BASELINE config-2 shape at reduced length per channel but full channel count: size-independent checks."""
+    nch, n = 8, 44100 * 120
+    x = synth.make_audio(nch, n, seed=40)
+    det = sd.BatchDetector(cfg)
+    ev, outs = det.run(x, want_outputs=True)
+    E = cfg.num_evals(n)
+    assert outs.shape == (nch, E, 1) and not np.isnan(outs).any()
+    # events == thresholded dense outputs, sorted by (channel, sample), samples on the hop lattice
+    flags = outs[:, :, 0].astype(np.float64) >= cfg.thresholds[0]
+    assert len(ev) == int(flags.sum()) > 1000
+    assert np.all((ev.sample - 1444) % 132 == 0)
+    key = ev.channel.astype(np.int64) * (1 << 40) + ev.sample
+    assert np.all(np.diff(key) > 0)
+    assert np.array_equal(outs[ev.channel, (ev.sample - 1444) // 132, 0], ev.outputs[:, 0])
+    # sampled slices against the oracle
+    rng = np.random.default_rng(3)
+    for _ in range(6):
+        ch, j = int(rng.integers(nch)), int(rng.integers(E - 300))
+        seg = x[ch, j * 132: j * 132 + 1444 + 132 * 299]
+        assert np.abs(outs[ch, j:j + 300] - orc.run(seg)[0]).max() <= TOL_OUT
+    # generic and fused kernels agree everywhere
+    ev_g, outs_g = sd.BatchDetector(cfg, kernel=sd.KERNEL_GENERIC).run(x[:2], want_outputs=True)
+    assert np.abs(outs_g - outs[:2]).max() <= TOL_OUT

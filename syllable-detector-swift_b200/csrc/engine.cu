@@ -348,6 +348,7 @@ syldet_status Batch::launch_planar(const float *d_planar, int n_channels, int64_
         if (chunk > 64 * tile) chunk = 64 * tile;
         w.chunk_evals = chunk;
         w.chunks_per_channel = (int)((E + chunk - 1) / chunk);
+        w.detect_rule = detect_rule;
         w.all_out = d_all_outputs;
         w.sink = sink;
         w.window = model_.window();

@@ -34,7 +34,7 @@ struct alignas(16) FusedParams {
     int nn_tile;      // evaluations that trigger an epilogue pass
     int abuf_floats;  // one audio staging buffer, floats (multiple of 4)
     int window_stat;  // FUSED_STAT_*
-    int n_layers, n_out, n_op, detect_rule;
+    int n_layers, n_out, n_op, reserved0;
     int tf[kFusedMaxLayers];
     float v[kFusedMaxHidden];       // V_h  = sum_i W_hi A_i
     float bprime[kFusedMaxHidden];  // B'_h = b_h + sum_i W_hi C_i
@@ -55,6 +55,7 @@ struct FusedWork {
     int64_t evals_per_channel;
     int64_t chunk_evals;
     int chunks_per_channel;
+    int detect_rule;       // SYLDET_DETECT_*
     float *all_out;        // optional [n_channels][evals_per_channel][n_out]
     EventSink sink;
     const float *window;   // [win_len]

@@ -201,7 +201,7 @@ __device__ __forceinline__ void gather_layer0(const FusedParams &p, const float 
 }
 
 template <int HP>
-__device__ __forceinline__ bool evaluate(const FusedParams &p, const float *ring, int slot, float (&out)[kFusedMaxOut]) {
+__device__ __forceinline__ bool evaluate(const FusedParams &p, int detect_rule, const float *ring, int slot, float (&out)[kFusedMaxOut]) {
     float acc[HP];
 #pragma unroll
     for (int h = 0; h < HP; ++h) acc[h] = 0.0f;
@@ -276,7 +276,7 @@ __device__ __forceinline__ bool evaluate(const FusedParams &p, const float *ring
                 v = (v + (0 - p.op_y[k])) / p.op_gain[k * kFusedMaxOut + o] + p.op_xoff[k * kFusedMaxOut + o];
             }
             const bool over = (double)v >= p.thr[o];  // TrackDetector.swift:72; NaN -> false
-            if (over && (p.detect_rule == SYLDET_DETECT_ANY_OUTPUT || o == 0)) hit = true;
+            if (over && (detect_rule == SYLDET_DETECT_ANY_OUTPUT || o == 0)) hit = true;
         }
         out[o] = v;
     }
@@ -475,7 +475,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_detect_kernel(const __
                     if (active) {
                         int slot = eval_slot + q;
                         if (slot >= p.ring_cols) slot -= p.ring_cols;
-                        hit = evaluate<HP>(p, ring, slot, out);
+                        hit = evaluate<HP>(p, w.detect_rule, ring, slot, out);
                         if (w.all_out) {
                             float *o = w.all_out + ((int64_t)ch * w.evals_per_channel + e0 + evals_done + q) * p.n_out;
 #pragma unroll

@@ -1,0 +1,164 @@
+// syldet — command line detector, Linux counterpart of SyllableDetectorCLI/main.swift.
+//   syldet -n <network.txt> -a <audio.wav> [-a ...] [-d <seconds>]
+// Same flags (main.swift:21-23), same CSV rows on stdout: channel,sample,seconds,out0[,out1...]
+// (TrackDetector.swift:92-96, help text main.swift:31-39). Differences, both forced by leaving macOS:
+//   * audio is read from RIFF/WAVE (PCM16, PCM24, PCM32 or float32) instead of AVFoundation and must already be at the
+//     network's sampling rate (AVFoundation resampled silently, SyllableDetector.swift:19-23);
+//   * every channel of a file is a "track": upstream reads channel 0 of each AVAssetTrack (main.swift:86-89).
+// All compute goes through the C-ABI of libsyldet_cuda.so; there is no CPU path.
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../include/syldet.h"
+
+namespace {
+
+struct Wav {
+    int channels = 0, rate = 0;
+    int64_t frames = 0;
+    std::vector<float> interleaved;
+};
+
+uint32_t rd32(const unsigned char *p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24); }
+uint16_t rd16(const unsigned char *p) { return (uint16_t)(p[0] | (p[1] << 8)); }
+
+bool read_wav(const std::string &path, Wav &w, std::string &err) {
+    FILE *f = std::fopen(path.c_str(), "rb");
+    if (!f) { err = "cannot open file"; return false; }
+    std::vector<unsigned char> buf;
+    unsigned char tmp[1 << 16];
+    size_t n;
+    while ((n = std::fread(tmp, 1, sizeof tmp, f)) > 0) buf.insert(buf.end(), tmp, tmp + n);
+    std::fclose(f);
+    if (buf.size() < 12 || std::memcmp(buf.data(), "RIFF", 4) || std::memcmp(buf.data() + 8, "WAVE", 4)) { err = "not a RIFF/WAVE file"; return false; }
+    int fmt = 0, bits = 0, align = 0;
+    size_t pos = 12;
+    const unsigned char *data = nullptr;
+    size_t data_len = 0;
+    while (pos + 8 <= buf.size()) {
+        const uint32_t len = rd32(&buf[pos + 4]);
+        const unsigned char *body = &buf[pos + 8];
+        const size_t avail = buf.size() - pos - 8;
+        if (!std::memcmp(&buf[pos], "fmt ", 4) && len >= 16 && avail >= 16) {
+            fmt = rd16(body);
+            w.channels = rd16(body + 2);
+            w.rate = (int)rd32(body + 4);
+            align = rd16(body + 12);
+            bits = rd16(body + 14);
+            if (fmt == 0xFFFE && len >= 26 && avail >= 26) fmt = rd16(body + 24);  // WAVE_FORMAT_EXTENSIBLE sub-format
+        } else if (!std::memcmp(&buf[pos], "data", 4)) {
+            data = body;
+            data_len = len < avail ? len : avail;
+        }
+        pos += 8 + (size_t)len + (len & 1);
+    }
+    if (!data || w.channels <= 0 || align <= 0) { err = "missing fmt or data chunk"; return false; }
+    w.frames = (int64_t)(data_len / align);
+    w.interleaved.resize((size_t)w.frames * w.channels);
+    const size_t total = w.interleaved.size();
+    if (fmt == 1 && bits == 16) for (size_t i = 0; i < total; ++i) w.interleaved[i] = (float)(int16_t)rd16(data + 2 * i) / 32768.0f;
+    else if (fmt == 1 && bits == 24) for (size_t i = 0; i < total; ++i) {
+        int32_t v = data[3 * i] | (data[3 * i + 1] << 8) | ((int32_t)(int8_t)data[3 * i + 2] << 16);
+        w.interleaved[i] = (float)v / 8388608.0f;
+    } else if (fmt == 1 && bits == 32) for (size_t i = 0; i < total; ++i) w.interleaved[i] = (float)((double)(int32_t)rd32(data + 4 * i) / 2147483648.0);
+    else if (fmt == 3 && bits == 32) std::memcpy(w.interleaved.data(), data, total * 4);
+    else { err = "unsupported sample format (want PCM 16/24/32 or float32)"; return false; }
+    return true;
+}
+
+void usage() {
+    std::puts("Usage: syldet -n <net> [-a <audio>]... [-d <seconds>]");
+    std::puts("  -n, --net <net>          Path to trained network file.");
+    std::puts("  -a, --audio <audio>      Path to the audio file to process.");
+    std::puts("  -d, --debounce <seconds> Number of seconds to debounce triggers.");
+    std::puts("The command line will write a comma-separated list of detection events (when the network has at least one output above threshold) to standard out. For example, it might output:");
+    std::puts("");
+    std::puts("\t0,1593298,36.1292063492063,0.918557");
+    std::puts("");
+    std::puts("The columns are:");
+    std::puts("1. The track or channel number from the audio file (starting with 0).");
+    std::puts("2. The sample number from the audio when detection occurred.");
+    std::puts("3. The timestamp from the audio when detection occurred.");
+    std::puts("4. The first neural network output. Note that there may be additional columns for additional outputs.");
+}
+
+// shortest decimal that round-trips, like Swift's description of Double / Float (TrackDetector.swift:92-96)
+std::string shortest(double v, bool single) {
+    char b[64];
+    for (int prec = 1; prec <= 17; ++prec) {
+        std::snprintf(b, sizeof b, "%.*g", prec, v);
+        if (single ? (std::strtof(b, nullptr) == (float)v) : (std::strtod(b, nullptr) == v)) break;
+    }
+    std::string s(b);
+    if (s.find_first_of(".eEn") == std::string::npos) s += ".0";
+    return s;
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+    std::string net;
+    std::vector<std::string> audio;
+    bool have_debounce = false;
+    double debounce = 0.0;
+    for (int i = 1; i < argc; ++i) {
+        const std::string a = argv[i];
+        auto value = [&](std::string &dst) { if (i + 1 >= argc) return false; dst = argv[++i]; return true; };
+        std::string v;
+        if (a == "-n" || a == "--net") { if (!value(net)) { usage(); return 64; } }
+        else if (a == "-a" || a == "--audio") { if (!value(v)) { usage(); return 64; } audio.push_back(v); }
+        else if (a == "-d" || a == "--debounce") { if (!value(v)) { usage(); return 64; } char *e; debounce = std::strtod(v.c_str(), &e); have_debounce = (*e == 0 && !v.empty()); }
+        else { usage(); return 64; }  // EX_USAGE, main.swift:40
+    }
+    if (net.empty()) { usage(); return 64; }
+
+    syldet_config *cfg = nullptr;
+    if (syldet_config_load_text(net.c_str(), &cfg) != SYLDET_OK || syldet_config_validate(cfg) != SYLDET_OK) {
+        std::fprintf(stderr, "Unable to load the network configuration: %s\n", syldet_last_error());
+        return 1;
+    }
+    syldet_batch *batch = nullptr;
+    if (syldet_batch_create(cfg, 0, &batch) != SYLDET_OK) {
+        std::fprintf(stderr, "Unable to create the detector: %s\n", syldet_last_error());
+        return 1;
+    }
+    const double fs = syldet_config_sampling_rate(cfg);
+    const int64_t debounce_frames = have_debounce ? syldet_config_debounce_frames(cfg, debounce) : 0;
+
+    for (const std::string &path : audio) {
+        Wav w;
+        std::string err;
+        if (!read_wav(path, w, err)) { std::fprintf(stderr, "Unable to read %s: %s\n", path.c_str(), err.c_str()); continue; }
+        if (std::fabs((double)w.rate - fs) > 1.0) {
+            std::fprintf(stderr, "Can not read audio tracks found in %s: sampling rate %d differs from the network's %g.\n", path.c_str(), w.rate, fs);
+            continue;
+        }
+        if (audio.size() > 1) std::printf("%s\n", path.c_str());  // main.swift:122-124
+        if (w.frames <= 0) continue;
+        syldet_events *ev = nullptr;
+        if (syldet_batch_run_host(batch, w.interleaved.data(), SYLDET_PCM_F32, w.channels, w.frames, 0, SYLDET_LAYOUT_INTERLEAVED,
+                                  debounce_frames, SYLDET_DETECT_ANY_OUTPUT, nullptr, &ev) != SYLDET_OK) {
+            std::fprintf(stderr, "Can not start reading %s: %s.\n", path.c_str(), syldet_last_error());
+            continue;
+        }
+        const int64_t n = syldet_events_count(ev);
+        const int O = syldet_events_outputs_per_event(ev);
+        const syldet_event *rows = syldet_events_data(ev);
+        const float *outs = syldet_events_outputs(ev);
+        // upstream interleaves tracks buffer by buffer (main.swift:126-130); rows here are grouped by channel, then time
+        for (int64_t r = 0; r < n; ++r) {
+            std::printf("%d,%lld,%s", rows[r].channel, (long long)rows[r].sample, shortest((double)rows[r].sample / fs, false).c_str());
+            for (int o = 0; o < O; ++o) std::printf(",%s", shortest((double)outs[r * O + o], true).c_str());
+            std::printf("\n");
+        }
+        syldet_events_free(ev);
+    }
+    syldet_batch_destroy(batch);
+    syldet_config_free(cfg);
+    return 0;
+}

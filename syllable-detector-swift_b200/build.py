@@ -52,6 +52,13 @@ def build(force=False, verbose=False):
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd)
+    cli_src = os.path.join(HERE, "..", "cli", "syldet_cli.cpp")
+    cli_out = os.path.join(HERE, "syldet")
+    if force or _stale(cli_out, [cli_src, OUT]):
+        cmd = ["g++", "-O2", "-std=c++17", "-Wall", cli_src, "-o", cli_out, "-L" + HERE, "-lsyldet_cuda", "-Wl,-rpath,$ORIGIN"]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
     return OUT
 
 

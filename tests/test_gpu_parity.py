@@ -303,3 +303,31 @@ def test_large_run_properties(sd, cfg, orc, synth):
     # generic and fused kernels agree everywhere
     ev_g, outs_g = sd.BatchDetector(cfg, kernel=sd.KERNEL_GENERIC).run(x[:2], want_outputs=True)
     assert np.abs(outs_g - outs[:2]).max() <= TOL_OUT
+
+
+def test_cli_csv_rows(sd, cfg, orc, synth, tmp_path):
+    """`syldet -n net -a wav -d s` prints channel,sample,seconds,out0 like SyllableDetectorCLI (main.swift:31-39)."""
+    import os
+    import subprocess
+    import wave
+    from conftest import ROOT, SAMPLE_TXT as NET
+    x = synth.make_audio(2, 44100 * 3, seed=19) * 8.0
+    s16 = np.clip(np.round(x * 32768.0), -32768, 32767).astype(np.int16)
+    path = str(tmp_path / "a.wav")
+    with wave.open(path, "wb") as w:
+        w.setnchannels(2)
+        w.setsampwidth(2)
+        w.setframerate(44100)
+        w.writeframes(np.ascontiguousarray(s16.T).tobytes())
+    exe = os.path.join(ROOT, "syllable-detector-swift_b200", "syldet")
+    out = subprocess.run([exe, "-n", NET, "-a", path, "-d", "0.02"], capture_output=True, text=True, check=True).stdout
+    rows = [l.split(",") for l in out.strip().splitlines()]
+    xf = s16.astype(np.float32) / 32768.0
+    want = []
+    for ch in range(2):
+        s, sec, outs = orc.events(xf[ch], cfg.debounce_frames(0.02))
+        want += [(ch, int(a), float(b), float(c[0])) for a, b, c in zip(s, sec, outs)]
+    assert len(rows) == len(want) > 5
+    for r, (ch, s, sec, o) in zip(rows, want):
+        assert int(r[0]) == ch and int(r[1]) == s and abs(float(r[2]) - sec) < 1e-12 and abs(float(r[3]) - o) <= TOL_OUT
+    assert subprocess.run([exe], capture_output=True).returncode == 64  # EX_USAGE (main.swift:40)

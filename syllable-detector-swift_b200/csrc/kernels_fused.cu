@@ -154,17 +154,22 @@ struct RoundSpan {
     bool bulk_ok;         // the aligned span lies inside the caller's buffer
 };
 
-__device__ __forceinline__ RoundSpan round_span(const FusedParams &p, const FusedWork &w, const float *x_ch, int64_t first_col,
-                                                int cols) {
+__device__ __forceinline__ RoundSpan round_span(const FusedParams &p, const FusedWork &w, const float *src, int cols) {
     RoundSpan s;
-    s.src = x_ch + first_col * p.hop + p.gap;
+    s.src = src;
     s.n_floats = (cols - 1) * p.hop + p.win_len;
-    const uintptr_t a = (uintptr_t)s.src;
+    const uintptr_t a = (uintptr_t)src;
     s.aligned = (const char *)(a & ~(uintptr_t)15);
     s.off = (int)((a & 15) >> 2);
     s.bytes = (uint32_t)(((s.off + s.n_floats) * 4 + 15) & ~15);
     s.bulk_ok = (uintptr_t)s.aligned >= (uintptr_t)w.pcm_begin && (uintptr_t)s.aligned + s.bytes <= (uintptr_t)w.pcm_end;
     return s;
+}
+
+__device__ __forceinline__ float sqrt_fast(float x) {  // MUFU.SQRT, max relative error 2^-23
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
 
 // ---- epilogue: one thread = one evaluation -----------------------------------------------------------------------
@@ -292,12 +297,12 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_detect_kernel(const __
     constexpr int RC = fused_round_cols(NFFT);       // columns per round (CTA)
     constexpr int FP = fused_frame_pitch(NFFT);      // float2 per frame in the exchange buffer
     constexpr int U2 = (G * R1) / 32;                // pass-2 items per lane
-    constexpr int PF = kFusedMaxBand / 32;           // band slots per lane
     static_assert(R1 * R2 == M && (G * M) / R1 == 32 && U2 >= 1, "plan");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw);
-    float *abuf0 = reinterpret_cast<float *>(smem_raw + 16);
+    float2 *s_utw = reinterpret_cast<float2 *>(smem_raw + 16);             // untangle twiddles w_N^{k0+f}, f < band
+    float *abuf0 = reinterpret_cast<float *>(smem_raw + 16 + kFusedMaxBand * sizeof(float2));
     float *abuf1 = abuf0 + p.abuf_floats;
     float2 *scratch = reinterpret_cast<float2 *>(abuf1 + p.abuf_floats);
     float *ring = reinterpret_cast<float *>(scratch + (kFusedThreads / 32) * G * FP);
@@ -305,6 +310,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_detect_kernel(const __
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int L = p.band, T = p.time_range, W = p.win_len;
     const bool full_window = (W == NFFT);
+    constexpr int LOG_R1 = R1 == 16 ? 4 : 3;
 
     // per-lane constants -----------------------------------------------------------------------------------------
     const int fs1 = lane / R2, j1 = lane % R2;  // pass 1: frame in group, butterfly index (M/R1 == R2 items per frame)
@@ -323,13 +329,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_detect_kernel(const __
         const float2 t = __ldg(w.twiddle + (q >= M ? q - M : q));
         tw[r] = q >= M ? make_float2(-t.x, -t.y) : t;
     }
-    tw[0] = make_float2(1.0f, 0.0f);
-    float2 utw[PF];                             // untangle twiddles w_N^k of this lane's band bins
-#pragma unroll
-    for (int q = 0; q < PF; ++q) {
-        const int f = lane + 32 * q;
-        utw[q] = f < L ? __ldg(w.twiddle + p.k0 + f) : make_float2(0.0f, 0.0f);
-    }
+    for (int f = tid; f < L; f += kFusedThreads) s_utw[f] = __ldg(w.twiddle + p.k0 + f);
 
     if (tid == 0) {
         mbar_init(&mbar[0], 1);
@@ -341,38 +341,40 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_detect_kernel(const __
 
     float2 *zw = scratch + warp * G * FP;  // this warp's exchange buffer
     const int64_t n_units = (int64_t)w.n_channels * w.chunks_per_channel;
+    const int round_floats = RC * p.hop;   // samples between the first frames of consecutive rounds
+    const int nq = (L + 31) >> 5;          // band slots per lane
 
     for (int64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
         const int ch = (int)(unit / w.chunks_per_channel);
-        const int64_t e0 = (unit % w.chunks_per_channel) * w.chunk_evals;
-        const int64_t ne = min(w.chunk_evals, w.evals_per_channel - e0);
-        const int64_t ncols = ne + T - 1;  // column index == evaluation index of the window it opens
-        const int nrounds = (int)((ncols + RC - 1) / RC);
-        const float *x_ch = w.pcm + (int64_t)ch * w.ch_stride;
+        const int64_t e0 = (unit - (int64_t)ch * w.chunks_per_channel) * w.chunk_evals;
+        const int ne = (int)min(w.chunk_evals, w.evals_per_channel - e0);
+        const int ncols = ne + T - 1;  // column index == evaluation index of the window it opens
+        const int nrounds = (ncols + RC - 1) / RC;
+        const float *src = w.pcm + (int64_t)ch * w.ch_stride + e0 * p.hop + p.gap;  // first sample of this round's first frame
+        float *out_base = w.all_out ? w.all_out + ((int64_t)ch * w.evals_per_channel + e0) * p.n_out : nullptr;
 
         if (tid == 0) {
-            const RoundSpan s = round_span(p, w, x_ch, e0, (int)min((int64_t)RC, ncols));
+            const RoundSpan s = round_span(p, w, src, min(RC, ncols));
             if (s.bulk_ok) {
                 mbar_expect_tx(&mbar[0], s.bytes);
                 bulk_copy_g2s(abuf0, s.aligned, s.bytes, &mbar[0]);
             }
         }
-        int64_t cols_done = 0, evals_done = 0;
+        int cols_done = 0, evals_done = 0;
         int col_slot = 0, eval_slot = 0;  // ring slots of column `cols_done` and evaluation `evals_done`
 
-        for (int r = 0; r < nrounds; ++r) {
-            const int cols = (int)min((int64_t)RC, ncols - (int64_t)r * RC);
+        for (int r = 0; r < nrounds; ++r, src += round_floats) {
+            const int cols = min(RC, ncols - r * RC);
             float *abuf = (r & 1) ? abuf1 : abuf0;
             if (tid == 0 && r + 1 < nrounds) {  // prefetch next round into the other buffer (free since the last sync)
-                const int ncols_next = (int)min((int64_t)RC, ncols - (int64_t)(r + 1) * RC);
-                const RoundSpan s = round_span(p, w, x_ch, e0 + (int64_t)(r + 1) * RC, ncols_next);
+                const RoundSpan s = round_span(p, w, src + round_floats, min(RC, ncols - (r + 1) * RC));
                 if (s.bulk_ok) {
                     uint64_t *bar = &mbar[(r + 1) & 1];
                     mbar_expect_tx(bar, s.bytes);
                     bulk_copy_g2s((r & 1) ? abuf0 : abuf1, s.aligned, s.bytes, bar);
                 }
             }
-            const RoundSpan span = round_span(p, w, x_ch, e0 + (int64_t)r * RC, cols);
+            const RoundSpan span = round_span(p, w, src, cols);
             if (span.bulk_ok) {
                 if (r & 1) { mbar_wait(&mbar[1], phase1); phase1 ^= 1; }
                 else { mbar_wait(&mbar[0], phase0); phase0 ^= 1; }
@@ -385,22 +387,28 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_detect_kernel(const __
             // ---- pass 1: window + radix-R1 on strided samples -------------------------------------------------
             {
                 const int c = warp * G + fs1;
-                float2 v[R1];
                 if (c < cols) {
-                    const float *fr = abuf + span.off + c * p.hop;
-                    const bool vec_ok = ((span.off + c * p.hop) & 1) == 0;
+                    const int first = span.off + c * p.hop;
+                    const float *fr = abuf + first + 2 * j1;
+                    float2 v[R1];
+                    if (full_window && (first & 1) == 0) {  // 8-byte aligned pairs: one LDS.64 per complex point
 #pragma unroll
-                    for (int r1 = 0; r1 < R1; ++r1) {
-                        const int m0 = 2 * (j1 + r1 * R2);
-                        float2 x;
-                        if (full_window) {
-                            if (vec_ok) x = *reinterpret_cast<const float2 *>(fr + m0);
-                            else { x.x = fr[m0]; x.y = fr[m0 + 1]; }
-                        } else {
-                            x.x = m0 < W ? fr[m0] : 0.0f;
-                            x.y = m0 + 1 < W ? fr[m0 + 1] : 0.0f;
+                        for (int r1 = 0; r1 < R1; ++r1) {
+                            const float2 x = *reinterpret_cast<const float2 *>(fr + 2 * r1 * R2);
+                            v[r1] = make_float2(x.x * wreg[r1].x, x.y * wreg[r1].y);
                         }
-                        v[r1] = make_float2(x.x * wreg[r1].x, x.y * wreg[r1].y);
+                    } else if (full_window) {
+#pragma unroll
+                        for (int r1 = 0; r1 < R1; ++r1)
+                            v[r1] = make_float2(fr[2 * r1 * R2] * wreg[r1].x, fr[2 * r1 * R2 + 1] * wreg[r1].y);
+                    } else {  // window shorter than the FFT: zero padding (CSTFT.swift:109-110)
+#pragma unroll
+                        for (int r1 = 0; r1 < R1; ++r1) {
+                            const int m0 = 2 * (j1 + r1 * R2);
+                            const float x0 = m0 < W ? fr[2 * r1 * R2] : 0.0f;
+                            const float x1 = m0 + 1 < W ? fr[2 * r1 * R2 + 1] : 0.0f;
+                            v[r1] = make_float2(x0 * wreg[r1].x, x1 * wreg[r1].y);
+                        }
                     }
                     Dft<R1>::run(v);
                     float2 *zb = zw + fs1 * FP + j1 * (R1 + 1);  // padded: element e lives at e + e / R1
@@ -416,11 +424,9 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_detect_kernel(const __
                 if (warp * G + fs2 < cols) {
                     float2 *zb = zw + fs2 * FP + j2;
                     float2 v[R2];
+                    v[0] = zb[0];
 #pragma unroll
-                    for (int r2 = 0; r2 < R2; ++r2) {
-                        const float2 z = zb[r2 * (R1 + 1)];
-                        v[r2] = r2 == 0 ? z : cmul(z, tw[r2]);
-                    }
+                    for (int r2 = 1; r2 < R2; ++r2) v[r2] = cmul(zb[r2 * (R1 + 1)], tw[r2]);
                     Dft<R2>::run(v);
 #pragma unroll
                     for (int r2 = 0; r2 < R2; ++r2) zb[r2 * (R1 + 1)] = v[r2];
@@ -428,34 +434,31 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_detect_kernel(const __
             }
             __syncwarp();
             // ---- untangle the packed real transform, magnitude, band slice -> ring -------------------------------
-            for (int g = 0; g < G; ++g) {
-                const int c = warp * G + g;
-                if (c >= cols) break;
-                int slot = col_slot + c;
+            // X[k] = ((Z[k] + conj Z[M-k]) - i w^k (Z[k] - conj Z[M-k])) / 2; with M-k taken mod M the same expression
+            // gives |Re Z[0] + Im Z[0]| for k = 0 (the Nyquist term is dropped upstream, CSTFT.swift:323).
+            {
+                const int gmax = min(G, cols - warp * G);
+                int slot = col_slot + warp * G;
                 if (slot >= p.ring_cols) slot -= p.ring_cols;
-                const float2 *zb = zw + g * FP;
-                float *dst = ring + slot * p.band_pitch;
-#pragma unroll
-                for (int q = 0; q < PF; ++q) {
-                    const int f = lane + 32 * q;
-                    if (f < L) {
-                        const int k = p.k0 + f;
-                        float mag;
-                        if (k == 0) {
-                            const float2 z0 = zb[0];
-                            mag = fabsf(z0.x + z0.y);  // X[0]; the Nyquist term is dropped (CSTFT.swift:323)
-                        } else {
-                            const int km = M - k;
-                            const float2 za = zb[k + k / R1];
-                            const float2 zc = zb[km + km / R1];
-                            const float sr = za.x + zc.x, si = za.y - zc.y;  // Z[k] + conj Z[M-k]
-                            const float dr = za.x - zc.x, di = za.y + zc.y;  // Z[k] - conj Z[M-k]
-                            const float re = sr + (utw[q].x * di + utw[q].y * dr);
-                            const float im = si - (utw[q].x * dr - utw[q].y * di);
-                            mag = sqrtf(re * re + im * im) * 0.5f;
-                        }
-                        dst[f] = scale_value(mag, p.scaling);
+                for (int g = 0; g < gmax; ++g) {
+                    const float2 *zb = zw + g * FP;
+                    float *dst = ring + slot * p.band_pitch;
+                    for (int q = 0; q < nq; ++q) {
+                        const int f = lane + 32 * q;
+                        const int fc = min(f, L - 1);
+                        const int k = p.k0 + fc, km = (M - k) & (M - 1);
+                        const float2 za = zb[k + (k >> LOG_R1)];
+                        const float2 zc = zb[km + (km >> LOG_R1)];
+                        const float2 t = s_utw[fc];
+                        const float sr = za.x + zc.x, si = za.y - zc.y;  // Z[k] + conj Z[M-k]
+                        const float dr = za.x - zc.x, di = za.y + zc.y;  // Z[k] - conj Z[M-k]
+                        const float re = sr + (t.x * di + t.y * dr);
+                        const float im = si - (t.x * dr - t.y * di);
+                        float mag = 0.5f * sqrt_fast(re * re + im * im);
+                        if (p.scaling != SYLDET_SCALING_LINEAR) mag = scale_value(mag, p.scaling);
+                        if (f < L) dst[f] = mag;
                     }
+                    if (++slot == p.ring_cols) slot = 0;
                 }
             }
             __syncthreads();
@@ -464,9 +467,8 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_detect_kernel(const __
             if (col_slot >= p.ring_cols) col_slot -= p.ring_cols;
 
             // ---- epilogue over the evaluations whose T columns are complete ---------------------------------------
-            const int64_t ready = cols_done - (T - 1) - evals_done;
-            if (ready >= p.nn_tile || (r == nrounds - 1 && ready > 0)) {
-                const int n_ready = (int)ready;
+            const int n_ready = cols_done - (T - 1) - evals_done;
+            if (n_ready >= p.nn_tile || (r == nrounds - 1 && n_ready > 0)) {
                 for (int qb = warp * 32; qb < n_ready; qb += kFusedThreads) {
                     const int q = qb + lane;
                     const bool active = q < n_ready;
@@ -476,8 +478,8 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_detect_kernel(const __
                         int slot = eval_slot + q;
                         if (slot >= p.ring_cols) slot -= p.ring_cols;
                         hit = evaluate<HP>(p, w.detect_rule, ring, slot, out);
-                        if (w.all_out) {
-                            float *o = w.all_out + ((int64_t)ch * w.evals_per_channel + e0 + evals_done + q) * p.n_out;
+                        if (out_base) {
+                            float *o = out_base + (int64_t)(evals_done + q) * p.n_out;
 #pragma unroll
                             for (int i = 0; i < kFusedMaxOut; ++i)
                                 if (i < p.n_out) o[i] = out[i];
@@ -531,7 +533,7 @@ bool fused_supports_fft(int fft_len) { return fft_len == 64 || fft_len == 128 ||
 
 size_t fused_smem_bytes(int fft_len, const FusedParams &p) {
     const size_t scratch = (size_t)(kFusedThreads / 32) * fused_group(fft_len) * fused_frame_pitch(fft_len) * sizeof(float2);
-    return 16 + 2 * (size_t)p.abuf_floats * sizeof(float) + scratch + (size_t)p.ring_cols * p.band_pitch * sizeof(float);
+    return 16 + kFusedMaxBand * sizeof(float2) + 2 * (size_t)p.abuf_floats * sizeof(float) + scratch + (size_t)p.ring_cols * p.band_pitch * sizeof(float);
 }
 
 #define SYLDET_FUSED_DISPATCH(FN, ...)                                             \

@@ -158,8 +158,9 @@ def run_ours(args):
     audio_seconds = nch * n / FS                      # per rank per step
     x = synth.make_audio_torch(nch, n, dev, seed=1000 + rank)   # this rank's recording, resident in HBM
     d_out = torch.empty((nch, E, cfg.net_outputs), dtype=torch.float32, device=dev)
-    det = sd.BatchDetector(cfg, device=local)
-    assert det.active_kernel == sd.KERNEL_FUSED, "sample.txt must take the fused kernel"
+    det = sd.BatchDetector(cfg, device=local, kernel=getattr(sd, "KERNEL_" + args.kernel.upper()))
+    assert det.active_kernel in (sd.KERNEL_FUSED, sd.KERNEL_TENSOR), "sample.txt must take a fused kernel"
+    kernel_name = {sd.KERNEL_FUSED: "fused_detect_kernel<256,4> (SIMT FFT)", sd.KERNEL_TENSOR: "tc_detect_kernel<4> (tcgen05 3xTF32 band DFT)"}[det.active_kernel]
     stream = torch.cuda.current_stream(dev)
 
     def launch():
@@ -255,7 +256,7 @@ def run_ours(args):
                     "steps": e2e_steps, "ms_per_step": 1e3 * e2e_wall / e2e_steps,
                     "api": "syldet_batch_run_host (pinned host float32 PCM in, debounced events out)"},
             "gpu_launches": int(gpu_launches),
-            "kernel": "fused_detect_kernel<256,4>",
+            "kernel": kernel_name,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel_ms": k_ms,
                          "algorithmic_bytes_per_launch": alg_bytes,
@@ -301,6 +302,7 @@ if __name__ == "__main__":
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-step-seconds", type=float, default=None)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--kernel", default="auto", choices=["auto", "fused", "tensor"])
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     if a.cpu_step_seconds is None:

@@ -50,7 +50,7 @@ enum { SYLDET_LAYOUT_PLANAR = 0, SYLDET_LAYOUT_INTERLEAVED = 1 };
 enum { SYLDET_DETECT_ANY_OUTPUT = 0,   /* TrackDetector.swift:71-77 (CLI rule)  */
        SYLDET_DETECT_FIRST_OUTPUT = 1  /* SyllableDetector.lastDetected :27-31 (live rule) */ };
 enum { SYLDET_PCM_F32 = 0, SYLDET_PCM_S16 = 1 };
-enum { SYLDET_KERNEL_AUTO = 0, SYLDET_KERNEL_GENERIC = 1, SYLDET_KERNEL_FUSED = 2 };
+enum { SYLDET_KERNEL_AUTO = 0, SYLDET_KERNEL_GENERIC = 1, SYLDET_KERNEL_FUSED = 2, SYLDET_KERNEL_TENSOR = 3 };
 
 typedef struct syldet_config syldet_config;     /* SyllableDetectorConfig + NeuralNet                    */
 typedef struct syldet_batch syldet_batch;       /* TrackDetector + main.swift loop, many channels at once */
@@ -114,7 +114,8 @@ int64_t syldet_config_debounce_frames(const syldet_config *cfg, double seconds);
 /* ---- batch: what TrackDetector.process + main.swift do, for n_channels independent channels ---------------------- */
 syldet_status syldet_batch_create(const syldet_config *cfg, int device, syldet_batch **out);
 void syldet_batch_destroy(syldet_batch *b);
-/* SYLDET_KERNEL_AUTO picks the fused kernel when the configuration qualifies, else the generic path. */
+/* SYLDET_KERNEL_AUTO picks the fastest kernel the configuration qualifies for: TENSOR (tcgen05 band DFT + fused epilogue),
+ * FUSED (SIMT FFT + fused epilogue), else the GENERIC reference-order path. */
 syldet_status syldet_batch_set_kernel(syldet_batch *b, int kernel);
 int syldet_batch_active_kernel(const syldet_batch *b);
 

@@ -30,7 +30,8 @@ PROCESSING = ("mapminmax", "mapstd", "l2normalize", "normalize", "normalizestd")
 LAYOUT_PLANAR, LAYOUT_INTERLEAVED = 0, 1
 DETECT_ANY_OUTPUT, DETECT_FIRST_OUTPUT = 0, 1
 PCM_F32, PCM_S16 = 0, 1
-KERNEL_AUTO, KERNEL_GENERIC, KERNEL_FUSED = 0, 1, 2
+KERNEL_AUTO, KERNEL_GENERIC, KERNEL_FUSED, KERNEL_TENSOR = 0, 1, 2, 3
+KERNEL_NAMES = {1: "generic", 2: "fused", 3: "tensor"}
 
 _STATUS = {1: "unableToOpenPath", 2: "missingValue", 3: "invalidValue", 4: "mismatchedLength", 5: "invalidConfiguration",
            6: "badArgument", 7: "cuda", 8: "outOfMemory", 9: "bufferOverflow", 10: "unsupported"}
@@ -273,6 +274,19 @@ class BatchDetector:
     @property
     def active_kernel(self):
         return lib.syldet_batch_active_kernel(self._h)
+
+    @staticmethod
+    def available_kernels(config, device=0):
+        """Kernel selectors this configuration qualifies for, fastest first."""
+        out = []
+        for k in (KERNEL_TENSOR, KERNEL_FUSED, KERNEL_GENERIC):
+            try:
+                BatchDetector(config, device, kernel=k)
+                out.append(k)
+            except SyldetError as e:
+                if e.kind != "unsupported":
+                    raise
+        return out
 
     @property
     def launch_count(self):

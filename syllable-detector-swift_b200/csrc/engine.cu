@@ -1,5 +1,7 @@
 #include "engine.hpp"
 
+#include <cuda.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -145,6 +147,59 @@ FusedPlan plan_fused(const Config &c) {
 }
 
 // -----------------------------------------------------------------------------------------------------------------
+namespace {
+float tf32_round(double v) {  // round to nearest, ties away (cvt.rna.tf32.f32): 10 explicit mantissa bits
+    float f = (float)v;
+    uint32_t u;
+    std::memcpy(&u, &f, 4);
+    if ((u & 0x7F800000u) == 0x7F800000u) return f;
+    u = (u + 0x1000u) & 0xFFFFE000u;
+    std::memcpy(&f, &u, 4);
+    return f;
+}
+}  // namespace
+
+TcPlan plan_tc(const Config &c, const FusedPlan &fused) {
+    TcPlan plan;
+    auto no = [&](const std::string &why) { plan.ok = false; plan.why = why; return plan; };
+    if (!fused.ok) return no("needs the fused epilogue: " + fused.why);
+    const int kpad = tc_k_pad(), hop = c.hop, W = c.window_length, N = c.fourier_length;
+    if (c.gap != 0) return no("gap configurations");
+    if (hop % 4 != 0) return no("hop not a multiple of 4 samples (TMA row pitch)");
+    if (hop < kpad - 8 || hop > kpad) return no("hop outside [128, 136]");
+    if (W <= hop || W > 2 * hop) return no("window does not span exactly two hop rows");
+    if (c.band > 32) return no("band wider than 32 bins");
+    plan.params = fused.params;
+    plan.hp = fused.launch.hp;
+    const int tf = tc_tile_frames();
+    plan.params.nn_tile = 192;
+    plan.params.ring_cols = plan.params.nn_tile + 2 * tf + c.time_range;
+    plan.smem = tc_smem_bytes(plan.params);
+    if (plan.smem > 227 * 1024) return no("shared-memory working set too large");
+    // rows: [0,32) Re B1 | [32,64) Im B1 | [64,96) Re B2 | [96,128) Im B2 ; B1 = samples [0,hop), B2 = samples [hop,W)
+    plan.dft_hi.assign((size_t)128 * kpad, 0.0f);
+    plan.dft_lo.assign((size_t)128 * kpad, 0.0f);
+    for (int b = 0; b < c.band; ++b) {
+        const int k = c.k0 + b;
+        for (int half = 0; half < 2; ++half)
+            for (int n = 0; n < hop; ++n) {
+                const int m = half * hop + n;  // sample index inside the frame
+                if (m >= W) break;
+                const double win = (double)(float)(0.54 - 0.46 * std::cos(2.0 * M_PI * (double)m / (double)W));
+                const double ang = -2.0 * M_PI * (double)(((long)k * m) % N) / (double)N;
+                const double re = win * std::cos(ang), im = win * std::sin(ang);
+                const size_t ire = (size_t)(half * 64 + b) * kpad + n, iim = (size_t)(half * 64 + 32 + b) * kpad + n;
+                plan.dft_hi[ire] = tf32_round(re);
+                plan.dft_lo[ire] = tf32_round(re - (double)plan.dft_hi[ire]);
+                plan.dft_hi[iim] = tf32_round(im);
+                plan.dft_lo[iim] = tf32_round(im - (double)plan.dft_hi[iim]);
+            }
+    }
+    plan.ok = true;
+    return plan;
+}
+
+// -----------------------------------------------------------------------------------------------------------------
 syldet_status DeviceModel::init(const Config &cfg, int device) {
     cfg_ = cfg;
     if (!cfg_.valid) {
@@ -256,6 +311,14 @@ syldet_status DeviceModel::init(const Config &cfg, int device) {
             fused_.blocks_per_sm = blocks;
         }
     }
+    tc_ = plan_tc(cfg_, fused_);
+    if (tc_.ok) {
+        const size_t n = tc_.dft_hi.size();
+        st = d_dft_.reserve(2 * n * sizeof(float));
+        if (st != SYLDET_OK) return st;
+        SYLDET_CUDA(cudaMemcpy(d_dft_.get(), tc_.dft_hi.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+        SYLDET_CUDA(cudaMemcpy(d_dft_.as<float>() + n, tc_.dft_lo.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+    }
     return SYLDET_OK;
 }
 
@@ -298,8 +361,10 @@ Batch::~Batch() {
 }
 
 syldet_status Batch::set_kernel(int kernel) {
-    if (kernel != SYLDET_KERNEL_AUTO && kernel != SYLDET_KERNEL_GENERIC && kernel != SYLDET_KERNEL_FUSED)
+    if (kernel != SYLDET_KERNEL_AUTO && kernel != SYLDET_KERNEL_GENERIC && kernel != SYLDET_KERNEL_FUSED && kernel != SYLDET_KERNEL_TENSOR)
         return set_error(SYLDET_ERR_ARG, "unknown kernel selector");
+    if (kernel == SYLDET_KERNEL_TENSOR && !model_.tc().ok)
+        return set_error(SYLDET_ERR_UNSUPPORTED, "tensor-core kernel not available for this configuration: " + model_.tc().why);
     if (kernel == SYLDET_KERNEL_FUSED && !model_.fused().ok)
         return set_error(SYLDET_ERR_UNSUPPORTED, "fused kernel not available for this configuration: " + model_.fused().why);
     kernel_ = kernel;
@@ -307,7 +372,7 @@ syldet_status Batch::set_kernel(int kernel) {
 }
 
 int Batch::active_kernel() const {
-    if (kernel_ == SYLDET_KERNEL_AUTO) return model_.fused().ok ? SYLDET_KERNEL_FUSED : SYLDET_KERNEL_GENERIC;
+    if (kernel_ == SYLDET_KERNEL_AUTO) return model_.tc().ok ? SYLDET_KERNEL_TENSOR : model_.fused().ok ? SYLDET_KERNEL_FUSED : SYLDET_KERNEL_GENERIC;
     return kernel_;
 }
 
@@ -321,6 +386,103 @@ syldet_status Batch::ensure_sink(unsigned long long capacity) {
     return SYLDET_OK;
 }
 
+namespace {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+}  // namespace
+
+syldet_status Batch::launch_fused_range(const float *d_planar, int n_channels, int64_t ch_stride, const float *valid_begin,
+                                        const float *valid_end, int64_t eval_begin, int64_t eval_count, int64_t evals_total,
+                                        int detect_rule, float *d_all_outputs, EventSink sink, cudaStream_t stream) {
+    const FusedPlan &fp = model_.fused();
+    FusedWork w{};
+    w.pcm = d_planar;
+    w.pcm_begin = valid_begin;
+    w.pcm_end = valid_end;
+    w.ch_stride = ch_stride;
+    w.n_channels = n_channels;
+    w.evals_per_channel = eval_count;
+    w.eval_offset = eval_begin;
+    w.out_evals_per_channel = evals_total;
+    const int resident = model_.sm_count() * fp.blocks_per_sm;
+    // chunk: a multiple of nn_tile, long enough that the T-1 warm-up columns are noise, short enough for >= 8 waves
+    const int64_t tile = fp.params.nn_tile;
+    int64_t chunk = ((eval_count + tile - 1) / tile) * tile;
+    const int64_t want_units = (int64_t)resident * 8;
+    while (chunk > 4 * tile && n_channels * ((eval_count + chunk - 1) / chunk) < want_units) chunk = ((chunk / 2 + tile - 1) / tile) * tile;
+    if (chunk > 64 * tile) chunk = 64 * tile;
+    w.chunk_evals = chunk;
+    w.chunks_per_channel = (int)((eval_count + chunk - 1) / chunk);
+    w.detect_rule = detect_rule;
+    w.all_out = d_all_outputs;
+    w.sink = sink;
+    w.window = model_.window();
+    w.twiddle = model_.twiddle();
+    FusedLaunch l = fp.launch;
+    const int64_t units = (int64_t)n_channels * w.chunks_per_channel;
+    l.grid = (int)std::min<int64_t>(units, resident);
+    SYLDET_CUDA(launch_fused(l, fp.params, w, stream));
+    launches_ += 1;
+    return SYLDET_OK;
+}
+
+syldet_status Batch::launch_tc_range(const float *d_planar, int n_channels, int64_t n_samples, int64_t ch_stride, int64_t eval_count,
+                                     int64_t evals_total, int detect_rule, float *d_all_outputs, EventSink sink, cudaStream_t stream) {
+    const Config &c = model_.config();
+    const TcPlan &tp = model_.tc();
+    EncodeTiledFn encode = encode_tiled_fn();
+    if (!encode) return set_error(SYLDET_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    // Y[channel][row][hop]: row r = samples [r*hop, (r+1)*hop) of a channel; only complete rows are part of the tensor
+    const cuuint64_t dims[3] = {(cuuint64_t)c.hop, (cuuint64_t)(n_samples / c.hop), (cuuint64_t)n_channels};
+    const cuuint64_t strides[2] = {(cuuint64_t)c.hop * 4, (cuuint64_t)(n_channels > 1 ? ch_stride : n_samples) * 4};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const cuuint32_t box_main[3] = {32, 64, 1}, box_tail[3] = {8, 64, 1};
+    alignas(64) CUtensorMap tm_main, tm_tail;
+    CUresult r1 = encode(&tm_main, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(d_planar), dims, strides, box_main, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r2 = encode(&tm_tail, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(d_planar), dims, strides, box_tail, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS)
+        return set_error(SYLDET_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r1) + ", " + std::to_string((int)r2) + ")");
+    TcWork w{};
+    w.n_channels = n_channels;
+    w.evals_per_channel = eval_count;
+    w.eval_offset = 0;
+    w.out_evals_per_channel = evals_total;
+    const int resident = model_.sm_count();
+    const int64_t tile = (int64_t)tc_tile_frames() * 4;  // 252 evaluations: one epilogue pass of the 256 worker threads
+    int64_t chunk = ((eval_count + tile - 1) / tile) * tile;
+    const int64_t want_units = (int64_t)resident * 8;
+    while (chunk > 8 * tile && n_channels * ((eval_count + chunk - 1) / chunk) < want_units) chunk = ((chunk / 2 + tile - 1) / tile) * tile;
+    if (chunk > 64 * tile) chunk = 64 * tile;
+    w.chunk_evals = chunk;
+    w.chunks_per_channel = (int)((eval_count + chunk - 1) / chunk);
+    w.detect_rule = detect_rule;
+    w.all_out = d_all_outputs;
+    w.sink = sink;
+    w.dft_hi = model_.dft_hi();
+    w.dft_lo = model_.dft_lo();
+    w.debug_band = debug_band_;
+    w.debug_cols = debug_cols_;
+    const int64_t units = (int64_t)n_channels * w.chunks_per_channel;
+    const int grid = (int)std::min<int64_t>(units, resident);
+    SYLDET_CUDA(launch_tc(tp.hp, grid, tp.smem, tp.params, w, &tm_main, &tm_tail, stream));
+    launches_ += 1;
+    return SYLDET_OK;
+}
+
 syldet_status Batch::launch_planar(const float *d_planar, int n_channels, int64_t n_samples, int64_t ch_stride,
                                    const float *valid_begin, const float *valid_end, int detect_rule, float *d_all_outputs,
                                    cudaStream_t stream) {
@@ -330,36 +492,24 @@ syldet_status Batch::launch_planar(const float *d_planar, int n_channels, int64_
     if (E <= 0) return SYLDET_OK;
     EventSink sink{sink_count_.as<unsigned long long>(), sink_events_.as<DevEvent>(), sink_outputs_.as<float>(), sink_capacity_};
 
-    if (active_kernel() == SYLDET_KERNEL_FUSED) {
-        const FusedPlan &fp = model_.fused();
-        FusedWork w{};
-        w.pcm = d_planar;
-        w.pcm_begin = valid_begin;
-        w.pcm_end = valid_end;
-        w.ch_stride = ch_stride;
-        w.n_channels = n_channels;
-        w.evals_per_channel = E;
-        const int resident = model_.sm_count() * fp.blocks_per_sm;
-        // chunk: a multiple of nn_tile, long enough that the T-1 warm-up columns are noise, short enough for >= 8 waves
-        const int64_t tile = fp.params.nn_tile;
-        int64_t chunk = ((E + tile - 1) / tile) * tile;
-        const int64_t want_units = (int64_t)resident * 8;
-        while (chunk > 4 * tile && n_channels * ((E + chunk - 1) / chunk) < want_units) chunk = ((chunk / 2 + tile - 1) / tile) * tile;
-        if (chunk > 64 * tile) chunk = 64 * tile;
-        w.chunk_evals = chunk;
-        w.chunks_per_channel = (int)((E + chunk - 1) / chunk);
-        w.detect_rule = detect_rule;
-        w.all_out = d_all_outputs;
-        w.sink = sink;
-        w.window = model_.window();
-        w.twiddle = model_.twiddle();
-        FusedLaunch l = fp.launch;
-        const int64_t units = (int64_t)n_channels * w.chunks_per_channel;
-        l.grid = (int)std::min<int64_t>(units, resident);
-        SYLDET_CUDA(launch_fused(l, fp.params, w, stream));
-        launches_ += 1;
+    const int kernel = active_kernel();
+    if (kernel == SYLDET_KERNEL_TENSOR) {
+        // evaluations whose rows [e, e+T] are all complete hop-rows go to the tensor-core kernel; the last few (and inputs
+        // whose base/pitch are not 16-byte aligned) go to the SIMT fused kernel
+        const int64_t n_rows = n_samples / c.hop;
+        const bool aligned = ((uintptr_t)d_planar % 16 == 0) && (ch_stride % 4 == 0 || n_channels == 1);
+        const int64_t e_tc = aligned ? std::max<int64_t>(0, std::min<int64_t>(E, n_rows - c.time_range)) : 0;
+        if (e_tc > 0) {
+            syldet_status st = launch_tc_range(d_planar, n_channels, n_samples, ch_stride, e_tc, E, detect_rule, d_all_outputs, sink, stream);
+            if (st != SYLDET_OK) return st;
+        }
+        if (e_tc < E)
+            return launch_fused_range(d_planar, n_channels, ch_stride, valid_begin, valid_end, e_tc, E - e_tc, E, detect_rule,
+                                      d_all_outputs, sink, stream);
         return SYLDET_OK;
     }
+    if (kernel == SYLDET_KERNEL_FUSED)
+        return launch_fused_range(d_planar, n_channels, ch_stride, valid_begin, valid_end, 0, E, E, detect_rule, d_all_outputs, sink, stream);
 
     // generic two-kernel path, segmented in time so the band-feature buffer stays bounded
     const int L = c.band, T = c.time_range;

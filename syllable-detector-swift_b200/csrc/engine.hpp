@@ -52,6 +52,17 @@ struct FusedPlan {
 // Folds the input-processing chain into layer 0 and packs everything the fused kernel reads from parameter space.
 FusedPlan plan_fused(const Config &cfg);
 
+// Tensor-core variant (kernels_tc.cu): same folded parameters, its own ring geometry, plus the windowed DFT matrix.
+struct TcPlan {
+    bool ok = false;
+    std::string why;
+    FusedParams params{};
+    int hp = 0;
+    size_t smem = 0;
+    std::vector<float> dft_hi, dft_lo;  // [128][k_pad]
+};
+TcPlan plan_tc(const Config &cfg, const FusedPlan &fused);
+
 // Device-resident copy of one configuration (weights, window, twiddles, DevNet record).
 class DeviceModel {
 public:
@@ -66,12 +77,16 @@ public:
     const float2 *twiddle() const { return d_twiddle_; }
     int max_width() const { return max_width_; }
     const FusedPlan &fused() const { return fused_; }
+    const TcPlan &tc() const { return tc_; }
+    const float *dft_hi() const { return d_dft_.as<float>(); }
+    const float *dft_lo() const { return d_dft_.as<float>() + 128 * (size_t)tc_k_pad(); }
     int sm_count() const { return sm_count_; }
 
 private:
     Config cfg_;
     int device_ = -1, max_width_ = 0, sm_count_ = 148;
-    DeviceBuffer d_blob_, d_net_;
+    DeviceBuffer d_blob_, d_net_, d_dft_;
+    TcPlan tc_;
     const float *d_window_ = nullptr;
     const float2 *d_twiddle_ = nullptr;
     FusedPlan fused_;
@@ -96,6 +111,7 @@ public:
     syldet_status collect(int64_t debounce_frames, Events &out);
     syldet_status last_detection_count(int64_t *count);
     int64_t launch_count() const { return launches_; }
+    void set_debug_band(float *d_band, int64_t cols) { debug_band_ = d_band; debug_cols_ = cols; }
     const DeviceModel &model() const { return model_; }
 
 private:
@@ -103,6 +119,11 @@ private:
                                 const float *valid_begin, const float *valid_end, int detect_rule, float *d_all_outputs,
                                 cudaStream_t stream);
     syldet_status ensure_sink(unsigned long long capacity);
+    syldet_status launch_fused_range(const float *d_planar, int n_channels, int64_t ch_stride, const float *valid_begin,
+                                     const float *valid_end, int64_t eval_begin, int64_t eval_count, int64_t evals_total,
+                                     int detect_rule, float *d_all_outputs, EventSink sink, cudaStream_t stream);
+    syldet_status launch_tc_range(const float *d_planar, int n_channels, int64_t n_samples, int64_t ch_stride, int64_t eval_count,
+                                  int64_t evals_total, int detect_rule, float *d_all_outputs, EventSink sink, cudaStream_t stream);
 
     DeviceModel model_;
     int kernel_ = SYLDET_KERNEL_AUTO;
@@ -110,6 +131,8 @@ private:
     DeviceBuffer planar_, feat_, sink_count_, sink_events_, sink_outputs_, staging_;
     unsigned long long sink_capacity_ = 0;
     int64_t launches_ = 0;
+    float *debug_band_ = nullptr;
+    int64_t debug_cols_ = 0;
     // last launch, kept so that an event-buffer overflow can be replayed with a larger buffer
     struct Last {
         bool valid = false;

@@ -1,0 +1,147 @@
+// Epilogue shared by the fused kernels: one thread = one evaluation, reading its T band columns from the shared-memory
+// ring (NeuralNet.apply, Common/NeuralNet.swift:294-326; threshold test, SyllableDetectorCLI/TrackDetector.swift:71-77).
+#pragma once
+#include "kernels.hpp"
+
+namespace syldet {
+namespace {
+
+__device__ __forceinline__ float scale_value(float v, int scaling) {
+    if (scaling == SYLDET_SCALING_DB) return 20.0f * log10f(v);
+    if (scaling == SYLDET_SCALING_LOG) return logf(v);
+    return v;
+}
+
+__device__ __forceinline__ float transfer(int tf, float v) {
+    switch (tf) {
+        case SYLDET_TF_TANSIG: return tanhf(v);
+        case SYLDET_TF_LOGSIG: return 1.0f / (1.0f + expf(-v));
+        case SYLDET_TF_SATLIN: return fminf(fmaxf(v, 0.0f), 1.0f);
+        default: return v;
+    }
+}
+
+__device__ __forceinline__ float sqrt_fast(float x) {  // MUFU.SQRT, max relative error 2^-23
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// ---- epilogue: one thread = one evaluation -----------------------------------------------------------------------
+template <int HP, int STAT>
+__device__ __forceinline__ void gather_layer0(const FusedParams &p, const float *ring, int slot, float (&acc)[HP], float &s0,
+                                              float &s1) {
+    // s0/s1: STAT_L2 -> (sum x^2, -) ; STAT_MINMAX -> (min, max) ; STAT_STD -> (sum x, -)
+    const int L = p.band, T = p.time_range;
+    int widx = 0;
+    for (int t = 0; t < T; ++t) {
+        const float *row = ring + slot * p.band_pitch;
+#pragma unroll 4
+        for (int f = 0; f < L; ++f) {
+            const float x = row[f];
+            if constexpr (STAT == FUSED_STAT_L2) s0 = fmaf(x, x, s0);
+            if constexpr (STAT == FUSED_STAT_MINMAX) { s0 = fminf(s0, x); s1 = fmaxf(s1, x); }
+            if constexpr (STAT == FUSED_STAT_STD) s0 += x;
+            const float4 wa = *reinterpret_cast<const float4 *>(&p.w0[widx]);
+            acc[0] = fmaf(x, wa.x, acc[0]);
+            acc[1] = fmaf(x, wa.y, acc[1]);
+            acc[2] = fmaf(x, wa.z, acc[2]);
+            acc[3] = fmaf(x, wa.w, acc[3]);
+            if constexpr (HP == 8) {
+                const float4 wb = *reinterpret_cast<const float4 *>(&p.w0[widx + 4]);
+                acc[4] = fmaf(x, wb.x, acc[4]);
+                acc[5] = fmaf(x, wb.y, acc[5]);
+                acc[6] = fmaf(x, wb.z, acc[6]);
+                acc[7] = fmaf(x, wb.w, acc[7]);
+            }
+            widx += HP;
+        }
+        if (++slot == p.ring_cols) slot = 0;
+    }
+}
+
+template <int HP>
+__device__ __forceinline__ bool evaluate(const FusedParams &p, int detect_rule, const float *ring, int slot, float (&out)[kFusedMaxOut]) {
+    float acc[HP];
+#pragma unroll
+    for (int h = 0; h < HP; ++h) acc[h] = 0.0f;
+    float alpha_div = 1.0f, beta = 0.0f;  // z = acc / alpha_div + beta * V + B'
+    bool constant_input = false;          // `normalize` of a flat window: every input becomes -1 (NeuralNet.swift:84-88)
+    switch (p.window_stat) {
+        case FUSED_STAT_L2: {  // x / sqrt(sum x^2)  (NeuralNet.swift:47-59)
+            float ss = 0.0f, unused = 0.0f;
+            gather_layer0<HP, FUSED_STAT_L2>(p, ring, slot, acc, ss, unused);
+            alpha_div = sqrtf(ss);
+            break;
+        }
+        case FUSED_STAT_MINMAX: {  // x * 2/range + (-mn-mx)/range  (NeuralNet.swift:69-96)
+            float mn = INFINITY, mx = -INFINITY;
+            gather_layer0<HP, FUSED_STAT_MINMAX>(p, ring, slot, acc, mn, mx);
+            const float range = mx - mn;
+            if (0 == range) { constant_input = true; beta = -1.0f; }
+            else { alpha_div = range * 0.5f; beta = (0 - mn - mx) / range; }
+            break;
+        }
+        case FUSED_STAT_STD: {  // (x - mean) / std_pop  (NeuralNet.swift:105-108)
+            float sum = 0.0f, unused = 0.0f;
+            gather_layer0<HP, FUSED_STAT_STD>(p, ring, slot, acc, sum, unused);
+            const int n = p.band * p.time_range;
+            const float mean = sum / (float)n;
+            float var = 0.0f;
+            int s = slot;
+            for (int t = 0; t < p.time_range; ++t) {
+                const float *row = ring + s * p.band_pitch;
+                for (int f = 0; f < p.band; ++f) { const float d = row[f] - mean; var = fmaf(d, d, var); }
+                if (++s == p.ring_cols) s = 0;
+            }
+            alpha_div = sqrtf(var / (float)n);
+            beta = -mean / alpha_div;
+            break;
+        }
+        default: {
+            float a = 0.0f, b = 0.0f;
+            gather_layer0<HP, FUSED_STAT_NONE>(p, ring, slot, acc, a, b);
+        }
+    }
+    float a[kFusedMaxHidden], b[kFusedMaxHidden];
+#pragma unroll
+    for (int h = 0; h < kFusedMaxHidden; ++h) {
+        float z = 0.0f;
+        if (h < HP) {
+            const float u = constant_input ? 0.0f : acc[h] / alpha_div;
+            z = u + fmaf(beta, p.v[h], p.bprime[h]);
+            z = transfer(p.tf[0], z);
+        }
+        a[h] = z;
+    }
+    for (int l = 1; l < p.n_layers; ++l) {
+        const float *w = &p.rest_w[(l - 1) * kFusedMaxHidden * kFusedMaxHidden];
+        const float *bias = &p.rest_b[(l - 1) * kFusedMaxHidden];
+#pragma unroll
+        for (int o = 0; o < kFusedMaxHidden; ++o) {
+            float s = 0.0f;
+#pragma unroll
+            for (int i = 0; i < kFusedMaxHidden; ++i) s = fmaf(w[o * kFusedMaxHidden + i], a[i], s);
+            b[o] = transfer(p.tf[l], s + bias[o]);
+        }
+#pragma unroll
+        for (int o = 0; o < kFusedMaxHidden; ++o) a[o] = b[o];
+    }
+    bool hit = false;
+#pragma unroll
+    for (int o = 0; o < kFusedMaxOut; ++o) {
+        float v = a[o];
+        if (o < p.n_out) {
+            for (int k = 0; k < p.n_op; ++k) {  // reverse maps in index order (NeuralNet.swift:316-323)
+                v = (v + (0 - p.op_y[k])) / p.op_gain[k * kFusedMaxOut + o] + p.op_xoff[k * kFusedMaxOut + o];
+            }
+            const bool over = (double)v >= p.thr[o];  // TrackDetector.swift:72; NaN -> false
+            if (over && (detect_rule == SYLDET_DETECT_ANY_OUTPUT || o == 0)) hit = true;
+        }
+        out[o] = v;
+    }
+    return hit;
+}
+
+}  // namespace
+}  // namespace syldet

@@ -56,7 +56,9 @@ struct FusedWork {
     int64_t chunk_evals;
     int chunks_per_channel;
     int detect_rule;       // SYLDET_DETECT_*
-    float *all_out;        // optional [n_channels][evals_per_channel][n_out]
+    int64_t eval_offset;   // index of the first evaluation this launch handles (events, outputs and audio are offset by it)
+    int64_t out_evals_per_channel;  // evaluations per channel in all_out (its channel pitch)
+    float *all_out;        // optional [n_channels][out_evals_per_channel][n_out]
     EventSink sink;
     const float *window;   // [win_len]
     const float2 *twiddle; // [fft_len/2]
@@ -74,6 +76,26 @@ __host__ __device__ constexpr int fused_r2(int fft_len) { return (fft_len / 2) /
 __host__ __device__ constexpr int fused_group(int fft_len) { return 32 * fused_r1(fft_len) / (fft_len / 2); }  // frames per warp pass
 __host__ __device__ constexpr int fused_round_cols(int fft_len) { return (kFusedThreads / 32) * fused_group(fft_len); }
 __host__ __device__ constexpr int fused_frame_pitch(int fft_len) { return fft_len / 2 + (fft_len / 2) / fused_r1(fft_len); }  // float2 per frame
+
+// ---- tensor-core variant: kernels_tc.cu ---------------------------------------------------------------------------
+struct TcWork {
+    int n_channels;
+    int chunks_per_channel;
+    int64_t evals_per_channel;      // evaluations this launch handles per channel (all of their rows are complete)
+    int64_t chunk_evals;
+    int64_t eval_offset, out_evals_per_channel;
+    int detect_rule;
+    float *all_out;
+    EventSink sink;
+    const float *dft_hi, *dft_lo;   // [128][k_pad] windowed DFT matrix, tf32 hi / lo parts
+    float *debug_band;              // optional [n_channels][debug_cols][band] band magnitudes (tests)
+    int64_t debug_cols;
+};
+size_t tc_smem_bytes(const FusedParams &p);
+int tc_tile_frames();
+int tc_k_pad();
+cudaError_t launch_tc(int hp, int grid, size_t smem, const FusedParams &p, const TcWork &w, const void *tmap_main,
+                      const void *tmap_tail, cudaStream_t stream);
 
 bool fused_supports_fft(int fft_len);
 size_t fused_smem_bytes(int fft_len, const FusedParams &p);

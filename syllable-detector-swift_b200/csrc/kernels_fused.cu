@@ -20,7 +20,8 @@
 //            warp-aggregated event append.
 #include <cstdio>
 
-#include "kernels.hpp"
+#include "fused_epilogue.cuh"
+#include "ptx_sm100.cuh"
 
 namespace syldet {
 
@@ -101,49 +102,6 @@ struct Dft<1> {
     static __device__ __forceinline__ void run(float2 *) {}
 };
 
-// ---- mbarrier / bulk copy (TMA 1-D) ------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(done)
-            : "r"(smem_addr(bar)), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
-                 : "memory");
-}
-
-__device__ __forceinline__ float scale_value(float v, int scaling) {
-    if (scaling == SYLDET_SCALING_DB) return 20.0f * log10f(v);
-    if (scaling == SYLDET_SCALING_LOG) return logf(v);
-    return v;
-}
-
-__device__ __forceinline__ float transfer(int tf, float v) {
-    switch (tf) {
-        case SYLDET_TF_TANSIG: return tanhf(v);
-        case SYLDET_TF_LOGSIG: return 1.0f / (1.0f + expf(-v));
-        case SYLDET_TF_SATLIN: return fminf(fmaxf(v, 0.0f), 1.0f);
-        default: return v;
-    }
-}
-
 // Where the audio of one round sits in global memory and in the staging buffer.
 struct RoundSpan {
     const float *src;     // first sample of the round's first frame
@@ -164,128 +122,6 @@ __device__ __forceinline__ RoundSpan round_span(const FusedParams &p, const Fuse
     s.bytes = (uint32_t)(((s.off + s.n_floats) * 4 + 15) & ~15);
     s.bulk_ok = (uintptr_t)s.aligned >= (uintptr_t)w.pcm_begin && (uintptr_t)s.aligned + s.bytes <= (uintptr_t)w.pcm_end;
     return s;
-}
-
-__device__ __forceinline__ float sqrt_fast(float x) {  // MUFU.SQRT, max relative error 2^-23
-    float r;
-    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-
-// ---- epilogue: one thread = one evaluation -----------------------------------------------------------------------
-template <int HP, int STAT>
-__device__ __forceinline__ void gather_layer0(const FusedParams &p, const float *ring, int slot, float (&acc)[HP], float &s0,
-                                              float &s1) {
-    // s0/s1: STAT_L2 -> (sum x^2, -) ; STAT_MINMAX -> (min, max) ; STAT_STD -> (sum x, -)
-    const int L = p.band, T = p.time_range;
-    int widx = 0;
-    for (int t = 0; t < T; ++t) {
-        const float *row = ring + slot * p.band_pitch;
-#pragma unroll 4
-        for (int f = 0; f < L; ++f) {
-            const float x = row[f];
-            if constexpr (STAT == FUSED_STAT_L2) s0 = fmaf(x, x, s0);
-            if constexpr (STAT == FUSED_STAT_MINMAX) { s0 = fminf(s0, x); s1 = fmaxf(s1, x); }
-            if constexpr (STAT == FUSED_STAT_STD) s0 += x;
-            const float4 wa = *reinterpret_cast<const float4 *>(&p.w0[widx]);
-            acc[0] = fmaf(x, wa.x, acc[0]);
-            acc[1] = fmaf(x, wa.y, acc[1]);
-            acc[2] = fmaf(x, wa.z, acc[2]);
-            acc[3] = fmaf(x, wa.w, acc[3]);
-            if constexpr (HP == 8) {
-                const float4 wb = *reinterpret_cast<const float4 *>(&p.w0[widx + 4]);
-                acc[4] = fmaf(x, wb.x, acc[4]);
-                acc[5] = fmaf(x, wb.y, acc[5]);
-                acc[6] = fmaf(x, wb.z, acc[6]);
-                acc[7] = fmaf(x, wb.w, acc[7]);
-            }
-            widx += HP;
-        }
-        if (++slot == p.ring_cols) slot = 0;
-    }
-}
-
-template <int HP>
-__device__ __forceinline__ bool evaluate(const FusedParams &p, int detect_rule, const float *ring, int slot, float (&out)[kFusedMaxOut]) {
-    float acc[HP];
-#pragma unroll
-    for (int h = 0; h < HP; ++h) acc[h] = 0.0f;
-    float alpha_div = 1.0f, beta = 0.0f;  // z = acc / alpha_div + beta * V + B'
-    bool constant_input = false;          // `normalize` of a flat window: every input becomes -1 (NeuralNet.swift:84-88)
-    switch (p.window_stat) {
-        case FUSED_STAT_L2: {  // x / sqrt(sum x^2)  (NeuralNet.swift:47-59)
-            float ss = 0.0f, unused = 0.0f;
-            gather_layer0<HP, FUSED_STAT_L2>(p, ring, slot, acc, ss, unused);
-            alpha_div = sqrtf(ss);
-            break;
-        }
-        case FUSED_STAT_MINMAX: {  // x * 2/range + (-mn-mx)/range  (NeuralNet.swift:69-96)
-            float mn = INFINITY, mx = -INFINITY;
-            gather_layer0<HP, FUSED_STAT_MINMAX>(p, ring, slot, acc, mn, mx);
-            const float range = mx - mn;
-            if (0 == range) { constant_input = true; beta = -1.0f; }
-            else { alpha_div = range * 0.5f; beta = (0 - mn - mx) / range; }
-            break;
-        }
-        case FUSED_STAT_STD: {  // (x - mean) / std_pop  (NeuralNet.swift:105-108)
-            float sum = 0.0f, unused = 0.0f;
-            gather_layer0<HP, FUSED_STAT_STD>(p, ring, slot, acc, sum, unused);
-            const int n = p.band * p.time_range;
-            const float mean = sum / (float)n;
-            float var = 0.0f;
-            int s = slot;
-            for (int t = 0; t < p.time_range; ++t) {
-                const float *row = ring + s * p.band_pitch;
-                for (int f = 0; f < p.band; ++f) { const float d = row[f] - mean; var = fmaf(d, d, var); }
-                if (++s == p.ring_cols) s = 0;
-            }
-            alpha_div = sqrtf(var / (float)n);
-            beta = -mean / alpha_div;
-            break;
-        }
-        default: {
-            float a = 0.0f, b = 0.0f;
-            gather_layer0<HP, FUSED_STAT_NONE>(p, ring, slot, acc, a, b);
-        }
-    }
-    float a[kFusedMaxHidden], b[kFusedMaxHidden];
-#pragma unroll
-    for (int h = 0; h < kFusedMaxHidden; ++h) {
-        float z = 0.0f;
-        if (h < HP) {
-            const float u = constant_input ? 0.0f : acc[h] / alpha_div;
-            z = u + fmaf(beta, p.v[h], p.bprime[h]);
-            z = transfer(p.tf[0], z);
-        }
-        a[h] = z;
-    }
-    for (int l = 1; l < p.n_layers; ++l) {
-        const float *w = &p.rest_w[(l - 1) * kFusedMaxHidden * kFusedMaxHidden];
-        const float *bias = &p.rest_b[(l - 1) * kFusedMaxHidden];
-#pragma unroll
-        for (int o = 0; o < kFusedMaxHidden; ++o) {
-            float s = 0.0f;
-#pragma unroll
-            for (int i = 0; i < kFusedMaxHidden; ++i) s = fmaf(w[o * kFusedMaxHidden + i], a[i], s);
-            b[o] = transfer(p.tf[l], s + bias[o]);
-        }
-#pragma unroll
-        for (int o = 0; o < kFusedMaxHidden; ++o) a[o] = b[o];
-    }
-    bool hit = false;
-#pragma unroll
-    for (int o = 0; o < kFusedMaxOut; ++o) {
-        float v = a[o];
-        if (o < p.n_out) {
-            for (int k = 0; k < p.n_op; ++k) {  // reverse maps in index order (NeuralNet.swift:316-323)
-                v = (v + (0 - p.op_y[k])) / p.op_gain[k * kFusedMaxOut + o] + p.op_xoff[k * kFusedMaxOut + o];
-            }
-            const bool over = (double)v >= p.thr[o];  // TrackDetector.swift:72; NaN -> false
-            if (over && (detect_rule == SYLDET_DETECT_ANY_OUTPUT || o == 0)) hit = true;
-        }
-        out[o] = v;
-    }
-    return hit;
 }
 
 // ---- the kernel --------------------------------------------------------------------------------------------------
@@ -332,9 +168,9 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_detect_kernel(const __
     for (int f = tid; f < L; f += kFusedThreads) s_utw[f] = __ldg(w.twiddle + p.k0 + f);
 
     if (tid == 0) {
-        mbar_init(&mbar[0], 1);
-        mbar_init(&mbar[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        ptx::mbar_init(&mbar[0], 1);
+        ptx::mbar_init(&mbar[1], 1);
+        ptx::fence_mbar_init();
     }
     __syncthreads();
     uint32_t phase0 = 0, phase1 = 0;
@@ -350,14 +186,14 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_detect_kernel(const __
         const int ne = (int)min(w.chunk_evals, w.evals_per_channel - e0);
         const int ncols = ne + T - 1;  // column index == evaluation index of the window it opens
         const int nrounds = (ncols + RC - 1) / RC;
-        const float *src = w.pcm + (int64_t)ch * w.ch_stride + e0 * p.hop + p.gap;  // first sample of this round's first frame
-        float *out_base = w.all_out ? w.all_out + ((int64_t)ch * w.evals_per_channel + e0) * p.n_out : nullptr;
+        const float *src = w.pcm + (int64_t)ch * w.ch_stride + (w.eval_offset + e0) * p.hop + p.gap;  // first sample of this round's first frame
+        float *out_base = w.all_out ? w.all_out + ((int64_t)ch * w.out_evals_per_channel + w.eval_offset + e0) * p.n_out : nullptr;
 
         if (tid == 0) {
             const RoundSpan s = round_span(p, w, src, min(RC, ncols));
             if (s.bulk_ok) {
-                mbar_expect_tx(&mbar[0], s.bytes);
-                bulk_copy_g2s(abuf0, s.aligned, s.bytes, &mbar[0]);
+                ptx::mbar_expect_tx(&mbar[0], s.bytes);
+                ptx::bulk_copy_g2s(abuf0, s.aligned, s.bytes, &mbar[0]);
             }
         }
         int cols_done = 0, evals_done = 0;
@@ -370,18 +206,18 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_detect_kernel(const __
                 const RoundSpan s = round_span(p, w, src + round_floats, min(RC, ncols - (r + 1) * RC));
                 if (s.bulk_ok) {
                     uint64_t *bar = &mbar[(r + 1) & 1];
-                    mbar_expect_tx(bar, s.bytes);
-                    bulk_copy_g2s((r & 1) ? abuf0 : abuf1, s.aligned, s.bytes, bar);
+                    ptx::mbar_expect_tx(bar, s.bytes);
+                    ptx::bulk_copy_g2s((r & 1) ? abuf0 : abuf1, s.aligned, s.bytes, bar);
                 }
             }
             const RoundSpan span = round_span(p, w, src, cols);
             if (span.bulk_ok) {
-                if (r & 1) { mbar_wait(&mbar[1], phase1); phase1 ^= 1; }
-                else { mbar_wait(&mbar[0], phase0); phase0 ^= 1; }
+                if (r & 1) { ptx::mbar_wait(&mbar[1], phase1); phase1 ^= 1; }
+                else { ptx::mbar_wait(&mbar[0], phase0); phase0 ^= 1; }
             } else {  // edge of the caller's buffer: guarded cooperative copy
                 for (int i = tid; i < span.n_floats; i += kFusedThreads) abuf[span.off + i] = span.src[i];
                 __syncthreads();
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                ptx::fence_proxy_async_smem();
             }
 
             // ---- pass 1: window + radix-R1 on strided samples -------------------------------------------------
@@ -493,7 +329,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_detect_kernel(const __
                         if (hit) {
                             const unsigned long long idx = base + __popc(hits & ((1u << lane) - 1));
                             if (idx < w.sink.capacity) {
-                                w.sink.events[idx] = DevEvent{ch, 0, e0 + evals_done + q};
+                                w.sink.events[idx] = DevEvent{ch, 0, w.eval_offset + e0 + evals_done + q};
 #pragma unroll
                                 for (int i = 0; i < kFusedMaxOut; ++i)
                                     if (i < p.n_out) w.sink.outputs[idx * p.n_out + i] = out[i];

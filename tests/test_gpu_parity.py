@@ -26,7 +26,7 @@ def orc(oracle_mod):
 
 
 def _kernels(sd):
-    return [(sd.KERNEL_FUSED, "fused"), (sd.KERNEL_GENERIC, "generic")]
+    return [(sd.KERNEL_TENSOR, "tensor"), (sd.KERNEL_FUSED, "fused"), (sd.KERNEL_GENERIC, "generic")]
 
 
 def _check_channel(orc, x, outs, ev_samples, tol, debounce=0):
@@ -78,10 +78,11 @@ def test_golden_cases(sd, oracle_mod, golden):
         o = oracle_mod.Oracle(text=g["config"])
         scale = max(1.0, float(np.nanmax(np.abs(g["outputs"]))))
         tol = TOL_OUT * scale if c.spectrogram_scaling == "linear" else 2e-4 * scale
-        det = sd.BatchDetector(c)
-        kernels = [sd.KERNEL_GENERIC] + ([sd.KERNEL_FUSED] if det.active_kernel == sd.KERNEL_FUSED else [])
+        kernels = sd.BatchDetector.available_kernels(c)
         if name in ("sample", "log_std_128"):
-            assert det.active_kernel == sd.KERNEL_FUSED, name  # these shapes must take the fast path
+            assert sd.KERNEL_FUSED in kernels, name  # these shapes must take a fast path
+        if name == "sample":
+            assert kernels[0] == sd.KERNEL_TENSOR
         for kernel in kernels:
             ev, outs = sd.BatchDetector(c, kernel=kernel).run(g["audio"], want_outputs=True)
             err = np.abs(outs[0] - g["outputs"])
@@ -113,8 +114,7 @@ def test_generated_configs_fused_and_generic(sd, oracle_mod, cw, kw):
     t = np.arange(n)
     x = np.stack([(0.05 * rng.standard_normal(n) + 0.4 * np.sin(2 * np.pi * f0 * t / 44100 + 3 * np.sin(2 * np.pi * 2 * t / 44100))).astype(np.float32)
                   for f0 in (2500.0, 5200.0)])
-    det = sd.BatchDetector(c)
-    kernels = [sd.KERNEL_GENERIC] + ([sd.KERNEL_FUSED] if det.active_kernel == sd.KERNEL_FUSED else [])
+    kernels = sd.BatchDetector.available_kernels(c)
     if kw["fft_len"] <= 512 and all(h <= 8 for h in kw.get("hidden", ())) and kw.get("input_funcs", ())[1:2] != ("normalize",):
         assert sd.KERNEL_FUSED in kernels
     for kernel in kernels:
@@ -300,9 +300,10 @@ def test_large_run_properties(sd, cfg, orc, synth):
         ch, j = int(rng.integers(nch)), int(rng.integers(E - 300))
         seg = x[ch, j * 132: j * 132 + 1444 + 132 * 299]
         assert np.abs(outs[ch, j:j + 300] - orc.run(seg)[0]).max() <= TOL_OUT
-    # generic and fused kernels agree everywhere
-    ev_g, outs_g = sd.BatchDetector(cfg, kernel=sd.KERNEL_GENERIC).run(x[:2], want_outputs=True)
-    assert np.abs(outs_g - outs[:2]).max() <= TOL_OUT
+    # all kernels agree everywhere
+    for k in (sd.KERNEL_GENERIC, sd.KERNEL_FUSED, sd.KERNEL_TENSOR):
+        ev_g, outs_g = sd.BatchDetector(cfg, kernel=k).run(x[:2], want_outputs=True)
+        assert np.abs(outs_g - outs[:2]).max() <= TOL_OUT, k
 
 
 def test_cli_csv_rows(sd, cfg, orc, synth, tmp_path):

@@ -169,13 +169,23 @@ TcPlan plan_tc(const Config &c, const FusedPlan &fused) {
     if (hop < kpad - 8 || hop > kpad) return no("hop outside [128, 136]");
     if (W <= hop || W > 2 * hop) return no("window does not span exactly two hop rows");
     if (c.band > 32) return no("band wider than 32 bins");
+    if (fused.params.window_stat == FUSED_STAT_STD) return no("normalizestd needs a second pass over the window");
     plan.params = fused.params;
     plan.hp = fused.launch.hp;
-    const int tf = tc_tile_frames();
-    plan.params.nn_tile = 192;
-    plan.params.ring_cols = plan.params.nn_tile + 2 * tf + c.time_range;
+    plan.n0 = ((c.time_range * plan.hp + 15) / 16) * 16;
+    if (!tc_layout_fits(c.time_range, plan.n0)) return no("time range x hidden width too large for the layer-0 product buffers");
     plan.smem = tc_smem_bytes(plan.params);
-    if (plan.smem > 227 * 1024) return no("shared-memory working set too large");
+    // layer-0 weights as the B operand of the second contraction: Wcat[(t, h)][f] = W'[t*L + f][h], hi / lo
+    plan.wcat_hi.assign((size_t)plan.n0 * 32, 0.0f);
+    plan.wcat_lo.assign((size_t)plan.n0 * 32, 0.0f);
+    for (int t = 0; t < c.time_range; ++t)
+        for (int h = 0; h < plan.hp; ++h)
+            for (int f = 0; f < c.band; ++f) {
+                const double v = (double)fused.params.w0[(size_t)(t * c.band + f) * plan.hp + h];
+                const size_t i = (size_t)(t * plan.hp + h) * 32 + f;
+                plan.wcat_hi[i] = tf32_round(v);
+                plan.wcat_lo[i] = tf32_round(v - (double)plan.wcat_hi[i]);
+            }
     // rows: [0,32) Re B1 | [32,64) Im B1 | [64,96) Re B2 | [96,128) Im B2 ; B1 = samples [0,hop), B2 = samples [hop,W)
     plan.dft_hi.assign((size_t)128 * kpad, 0.0f);
     plan.dft_lo.assign((size_t)128 * kpad, 0.0f);
@@ -313,11 +323,13 @@ syldet_status DeviceModel::init(const Config &cfg, int device) {
     }
     tc_ = plan_tc(cfg_, fused_);
     if (tc_.ok) {
-        const size_t n = tc_.dft_hi.size();
-        st = d_dft_.reserve(2 * n * sizeof(float));
+        const size_t n = tc_.dft_hi.size(), nw = tc_.wcat_hi.size();
+        st = d_dft_.reserve((2 * n + 2 * nw) * sizeof(float));
         if (st != SYLDET_OK) return st;
         SYLDET_CUDA(cudaMemcpy(d_dft_.get(), tc_.dft_hi.data(), n * sizeof(float), cudaMemcpyHostToDevice));
         SYLDET_CUDA(cudaMemcpy(d_dft_.as<float>() + n, tc_.dft_lo.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+        SYLDET_CUDA(cudaMemcpy(d_dft_.as<float>() + 2 * n, tc_.wcat_hi.data(), nw * sizeof(float), cudaMemcpyHostToDevice));
+        SYLDET_CUDA(cudaMemcpy(d_dft_.as<float>() + 2 * n + nw, tc_.wcat_lo.data(), nw * sizeof(float), cudaMemcpyHostToDevice));
     }
     return SYLDET_OK;
 }
@@ -444,7 +456,7 @@ syldet_status Batch::launch_tc_range(const float *d_planar, int n_channels, int6
     if (!encode) return set_error(SYLDET_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
     // Y[channel][row][hop]: row r = samples [r*hop, (r+1)*hop) of a channel; only complete rows are part of the tensor
     const cuuint64_t dims[3] = {(cuuint64_t)c.hop, (cuuint64_t)(n_samples / c.hop), (cuuint64_t)n_channels};
-    const cuuint64_t strides[2] = {(cuuint64_t)c.hop * 4, (cuuint64_t)(n_channels > 1 ? ch_stride : n_samples) * 4};
+    const cuuint64_t strides[2] = {(cuuint64_t)c.hop * 4, n_channels > 1 ? (cuuint64_t)ch_stride * 4 : (((cuuint64_t)n_samples * 4 + 15) & ~(cuuint64_t)15)};
     const cuuint32_t estr[3] = {1, 1, 1};
     const cuuint32_t box_main[3] = {32, 64, 1}, box_tail[3] = {8, 64, 1};
     alignas(64) CUtensorMap tm_main, tm_tail;
@@ -462,7 +474,7 @@ syldet_status Batch::launch_tc_range(const float *d_planar, int n_channels, int6
     w.eval_offset = 0;
     w.out_evals_per_channel = evals_total;
     const int resident = model_.sm_count();
-    const int64_t tile = (int64_t)tc_tile_frames() * 4;  // 252 evaluations: one epilogue pass of the 256 worker threads
+    const int64_t tile = (int64_t)tc_group_cols() * 2;    // chunk granularity: whole layer-0 groups
     int64_t chunk = ((eval_count + tile - 1) / tile) * tile;
     const int64_t want_units = (int64_t)resident * 8;
     while (chunk > 8 * tile && n_channels * ((eval_count + chunk - 1) / chunk) < want_units) chunk = ((chunk / 2 + tile - 1) / tile) * tile;
@@ -474,6 +486,9 @@ syldet_status Batch::launch_tc_range(const float *d_planar, int n_channels, int6
     w.sink = sink;
     w.dft_hi = model_.dft_hi();
     w.dft_lo = model_.dft_lo();
+    w.wcat_hi = model_.wcat_hi();
+    w.wcat_lo = model_.wcat_lo();
+    w.n0 = tp.n0;
     w.debug_band = debug_band_;
     w.debug_cols = debug_cols_;
     const int64_t units = (int64_t)n_channels * w.chunks_per_channel;

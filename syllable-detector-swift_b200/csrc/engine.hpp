@@ -60,6 +60,8 @@ struct TcPlan {
     int hp = 0;
     size_t smem = 0;
     std::vector<float> dft_hi, dft_lo;  // [128][k_pad]
+    std::vector<float> wcat_hi, wcat_lo;  // [n0][32]
+    int n0 = 0;
 };
 TcPlan plan_tc(const Config &cfg, const FusedPlan &fused);
 
@@ -80,6 +82,8 @@ public:
     const TcPlan &tc() const { return tc_; }
     const float *dft_hi() const { return d_dft_.as<float>(); }
     const float *dft_lo() const { return d_dft_.as<float>() + 128 * (size_t)tc_k_pad(); }
+    const float *wcat_hi() const { return d_dft_.as<float>() + 2 * 128 * (size_t)tc_k_pad(); }
+    const float *wcat_lo() const { return wcat_hi() + (size_t)tc_.n0 * 32; }
     int sm_count() const { return sm_count_; }
 
 private:

@@ -60,6 +60,65 @@ __device__ __forceinline__ void gather_layer0(const FusedParams &p, const float 
     }
 }
 
+// Everything after the layer-0 dot products: z_h = acc_h / alpha_div + beta V_h + B'_h, transfer functions, remaining
+// layers, reverse output maps, threshold test. Returns true when the evaluation counts as a detection.
+template <int HP>
+__device__ __forceinline__ bool finish_eval(const FusedParams &p, int detect_rule, const float (&acc)[HP], float alpha_div, float beta,
+                                            bool constant_input, float (&out)[kFusedMaxOut]) {
+    float a[kFusedMaxHidden], b[kFusedMaxHidden];
+#pragma unroll
+    for (int h = 0; h < kFusedMaxHidden; ++h) {
+        float z = 0.0f;
+        if (h < HP) {
+            const float u = constant_input ? 0.0f : acc[h] / alpha_div;
+            z = u + fmaf(beta, p.v[h], p.bprime[h]);
+            z = transfer(p.tf[0], z);
+        }
+        a[h] = z;
+    }
+    for (int l = 1; l < p.n_layers; ++l) {
+        const float *w = &p.rest_w[(l - 1) * kFusedMaxHidden * kFusedMaxHidden];
+        const float *bias = &p.rest_b[(l - 1) * kFusedMaxHidden];
+#pragma unroll
+        for (int o = 0; o < kFusedMaxHidden; ++o) {
+            float s = 0.0f;
+#pragma unroll
+            for (int i = 0; i < kFusedMaxHidden; ++i) s = fmaf(w[o * kFusedMaxHidden + i], a[i], s);
+            b[o] = transfer(p.tf[l], s + bias[o]);
+        }
+#pragma unroll
+        for (int o = 0; o < kFusedMaxHidden; ++o) a[o] = b[o];
+    }
+    bool hit = false;
+#pragma unroll
+    for (int o = 0; o < kFusedMaxOut; ++o) {
+        float v = a[o];
+        if (o < p.n_out) {
+            for (int k = 0; k < p.n_op; ++k) {  // reverse maps in index order (NeuralNet.swift:316-323)
+                v = (v + (0 - p.op_y[k])) / p.op_gain[k * kFusedMaxOut + o] + p.op_xoff[k * kFusedMaxOut + o];
+            }
+            const bool over = (double)v >= p.thr[o];  // TrackDetector.swift:72; NaN -> false
+            if (over && (detect_rule == SYLDET_DETECT_ANY_OUTPUT || o == 0)) hit = true;
+        }
+        out[o] = v;
+    }
+    return hit;
+}
+
+// Window statistic -> (alpha_div, beta, constant_input) for the two-moment-free normalisers.
+__device__ __forceinline__ void stat_to_affine(int window_stat, float s0, float s1, float &alpha_div, float &beta, bool &constant_input) {
+    alpha_div = 1.0f;
+    beta = 0.0f;
+    constant_input = false;
+    if (window_stat == FUSED_STAT_L2) {            // x / sqrt(sum x^2)  (NeuralNet.swift:47-59)
+        alpha_div = sqrtf(s0);
+    } else if (window_stat == FUSED_STAT_MINMAX) {  // x * 2/range + (-mn-mx)/range  (NeuralNet.swift:69-96)
+        const float range = s1 - s0;
+        if (0 == range) { constant_input = true; beta = -1.0f; }
+        else { alpha_div = range * 0.5f; beta = (0 - s0 - s1) / range; }
+    }
+}
+
 template <int HP>
 __device__ __forceinline__ bool evaluate(const FusedParams &p, int detect_rule, const float *ring, int slot, float (&out)[kFusedMaxOut]) {
     float acc[HP];
@@ -103,44 +162,7 @@ __device__ __forceinline__ bool evaluate(const FusedParams &p, int detect_rule, 
             gather_layer0<HP, FUSED_STAT_NONE>(p, ring, slot, acc, a, b);
         }
     }
-    float a[kFusedMaxHidden], b[kFusedMaxHidden];
-#pragma unroll
-    for (int h = 0; h < kFusedMaxHidden; ++h) {
-        float z = 0.0f;
-        if (h < HP) {
-            const float u = constant_input ? 0.0f : acc[h] / alpha_div;
-            z = u + fmaf(beta, p.v[h], p.bprime[h]);
-            z = transfer(p.tf[0], z);
-        }
-        a[h] = z;
-    }
-    for (int l = 1; l < p.n_layers; ++l) {
-        const float *w = &p.rest_w[(l - 1) * kFusedMaxHidden * kFusedMaxHidden];
-        const float *bias = &p.rest_b[(l - 1) * kFusedMaxHidden];
-#pragma unroll
-        for (int o = 0; o < kFusedMaxHidden; ++o) {
-            float s = 0.0f;
-#pragma unroll
-            for (int i = 0; i < kFusedMaxHidden; ++i) s = fmaf(w[o * kFusedMaxHidden + i], a[i], s);
-            b[o] = transfer(p.tf[l], s + bias[o]);
-        }
-#pragma unroll
-        for (int o = 0; o < kFusedMaxHidden; ++o) a[o] = b[o];
-    }
-    bool hit = false;
-#pragma unroll
-    for (int o = 0; o < kFusedMaxOut; ++o) {
-        float v = a[o];
-        if (o < p.n_out) {
-            for (int k = 0; k < p.n_op; ++k) {  // reverse maps in index order (NeuralNet.swift:316-323)
-                v = (v + (0 - p.op_y[k])) / p.op_gain[k * kFusedMaxOut + o] + p.op_xoff[k * kFusedMaxOut + o];
-            }
-            const bool over = (double)v >= p.thr[o];  // TrackDetector.swift:72; NaN -> false
-            if (over && (detect_rule == SYLDET_DETECT_ANY_OUTPUT || o == 0)) hit = true;
-        }
-        out[o] = v;
-    }
-    return hit;
+    return finish_eval<HP>(p, detect_rule, acc, alpha_div, beta, constant_input, out);
 }
 
 }  // namespace

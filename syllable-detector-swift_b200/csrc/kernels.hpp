@@ -88,12 +88,17 @@ struct TcWork {
     float *all_out;
     EventSink sink;
     const float *dft_hi, *dft_lo;   // [128][k_pad] windowed DFT matrix, tf32 hi / lo parts
+    const float *wcat_hi, *wcat_lo; // [n0][32] folded layer-0 weights, row (t*HP + h), column = band bin
+    int n0;                         // T*HP rounded up to a multiple of 16
     float *debug_band;              // optional [n_channels][debug_cols][band] band magnitudes (tests)
     int64_t debug_cols;
 };
 size_t tc_smem_bytes(const FusedParams &p);
 int tc_tile_frames();
 int tc_k_pad();
+int tc_group_cols();
+int tc_max_n0();
+bool tc_layout_fits(int time_range, int n0);
 cudaError_t launch_tc(int hp, int grid, size_t smem, const FusedParams &p, const TcWork &w, const void *tmap_main,
                       const void *tmap_tail, cudaStream_t stream);
 

@@ -126,10 +126,22 @@ def test_generated_configs_fused_and_generic(sd, oracle_mod, cw, kw):
             _check_channel(o, x[ch], outs[ch], ev.sample[ev.channel == ch], tol)
 
 
-def test_chunk_and_batch_invariance(sd, cfg, synth):
-    """Any split of the work gives identical results: channels together or alone, long or short recordings."""
+@pytest.mark.parametrize("kernel_name", ["KERNEL_FUSED", "KERNEL_TENSOR", "KERNEL_GENERIC"])
+def test_chunk_and_batch_invariance(sd, cfg, synth, kernel_name):
+    """Any split of the work gives identical results: channels together or alone, long or short recordings.
+    The tensor-core kernel hands the last time_range + 1 evaluations of a buffer (whose hop-rows are incomplete) to the SIMT
+    kernel, so there the match is bit-exact up to that tail and within TOL_OUT inside it."""
+    kernel = getattr(sd, kernel_name)
+    tail = cfg.time_range + 1 if kernel == sd.KERNEL_TENSOR else 0
+
+    def same(a, b):
+        assert a.shape == b.shape
+        n = a.shape[-2] - tail
+        assert np.array_equal(a[..., :n, :], b[..., :n, :])
+        assert np.abs(a - b).max() <= TOL_OUT
+
     x = synth.make_audio(5, 132 * 3000 + 77, seed=33)
-    det = sd.BatchDetector(cfg)
+    det = sd.BatchDetector(cfg, kernel=kernel)
     ev_all, out_all = det.run(x, want_outputs=True)
     for ch in (0, 4):
         ev1, out1 = det.run(x[ch], want_outputs=True)
@@ -137,10 +149,10 @@ def test_chunk_and_batch_invariance(sd, cfg, synth):
     # prefix property: outputs of a prefix equal the prefix of the outputs
     n2 = 132 * 1000 + 1444
     ev2, out2 = det.run(x[:, :n2], want_outputs=True)
-    assert np.array_equal(out2, out_all[:, :out2.shape[1]])
+    same(out2, out_all[:, :out2.shape[1]])
     # time-shift by whole hops shifts evaluations (pure function of the sample span)
     ev3, out3 = det.run(x[:, 132 * 17:], want_outputs=True)
-    assert np.array_equal(out3, out_all[:, 17:])
+    same(out3, out_all[:, 17:])
 
 
 def test_edge_sizes(sd, cfg, orc):

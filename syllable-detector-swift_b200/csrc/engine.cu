@@ -474,11 +474,14 @@ syldet_status Batch::launch_tc_range(const float *d_planar, int n_channels, int6
     w.eval_offset = 0;
     w.out_evals_per_channel = evals_total;
     const int resident = model_.sm_count();
-    const int64_t tile = (int64_t)tc_group_cols() * 2;    // chunk granularity: whole layer-0 groups
-    int64_t chunk = ((eval_count + tile - 1) / tile) * tile;
-    const int64_t want_units = (int64_t)resident * 8;
-    while (chunk > 8 * tile && n_channels * ((eval_count + chunk - 1) / chunk) < want_units) chunk = ((chunk / 2 + tile - 1) / tile) * tile;
-    if (chunk > 64 * tile) chunk = 64 * tile;
+    // a unit covers whole tiles: chunk = n_tiles * tile_frames - (T - 1) evaluations (the first T-1 columns of a unit only warm
+    // the window up); long enough that the warm-up is noise, short enough that every CTA gets many units
+    const int64_t tf = tc_tile_frames(), warm = c.time_range - 1;
+    int64_t tiles_per_unit = 32;
+    const int64_t total_tiles = (int64_t)n_channels * ((eval_count + warm + tf - 1) / tf);
+    while (tiles_per_unit > 4 && total_tiles / tiles_per_unit < (int64_t)resident * 16) tiles_per_unit /= 2;
+    while (tiles_per_unit * tf <= 4 * warm) tiles_per_unit *= 2;
+    const int64_t chunk = tiles_per_unit * tf - warm;
     w.chunk_evals = chunk;
     w.chunks_per_channel = (int)((eval_count + chunk - 1) / chunk);
     w.detect_rule = detect_rule;

@@ -96,7 +96,6 @@ struct TcWork {
 size_t tc_smem_bytes(const FusedParams &p);
 int tc_tile_frames();
 int tc_k_pad();
-int tc_group_cols();
 int tc_max_n0();
 bool tc_layout_fits(int time_range, int n0);
 cudaError_t launch_tc(int hp, int grid, size_t smem, const FusedParams &p, const TcWork &w, const void *tmap_main,

@@ -10,6 +10,15 @@ namespace ptx {
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a converged warp. The compiler treats code under this predicate as warp-uniform, so tcgen05.mma / TMA operands
+// go to uniform registers directly; under `if (lane == 0)` it wraps every such instruction in an ELECT / R2UR.BROADCAST /
+// BRA.U.ANY loop that costs > 100 cycles per instruction (measured, tools/mma_rate.cu).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- mbarrier --------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));

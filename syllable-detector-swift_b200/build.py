@@ -19,7 +19,7 @@ SOURCES = [
     ("stream.cu", []),
     ("kernels_generic.cu", ["-fmad=false"]),
     ("kernels_fused.cu", ["-Xptxas", "-v"]),
-    ("kernels_tc.cu", ["-Xptxas", "-v"]),
+    ("kernels_tc.cu", ["-Xptxas", "-v"] + os.environ.get("SYLDET_TC_DEFS", "").split()),
 ]
 
 

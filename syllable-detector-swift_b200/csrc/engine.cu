@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 
@@ -104,6 +105,7 @@ FusedPlan plan_fused(const Config &c) {
     }
     p.n_layers = (int)c.layers.size();
     for (int l = 0; l < p.n_layers; ++l) p.tf[l] = c.layers[l].transfer;
+    for (int l = 0; l < p.n_layers; ++l) p.width[l] = c.layers[l].outputs;
     for (int l = 1; l < p.n_layers; ++l) {
         const Layer &ly = c.layers[l];
         for (int o = 0; o < ly.outputs; ++o) {
@@ -122,7 +124,12 @@ FusedPlan plan_fused(const Config &c) {
             p.op_xoff[k * kFusedMaxOut + o] = pr.x_offsets[o];
         }
     }
-    for (int o = 0; o < c.outputs; ++o) p.thr[o] = c.thresholds[o];
+    for (int o = 0; o < c.outputs; ++o) {
+        p.thr[o] = c.thresholds[o];
+        float t = (float)c.thresholds[o];
+        if ((double)t < c.thresholds[o]) t = std::nextafterf(t, INFINITY);  // NaN thresholds stay NaN: never detected
+        p.thr_f[o] = t;
+    }
 
     p.win_len = c.window_length;
     p.gap = c.gap;
@@ -174,7 +181,8 @@ TcPlan plan_tc(const Config &c, const FusedPlan &fused) {
     plan.hp = fused.launch.hp;
     plan.n0 = ((c.time_range * plan.hp + 15) / 16) * 16;
     if (!tc_layout_fits(c.time_range, plan.n0)) return no("time range x hidden width too large for the layer-0 product buffers");
-    plan.smem = tc_smem_bytes(plan.params);
+    plan.smem = tc_smem_bytes(plan.params, plan.hp);
+    if (plan.smem > 227 * 1024) return no("shared-memory working set too large");
     // layer-0 weights as the B operand of the second contraction: Wcat[(t, h)][f] = W'[t*L + f][h], hi / lo
     plan.wcat_hi.assign((size_t)plan.n0 * 32, 0.0f);
     plan.wcat_lo.assign((size_t)plan.n0 * 32, 0.0f);
@@ -496,8 +504,32 @@ syldet_status Batch::launch_tc_range(const float *d_planar, int n_channels, int6
     w.debug_cols = debug_cols_;
     const int64_t units = (int64_t)n_channels * w.chunks_per_channel;
     const int grid = (int)std::min<int64_t>(units, resident);
+    static const bool timing = std::getenv("SYLDET_TC_TIMING") != nullptr;  // debug: per-role wait/busy cycles on stderr
+    DeviceBuffer d_timing;
+    if (timing) {
+        syldet_status st = d_timing.reserve((size_t)grid * 32 * sizeof(long long));
+        if (st != SYLDET_OK) return st;
+        SYLDET_CUDA(cudaMemsetAsync(d_timing.get(), 0, (size_t)grid * 32 * sizeof(long long), stream));
+        w.debug_timing = d_timing.as<long long>();
+    }
     SYLDET_CUDA(launch_tc(tp.hp, grid, tp.smem, tp.params, w, &tm_main, &tm_tail, stream));
     launches_ += 1;
+    if (timing) {
+        std::vector<long long> h((size_t)grid * 32);
+        SYLDET_CUDA(cudaStreamSynchronize(stream));
+        SYLDET_CUDA(cudaMemcpy(h.data(), d_timing.get(), h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        static const char *names[30] = {"tma.hi_free", "", "", "", "", "tma.total", "mma.full", "mma.tmem_empty", "mma.lo_ready", "mma.a_ready",
+                                        "mma.p_empty", "mma.total", "F.p_full", "F.bar1", "F.bar2", "F.tmem_ld", "F.sums+l0", "F.total", "D.tmem_full", "D.bar1",
+                                        "D.a_free", "D.bar2", "D.tmem_ld", "D.total", "S.full", "S.lo_free", "", "", "", "S.total"};
+        const double tiles = (double)n_channels * w.chunks_per_channel * ((w.chunk_evals + c.time_range - 1 + tc_tile_frames() - 1) / tc_tile_frames()) / grid;
+        std::fprintf(stderr, "[syldet tc timing] grid %d, ~%.0f tiles per CTA; mean cycles per tile:\n", grid, tiles);
+        for (int k = 0; k < 30; ++k) {
+            if (!names[k][0]) continue;
+            double sum = 0;
+            for (int b = 0; b < grid; ++b) sum += (double)h[(size_t)b * 32 + k];
+            std::fprintf(stderr, "  %-16s %10.0f\n", names[k], sum / grid / tiles);
+        }
+    }
     return SYLDET_OK;
 }
 

@@ -21,6 +21,28 @@ __device__ __forceinline__ float transfer(int tf, float v) {
     }
 }
 
+// Out-of-line copy for the warp-specialised kernel, whose roles share the instruction cache: one body instead of one per use.
+__device__ __noinline__ float scale_value_nl(float v, int scaling) { return scale_value(v, scaling); }
+
+__device__ __forceinline__ float ex2_fast(float x) {  // MUFU.EX2, max relative error 2^-22
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float rcp_fast(float x) {  // MUFU.RCP, 1 ulp
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+// Transfer functions on the special-function unit (tensor-core kernel): tanh(v) = 1 - 2 / (e^{2v} + 1), absolute error
+// <= 4e-7 for every v (the 1e-5 output tolerance leaves room for it); e^{2v} = inf gives 1, 0 gives -1, NaN stays NaN.
+__device__ __forceinline__ float transfer_fast(int tf, float v) {
+    if (tf == SYLDET_TF_TANSIG) return fmaf(-2.0f, rcp_fast(ex2_fast(v * 2.8853900817779268f) + 1.0f), 1.0f);
+    if (tf == SYLDET_TF_LOGSIG) return rcp_fast(1.0f + ex2_fast(v * -1.4426950408889634f));
+    if (tf == SYLDET_TF_SATLIN) return fminf(fmaxf(v, 0.0f), 1.0f);
+    return v;
+}
+
 __device__ __forceinline__ float sqrt_fast(float x) {  // MUFU.SQRT, max relative error 2^-23
     float r;
     asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -101,6 +123,55 @@ __device__ __forceinline__ bool finish_eval(const FusedParams &p, int detect_rul
             if (over && (detect_rule == SYLDET_DETECT_ANY_OUTPUT || o == 0)) hit = true;
         }
         out[o] = v;
+    }
+    return hit;
+}
+
+// a[k] / a[k] = v with a runtime index, without spilling the array to local memory
+template <int N>
+__device__ __forceinline__ float pick(const float (&a)[N], int k) {
+    float v = a[0];
+#pragma unroll
+    for (int i = 1; i < N; ++i) v = (k == i) ? a[i] : v;
+    return v;
+}
+template <int N>
+__device__ __forceinline__ void put(float (&a)[N], int k, float v) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) a[i] = (k == i) ? v : a[i];
+}
+
+// Compact form of the network tail (layers >= 1, reverse output maps, threshold test) for callers that hold the layer-0
+// activations in a[] (zero padded): loops run over the real layer widths, so a 4 -> 1 tail costs ~40 instructions.
+__device__ __forceinline__ bool network_tail(const FusedParams &p, int detect_rule, float (&a)[kFusedMaxHidden], float (&out)[kFusedMaxOut]) {
+    for (int l = 1; l < p.n_layers; ++l) {
+        const float *w = &p.rest_w[(l - 1) * kFusedMaxHidden * kFusedMaxHidden];
+        const float *bias = &p.rest_b[(l - 1) * kFusedMaxHidden];
+        float b[kFusedMaxHidden];
+#pragma unroll
+        for (int o = 0; o < kFusedMaxHidden; ++o) b[o] = 0.0f;
+        const int wo = p.width[l];
+#pragma unroll 1
+        for (int o = 0; o < wo; ++o) {
+            float s = 0.0f;
+#pragma unroll
+            for (int i = 0; i < kFusedMaxHidden; ++i) s = fmaf(w[o * kFusedMaxHidden + i], a[i], s);  // padding weights are zero
+            put(b, o, transfer_fast(p.tf[l], s + bias[o]));
+        }
+#pragma unroll
+        for (int o = 0; o < kFusedMaxHidden; ++o) a[o] = b[o];
+    }
+    bool hit = false;
+#pragma unroll
+    for (int o = 0; o < kFusedMaxOut; ++o) out[o] = 0.0f;
+#pragma unroll 1
+    for (int o = 0; o < p.n_out; ++o) {
+        float v = pick(a, o);
+        for (int k = 0; k < p.n_op; ++k)  // reverse maps in index order (NeuralNet.swift:316-323)
+            v = (v + (0 - p.op_y[k])) / p.op_gain[k * kFusedMaxOut + o] + p.op_xoff[k * kFusedMaxOut + o];
+        const bool over = v >= p.thr_f[o];  // == (double)v >= thr (TrackDetector.swift:72); NaN -> false
+        if (over && (detect_rule == SYLDET_DETECT_ANY_OUTPUT || o == 0)) hit = true;
+        put(out, o, v);
     }
     return hit;
 }

@@ -36,6 +36,7 @@ struct alignas(16) FusedParams {
     int window_stat;  // FUSED_STAT_*
     int n_layers, n_out, n_op, reserved0;
     int tf[kFusedMaxLayers];
+    int width[kFusedMaxLayers];     // outputs of each layer
     float v[kFusedMaxHidden];       // V_h  = sum_i W_hi A_i
     float bprime[kFusedMaxHidden];  // B'_h = b_h + sum_i W_hi C_i
     float rest_w[(kFusedMaxLayers - 1) * kFusedMaxHidden * kFusedMaxHidden];  // layers >= 1, [out][in] padded to 8x8
@@ -44,6 +45,7 @@ struct alignas(16) FusedParams {
     float op_gain[kMaxProcessing * kFusedMaxOut];
     float op_xoff[kMaxProcessing * kFusedMaxOut];
     double thr[kFusedMaxOut];
+    float thr_f[kFusedMaxOut];      // smallest float >= thr: (double)v >= thr  <=>  v >= thr_f for every float v
     alignas(16) float w0[kFusedMaxW0];  // [inputs][HP]: W_hi * A_i, hidden index fastest
 };
 
@@ -92,8 +94,9 @@ struct TcWork {
     int n0;                         // T*HP rounded up to a multiple of 16
     float *debug_band;              // optional [n_channels][debug_cols][band] band magnitudes (tests)
     int64_t debug_cols;
+    long long *debug_timing;        // optional [grid][32] cycle counters per role (SYLDET_TC_TIMING=1)
 };
-size_t tc_smem_bytes(const FusedParams &p);
+size_t tc_smem_bytes(const FusedParams &p, int hp);
 int tc_tile_frames();
 int tc_k_pad();
 int tc_max_n0();

@@ -33,8 +33,9 @@ namespace syldet {
 
 namespace {
 
-constexpr int kWarpTma = 0, kWarpMma = 1, kWarpF0 = 2, kNumF = 4, kWarpD0 = 6, kNumD = 8, kWarpS0 = 14, kNumS = 4;
-constexpr int kTcThreads = (kWarpS0 + kNumS) * 32;  // 576
+constexpr int kWarpTma = 0, kWarpMma = 1, kWarpF0 = 2, kNumF = 8, kWarpD0 = 10, kNumD = 8, kWarpS0 = 18, kNumS = 4;
+constexpr int kTcThreads = (kWarpS0 + kNumS) * 32;  // 704
+static_assert(kWarpF0 % 4 == 2 && kWarpD0 % 4 == 2, "quadrant / half assignment below assumes these starts");
 constexpr int kTileRows = 64;                  // rows of Y per tile = N of the DFT MMA
 constexpr int kTileFrames = kTileRows - 1;     // frames completed per tile
 constexpr int kMainChunks = 4;                 // 32-float K chunks (SWIZZLE_128B)
@@ -51,52 +52,67 @@ constexpr int kXPitch = 36;                    // floats per xbuf row: 16-byte a
 constexpr int kPRing = 128;                    // product-row ring (rows = columns)
 constexpr int kStatRing = 512;                 // per-column statistic ring
 constexpr int kBarD = 1, kBarF = 2;            // named barriers of the D and F groups
+constexpr int kEvCap = 128;                    // shared-memory event buffer (flushed with one global atomic)
 
 struct TcSmem {  // byte offsets from the 1024-byte aligned base
     static constexpr int hi0 = 0, hi1 = 35840, lo = 71680;          // audio tiles (34 816 rounded up to 1024)
     static constexpr int abuf = 107520;                             // [2 buffers][hi, lo][64 rows x 128 B]
     static constexpr int wcat = abuf + 4 * 8192;                    // [hi, lo][<= 56 rows x 128 B]
     static constexpr int xbuf = wcat + 2 * kMaxN0 * 128;            // [4 parts][64 rows][kXPitch] float
-    static constexpr int pbuf = xbuf + 4 * kTileRows * kXPitch * 4; // [kPRing][ppitch] float, ppitch <= 64
-    static constexpr int colstat = pbuf + kPRing * 64 * 4;          // float2[kStatRing]
-    static constexpr int bars = colstat + kStatRing * 8;
-    static constexpr int total = bars + 256;
+    static constexpr int pbuf = xbuf + 4 * kTileRows * kXPitch * 4; // [kPRing][ppitch] float; everything after it is placed at run time
+    // then: float2 colstat[kStatRing] | event meta int4[kEvCap] | event outputs float[kEvCap][n_out] | barriers (256 B)
+    __host__ __device__ static constexpr int ppitch(int np) { return (((np + 3) >> 2) | 1) << 2; }  // an odd number of float4
+    __host__ __device__ static constexpr int colstat(int np) { return pbuf + kPRing * ppitch(np) * 4; }
+    __host__ __device__ static constexpr int evmeta(int np) { return colstat(np) + kStatRing * 8; }
+    __host__ __device__ static constexpr int evout(int np) { return evmeta(np) + kEvCap * 16; }
+    __host__ __device__ static constexpr int bars(int np, int n_out) { return evout(np) + kEvCap * n_out * 4; }
+    __host__ __device__ static constexpr int total(int np, int n_out) { return bars(np, n_out) + 256; }
     __host__ __device__ static constexpr int hi(int stage) { return stage ? hi1 : hi0; }
     __host__ __device__ static constexpr int a(int buf, int part) { return abuf + (buf * 2 + part) * 8192; }
 };
 static_assert(TcSmem::abuf % 1024 == 0 && TcSmem::wcat % 1024 == 0 && (kMaxN0 * 128) % 1024 == 0, "swizzle atoms need 1024-byte alignment");
-static_assert(TcSmem::xbuf % 16 == 0 && TcSmem::pbuf % 16 == 0 && TcSmem::colstat % 8 == 0 && TcSmem::bars % 8 == 0, "alignment");
-static_assert(TcSmem::total + 1024 <= 227 * 1024, "shared memory budget");
+static_assert(TcSmem::xbuf % 16 == 0 && TcSmem::pbuf % 16 == 0, "alignment");
 
 // Linear walk over (unit, tile) pairs owned by this CTA; every role iterates the identical sequence.
 struct TileWalk {
-    int64_t unit, n_units;
-    int tile, ntiles, ch, ncols, ne;
+    int units_left;       // units this CTA still has to start (including the current one)
+    int ch, chunk;        // current unit = (channel, chunk of evaluations); advanced by gridDim.x units without divisions
+    int tile, ntiles, ncols, ne;
     int64_t e0;
-    __device__ void load(const TcWork &w, int T) {
-        if (unit >= n_units) return;
-        ch = (int)(unit / w.chunks_per_channel);
-        e0 = (unit - (int64_t)ch * w.chunks_per_channel) * w.chunk_evals;
+    __device__ __forceinline__ void load(const TcWork &w, int T) {
+        e0 = (int64_t)chunk * w.chunk_evals;
         ne = (int)min(w.chunk_evals, w.evals_per_channel - e0);
         ncols = ne + T - 1;
         ntiles = (ncols + kTileFrames - 1) / kTileFrames;
         tile = 0;
     }
-    __device__ void init(const TcWork &w, int T) {
-        n_units = (int64_t)w.n_channels * w.chunks_per_channel;
-        unit = blockIdx.x;
-        load(w, T);
-    }
-    __device__ bool valid() const { return unit < n_units; }
-    __device__ void next(const TcWork &w, int T) {
-        if (++tile >= ntiles) {
-            unit += gridDim.x;
-            load(w, T);
+    __device__ __forceinline__ void advance(const TcWork &w, int by) {
+        chunk += by;
+        while (chunk >= w.chunks_per_channel) {
+            chunk -= w.chunks_per_channel;
+            ++ch;
         }
     }
-    __device__ int first_row() const { return (int)e0 + tile * kTileFrames; }  // row index == column (frame) index
-    __device__ int cols_before() const { return tile * kTileFrames; }
-    __device__ int frames() const { return min(ncols - tile * kTileFrames, kTileFrames); }
+    __device__ __forceinline__ void init(const TcWork &w, int T) {
+        const int n_units = w.n_channels * w.chunks_per_channel;
+        units_left = n_units > (int)blockIdx.x ? (n_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+        ch = 0;
+        chunk = 0;
+        advance(w, (int)blockIdx.x);
+        if (units_left > 0) load(w, T);
+    }
+    __device__ __forceinline__ bool valid() const { return units_left > 0; }
+    __device__ __forceinline__ void next(const TcWork &w, int T) {
+        if (++tile >= ntiles) {
+            if (--units_left > 0) {
+                advance(w, (int)gridDim.x);
+                load(w, T);
+            }
+        }
+    }
+    __device__ __forceinline__ int first_row() const { return (int)e0 + tile * kTileFrames; }  // row index == column (frame) index
+    __device__ __forceinline__ int cols_before() const { return tile * kTileFrames; }
+    __device__ __forceinline__ int frames() const { return min(ncols - tile * kTileFrames, kTileFrames); }
 };
 
 __device__ __forceinline__ void bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
@@ -104,25 +120,55 @@ __device__ __forceinline__ void bar_sync(int id, int nthreads) { asm volatile("b
 __device__ __forceinline__ int sw128(int row, int col) { return row * 128 + ((((col >> 2) ^ row) & 7) << 4) + ((col & 3) << 2); }
 __device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
-template <int HP>
+// Optional per-role cycle accounting (debug_timing != nullptr): slot += cycles spent in a wait / in the whole role loop.
+struct RoleTimer {
+    long long *dst;
+    long long acc[6];
+    long long t_start;
+    __device__ RoleTimer(long long *base, int first_slot) : dst(base ? base + blockIdx.x * 32 + first_slot : nullptr), acc{0, 0, 0, 0, 0, 0}, t_start(0) {
+        if (dst) t_start = clock64();
+    }
+    __device__ __forceinline__ void wait(uint64_t *bar, uint32_t parity, int k) {
+        const long long t0 = dst ? clock64() : 0;
+        ptx::mbar_wait(bar, parity);
+        if (dst) acc[k] += clock64() - t0;
+    }
+    __device__ __forceinline__ void sync(int id, int n, int k) {
+        const long long t0 = dst ? clock64() : 0;
+        bar_sync(id, n);
+        if (dst) acc[k] += clock64() - t0;
+    }
+    __device__ void flush(bool writer) {
+        if (dst && writer) {
+            acc[5] = clock64() - t_start;
+            for (int k = 0; k < 6; ++k) dst[k] = acc[k];
+        }
+    }
+};
+
+template <int HP, bool kScaled>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __grid_constant__ CUtensorMap tmap_main,
                  const __grid_constant__ CUtensorMap tmap_tail) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TcSmem::bars);
-    uint64_t *full = bars, *hi_free = bars + 2, *lo_ready = bars + 4, *lo_free = bars + 5, *tmem_full = bars + 6, *tmem_empty = bars + 8;
-    uint64_t *a_ready = bars + 10, *a_free = bars + 12, *p_full = bars + 14, *p_empty = bars + 16;
-    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 18);
-    float *xbuf = reinterpret_cast<float *>(smem + TcSmem::xbuf);
-    float *pbuf = reinterpret_cast<float *>(smem + TcSmem::pbuf);
-    float2 *colstat = reinterpret_cast<float2 *>(smem + TcSmem::colstat);
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int L = p.band, T = p.time_range;
     const int n0 = w.n0;                           // layer-0 product row length (multiple of 16)
     const int np = T * HP;                         // its meaningful prefix
-    const int ppitch = (((np + 3) >> 2) | 1) << 2; // product ring pitch in floats: an odd number of float4
+    const int ppitch = TcSmem::ppitch(np);         // product ring pitch in floats
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TcSmem::bars(np, p.n_out));
+    uint64_t *full = bars, *hi_free = bars + 2, *lo_ready = bars + 4, *lo_free = bars + 5, *tmem_full = bars + 6, *tmem_empty = bars + 8;
+    uint64_t *a_ready = bars + 10, *a_free = bars + 12, *p_full = bars + 14, *p_empty = bars + 16;
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 18);
+    int *ev_count = reinterpret_cast<int *>(bars + 19);                       // events waiting in shared memory
+    unsigned long long *ev_base = reinterpret_cast<unsigned long long *>(bars + 20);
+    int4 *ev_meta = reinterpret_cast<int4 *>(smem + TcSmem::evmeta(np));      // (channel, -, eval lo, eval hi)
+    float *ev_out = reinterpret_cast<float *>(smem + TcSmem::evout(np));
+    float *xbuf = reinterpret_cast<float *>(smem + TcSmem::xbuf);
+    float *pbuf = reinterpret_cast<float *>(smem + TcSmem::pbuf);
+    float2 *colstat = reinterpret_cast<float2 *>(smem + TcSmem::colstat(np));
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
@@ -137,6 +183,7 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
         }
         ptx::mbar_init(lo_ready, kNumS);
         ptx::mbar_init(lo_free, 1);
+        *ev_count = 0;
         ptx::fence_mbar_init();
     }
     if (warp == kWarpMma) {
@@ -183,9 +230,10 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
             ptx::prefetch_tmap(&tmap_tail);
             TileWalk tw;
             tw.init(w, T);
+            RoleTimer tm(w.debug_timing, 0);
             for (uint32_t it = 0; tw.valid(); ++it, tw.next(w, T)) {
                 const int s = it & 1;
-                ptx::mbar_wait(&hi_free[s], ((it >> 1) & 1) ^ 1);  // first use of each stage passes immediately
+                tm.wait(&hi_free[s], ((it >> 1) & 1) ^ 1, 0);  // first use of each stage passes immediately
                 unsigned char *dst = smem + TcSmem::hi(s);
                 ptx::mbar_expect_tx(&full[s], kTileBytes);
                 const int row = tw.first_row();
@@ -193,6 +241,7 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
                 for (int j = 0; j < kMainChunks; ++j) ptx::tma_load_3d(dst + j * kMainBytes, &tmap_main, j * 32, row, tw.ch, &full[s]);
                 ptx::tma_load_3d(dst + kMainChunks * kMainBytes, &tmap_tail, kMainChunks * 32, row, tw.ch, &full[s]);
             }
+            tm.flush(true);
         }
     } else if (warp == kWarpMma) {
         // ================================ MMA issuer ==================================================================
@@ -201,31 +250,36 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
             const uint32_t idesc_l0 = ptx::idesc_tf32(64, n0);
             const uint32_t lo = ptx::smem_addr(smem + TcSmem::lo);
             const uint32_t wc_hi = ptx::smem_addr(smem + TcSmem::wcat), wc_lo = wc_hi + kMaxN0 * 128;
+            // one K sweep of the band DFT: 4 SWIZZLE_128B chunks of 4 k-steps + the 8-column SWIZZLE_32B tail (rolled: the
+            // instruction stream of every role has to stay small, the roles share the instruction cache)
             auto dft_pass = [&](uint32_t d, uint32_t a, uint32_t b, uint32_t acc) {
-#pragma unroll
-                for (int j = 0; j < kMainChunks; ++j)
+                uint64_t desc = ptx::smem_desc_kmajor(b, 1024, 2);
+#pragma unroll 1
+                for (int j = 0; j < kMainChunks; ++j, a += 32, desc += kMainBytes >> 4) {
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
-                        ptx::mma_tf32_ts(d, a + j * 32 + ks * 8, ptx::smem_desc_kmajor(b + j * kMainBytes + ks * 32, 1024, 2), idesc_dft, acc);
+                        ptx::mma_tf32_ts(d, a + ks * 8, desc + ks * 2, idesc_dft, acc);
                         acc = 1;
                     }
-                ptx::mma_tf32_ts(d, a + kMainChunks * 32, ptx::smem_desc_kmajor(b + kMainChunks * kMainBytes, 256, 6), idesc_dft, 1);
+                }
+                ptx::mma_tf32_ts(d, a, ptx::smem_desc_kmajor(b + kMainChunks * kMainBytes, 256, 6), idesc_dft, 1);
             };
+            RoleTimer tm(w.debug_timing, 6);
             auto issue_l0 = [&](uint32_t jt) {  // per-column layer-0 products of tile jt
                 const int ab = jt & 1;
                 const uint32_t ph = (jt >> 1) & 1;
-                ptx::mbar_wait(&a_ready[ab], ph);       // magnitudes written and fenced
-                ptx::mbar_wait(&p_empty[ab], ph ^ 1);   // product buffer drained by the evaluators
+                tm.wait(&a_ready[ab], ph, 3);       // magnitudes written and fenced
+                tm.wait(&p_empty[ab], ph ^ 1, 4);   // product buffer drained by the evaluators
                 ptx::tc_fence_after();
                 const uint32_t d = tmem_base + kColP0 + ab * kMaxN0;
                 const uint32_t a_hi = ptx::smem_addr(smem + TcSmem::a(ab, 0)), a_lo = ptx::smem_addr(smem + TcSmem::a(ab, 1));
                 uint32_t acc = 0;
-#pragma unroll
+#pragma unroll 1
                 for (int pass = 0; pass < 3; ++pass) {
-                    const uint32_t a = pass == 1 ? a_lo : a_hi, b = pass == 2 ? wc_lo : wc_hi;
+                    const uint64_t da = ptx::smem_desc_kmajor(pass == 1 ? a_lo : a_hi, 1024, 2), db = ptx::smem_desc_kmajor(pass == 2 ? wc_lo : wc_hi, 1024, 2);
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
-                        ptx::mma_tf32_ss(d, ptx::smem_desc_kmajor(a + ks * 32, 1024, 2), ptx::smem_desc_kmajor(b + ks * 32, 1024, 2), idesc_l0, acc);
+                        ptx::mma_tf32_ss(d, da + ks * 2, db + ks * 2, idesc_l0, acc);
                         acc = 1;
                     }
                 }
@@ -238,15 +292,15 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
             for (; tw.valid(); ++it, tw.next(w, T)) {
                 const int s = it & 1;
                 const uint32_t ph = (it >> 1) & 1;
-                ptx::mbar_wait(&full[s], ph);             // hi landed (TMA)
-                ptx::mbar_wait(&tmem_empty[s], ph ^ 1);   // accumulator s drained by the spectrum warps
+                tm.wait(&full[s], ph, 0);             // hi landed (TMA)
+                tm.wait(&tmem_empty[s], ph ^ 1, 1);   // accumulator s drained by the spectrum warps
                 ptx::tc_fence_after();
                 const uint32_t d = tmem_base + kColD0 + s * kTileRows;
                 const uint32_t hi = ptx::smem_addr(smem + TcSmem::hi(s));
                 dft_pass(d, tmem_base + kColAhi, hi, 0);
                 dft_pass(d, tmem_base + kColAlo, hi, 1);
                 ptx::mma_commit(&hi_free[s]);             // the MMA side is done with hi[s]
-                ptx::mbar_wait(lo_ready, it & 1);         // lo written (splitters)
+                tm.wait(lo_ready, it & 1, 2);         // lo written (splitters)
                 ptx::tc_fence_after();
                 dft_pass(d, tmem_base + kColAhi, lo, 1);
                 ptx::mma_commit(&tmem_full[s]);
@@ -254,57 +308,86 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
                 if (it > 0) issue_l0(it - 1);             // its magnitudes were written while this tile's DFT was queued
             }
             if (it > 0) issue_l0(it - 1);
+            tm.flush(true);
         }
     } else if (warp < kWarpD0) {
         // ================================ evaluators (F) ==============================================================
-        const int quad = warp & 3;
+        // 4 lanes per evaluation: lane hq owns HP/4 hidden units (diagonal sums over all T columns, transfer function) and a
+        // quarter of the window statistic; the output layer is a 4-lane reduction. 63 evaluations x 4 lanes = 8 warps.
+        constexpr int UPL = HP / 4;                         // hidden units per lane
+        const int quad = warp & 3, fhalf = (warp - kWarpF0) >> 2;
         const int ft = (warp - kWarpF0) * 32 + lane;
-        const int i = ft >> 1, hf = ft & 1;                 // evaluation slot of the tile, half of its T columns
-        const int t_begin = hf ? (T + 1) / 2 : 0, t_end = hf ? T : (T + 1) / 2;
+        const int i = ft >> 2, hq = ft & 3;                 // evaluation slot of the tile, lane within the evaluation
+        const int nchunks = (np + 7) >> 3;                  // 8-column chunks of a product row; this warp takes every other one
         TileWalk tw;
         tw.init(w, T);
         uint32_t gcol = 0;                                  // columns seen so far (ring position), all units
+        RoleTimer tm(w.debug_timing, 12);
+        auto flush_events = [&](int n_ev) {                 // all F threads; one global atomic for the whole batch
+            if (ft == 0) *ev_base = atomicAdd(w.sink.count, (unsigned long long)n_ev);
+            bar_sync(kBarF, kNumF * 32);
+            const unsigned long long base = *ev_base;
+            for (int e = ft; e < n_ev; e += kNumF * 32) {
+                const unsigned long long idx = base + e;
+                if (idx < w.sink.capacity) {
+                    const int4 m = ev_meta[e];
+                    w.sink.events[idx] = DevEvent{m.x, 0, (int64_t)(((unsigned long long)(unsigned)m.w << 32) | (unsigned)m.z)};
+                    for (int k = 0; k < p.n_out; ++k) w.sink.outputs[idx * p.n_out + k] = ev_out[e * p.n_out + k];
+                }
+            }
+            bar_sync(kBarF, kNumF * 32);
+            if (ft == 0) *ev_count = 0;
+        };
         for (uint32_t it = 0; tw.valid(); ++it, tw.next(w, T)) {
             const int ab = it & 1;
             const int frames = tw.frames();
-            ptx::mbar_wait(&p_full[ab], (it >> 1) & 1);
+            tm.wait(&p_full[ab], (it >> 1) & 1, 0);
             ptx::tc_fence_after();
-            {   // P (M = 64: row c sits in lane 32*(c/16) + c%16) -> product ring
+            const long long t_f0 = tm.dst ? clock64() : 0;
+            {   // P (M = 64: row c sits in lane 32*(c/16) + c%16) -> product ring; loads first, one wait, then stores
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + kColP0 + ab * kMaxN0;
                 float *dst = pbuf + ((gcol + quad * 16 + lane) & (kPRing - 1)) * ppitch;
-                for (int cc = 0; cc < np; cc += 8) {
-                    uint32_t r[8];
-                    ptx::tmem_ld_x8(taddr + cc, r);
-                    ptx::tc_wait_ld();
-                    if (lane < 16) {
-                        *reinterpret_cast<float4 *>(dst + cc) = make_float4(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3]));
-                        if (cc + 4 < np)
-                            *reinterpret_cast<float4 *>(dst + cc + 4) = make_float4(__uint_as_float(r[4]), __uint_as_float(r[5]), __uint_as_float(r[6]), __uint_as_float(r[7]));
+                uint32_t r[4][8];
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (fhalf + 2 * q < nchunks) ptx::tmem_ld_x8(taddr + (fhalf + 2 * q) * 8, r[q]);
+                ptx::tc_wait_ld();
+                if (tm.dst) tm.acc[3] += clock64() - t_f0;
+                if (lane < 16) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int cc = (fhalf + 2 * q) * 8;
+                        if (cc < np) *reinterpret_cast<float4 *>(dst + cc) = make_float4(__uint_as_float(r[q][0]), __uint_as_float(r[q][1]), __uint_as_float(r[q][2]), __uint_as_float(r[q][3]));
+                        if (cc + 4 < np) *reinterpret_cast<float4 *>(dst + cc + 4) = make_float4(__uint_as_float(r[q][4]), __uint_as_float(r[q][5]), __uint_as_float(r[q][6]), __uint_as_float(r[q][7]));
                     }
                 }
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(&p_empty[ab]);
             }
-            bar_sync(kBarF, kNumF * 32);
+            tm.sync(kBarF, kNumF * 32, 1);
+            const long long t_f1 = tm.dst ? clock64() : 0;
             // evaluation whose newest column is column i of this tile: unit-local index j
             const int j = tw.cols_before() - (T - 1) + i;
+#ifdef TC_EXP_SKIP_EVAL
+            const bool valid = false;
+#else
             const bool valid = i < frames && j >= 0;
-            float acc[HP];
+#endif
+            float acc[UPL];
 #pragma unroll
-            for (int h = 0; h < HP; ++h) acc[h] = 0.0f;
+            for (int u = 0; u < UPL; ++u) acc[u] = 0.0f;
             float s0 = p.window_stat == FUSED_STAT_L2 ? 0.0f : INFINITY, s1 = -INFINITY;
             if (valid) {
                 const uint32_t c0 = gcol + (uint32_t)(i - (T - 1));  // ring position of the evaluation's oldest column
-                for (int t = t_begin; t < t_end; ++t) {
-                    const float *prow = pbuf + ((c0 + t) & (kPRing - 1)) * ppitch + t * HP;
-                    const float4 a = *reinterpret_cast<const float4 *>(prow);
-                    acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
-                    if constexpr (HP == 8) {
-                        const float4 b = *reinterpret_cast<const float4 *>(prow + 4);
-                        acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
-                    }
-                    if (p.window_stat != FUSED_STAT_NONE) {
+#pragma unroll 2
+                for (int t = 0; t < T; ++t) {
+                    const float *prow = pbuf + ((c0 + t) & (kPRing - 1)) * ppitch + t * HP + hq * UPL;
+                    if constexpr (UPL == 1) acc[0] += prow[0];
+                    else { const float2 v2 = *reinterpret_cast<const float2 *>(prow); acc[0] += v2.x; acc[1] += v2.y; }
+                }
+                if (p.window_stat != FUSED_STAT_NONE) {
+                    for (int t = hq; t < T; t += 4) {
                         const float2 cs = colstat[(c0 + t) & (kStatRing - 1)];
                         if (p.window_stat == FUSED_STAT_L2) s0 += cs.x;
                         else { s0 = fminf(s0, cs.x); s1 = fmaxf(s1, cs.y); }
@@ -312,44 +395,91 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
                 }
             }
 #pragma unroll
-            for (int h = 0; h < HP; ++h) acc[h] += __shfl_xor_sync(0xffffffffu, acc[h], 1);
-            {
-                const float o0 = __shfl_xor_sync(0xffffffffu, s0, 1), o1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+            for (int d = 1; d <= 2; d <<= 1) {
+                const float o0 = __shfl_xor_sync(0xffffffffu, s0, d), o1 = __shfl_xor_sync(0xffffffffu, s1, d);
                 if (p.window_stat == FUSED_STAT_L2) s0 += o0;
                 else { s0 = fminf(s0, o0); s1 = fmaxf(s1, o1); }
             }
+            float mine[UPL];                                 // this lane's layer-0 activations
+            {
+                float inv = 1.0f, beta = 0.0f;  // z = acc * inv + beta * V + B'
+                if (p.window_stat == FUSED_STAT_L2) {            // x / sqrt(sum x^2)  (NeuralNet.swift:47-59); silence: 0 * inf = NaN
+                    inv = rcp_fast(sqrt_fast(s0));
+                } else if (p.window_stat == FUSED_STAT_MINMAX) {  // x * 2/range + (-mn-mx)/range  (NeuralNet.swift:69-96)
+                    const float range = s1 - s0;
+                    if (0 == range) { inv = 0.0f; beta = -1.0f; }  // flat window: every input becomes -1
+                    else { inv = 2.0f / range; beta = (0 - s0 - s1) / range; }
+                }
+#pragma unroll
+                for (int u = 0; u < UPL; ++u) {
+                    const int h = hq * UPL + u;
+                    mine[u] = transfer_fast(p.tf[0], fmaf(acc[u], inv, fmaf(beta, p.v[h], p.bprime[h])));
+                }
+            }
+            if (tm.dst) tm.acc[4] += clock64() - t_f1;
             float out[kFusedMaxOut];
             bool hit = false;
-            if (valid && hf == 0) {
-                float alpha_div, beta;
-                bool constant_input;
-                stat_to_affine(p.window_stat, s0, s1, alpha_div, beta, constant_input);
-                hit = finish_eval<HP>(p, w.detect_rule, acc, alpha_div, beta, constant_input, out);
-                if (w.all_out) {
-                    float *o = w.all_out + ((int64_t)tw.ch * w.out_evals_per_channel + w.eval_offset + tw.e0 + j) * p.n_out;
+#ifdef TC_EXP_SKIP_EVAL
+            if (false) {
+#else
+            if (p.n_layers == 2) {
+#endif
+                // output layer as a 4-lane reduction: out_o = tf(sum_h W1[o][h] a_h + b1[o]), then reverse maps and threshold
 #pragma unroll
-                    for (int k = 0; k < kFusedMaxOut; ++k)
-                        if (k < p.n_out) o[k] = out[k];
+                for (int o = 0; o < kFusedMaxOut; ++o) out[o] = 0.0f;
+#pragma unroll 1
+                for (int o = 0; o < p.n_out; ++o) {
+                    float sacc = 0.0f;
+#pragma unroll
+                    for (int u = 0; u < UPL; ++u) sacc = fmaf(p.rest_w[o * kFusedMaxHidden + hq * UPL + u], mine[u], sacc);
+                    sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+                    sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+                    float v = transfer_fast(p.tf[1], sacc + p.rest_b[o]);
+                    for (int k = 0; k < p.n_op; ++k)  // reverse maps in index order (NeuralNet.swift:316-323)
+                        v = (v + (0 - p.op_y[k])) / p.op_gain[k * kFusedMaxOut + o] + p.op_xoff[k * kFusedMaxOut + o];
+                    if (v >= p.thr_f[o] && (w.detect_rule == SYLDET_DETECT_ANY_OUTPUT || o == 0)) hit = true;  // TrackDetector.swift:71-77
+                    put(out, o, v);
                 }
+#ifdef TC_EXP_SKIP_EVAL
+            } else if (false) {
+#else
+            } else {
+#endif
+                float a[kFusedMaxHidden];                    // gather every lane's activations, then the generic tail
+#pragma unroll
+                for (int h = 0; h < kFusedMaxHidden; ++h)
+                    a[h] = h < HP ? __shfl_sync(0xffffffffu, mine[h % UPL], (lane & ~3) | (h / UPL)) : 0.0f;
+                hit = network_tail(p, w.detect_rule, a, out);
+            }
+            hit = hit && valid && hq == 0;
+            if (valid && hq == 0 && w.all_out) {
+                float *o = w.all_out + ((int64_t)tw.ch * w.out_evals_per_channel + w.eval_offset + tw.e0 + j) * p.n_out;
+#pragma unroll 1
+                for (int k = 0; k < p.n_out; ++k) o[k] = pick(out, k);
             }
             const unsigned hits = __ballot_sync(0xffffffffu, hit);
-            if (hits) {
-                unsigned long long base = 0;
-                if (lane == 0) base = atomicAdd(w.sink.count, (unsigned long long)__popc(hits));
+            if (hits) {   // append to the shared-memory event buffer (room for a whole tile is guaranteed by the flush rule)
+                int base = 0;
+                if (lane == 0) base = atomicAdd(ev_count, __popc(hits));
                 base = __shfl_sync(0xffffffffu, base, 0);
                 if (hit) {
-                    const unsigned long long idx = base + __popc(hits & ((1u << lane) - 1));
-                    if (idx < w.sink.capacity) {
-                        w.sink.events[idx] = DevEvent{tw.ch, 0, w.eval_offset + tw.e0 + j};
-#pragma unroll
-                        for (int k = 0; k < kFusedMaxOut; ++k)
-                            if (k < p.n_out) w.sink.outputs[idx * p.n_out + k] = out[k];
-                    }
+                    const int e = base + __popc(hits & ((1u << lane) - 1));
+                    const int64_t ev = w.eval_offset + tw.e0 + j;
+                    ev_meta[e] = make_int4(tw.ch, 0, (int)(unsigned)(ev & 0xffffffffll), (int)(ev >> 32));
+#pragma unroll 1
+                    for (int k = 0; k < p.n_out; ++k) ev_out[e * p.n_out + k] = pick(out, k);
                 }
             }
-            bar_sync(kBarF, kNumF * 32);  // the next tile's rows overwrite ring rows this tile's evaluations read
+            tm.sync(kBarF, kNumF * 32, 2);  // the next tile's rows overwrite ring rows this tile's evaluations read
+            const int n_ev = *ev_count;
+            if (n_ev > kEvCap - kTileFrames) flush_events(n_ev);
             gcol += frames;
         }
+        {
+            const int n_ev = *ev_count;
+            if (n_ev > 0) flush_events(n_ev);
+        }
+        tm.flush(ft == 0);
     } else if (warp < kWarpS0) {
         // ================================ spectrum warps (D) ===========================================================
         const int quad = warp & 3, dw = warp - kWarpD0, half = dw >> 2;
@@ -362,23 +492,26 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
         TileWalk tw;
         tw.init(w, T);
         uint32_t gcol = 0;
+        RoleTimer tm(w.debug_timing, 18);
         for (uint32_t it = 0; tw.valid(); ++it, tw.next(w, T)) {
             const int s = it & 1;
             const uint32_t ph = (it >> 1) & 1;
             const int frames = tw.frames();
-            ptx::mbar_wait(&tmem_full[s], ph);
+            tm.wait(&tmem_full[s], ph, 0);
             ptx::tc_fence_after();
             uint32_t r[32];
+            const long long t_d0 = tm.dst ? clock64() : 0;
             ptx::tmem_ld_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + kColD0 + s * kTileRows + half * 32, r);
             ptx::tc_wait_ld();
+            if (tm.dst) tm.acc[4] += clock64() - t_d0;
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tmem_empty[s]);
-            bar_sync(kBarD, kNumD * 32);                    // everyone is done reading the previous tile's xbuf
+            tm.sync(kBarD, kNumD * 32, 1);                  // everyone is done reading the previous tile's xbuf
 #pragma unroll
             for (int j = 0; j < 32; ++j) x_dst[j * kXPitch] = __uint_as_float(r[j]);
-            ptx::mbar_wait(&a_free[s], ph ^ 1);             // layer 0 of tile it-2 has read this A buffer
-            bar_sync(kBarD, kNumD * 32);
+            tm.wait(&a_free[s], ph ^ 1, 2);                 // layer 0 of tile it-2 has read this A buffer
+            tm.sync(kBarD, kNumD * 32, 3);
             // ---- X_c = (Re1[c] + Re2[c+1]) + i (Im1[c] + Im2[c+1]); |X| of the band -> layer-0 A operand (hi, lo) ----------
             float s0 = p.window_stat == FUSED_STAT_L2 ? 0.0f : INFINITY, s1 = -INFINITY;
             if (c < frames) {
@@ -393,7 +526,7 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         float v = sqrt_fast(re[k] * re[k] + im[k] * im[k]);
-                        if (p.scaling != SYLDET_SCALING_LINEAR) v = scale_value(v, p.scaling);
+                        if constexpr (kScaled) v = scale_value_nl(v, p.scaling);
                         if (qq * 8 + u * 4 + k >= L) v = 0.0f;
                         else if (p.window_stat == FUSED_STAT_L2) s0 = fmaf(v, v, s0);
                         else if (p.window_stat == FUSED_STAT_MINMAX) { s0 = fminf(s0, v); s1 = fmaxf(s1, v); }
@@ -425,6 +558,7 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
             if (lane == 0) ptx::mbar_arrive(&a_ready[s]);
             gcol += frames;
         }
+        tm.flush(dt == 0);
     } else {
         // ================================ splitters (S) ================================================================
         const int st = (warp - kWarpS0) * 32 + lane;
@@ -432,16 +566,26 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
         static_assert(kPerThread * kNumS * 32 * 16 == kTileBytes, "tile size must divide over the splitters");
         TileWalk tw;
         tw.init(w, T);
+        RoleTimer tm(w.debug_timing, 24);
         for (uint32_t it = 0; tw.valid(); ++it, tw.next(w, T)) {
             const int s = it & 1;
-            ptx::mbar_wait(&full[s], (it >> 1) & 1);
-            ptx::mbar_wait(lo_free, (it & 1) ^ 1);          // pass 3 of the previous tile has read the lo buffer
+            tm.wait(&full[s], (it >> 1) & 1, 0);
+            tm.wait(lo_free, (it & 1) ^ 1, 1);          // pass 3 of the previous tile has read the lo buffer
             const float4 *hi4 = reinterpret_cast<const float4 *>(smem + TcSmem::hi(s)) + st;
             float4 *lo4 = reinterpret_cast<float4 *>(smem + TcSmem::lo) + st;
+            // lo = x - tf32_trunc(x); layout-agnostic: same offsets in both buffers. Two batches, loads in flight before stores.
+            constexpr int kBatch = (kPerThread + 1) / 2;
 #pragma unroll
-            for (int k = 0; k < kPerThread; ++k) {          // lo = x - tf32_trunc(x); layout-agnostic: same offsets in both buffers
-                const float4 v = hi4[k * kNumS * 32];
-                lo4[k * kNumS * 32] = make_float4(v.x - tf32_trunc(v.x), v.y - tf32_trunc(v.y), v.z - tf32_trunc(v.z), v.w - tf32_trunc(v.w));
+            for (int b0 = 0; b0 < kPerThread; b0 += kBatch) {
+                float4 v[kBatch];
+#pragma unroll
+                for (int k = 0; k < kBatch; ++k)
+                    if (b0 + k < kPerThread) v[k] = hi4[(b0 + k) * kNumS * 32];
+#pragma unroll
+                for (int k = 0; k < kBatch; ++k)
+                    if (b0 + k < kPerThread)
+                        lo4[(b0 + k) * kNumS * 32] = make_float4(v[k].x - tf32_trunc(v[k].x), v[k].y - tf32_trunc(v[k].y), v[k].z - tf32_trunc(v[k].z),
+                                                                 v[k].w - tf32_trunc(v[k].w));
             }
             ptx::fence_proxy_async_smem();
             __syncwarp();
@@ -450,6 +594,7 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
                 ptx::mbar_arrive(&hi_free[s]);
             }
         }
+        tm.flush(st == 0);
     }
 
     ptx::tc_fence_before();
@@ -459,7 +604,7 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
 
 }  // namespace
 
-size_t tc_smem_bytes(const FusedParams &) { return 1024 + TcSmem::total; }
+size_t tc_smem_bytes(const FusedParams &p, int hp) { return 1024 + TcSmem::total(p.time_range * hp, p.n_out); }
 int tc_tile_frames() { return kTileFrames; }
 int tc_k_pad() { return kKPad; }
 int tc_max_n0() { return kMaxN0; }
@@ -472,16 +617,17 @@ cudaError_t launch_tc(int hp, int grid, size_t smem, const FusedParams &p, const
                       cudaStream_t stream) {
     const CUtensorMap &tm = *static_cast<const CUtensorMap *>(tmap_main);
     const CUtensorMap &tt = *static_cast<const CUtensorMap *>(tmap_tail);
-    cudaError_t e;
-    if (hp == 4) {
-        e = cudaFuncSetAttribute(tc_detect_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        tc_detect_kernel<4><<<grid, kTcThreads, smem, stream>>>(p, w, tm, tt);
-    } else {
-        e = cudaFuncSetAttribute(tc_detect_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        tc_detect_kernel<8><<<grid, kTcThreads, smem, stream>>>(p, w, tm, tt);
-    }
+    cudaError_t e = cudaErrorInvalidValue;
+    auto go = [&](auto kern) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) kern<<<grid, kTcThreads, smem, stream>>>(p, w, tm, tt);
+    };
+    const bool scaled = p.scaling != SYLDET_SCALING_LINEAR;
+    if (hp == 4 && !scaled) go(tc_detect_kernel<4, false>);
+    else if (hp == 4) go(tc_detect_kernel<4, true>);
+    else if (!scaled) go(tc_detect_kernel<8, false>);
+    else go(tc_detect_kernel<8, true>);
+    if (e != cudaSuccess) return e;
     return cudaGetLastError();
 }
 

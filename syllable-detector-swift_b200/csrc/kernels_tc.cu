@@ -21,7 +21,8 @@
 //   warp 0        TMA producer                      full[s] <- hi_free[s]
 //   warp 1        MMA issuer + TMEM allocator       DFT(it): full, tmem_empty, lo_ready -> hi_free, tmem_full, lo_free
 //                                                   layer0(it-1): a_ready, p_empty -> p_full, a_free
-//   warps 2-5     evaluators (F)                    p_full -> product ring -> p_empty; diagonal sums, network tail, events
+//   warps 2-5     evaluators (F), one per TMEM lane quadrant: p_full -> product ring -> p_empty; one thread per evaluation:
+//                                                   diagonal sum (T x LDS.128), window statistic, network tail, events
 //   warps 6-13    spectrum warps (D)                tmem_full -> D -> xbuf -> tmem_empty; |X| -> layer-0 A operand -> a_ready
 //   warps 14-17   splitters (S)                     full, lo_free -> lo tile -> lo_ready, hi_free
 #include <cuda.h>
@@ -33,8 +34,8 @@ namespace syldet {
 
 namespace {
 
-constexpr int kWarpTma = 0, kWarpMma = 1, kWarpF0 = 2, kNumF = 8, kWarpD0 = 10, kNumD = 8, kWarpS0 = 18, kNumS = 4;
-constexpr int kTcThreads = (kWarpS0 + kNumS) * 32;  // 704
+constexpr int kWarpTma = 0, kWarpMma = 1, kWarpF0 = 2, kNumF = 4, kWarpD0 = 6, kNumD = 8, kWarpS0 = 14, kNumS = 4;
+constexpr int kTcThreads = (kWarpS0 + kNumS) * 32;  // 576
 static_assert(kWarpF0 % 4 == 2 && kWarpD0 % 4 == 2, "quadrant / half assignment below assumes these starts");
 constexpr int kTileRows = 64;                  // rows of Y per tile = N of the DFT MMA
 constexpr int kTileFrames = kTileRows - 1;     // frames completed per tile
@@ -61,7 +62,7 @@ struct TcSmem {  // byte offsets from the 1024-byte aligned base
     static constexpr int xbuf = wcat + 2 * kMaxN0 * 128;            // [4 parts][64 rows][kXPitch] float
     static constexpr int pbuf = xbuf + 4 * kTileRows * kXPitch * 4; // [kPRing][ppitch] float; everything after it is placed at run time
     // then: float2 colstat[kStatRing] | event meta int4[kEvCap] | event outputs float[kEvCap][n_out] | barriers (256 B)
-    __host__ __device__ static constexpr int ppitch(int np) { return (((np + 3) >> 2) | 1) << 2; }  // an odd number of float4
+    __host__ __device__ static constexpr int ppitch(int np) { return ((((np + 7) >> 3) << 1) | 1) << 2; }  // whole 8-float chunks + 1: an odd number of float4
     __host__ __device__ static constexpr int colstat(int np) { return pbuf + kPRing * ppitch(np) * 4; }
     __host__ __device__ static constexpr int evmeta(int np) { return colstat(np) + kStatRing * 8; }
     __host__ __device__ static constexpr int evout(int np) { return evmeta(np) + kEvCap * 16; }
@@ -120,38 +121,53 @@ __device__ __forceinline__ void bar_sync(int id, int nthreads) { asm volatile("b
 __device__ __forceinline__ int sw128(int row, int col) { return row * 128 + ((((col >> 2) ^ row) & 7) << 4) + ((col & 3) << 2); }
 __device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
-// Optional per-role cycle accounting (debug_timing != nullptr): slot += cycles spent in a wait / in the whole role loop.
+// Optional per-role cycle accounting (kOn: the SYLDET_TC_TIMING instantiation): slot += cycles spent in a wait / in the whole
+// role loop. The production instantiation compiles to the bare waits.
+template <bool kOn>
 struct RoleTimer {
     long long *dst;
     long long acc[6];
     long long t_start;
-    __device__ RoleTimer(long long *base, int first_slot) : dst(base ? base + blockIdx.x * 32 + first_slot : nullptr), acc{0, 0, 0, 0, 0, 0}, t_start(0) {
-        if (dst) t_start = clock64();
+    __device__ RoleTimer(long long *base, int first_slot) : dst(nullptr), acc{0, 0, 0, 0, 0, 0}, t_start(0) {
+        if constexpr (kOn) {
+            dst = base + blockIdx.x * 32 + first_slot;
+            t_start = clock64();
+        }
+    }
+    __device__ __forceinline__ long long now() const {
+        if constexpr (kOn) return clock64();
+        return 0;
+    }
+    __device__ __forceinline__ void add(int k, long long t0) {
+        if constexpr (kOn) acc[k] += clock64() - t0;
     }
     __device__ __forceinline__ void wait(uint64_t *bar, uint32_t parity, int k) {
-        const long long t0 = dst ? clock64() : 0;
+        const long long t0 = now();
         ptx::mbar_wait(bar, parity);
-        if (dst) acc[k] += clock64() - t0;
+        add(k, t0);
     }
     __device__ __forceinline__ void sync(int id, int n, int k) {
-        const long long t0 = dst ? clock64() : 0;
+        const long long t0 = now();
         bar_sync(id, n);
-        if (dst) acc[k] += clock64() - t0;
+        add(k, t0);
     }
     __device__ void flush(bool writer) {
-        if (dst && writer) {
-            acc[5] = clock64() - t_start;
-            for (int k = 0; k < 6; ++k) dst[k] = acc[k];
+        if constexpr (kOn) {
+            if (writer) {
+                acc[5] = clock64() - t_start;
+                for (int k = 0; k < 6; ++k) dst[k] = acc[k];
+            }
         }
     }
 };
 
-template <int HP, bool kScaled>
+template <int HP, bool kScaled, bool kTiming>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __grid_constant__ CUtensorMap tmap_main,
                  const __grid_constant__ CUtensorMap tmap_tail) {
-    extern __shared__ unsigned char smem_dyn[];
-    unsigned char *smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    // 1024-byte aligned base (swizzle atoms); plain pointer arithmetic so that the compiler keeps the shared address space
+    unsigned char *smem = smem_dyn + ((1024u - (ptx::smem_addr(smem_dyn) & 1023u)) & 1023u);
     const int L = p.band, T = p.time_range;
     const int n0 = w.n0;                           // layer-0 product row length (multiple of 16)
     const int np = T * HP;                         // its meaningful prefix
@@ -230,7 +246,7 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
             ptx::prefetch_tmap(&tmap_tail);
             TileWalk tw;
             tw.init(w, T);
-            RoleTimer tm(w.debug_timing, 0);
+            RoleTimer<kTiming> tm(w.debug_timing, 0);
             for (uint32_t it = 0; tw.valid(); ++it, tw.next(w, T)) {
                 const int s = it & 1;
                 tm.wait(&hi_free[s], ((it >> 1) & 1) ^ 1, 0);  // first use of each stage passes immediately
@@ -264,7 +280,7 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
                 }
                 ptx::mma_tf32_ts(d, a, ptx::smem_desc_kmajor(b + kMainChunks * kMainBytes, 256, 6), idesc_dft, 1);
             };
-            RoleTimer tm(w.debug_timing, 6);
+            RoleTimer<kTiming> tm(w.debug_timing, 6);
             auto issue_l0 = [&](uint32_t jt) {  // per-column layer-0 products of tile jt
                 const int ab = jt & 1;
                 const uint32_t ph = (jt >> 1) & 1;
@@ -312,17 +328,18 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
         }
     } else if (warp < kWarpD0) {
         // ================================ evaluators (F) ==============================================================
-        // 4 lanes per evaluation: lane hq owns HP/4 hidden units (diagonal sums over all T columns, transfer function) and a
-        // quarter of the window statistic; the output layer is a 4-lane reduction. 63 evaluations x 4 lanes = 8 warps.
-        constexpr int UPL = HP / 4;                         // hidden units per lane
-        const int quad = warp & 3, fhalf = (warp - kWarpF0) >> 2;
+        // One warp per TMEM lane quadrant. The layer-0 accumulator is an M = 64 tile: product row c (= column c of the tile)
+        // sits in lane 32*(c/16) + c%16, so lanes 0-15 of every warp own one row each: they move it to the product ring and
+        // then evaluate the network whose newest column is c (one thread = one evaluation; T x LDS.128 for the diagonal sum).
+        const int quad = warp & 3;
         const int ft = (warp - kWarpF0) * 32 + lane;
-        const int i = ft >> 2, hq = ft & 3;                 // evaluation slot of the tile, lane within the evaluation
-        const int nchunks = (np + 7) >> 3;                  // 8-column chunks of a product row; this warp takes every other one
+        const int c = quad * 16 + (lane & 15);              // column of the tile this thread owns
+        const bool owner = lane < 16;
+        const int nchunks = (np + 7) >> 3;                  // 8-column chunks of a product row
         TileWalk tw;
         tw.init(w, T);
         uint32_t gcol = 0;                                  // columns seen so far (ring position), all units
-        RoleTimer tm(w.debug_timing, 12);
+        RoleTimer<kTiming> tm(w.debug_timing, 12);
         auto flush_events = [&](int n_ev) {                 // all F threads; one global atomic for the whole batch
             if (ft == 0) *ev_base = atomicAdd(w.sink.count, (unsigned long long)n_ev);
             bar_sync(kBarF, kNumF * 32);
@@ -343,65 +360,65 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
             const int frames = tw.frames();
             tm.wait(&p_full[ab], (it >> 1) & 1, 0);
             ptx::tc_fence_after();
-            const long long t_f0 = tm.dst ? clock64() : 0;
-            {   // P (M = 64: row c sits in lane 32*(c/16) + c%16) -> product ring; loads first, one wait, then stores
+            const long long t_f0 = tm.now();
+            {   // P row -> product ring, four 8-column chunks at a time: loads in flight, one wait, then the stores
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + kColP0 + ab * kMaxN0;
-                float *dst = pbuf + ((gcol + quad * 16 + lane) & (kPRing - 1)) * ppitch;
-                uint32_t r[4][8];
+                float4 *dst = reinterpret_cast<float4 *>(pbuf + ((gcol + c) & (kPRing - 1)) * ppitch);
+                const bool store = owner && c < frames;
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (fhalf + 2 * q < nchunks) ptx::tmem_ld_x8(taddr + (fhalf + 2 * q) * 8, r[q]);
-                ptx::tc_wait_ld();
-                if (tm.dst) tm.acc[3] += clock64() - t_f0;
-                if (lane < 16) {
+                for (int q0 = 0; q0 < kMaxN0 / 8; q0 += 4) {
+                    if (q0 < nchunks) {
+                        uint32_t r[4][8];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int cc = (fhalf + 2 * q) * 8;
-                        if (cc < np) *reinterpret_cast<float4 *>(dst + cc) = make_float4(__uint_as_float(r[q][0]), __uint_as_float(r[q][1]), __uint_as_float(r[q][2]), __uint_as_float(r[q][3]));
-                        if (cc + 4 < np) *reinterpret_cast<float4 *>(dst + cc + 4) = make_float4(__uint_as_float(r[q][4]), __uint_as_float(r[q][5]), __uint_as_float(r[q][6]), __uint_as_float(r[q][7]));
+                        for (int q = 0; q < 4; ++q)
+                            if (q0 + q < nchunks) ptx::tmem_ld_x8(taddr + (q0 + q) * 8, r[q]);
+                        ptx::tc_wait_ld();
+                        if (store) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                if (q0 + q < nchunks) {  // the ring pitch covers whole chunks
+                                    dst[2 * (q0 + q)] = make_float4(__uint_as_float(r[q][0]), __uint_as_float(r[q][1]), __uint_as_float(r[q][2]), __uint_as_float(r[q][3]));
+                                    dst[2 * (q0 + q) + 1] = make_float4(__uint_as_float(r[q][4]), __uint_as_float(r[q][5]), __uint_as_float(r[q][6]), __uint_as_float(r[q][7]));
+                                }
+                        }
                     }
                 }
+                tm.add(3, t_f0);
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(&p_empty[ab]);
             }
             tm.sync(kBarF, kNumF * 32, 1);
-            const long long t_f1 = tm.dst ? clock64() : 0;
-            // evaluation whose newest column is column i of this tile: unit-local index j
-            const int j = tw.cols_before() - (T - 1) + i;
+            const long long t_f1 = tm.now();
+            // evaluation whose newest column is column c of this tile: unit-local index j
+            const int j = tw.cols_before() - (T - 1) + c;
 #ifdef TC_EXP_SKIP_EVAL
             const bool valid = false;
 #else
-            const bool valid = i < frames && j >= 0;
+            const bool valid = owner && c < frames && j >= 0;
 #endif
-            float acc[UPL];
-#pragma unroll
-            for (int u = 0; u < UPL; ++u) acc[u] = 0.0f;
-            float s0 = p.window_stat == FUSED_STAT_L2 ? 0.0f : INFINITY, s1 = -INFINITY;
+            bool hit = false;
+            float out[kFusedMaxOut];
             if (valid) {
-                const uint32_t c0 = gcol + (uint32_t)(i - (T - 1));  // ring position of the evaluation's oldest column
-#pragma unroll 2
-                for (int t = 0; t < T; ++t) {
-                    const float *prow = pbuf + ((c0 + t) & (kPRing - 1)) * ppitch + t * HP + hq * UPL;
-                    if constexpr (UPL == 1) acc[0] += prow[0];
-                    else { const float2 v2 = *reinterpret_cast<const float2 *>(prow); acc[0] += v2.x; acc[1] += v2.y; }
-                }
-                if (p.window_stat != FUSED_STAT_NONE) {
-                    for (int t = hq; t < T; t += 4) {
-                        const float2 cs = colstat[(c0 + t) & (kStatRing - 1)];
-                        if (p.window_stat == FUSED_STAT_L2) s0 += cs.x;
-                        else { s0 = fminf(s0, cs.x); s1 = fmaxf(s1, cs.y); }
-                    }
-                }
-            }
+                float acc[HP];
 #pragma unroll
-            for (int d = 1; d <= 2; d <<= 1) {
-                const float o0 = __shfl_xor_sync(0xffffffffu, s0, d), o1 = __shfl_xor_sync(0xffffffffu, s1, d);
-                if (p.window_stat == FUSED_STAT_L2) s0 += o0;
-                else { s0 = fminf(s0, o0); s1 = fmaxf(s1, o1); }
-            }
-            float mine[UPL];                                 // this lane's layer-0 activations
-            {
+                for (int h = 0; h < HP; ++h) acc[h] = 0.0f;
+                float s0 = p.window_stat == FUSED_STAT_L2 ? 0.0f : INFINITY, s1 = -INFINITY;
+                uint32_t col = gcol + (uint32_t)(c - (T - 1));   // ring position of the evaluation's oldest column
+                const float *pt = pbuf;                          // + t * HP as the loop advances
+#pragma unroll 2
+                for (int t = 0; t < T; ++t, ++col, pt += HP) {
+                    const float4 *prow = reinterpret_cast<const float4 *>(pt + (col & (kPRing - 1)) * ppitch);
+                    const float4 v0 = prow[0];
+                    acc[0] += v0.x; acc[1] += v0.y; acc[2] += v0.z; acc[3] += v0.w;
+                    if constexpr (HP == 8) {
+                        const float4 v1 = prow[1];
+                        acc[4] += v1.x; acc[5] += v1.y; acc[6] += v1.z; acc[7] += v1.w;
+                    }
+                    const float2 cs = colstat[col & (kStatRing - 1)];
+                    if (p.window_stat == FUSED_STAT_L2) s0 += cs.x;
+                    else { s0 = fminf(s0, cs.x); s1 = fmaxf(s1, cs.y); }
+                }
                 float inv = 1.0f, beta = 0.0f;  // z = acc * inv + beta * V + B'
                 if (p.window_stat == FUSED_STAT_L2) {            // x / sqrt(sum x^2)  (NeuralNet.swift:47-59); silence: 0 * inf = NaN
                     inv = rcp_fast(sqrt_fast(s0));
@@ -410,52 +427,17 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
                     if (0 == range) { inv = 0.0f; beta = -1.0f; }  // flat window: every input becomes -1
                     else { inv = 2.0f / range; beta = (0 - s0 - s1) / range; }
                 }
-#pragma unroll
-                for (int u = 0; u < UPL; ++u) {
-                    const int h = hq * UPL + u;
-                    mine[u] = transfer_fast(p.tf[0], fmaf(acc[u], inv, fmaf(beta, p.v[h], p.bprime[h])));
-                }
-            }
-            if (tm.dst) tm.acc[4] += clock64() - t_f1;
-            float out[kFusedMaxOut];
-            bool hit = false;
-#ifdef TC_EXP_SKIP_EVAL
-            if (false) {
-#else
-            if (p.n_layers == 2) {
-#endif
-                // output layer as a 4-lane reduction: out_o = tf(sum_h W1[o][h] a_h + b1[o]), then reverse maps and threshold
-#pragma unroll
-                for (int o = 0; o < kFusedMaxOut; ++o) out[o] = 0.0f;
-#pragma unroll 1
-                for (int o = 0; o < p.n_out; ++o) {
-                    float sacc = 0.0f;
-#pragma unroll
-                    for (int u = 0; u < UPL; ++u) sacc = fmaf(p.rest_w[o * kFusedMaxHidden + hq * UPL + u], mine[u], sacc);
-                    sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
-                    sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
-                    float v = transfer_fast(p.tf[1], sacc + p.rest_b[o]);
-                    for (int k = 0; k < p.n_op; ++k)  // reverse maps in index order (NeuralNet.swift:316-323)
-                        v = (v + (0 - p.op_y[k])) / p.op_gain[k * kFusedMaxOut + o] + p.op_xoff[k * kFusedMaxOut + o];
-                    if (v >= p.thr_f[o] && (w.detect_rule == SYLDET_DETECT_ANY_OUTPUT || o == 0)) hit = true;  // TrackDetector.swift:71-77
-                    put(out, o, v);
-                }
-#ifdef TC_EXP_SKIP_EVAL
-            } else if (false) {
-#else
-            } else {
-#endif
-                float a[kFusedMaxHidden];                    // gather every lane's activations, then the generic tail
+                float a[kFusedMaxHidden];
 #pragma unroll
                 for (int h = 0; h < kFusedMaxHidden; ++h)
-                    a[h] = h < HP ? __shfl_sync(0xffffffffu, mine[h % UPL], (lane & ~3) | (h / UPL)) : 0.0f;
+                    a[h] = h < HP ? transfer_fast(p.tf[0], fmaf(acc[h < HP ? h : 0], inv, fmaf(beta, p.v[h], p.bprime[h]))) : 0.0f;
+                tm.add(4, t_f1);
                 hit = network_tail(p, w.detect_rule, a, out);
-            }
-            hit = hit && valid && hq == 0;
-            if (valid && hq == 0 && w.all_out) {
-                float *o = w.all_out + ((int64_t)tw.ch * w.out_evals_per_channel + w.eval_offset + tw.e0 + j) * p.n_out;
+                if (w.all_out) {
+                    float *o = w.all_out + ((int64_t)tw.ch * w.out_evals_per_channel + w.eval_offset + tw.e0 + j) * p.n_out;
 #pragma unroll 1
-                for (int k = 0; k < p.n_out; ++k) o[k] = pick(out, k);
+                    for (int k = 0; k < p.n_out; ++k) o[k] = pick(out, k);
+                }
             }
             const unsigned hits = __ballot_sync(0xffffffffu, hit);
             if (hits) {   // append to the shared-memory event buffer (room for a whole tile is guaranteed by the flush rule)
@@ -492,7 +474,7 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
         TileWalk tw;
         tw.init(w, T);
         uint32_t gcol = 0;
-        RoleTimer tm(w.debug_timing, 18);
+        RoleTimer<kTiming> tm(w.debug_timing, 18);
         for (uint32_t it = 0; tw.valid(); ++it, tw.next(w, T)) {
             const int s = it & 1;
             const uint32_t ph = (it >> 1) & 1;
@@ -500,10 +482,10 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
             tm.wait(&tmem_full[s], ph, 0);
             ptx::tc_fence_after();
             uint32_t r[32];
-            const long long t_d0 = tm.dst ? clock64() : 0;
+            const long long t_d0 = tm.now();
             ptx::tmem_ld_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + kColD0 + s * kTileRows + half * 32, r);
             ptx::tc_wait_ld();
-            if (tm.dst) tm.acc[4] += clock64() - t_d0;
+            tm.add(4, t_d0);
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tmem_empty[s]);
@@ -566,7 +548,7 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
         static_assert(kPerThread * kNumS * 32 * 16 == kTileBytes, "tile size must divide over the splitters");
         TileWalk tw;
         tw.init(w, T);
-        RoleTimer tm(w.debug_timing, 24);
+        RoleTimer<kTiming> tm(w.debug_timing, 24);
         for (uint32_t it = 0; tw.valid(); ++it, tw.next(w, T)) {
             const int s = it & 1;
             tm.wait(&full[s], (it >> 1) & 1, 0);
@@ -623,10 +605,13 @@ cudaError_t launch_tc(int hp, int grid, size_t smem, const FusedParams &p, const
         if (e == cudaSuccess) kern<<<grid, kTcThreads, smem, stream>>>(p, w, tm, tt);
     };
     const bool scaled = p.scaling != SYLDET_SCALING_LINEAR;
-    if (hp == 4 && !scaled) go(tc_detect_kernel<4, false>);
-    else if (hp == 4) go(tc_detect_kernel<4, true>);
-    else if (!scaled) go(tc_detect_kernel<8, false>);
-    else go(tc_detect_kernel<8, true>);
+    if (w.debug_timing) {   // SYLDET_TC_TIMING: instrumented build of the common shape only
+        if (hp == 4 && !scaled) go(tc_detect_kernel<4, false, true>);
+        else return cudaErrorNotSupported;
+    } else if (hp == 4 && !scaled) go(tc_detect_kernel<4, false, false>);
+    else if (hp == 4) go(tc_detect_kernel<4, true, false>);
+    else if (!scaled) go(tc_detect_kernel<8, false, false>);
+    else go(tc_detect_kernel<8, true, false>);
     if (e != cudaSuccess) return e;
     return cudaGetLastError();
 }

@@ -21,10 +21,13 @@
 //   warp 0        TMA producer                      full[s] <- hi_free[s]
 //   warp 1        MMA issuer + TMEM allocator       DFT(it): full, tmem_empty, lo_ready -> hi_free, tmem_full, lo_free
 //                                                   layer0(it-1): a_ready, p_empty -> p_full, a_free
-//   warps 2-5     evaluators (F), one per TMEM lane quadrant: p_full -> product ring -> p_empty; one thread per evaluation:
+//   warps 2-9     evaluators (F): two groups of four warps (one per TMEM lane quadrant) that take alternate tiles:
+//                                                   p_full, ring_ready[other] -> product ring -> p_empty, ring_ready[own];
 //                                                   diagonal sum (T x LDS.128), window statistic, network tail, events
-//   warps 6-13    spectrum warps (D)                tmem_full -> D -> xbuf -> tmem_empty; |X| -> layer-0 A operand -> a_ready
-//   warps 14-17   splitters (S)                     full, lo_free -> lo tile -> lo_ready, hi_free
+//   warps 10-17   spectrum warps (D)                tmem_full -> D -> xbuf -> tmem_empty; |X| -> layer-0 A operand -> a_ready
+//   warps 18-21   splitters (S)                     full, lo_free -> lo tile -> lo_ready, hi_free
+// Every role is a serial chain per tile and runs at ~0.1 IPC per warp (profiles/): the roles overlap through double buffers, and
+// the longest chain (the evaluators') is split over two groups so that no role needs more than one tile period per tile.
 #include <cuda.h>
 
 #include "fused_epilogue.cuh"
@@ -34,8 +37,9 @@ namespace syldet {
 
 namespace {
 
-constexpr int kWarpTma = 0, kWarpMma = 1, kWarpF0 = 2, kNumF = 4, kWarpD0 = 6, kNumD = 8, kWarpS0 = 14, kNumS = 4;
-constexpr int kTcThreads = (kWarpS0 + kNumS) * 32;  // 576
+constexpr int kWarpTma = 0, kWarpMma = 1, kWarpF0 = 2, kNumF = 8, kWarpD0 = 10, kNumD = 8, kWarpS0 = 18, kNumS = 4;
+constexpr int kFGroup = 4;                     // warps per evaluator group (one per TMEM lane quadrant)
+constexpr int kTcThreads = (kWarpS0 + kNumS) * 32;  // 704
 static_assert(kWarpF0 % 4 == 2 && kWarpD0 % 4 == 2, "quadrant / half assignment below assumes these starts");
 constexpr int kTileRows = 64;                  // rows of Y per tile = N of the DFT MMA
 constexpr int kTileFrames = kTileRows - 1;     // frames completed per tile
@@ -50,10 +54,10 @@ constexpr int kTmemCols = 512;
 constexpr int kColAhi = 0, kColAlo = kKPad, kColD0 = 2 * kKPad, kColP0 = kColD0 + 2 * kTileRows;
 static_assert(kColP0 + 2 * kMaxN0 <= kTmemCols, "TMEM budget");
 constexpr int kXPitch = 36;                    // floats per xbuf row: 16-byte aligned, conflict-free for LDS.128 by column
-constexpr int kPRing = 128;                    // product-row ring (rows = columns)
+constexpr int kPRing = 160;                    // product-row ring (rows = columns): two tiles in flight + the T-1 rows before them
 constexpr int kStatRing = 512;                 // per-column statistic ring
-constexpr int kBarD = 1, kBarF = 2;            // named barriers of the D and F groups
-constexpr int kEvCap = 128;                    // shared-memory event buffer (flushed with one global atomic)
+constexpr int kBarD = 1, kBarF = 2;            // named barriers: D group; F groups use kBarF and kBarF + 1
+constexpr int kEvCap = 96;                     // shared-memory event buffer per F group (flushed with one global atomic)
 
 struct TcSmem {  // byte offsets from the 1024-byte aligned base
     static constexpr int hi0 = 0, hi1 = 35840, lo = 71680;          // audio tiles (34 816 rounded up to 1024)
@@ -61,12 +65,12 @@ struct TcSmem {  // byte offsets from the 1024-byte aligned base
     static constexpr int wcat = abuf + 4 * 8192;                    // [hi, lo][<= 56 rows x 128 B]
     static constexpr int xbuf = wcat + 2 * kMaxN0 * 128;            // [4 parts][64 rows][kXPitch] float
     static constexpr int pbuf = xbuf + 4 * kTileRows * kXPitch * 4; // [kPRing][ppitch] float; everything after it is placed at run time
-    // then: float2 colstat[kStatRing] | event meta int4[kEvCap] | event outputs float[kEvCap][n_out] | barriers (256 B)
+    // then: float2 colstat[kStatRing] | event meta int4[2][kEvCap] | event outputs float[2][kEvCap][n_out] | barriers (256 B)
     __host__ __device__ static constexpr int ppitch(int np) { return ((((np + 7) >> 3) << 1) | 1) << 2; }  // whole 8-float chunks + 1: an odd number of float4
     __host__ __device__ static constexpr int colstat(int np) { return pbuf + kPRing * ppitch(np) * 4; }
     __host__ __device__ static constexpr int evmeta(int np) { return colstat(np) + kStatRing * 8; }
-    __host__ __device__ static constexpr int evout(int np) { return evmeta(np) + kEvCap * 16; }
-    __host__ __device__ static constexpr int bars(int np, int n_out) { return evout(np) + kEvCap * n_out * 4; }
+    __host__ __device__ static constexpr int evout(int np) { return evmeta(np) + 2 * kEvCap * 16; }
+    __host__ __device__ static constexpr int bars(int np, int n_out) { return evout(np) + 2 * kEvCap * n_out * 4; }
     __host__ __device__ static constexpr int total(int np, int n_out) { return bars(np, n_out) + 256; }
     __host__ __device__ static constexpr int hi(int stage) { return stage ? hi1 : hi0; }
     __host__ __device__ static constexpr int a(int buf, int part) { return abuf + (buf * 2 + part) * 8192; }
@@ -175,11 +179,10 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TcSmem::bars(np, p.n_out));
     uint64_t *full = bars, *hi_free = bars + 2, *lo_ready = bars + 4, *lo_free = bars + 5, *tmem_full = bars + 6, *tmem_empty = bars + 8;
     uint64_t *a_ready = bars + 10, *a_free = bars + 12, *p_full = bars + 14, *p_empty = bars + 16;
-    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 18);
-    int *ev_count = reinterpret_cast<int *>(bars + 19);                       // events waiting in shared memory
-    unsigned long long *ev_base = reinterpret_cast<unsigned long long *>(bars + 20);
-    int4 *ev_meta = reinterpret_cast<int4 *>(smem + TcSmem::evmeta(np));      // (channel, -, eval lo, eval hi)
-    float *ev_out = reinterpret_cast<float *>(smem + TcSmem::evout(np));
+    uint64_t *ring_ready = bars + 18;                                         // [2]: an F group has written its tile's product rows
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 20);
+    int *ev_counts = reinterpret_cast<int *>(bars + 21);                      // [2] events waiting in shared memory, per F group
+    unsigned long long *ev_bases = reinterpret_cast<unsigned long long *>(bars + 22);  // [2]
     float *xbuf = reinterpret_cast<float *>(smem + TcSmem::xbuf);
     float *pbuf = reinterpret_cast<float *>(smem + TcSmem::pbuf);
     float2 *colstat = reinterpret_cast<float2 *>(smem + TcSmem::colstat(np));
@@ -195,11 +198,13 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
             ptx::mbar_init(&a_ready[i], kNumD);
             ptx::mbar_init(&a_free[i], 1);
             ptx::mbar_init(&p_full[i], 1);
-            ptx::mbar_init(&p_empty[i], kNumF);
+            ptx::mbar_init(&p_empty[i], kFGroup);
+            ptx::mbar_init(&ring_ready[i], kFGroup);
         }
         ptx::mbar_init(lo_ready, kNumS);
         ptx::mbar_init(lo_free, 1);
-        *ev_count = 0;
+        ev_counts[0] = 0;
+        ev_counts[1] = 0;
         ptx::fence_mbar_init();
     }
     if (warp == kWarpMma) {
@@ -301,6 +306,9 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
                 }
                 ptx::mma_commit(&p_full[ab]);
                 ptx::mma_commit(&a_free[ab]);
+#ifdef TC_EXP_SERIAL_P   // experiment: no MMA queued while the evaluators read P
+                ptx::mbar_wait(&p_empty[ab], ph);
+#endif
             };
             TileWalk tw;
             tw.init(w, T);
@@ -328,23 +336,31 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
         }
     } else if (warp < kWarpD0) {
         // ================================ evaluators (F) ==============================================================
-        // One warp per TMEM lane quadrant. The layer-0 accumulator is an M = 64 tile: product row c (= column c of the tile)
-        // sits in lane 32*(c/16) + c%16, so lanes 0-15 of every warp own one row each: they move it to the product ring and
-        // then evaluate the network whose newest column is c (one thread = one evaluation; T x LDS.128 for the diagonal sum).
-        const int quad = warp & 3;
-        const int ft = (warp - kWarpF0) * 32 + lane;
+        // Two groups of four warps (one warp per TMEM lane quadrant); group g takes the tiles with it % 2 == g, i.e. always the
+        // layer-0 accumulator P[g]. The accumulator is an M = 64 tile: product row c (= column c of the tile) sits in lane
+        // 32*(c/16) + c%16, so lanes 0-15 of a warp own one row each: they move it to the product ring and then evaluate the
+        // network whose newest column is c. The ring is shared by the groups: ring_ready[g] says "group g wrote its tile's rows",
+        // which also proves it finished the evaluations of its previous tile (whose rows the writer of tile it + 1 may reuse).
+        const int quad = warp & 3, grp = (warp - kWarpF0) >> 2;
+        const int ft = (warp - kWarpF0 - grp * kFGroup) * 32 + lane;   // thread index inside the group
+        const int bar_f = kBarF + grp;
+        int *ev_count = ev_counts + grp;
+        unsigned long long *ev_base = ev_bases + grp;
+        int4 *ev_meta = reinterpret_cast<int4 *>(smem + TcSmem::evmeta(np)) + grp * kEvCap;   // (channel, -, eval lo, eval hi)
+        float *ev_out = reinterpret_cast<float *>(smem + TcSmem::evout(np)) + grp * kEvCap * p.n_out;
         const int c = quad * 16 + (lane & 15);              // column of the tile this thread owns
         const bool owner = lane < 16;
         const int nchunks = (np + 7) >> 3;                  // 8-column chunks of a product row
         TileWalk tw;
         tw.init(w, T);
-        uint32_t gcol = 0;                                  // columns seen so far (ring position), all units
+        int gcol = 0;                                       // product-ring position of the tile's first column (mod kPRing)
+        uint32_t scol = 0;                                  // columns seen so far, all units (statistic ring position)
         RoleTimer<kTiming> tm(w.debug_timing, 12);
-        auto flush_events = [&](int n_ev) {                 // all F threads; one global atomic for the whole batch
+        auto flush_events = [&](int n_ev) {                 // all threads of the group; one global atomic for the whole batch
             if (ft == 0) *ev_base = atomicAdd(w.sink.count, (unsigned long long)n_ev);
-            bar_sync(kBarF, kNumF * 32);
+            bar_sync(bar_f, kFGroup * 32);
             const unsigned long long base = *ev_base;
-            for (int e = ft; e < n_ev; e += kNumF * 32) {
+            for (int e = ft; e < n_ev; e += kFGroup * 32) {
                 const unsigned long long idx = base + e;
                 if (idx < w.sink.capacity) {
                     const int4 m = ev_meta[e];
@@ -352,18 +368,28 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
                     for (int k = 0; k < p.n_out; ++k) w.sink.outputs[idx * p.n_out + k] = ev_out[e * p.n_out + k];
                 }
             }
-            bar_sync(kBarF, kNumF * 32);
+            bar_sync(bar_f, kFGroup * 32);
             if (ft == 0) *ev_count = 0;
         };
         for (uint32_t it = 0; tw.valid(); ++it, tw.next(w, T)) {
             const int ab = it & 1;
             const int frames = tw.frames();
+            if (ab != grp) {                                // the other group's tile: only keep the ring positions in step
+                gcol += frames;
+                if (gcol >= kPRing) gcol -= kPRing;
+                scol += frames;
+                continue;
+            }
             tm.wait(&p_full[ab], (it >> 1) & 1, 0);
+            // the other group has written tile it-1 (history rows) and is done with tile it-3 (whose ring rows this tile reuses)
+            if (it > 0) tm.wait(&ring_ready[grp ^ 1], ((it - 1) >> 1) & 1, 0);
             ptx::tc_fence_after();
             const long long t_f0 = tm.now();
             {   // P row -> product ring, four 8-column chunks at a time: loads in flight, one wait, then the stores
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + kColP0 + ab * kMaxN0;
-                float4 *dst = reinterpret_cast<float4 *>(pbuf + ((gcol + c) & (kPRing - 1)) * ppitch);
+                int row = gcol + c;
+                if (row >= kPRing) row -= kPRing;
+                float4 *dst = reinterpret_cast<float4 *>(pbuf + row * ppitch);
                 const bool store = owner && c < frames;
 #pragma unroll
                 for (int q0 = 0; q0 < kMaxN0 / 8; q0 += 4) {
@@ -386,38 +412,58 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
                 tm.add(3, t_f0);
                 ptx::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&p_empty[ab]);
+                if (lane == 0) {
+                    ptx::mbar_arrive(&p_empty[ab]);
+                    ptx::mbar_arrive(&ring_ready[grp]);
+                }
             }
-            tm.sync(kBarF, kNumF * 32, 1);
+            tm.sync(bar_f, kFGroup * 32, 1);
             const long long t_f1 = tm.now();
             // evaluation whose newest column is column c of this tile: unit-local index j
             const int j = tw.cols_before() - (T - 1) + c;
 #ifdef TC_EXP_SKIP_EVAL
             const bool valid = false;
 #else
-            const bool valid = owner && c < frames && j >= 0;
+            const bool valid = c < frames && j >= 0;
 #endif
+            // Lanes l and l + 16 share evaluation c: each sums half of the T columns, one shuffle round combines them, both run
+            // the (cheap) network tail and lane l stores.
             bool hit = false;
             float out[kFusedMaxOut];
-            if (valid) {
+            {
                 float acc[HP];
 #pragma unroll
                 for (int h = 0; h < HP; ++h) acc[h] = 0.0f;
                 float s0 = p.window_stat == FUSED_STAT_L2 ? 0.0f : INFINITY, s1 = -INFINITY;
-                uint32_t col = gcol + (uint32_t)(c - (T - 1));   // ring position of the evaluation's oldest column
-                const float *pt = pbuf;                          // + t * HP as the loop advances
+                if (valid) {
+                    const int th = (T + 1) >> 1, t0 = owner ? 0 : th, t1 = owner ? th : T;
+                    int row = gcol + c - (T - 1) + t0;                     // ring position of this lane's first column
+                    if (row < 0) row += kPRing;
+                    else if (row >= kPRing) row -= kPRing;
+                    uint32_t col = scol + (uint32_t)(c - (T - 1) + t0);    // same column in the statistic ring
+                    const float *pt = pbuf + t0 * HP + row * ppitch;       // advances by one ring row and one (t, :) block per step
 #pragma unroll 2
-                for (int t = 0; t < T; ++t, ++col, pt += HP) {
-                    const float4 *prow = reinterpret_cast<const float4 *>(pt + (col & (kPRing - 1)) * ppitch);
-                    const float4 v0 = prow[0];
-                    acc[0] += v0.x; acc[1] += v0.y; acc[2] += v0.z; acc[3] += v0.w;
-                    if constexpr (HP == 8) {
-                        const float4 v1 = prow[1];
-                        acc[4] += v1.x; acc[5] += v1.y; acc[6] += v1.z; acc[7] += v1.w;
+                    for (int t = t0; t < t1; ++t, ++col) {
+                        const float4 *prow = reinterpret_cast<const float4 *>(pt);
+                        pt += ppitch + HP;
+                        if (++row == kPRing) { row = 0; pt -= kPRing * ppitch; }
+                        const float4 v0 = prow[0];
+                        acc[0] += v0.x; acc[1] += v0.y; acc[2] += v0.z; acc[3] += v0.w;
+                        if constexpr (HP == 8) {
+                            const float4 v1 = prow[1];
+                            acc[4] += v1.x; acc[5] += v1.y; acc[6] += v1.z; acc[7] += v1.w;
+                        }
+                        const float2 cs = colstat[col & (kStatRing - 1)];
+                        if (p.window_stat == FUSED_STAT_L2) s0 += cs.x;
+                        else { s0 = fminf(s0, cs.x); s1 = fmaxf(s1, cs.y); }
                     }
-                    const float2 cs = colstat[col & (kStatRing - 1)];
-                    if (p.window_stat == FUSED_STAT_L2) s0 += cs.x;
-                    else { s0 = fminf(s0, cs.x); s1 = fmaxf(s1, cs.y); }
+                }
+#pragma unroll
+                for (int h = 0; h < HP; ++h) acc[h] += __shfl_xor_sync(0xffffffffu, acc[h], 16);
+                {
+                    const float o0 = __shfl_xor_sync(0xffffffffu, s0, 16), o1 = __shfl_xor_sync(0xffffffffu, s1, 16);
+                    if (p.window_stat == FUSED_STAT_L2) s0 += o0;
+                    else { s0 = fminf(s0, o0); s1 = fmaxf(s1, o1); }
                 }
                 float inv = 1.0f, beta = 0.0f;  // z = acc * inv + beta * V + B'
                 if (p.window_stat == FUSED_STAT_L2) {            // x / sqrt(sum x^2)  (NeuralNet.swift:47-59); silence: 0 * inf = NaN
@@ -432,12 +478,26 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
                 for (int h = 0; h < kFusedMaxHidden; ++h)
                     a[h] = h < HP ? transfer_fast(p.tf[0], fmaf(acc[h < HP ? h : 0], inv, fmaf(beta, p.v[h], p.bprime[h]))) : 0.0f;
                 tm.add(4, t_f1);
-                hit = network_tail(p, w.detect_rule, a, out);
-                if (w.all_out) {
-                    float *o = w.all_out + ((int64_t)tw.ch * w.out_evals_per_channel + w.eval_offset + tw.e0 + j) * p.n_out;
+                float *o = w.all_out + ((int64_t)tw.ch * w.out_evals_per_channel + w.eval_offset + tw.e0 + j) * p.n_out;
+                const bool store = valid && owner && w.all_out != nullptr;
+                if (p.n_layers == 2 && p.n_out == 1) {   // the common shape: hidden layer -> one output (NeuralNet.swift:310-323)
+                    float sacc = p.rest_b[0];
+#pragma unroll
+                    for (int h = 0; h < HP; ++h) sacc = fmaf(p.rest_w[h], a[h], sacc);
+                    float v = transfer_fast(p.tf[1], sacc);
+                    for (int k = 0; k < p.n_op; ++k)  // reverse maps in index order
+                        v = (v + (0 - p.op_y[k])) / p.op_gain[k * kFusedMaxOut] + p.op_xoff[k * kFusedMaxOut];
+                    hit = v >= p.thr_f[0];            // == (double)v >= thr (TrackDetector.swift:72); NaN -> false
+                    out[0] = v;
+                    if (store) o[0] = v;
+                } else {
+                    hit = network_tail(p, w.detect_rule, a, out);
+                    if (store) {
 #pragma unroll 1
-                    for (int k = 0; k < p.n_out; ++k) o[k] = pick(out, k);
+                        for (int k = 0; k < p.n_out; ++k) o[k] = pick(out, k);
+                    }
                 }
+                hit = hit && valid && owner;
             }
             const unsigned hits = __ballot_sync(0xffffffffu, hit);
             if (hits) {   // append to the shared-memory event buffer (room for a whole tile is guaranteed by the flush rule)
@@ -452,16 +512,18 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
                     for (int k = 0; k < p.n_out; ++k) ev_out[e * p.n_out + k] = pick(out, k);
                 }
             }
-            tm.sync(kBarF, kNumF * 32, 2);  // the next tile's rows overwrite ring rows this tile's evaluations read
+            tm.sync(bar_f, kFGroup * 32, 2);  // this group's next tile overwrites ring rows that this tile's evaluations read
             const int n_ev = *ev_count;
             if (n_ev > kEvCap - kTileFrames) flush_events(n_ev);
             gcol += frames;
+            if (gcol >= kPRing) gcol -= kPRing;
+            scol += frames;
         }
         {
             const int n_ev = *ev_count;
             if (n_ev > 0) flush_events(n_ev);
         }
-        tm.flush(ft == 0);
+        tm.flush(ft == 0 && grp == 0);
     } else if (warp < kWarpS0) {
         // ================================ spectrum warps (D) ===========================================================
         const int quad = warp & 3, dw = warp - kWarpD0, half = dw >> 2;
@@ -592,7 +654,10 @@ int tc_k_pad() { return kKPad; }
 int tc_max_n0() { return kMaxN0; }
 bool tc_layout_fits(int time_range, int n0) {
     // product ring: a tile's rows plus the T-1 before them; statistic ring: the spectrum warps run at most 4 tiles ahead
-    return n0 <= kMaxN0 && kTileFrames + time_range - 1 <= kPRing && 5 * kTileFrames + time_range <= kStatRing;
+    // product ring: the writer of tile it+2 must not touch what the evaluations of tile it+1 read (rows of it+1 and the last T-1
+    // of it): 3 * tile - 1 - ring < tile - (T - 1); statistic ring: the spectrum warps run at most 5 tiles ahead
+    return n0 <= kMaxN0 && 3 * kTileFrames - 1 - kPRing < kTileFrames - (time_range - 1) && 2 * kTileFrames + time_range <= kPRing &&
+           6 * kTileFrames + time_range <= kStatRing;
 }
 
 cudaError_t launch_tc(int hp, int grid, size_t smem, const FusedParams &p, const TcWork &w, const void *tmap_main, const void *tmap_tail,

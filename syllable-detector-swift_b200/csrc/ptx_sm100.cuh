@@ -30,9 +30,24 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
 }
+// SYLDET_MBAR_HINT (ns) > 0: pass a suspend-time hint so a waiting warp sleeps in hardware instead of re-polling.
+#ifndef SYLDET_MBAR_HINT
+#define SYLDET_MBAR_HINT 0
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     uint32_t done;
     do {
+#if SYLDET_MBAR_HINT > 0
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_addr(bar)), "r"(parity), "r"((uint32_t)SYLDET_MBAR_HINT)
+            : "memory");
+#else
         asm volatile(
             "{\n"
             ".reg .pred p;\n"
@@ -42,6 +57,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
             : "=r"(done)
             : "r"(smem_addr(bar)), "r"(parity)
             : "memory");
+#endif
     } while (!done);
 }
 

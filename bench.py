@@ -119,11 +119,16 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def dram_traffic_per_launch():
-    """dram__bytes_read.sum + dram__bytes_write.sum of the fused kernel from the committed ncu capture, if any."""
+def dram_traffic_per_launch(tensor, alg_bytes):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the active kernel from the committed `ncu --set full` capture, scaled from
+    the captured workload to this launch by the ratio of algorithmic bytes (the capture is a shorter recording)."""
     try:
-        with open(os.path.join(ROOT, "profiles", "fused_traffic.json")) as f:
-            return json.load(f)
+        with open(os.path.join(ROOT, "profiles", "tc_traffic.json" if tensor else "fused_traffic.json")) as f:
+            t = json.load(f)
+        scale = alg_bytes / float(t["algorithmic_bytes"])
+        t["bytes_per_launch"] = (t["dram_bytes_read"] + t["dram_bytes_write"]) * scale
+        t["scaled_by"] = scale
+        return t
     except Exception:
         return None
 
@@ -244,7 +249,7 @@ def run_ours(args):
         k_ms = sum(kernel_ms) / len(kernel_ms)
         alg_bytes = (4 * cfg.hop + 4 * cfg.net_outputs) * E * nch          # per launch, this rank
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-        traffic = dram_traffic_per_launch()
+        traffic = dram_traffic_per_launch(det.active_kernel == sd.KERNEL_TENSOR, alg_bytes)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

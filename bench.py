@@ -218,6 +218,30 @@ def run_ours(args):
     t_clock1 = time.perf_counter()
     d2h_bytes = len(ev_h) * (16 + 4 * cfg.net_outputs) + 8
     assert len(ev_h) == len(events) and np.array_equal(ev_h.sample, events.sample)
+    del h, h_np
+
+    # ---- the same call with 16-bit PCM (what a WAV corpus holds; converted on the device as x/32768): half the PCIe bytes ----
+    e2e16 = None
+    if not args.no_pcm16:
+        q = torch.clamp(torch.round(x * 32768.0), -32768, 32767).to(torch.int16)
+        h16 = torch.empty((nch, n), dtype=torch.int16, pin_memory=True)
+        h16.copy_(q)
+        xq = q.to(torch.float32) / 32768.0             # what the device sees after the conversion
+        del q
+        det.launch_device(xq.data_ptr(), nch, n, n, detect_rule=sd.DETECT_ANY_OUTPUT, d_outputs_ptr=None, stream=stream.cuda_stream)
+        ev_q = det.collect(debounce_frames=0)
+        del xq
+        torch.cuda.synchronize(dev)
+        h16_np = h16.numpy()
+        ev16 = det.run(h16_np)
+        assert len(ev16) == len(ev_q) and np.array_equal(ev16.sample, ev_q.sample)
+        barrier()
+        tq0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            ev16 = det.run(h16_np)
+        barrier()
+        e2e16 = (time.perf_counter() - tq0, len(ev16) * (16 + 4 * cfg.net_outputs) + 8)
+        del h16, h16_np
 
     # ---- parity spot check against the oracle on slices of this rank's recording (outside the timed regions) -----------
     parity = None
@@ -236,10 +260,10 @@ def run_ours(args):
         parity = {"max_abs_err_vs_oracle": worst, "decision_flips": flips, "evaluations_checked": 1600}
 
     # ---- reduce over ranks: max time, summed units ------------------------------------------------------------------------
-    t = torch.tensor([wall, e2e_wall, dev_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([wall, e2e_wall, dev_ms, e2e16[0] if e2e16 else 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    wall, e2e_wall, dev_ms = [float(v) for v in t.tolist()]
+    wall, e2e_wall, dev_ms, e2e16_wall = [float(v) for v in t.tolist()]
     total_audio = audio_seconds * world
     value = total_audio * args.steps / wall
     e2e_value = total_audio * e2e_steps / e2e_wall
@@ -259,17 +283,22 @@ def run_ours(args):
             "device_ms_per_step": dev_ms / args.steps,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nch * n * 4, "d2h_bytes_per_step": d2h_bytes,
                     "steps": e2e_steps, "ms_per_step": 1e3 * e2e_wall / e2e_steps,
-                    "api": "syldet_batch_run_host (pinned host float32 PCM in, debounced events out)"},
+                    "api": "syldet_batch_run_host (pinned host float32 PCM in, debounced events out; time-sliced copy/detect/collect pipeline)"},
             "gpu_launches": int(gpu_launches),
             "kernel": kernel_name,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel_ms": k_ms,
+                         "traffic": traffic["bytes_per_launch"] if traffic else None, "traffic_source": traffic,
+                         "peak_source": peak_src, "kernel_ms": k_ms,
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "note": "532 B per evaluation (4*hop audio read once + 4*outputs written); FP32 work is 9572 FLOP per "
                                  "evaluation => %.2f TFLOP/s achieved" % (9572.0 * E * nch / (k_ms * 1e-3) / 1e12)},
             "detections_per_step": int(n_det), "events_per_step": len(events), "parity": parity,
             "clocks": clocks.summary(t_clock0, t_clock1),
         }
+        if e2e16:
+            line["e2e_pcm16"] = {"value": total_audio * e2e_steps / e2e16_wall, "unit": UNIT, "h2d_bytes_per_step": nch * n * 2,
+                                 "d2h_bytes_per_step": e2e16[1], "steps": e2e_steps, "ms_per_step": 1e3 * e2e16_wall / e2e_steps,
+                                 "api": "syldet_batch_run_host with SYLDET_PCM_S16 (the same recording quantised to 16-bit PCM)"}
         if world == 1 and not args.no_cpu:
             cb = cpu_reference(args, steps=1, warmup=0)
             line["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": "port", "sample": cb["sample"],
@@ -307,6 +336,7 @@ if __name__ == "__main__":
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-step-seconds", type=float, default=None)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-pcm16", action="store_true")
     ap.add_argument("--kernel", default="auto", choices=["auto", "fused", "tensor"])
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup

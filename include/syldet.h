@@ -118,6 +118,9 @@ void syldet_batch_destroy(syldet_batch *b);
  * FUSED (SIMT FFT + fused epilogue), else the GENERIC reference-order path. */
 syldet_status syldet_batch_set_kernel(syldet_batch *b, int kernel);
 int syldet_batch_active_kernel(const syldet_batch *b);
+/* syldet_batch_run_host cuts a recording into up to 16 time slices so that the PCIe copy of slice k+1 overlaps the detection and
+ * event read-back of slice k; a slice holds at least `evals` evaluations over all channels (default 262144; tuning knob). */
+syldet_status syldet_batch_set_slice_evals(syldet_batch *b, int64_t evals);
 
 /*
  * Host buffers in, events out (H2D copy, kernels, D2H of the sparse events, host-side debounce).

@@ -84,6 +84,7 @@ def _load():
         "syldet_config_first_output_sample": (i64, [vp]), "syldet_config_num_columns": (i64, [vp, i64]),
         "syldet_config_num_evals": (i64, [vp, i64]), "syldet_config_debounce_frames": (i64, [vp, dbl]),
         "syldet_batch_create": (i32, [vp, i32, pvp]), "syldet_batch_destroy": (None, [vp]),
+        "syldet_batch_set_slice_evals": (i32, [vp, i64]),
         "syldet_batch_set_kernel": (i32, [vp, i32]), "syldet_batch_active_kernel": (i32, [vp]),
         "syldet_batch_run_host": (i32, [vp, vp, i32, i32, i64, i64, i32, i64, i32, vp, pvp]),
         "syldet_batch_launch_device": (i32, [vp, vp, i32, i64, i64, i32, i32, vp, vp]),
@@ -291,6 +292,10 @@ class BatchDetector:
     @property
     def launch_count(self):
         return lib.syldet_batch_launch_count(self._h)
+
+    def set_slice_evals(self, evals):
+        """Minimum evaluations (all channels together) per time slice of run()'s copy/detect/collect pipeline."""
+        _check(lib.syldet_batch_set_slice_evals(self._h, int(evals)))
 
     def run(self, pcm, debounce_frames=0, detect_rule=DETECT_ANY_OUTPUT, want_outputs=False, layout=LAYOUT_PLANAR):
         """pcm: host array, planar [n_channels, n_samples] (or interleaved [n_samples, n_channels]); float32 or int16.

@@ -158,6 +158,11 @@ syldet_status syldet_batch_set_kernel(syldet_batch *b, int kernel) {
     return b->b.set_kernel(kernel);
 }
 int syldet_batch_active_kernel(const syldet_batch *b) { return b ? b->b.active_kernel() : -1; }
+syldet_status syldet_batch_set_slice_evals(syldet_batch *b, int64_t evals) {
+    if (!b || evals <= 0) return set_error(SYLDET_ERR_ARG, "slice size must be positive");
+    b->b.set_slice_evals(evals);
+    return SYLDET_OK;
+}
 
 syldet_status syldet_batch_run_host(syldet_batch *b, const void *pcm, int pcm_format, int n_channels, int64_t n_samples,
                                     int64_t channel_stride, int layout, int64_t debounce_frames, int detect_rule,

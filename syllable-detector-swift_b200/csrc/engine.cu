@@ -3,7 +3,9 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
@@ -378,6 +380,12 @@ Batch::~Batch() {
         cudaSetDevice(model_.device());
         cudaStreamDestroy(own_stream_);
     }
+    if (copy_stream_) cudaStreamDestroy(copy_stream_);
+    if (d2h_stream_) cudaStreamDestroy(d2h_stream_);
+    for (cudaEvent_t e : ev_copied_) cudaEventDestroy(e);
+    for (cudaEvent_t e : ev_done_) cudaEventDestroy(e);
+    if (h_counts_) cudaFreeHost(h_counts_);
+    if (h_events_) cudaFreeHost(h_events_);
 }
 
 syldet_status Batch::set_kernel(int kernel) {
@@ -456,8 +464,9 @@ syldet_status Batch::launch_fused_range(const float *d_planar, int n_channels, i
     return SYLDET_OK;
 }
 
-syldet_status Batch::launch_tc_range(const float *d_planar, int n_channels, int64_t n_samples, int64_t ch_stride, int64_t eval_count,
-                                     int64_t evals_total, int detect_rule, float *d_all_outputs, EventSink sink, cudaStream_t stream) {
+syldet_status Batch::launch_tc_range(const float *d_planar, int n_channels, int64_t n_samples, int64_t ch_stride, int64_t eval_offset,
+                                     int64_t eval_count, int64_t evals_total, int detect_rule, float *d_all_outputs, EventSink sink,
+                                     cudaStream_t stream) {
     const Config &c = model_.config();
     const TcPlan &tp = model_.tc();
     EncodeTiledFn encode = encode_tiled_fn();
@@ -479,7 +488,7 @@ syldet_status Batch::launch_tc_range(const float *d_planar, int n_channels, int6
     TcWork w{};
     w.n_channels = n_channels;
     w.evals_per_channel = eval_count;
-    w.eval_offset = 0;
+    w.eval_offset = eval_offset;   // d_planar already points at the first sample of evaluation eval_offset
     w.out_evals_per_channel = evals_total;
     const int resident = model_.sm_count();
     // a unit covers whole tiles: chunk = n_tiles * tile_frames - (T - 1) evaluations (the first T-1 columns of a unit only warm
@@ -536,37 +545,50 @@ syldet_status Batch::launch_tc_range(const float *d_planar, int n_channels, int6
 syldet_status Batch::launch_planar(const float *d_planar, int n_channels, int64_t n_samples, int64_t ch_stride,
                                    const float *valid_begin, const float *valid_end, int detect_rule, float *d_all_outputs,
                                    cudaStream_t stream) {
+    const int64_t E = model_.config().num_evals(n_samples);
+    return launch_planar_range(d_planar, n_channels, n_samples, n_samples, ch_stride, valid_begin, valid_end, 0, E, detect_rule,
+                               d_all_outputs, true, stream);
+}
+
+// Evaluations [eval_begin, eval_begin + eval_count) of a planar buffer whose first n_avail samples per channel are present
+// (n_samples is the length of the whole recording: it fixes the evaluation count and the pitch of the dense outputs).
+syldet_status Batch::launch_planar_range(const float *d_planar, int n_channels, int64_t n_samples, int64_t n_avail, int64_t ch_stride,
+                                         const float *valid_begin, const float *valid_end, int64_t eval_begin, int64_t eval_count,
+                                         int detect_rule, float *d_all_outputs, bool reset_sink, cudaStream_t stream) {
     const Config &c = model_.config();
     const int64_t E = c.num_evals(n_samples);
-    SYLDET_CUDA(cudaMemsetAsync(sink_count_.get(), 0, sizeof(unsigned long long), stream));
-    if (E <= 0) return SYLDET_OK;
+    if (reset_sink) SYLDET_CUDA(cudaMemsetAsync(sink_count_.get(), 0, sizeof(unsigned long long), stream));
+    if (eval_count <= 0) return SYLDET_OK;
     EventSink sink{sink_count_.as<unsigned long long>(), sink_events_.as<DevEvent>(), sink_outputs_.as<float>(), sink_capacity_};
 
     const int kernel = active_kernel();
     if (kernel == SYLDET_KERNEL_TENSOR) {
         // evaluations whose rows [e, e+T] are all complete hop-rows go to the tensor-core kernel; the last few (and inputs
         // whose base/pitch are not 16-byte aligned) go to the SIMT fused kernel
-        const int64_t n_rows = n_samples / c.hop;
-        const bool aligned = ((uintptr_t)d_planar % 16 == 0) && (ch_stride % 4 == 0 || n_channels == 1);
-        const int64_t e_tc = aligned ? std::max<int64_t>(0, std::min<int64_t>(E, n_rows - c.time_range)) : 0;
+        const float *base = d_planar + eval_begin * c.hop;
+        const int64_t n_rows = (n_avail - eval_begin * c.hop) / c.hop;
+        const bool aligned = ((uintptr_t)base % 16 == 0) && (ch_stride % 4 == 0 || n_channels == 1);
+        const int64_t e_tc = aligned ? std::max<int64_t>(0, std::min<int64_t>(eval_count, n_rows - c.time_range)) : 0;
         if (e_tc > 0) {
-            syldet_status st = launch_tc_range(d_planar, n_channels, n_samples, ch_stride, e_tc, E, detect_rule, d_all_outputs, sink, stream);
+            syldet_status st = launch_tc_range(base, n_channels, n_avail - eval_begin * c.hop, ch_stride, eval_begin, e_tc, E, detect_rule,
+                                               d_all_outputs, sink, stream);
             if (st != SYLDET_OK) return st;
         }
-        if (e_tc < E)
-            return launch_fused_range(d_planar, n_channels, ch_stride, valid_begin, valid_end, e_tc, E - e_tc, E, detect_rule,
-                                      d_all_outputs, sink, stream);
+        if (e_tc < eval_count)
+            return launch_fused_range(d_planar, n_channels, ch_stride, valid_begin, valid_end, eval_begin + e_tc, eval_count - e_tc, E,
+                                      detect_rule, d_all_outputs, sink, stream);
         return SYLDET_OK;
     }
     if (kernel == SYLDET_KERNEL_FUSED)
-        return launch_fused_range(d_planar, n_channels, ch_stride, valid_begin, valid_end, 0, E, E, detect_rule, d_all_outputs, sink, stream);
+        return launch_fused_range(d_planar, n_channels, ch_stride, valid_begin, valid_end, eval_begin, eval_count, E, detect_rule,
+                                  d_all_outputs, sink, stream);
 
     // generic two-kernel path, segmented in time so the band-feature buffer stays bounded
     const int L = c.band, T = c.time_range;
     const int64_t budget_cols = std::max<int64_t>(T + 1, (int64_t)(512ll << 20) / ((int64_t)n_channels * L * 4));
     const int64_t seg = std::max<int64_t>(1, budget_cols - (T - 1));
-    for (int64_t e0 = 0; e0 < E; e0 += seg) {
-        const int64_t ne = std::min(seg, E - e0), ncols = ne + T - 1;
+    for (int64_t e0 = eval_begin; e0 < eval_begin + eval_count; e0 += seg) {
+        const int64_t ne = std::min(seg, eval_begin + eval_count - e0), ncols = ne + T - 1;
         syldet_status st = feat_.reserve((size_t)n_channels * ncols * L * sizeof(float));
         if (st != SYLDET_OK) return st;
         SYLDET_CUDA(launch_stft_band_generic(model_.dev_net(), c.fourier_length, d_planar, ch_stride, n_channels, e0, ncols,
@@ -618,6 +640,15 @@ syldet_status Batch::last_detection_count(int64_t *count) {
     return SYLDET_OK;
 }
 
+namespace {
+// SYLDET_E2E_TIMING=1: host-side phase times of run_host / collect on stderr (debugging aid, adds synchronisation points)
+bool e2e_timing() {
+    static const bool on = std::getenv("SYLDET_E2E_TIMING") != nullptr;
+    return on;
+}
+double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+}  // namespace
+
 syldet_status Batch::collect(int64_t debounce_frames, Events &out) {
     if (!last_.valid) return set_error(SYLDET_ERR_ARG, "collect without a launch");
     if (debounce_frames < 0) return set_error(SYLDET_ERR_ARG, "negative debounce");
@@ -625,7 +656,9 @@ syldet_status Batch::collect(int64_t debounce_frames, Events &out) {
     if (st != SYLDET_OK) return st;
     const Config &c = model_.config();
     const int O = c.outputs;
+    const double t_c0 = now_ms();
     SYLDET_CUDA(cudaStreamSynchronize(last_.stream));
+    const double t_c1 = now_ms();
     unsigned long long n = 0;
     SYLDET_CUDA(cudaMemcpy(&n, sink_count_.get(), sizeof n, cudaMemcpyDeviceToHost));
     if (n > sink_capacity_) {  // more detections than the event buffer holds: grow to the worst case and replay
@@ -645,6 +678,7 @@ syldet_status Batch::collect(int64_t debounce_frames, Events &out) {
         SYLDET_CUDA(cudaMemcpy(ev.data(), sink_events_.get(), n * sizeof(DevEvent), cudaMemcpyDeviceToHost));
         SYLDET_CUDA(cudaMemcpy(outs.data(), sink_outputs_.get(), outs.size() * sizeof(float), cudaMemcpyDeviceToHost));
     }
+    const double t_c2 = now_ms();
     std::vector<size_t> order(n);
     std::iota(order.begin(), order.end(), (size_t)0);
     std::sort(order.begin(), order.end(), [&](size_t a, size_t b) {
@@ -659,10 +693,40 @@ syldet_status Batch::collect(int64_t debounce_frames, Events &out) {
         out.rows[r] = syldet_event{e.channel, 0, first + (int64_t)c.hop * e.eval};  // TrackDetector.swift:39-42,67-68
         std::copy(outs.begin() + order[r] * O, outs.begin() + (order[r] + 1) * O, out.outputs.begin() + r * O);
     }
+    const double t_c3 = now_ms();
     debounce_sorted(c, out.rows, out.outputs, O, debounce_frames);
+    if (e2e_timing())
+        std::fprintf(stderr, "[syldet e2e] collect: wait %.2f ms, event d2h %.2f ms (%llu events), sort+rows %.2f ms, debounce %.2f ms\n", t_c1 - t_c0,
+                     t_c2 - t_c1, n, t_c3 - t_c2, now_ms() - t_c3);
     return SYLDET_OK;
 }
 
+constexpr int kMaxSlices = 16;
+
+syldet_status Batch::ensure_pipeline(int slices, size_t event_bytes) {
+    if (!copy_stream_) SYLDET_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+    if (!d2h_stream_) SYLDET_CUDA(cudaStreamCreateWithFlags(&d2h_stream_, cudaStreamNonBlocking));
+    while ((int)ev_copied_.size() < slices) {
+        cudaEvent_t a = nullptr, b = nullptr;
+        SYLDET_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        ev_copied_.push_back(a);
+        SYLDET_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        ev_done_.push_back(b);
+    }
+    if (!h_counts_) SYLDET_CUDA(cudaMallocHost(&h_counts_, kMaxSlices * sizeof(unsigned long long)));
+    if (event_bytes > h_events_bytes_) {
+        if (h_events_) cudaFreeHost(h_events_);
+        h_events_ = nullptr;
+        h_events_bytes_ = 0;
+        SYLDET_CUDA(cudaMallocHost(&h_events_, event_bytes));
+        h_events_bytes_ = event_bytes;
+    }
+    return SYLDET_OK;
+}
+
+// The host entry point (what TrackDetector.process + the main.swift loop do for every track, TrackDetector.swift:45-105).
+// The recording is cut into time slices: slice k+1 crosses PCIe while slice k is detected and its events are read back and
+// sorted on the host, so everything except the copy itself hides behind the copy.
 syldet_status Batch::run_host(const void *pcm, int fmt, int n_channels, int64_t n_samples, int64_t ch_stride, int layout,
                               int64_t debounce_frames, int detect_rule, float *all_outputs, Events &out) {
     if (!pcm || n_channels <= 0 || n_samples < 0) return set_error(SYLDET_ERR_ARG, "bad pcm arguments");
@@ -670,42 +734,155 @@ syldet_status Batch::run_host(const void *pcm, int fmt, int n_channels, int64_t 
     if (fmt != SYLDET_PCM_F32 && fmt != SYLDET_PCM_S16) return set_error(SYLDET_ERR_ARG, "unknown pcm format");
     if (layout != SYLDET_LAYOUT_PLANAR && layout != SYLDET_LAYOUT_INTERLEAVED) return set_error(SYLDET_ERR_ARG, "unknown layout");
     if (layout == SYLDET_LAYOUT_PLANAR && n_channels > 1 && ch_stride < n_samples) return set_error(SYLDET_ERR_ARG, "channel_stride < n_samples");
+    if (debounce_frames < 0) return set_error(SYLDET_ERR_ARG, "negative debounce");
     syldet_status st = use_device(model_.device());
     if (st != SYLDET_OK) return st;
     const Config &c = model_.config();
+    const int O = c.outputs;
     const int64_t E = c.num_evals(n_samples);
     const int64_t pitch = (n_samples + 3) & ~(int64_t)3;
     st = planar_.reserve(std::max<size_t>(16, (size_t)n_channels * pitch * sizeof(float)));
     if (st != SYLDET_OK) return st;
     const size_t esz = fmt == SYLDET_PCM_S16 ? 2 : 4;
-    cudaStream_t s = own_stream_;
-    if (n_samples > 0) {
-        if (fmt == SYLDET_PCM_F32 && layout == SYLDET_LAYOUT_PLANAR) {
-            SYLDET_CUDA(cudaMemcpy2DAsync(planar_.get(), pitch * 4, pcm, (n_channels > 1 ? ch_stride : n_samples) * 4, n_samples * 4,
-                                          n_channels, cudaMemcpyHostToDevice, s));
-        } else {
-            const bool inter = layout == SYLDET_LAYOUT_INTERLEAVED;
-            const int64_t src_stride = inter ? 0 : (n_channels > 1 ? ch_stride : n_samples);
-            const size_t src_elems = inter ? (size_t)n_channels * n_samples : (size_t)(n_channels - 1) * src_stride + n_samples;
-            st = staging_.reserve(src_elems * esz);
-            if (st != SYLDET_OK) return st;
-            SYLDET_CUDA(cudaMemcpyAsync(staging_.get(), pcm, src_elems * esz, cudaMemcpyHostToDevice, s));
-            SYLDET_CUDA(launch_ingest(staging_.get(), fmt, inter ? 1 : 0, n_channels, n_samples, src_stride, planar_.as<float>(), pitch, s));
-            launches_ += 1;
-        }
+    const bool direct = fmt == SYLDET_PCM_F32 && layout == SYLDET_LAYOUT_PLANAR;   // lands in the planar buffer as is
+    const bool inter = layout == SYLDET_LAYOUT_INTERLEAVED;
+    const int64_t src_stride = inter ? 0 : (n_channels > 1 ? ch_stride : n_samples);
+    if (!direct && n_samples > 0) {
+        const size_t src_elems = inter ? (size_t)n_channels * n_samples : (size_t)(n_channels - 1) * src_stride + n_samples;
+        st = staging_.reserve(src_elems * esz);
+        if (st != SYLDET_OK) return st;
+    }
+    const unsigned long long total = (unsigned long long)E * n_channels;
+    if (sink_capacity_ == 0 || !last_.valid || last_.n_channels != n_channels || last_.n_samples != n_samples) {
+        st = ensure_sink(std::max<unsigned long long>(1, std::min<unsigned long long>(total, std::max<unsigned long long>(1ull << 20, total / 8))));
+        if (st != SYLDET_OK) return st;
     }
     DeviceBuffer d_outs;
     if (all_outputs && E > 0) {
-        st = d_outs.reserve((size_t)n_channels * E * c.outputs * sizeof(float));
+        st = d_outs.reserve((size_t)n_channels * E * O * sizeof(float));
         if (st != SYLDET_OK) return st;
     }
-    st = launch_device(planar_.as<float>(), n_channels, n_samples, pitch, SYLDET_LAYOUT_PLANAR, detect_rule,
-                       all_outputs && E > 0 ? d_outs.as<float>() : nullptr, s);
+    float *d_all = all_outputs && E > 0 ? d_outs.as<float>() : nullptr;
+
+    // ---- slices: evaluations [eb[k], eb[k+1]) become launchable once samples [0, sb[k+1]) are on the device ----------------
+    int K = (int)std::min<int64_t>(kMaxSlices, std::max<int64_t>(1, (int64_t)total / slice_evals_));
+    while (K > 1 && E / K < 4 * (int64_t)c.time_range + 16) --K;   // a slice is at least a few feature windows long
+    int64_t eb[kMaxSlices + 1], sb[kMaxSlices + 1];
+    sb[0] = 0;
+    for (int k = 0; k <= K; ++k) eb[k] = k == K ? E : ((E * k / K) & ~(int64_t)3);   // multiples of 4: 16-byte aligned slice starts
+    for (int k = 1; k <= K; ++k) {
+        // everything evaluations < eb[k] read, and their T+1 hop-rows complete (the tensor-core kernel's tile rule)
+        const int64_t need = std::max<int64_t>(c.samples_for_evals(eb[k]), (eb[k] + c.time_range + 1) * (int64_t)c.hop);
+        sb[k] = k == K ? n_samples : std::min<int64_t>(n_samples, (need + 3) & ~(int64_t)3);
+    }
+    st = ensure_pipeline(K, (size_t)sink_capacity_ * (sizeof(DevEvent) + sizeof(float) * O));
     if (st != SYLDET_OK) return st;
-    st = collect(debounce_frames, out);
-    if (st != SYLDET_OK) return st;
-    if (all_outputs && E > 0)
-        SYLDET_CUDA(cudaMemcpy(all_outputs, d_outs.get(), (size_t)n_channels * E * c.outputs * sizeof(float), cudaMemcpyDeviceToHost));
+    cudaStream_t sx = own_stream_;
+    last_ = Last{true, planar_.as<float>(), n_channels, n_samples, pitch, SYLDET_LAYOUT_PLANAR, detect_rule, d_all, sx};
+    const double t_start = now_ms();
+    float *planar = planar_.as<float>();
+    for (int k = 0; k < K; ++k) {
+        const int64_t s0 = sb[k], ns = sb[k + 1] - sb[k];
+        if (ns > 0) {
+            if (direct) {
+                SYLDET_CUDA(cudaMemcpy2DAsync(planar + s0, pitch * 4, (const float *)pcm + s0, src_stride * 4, ns * 4, n_channels,
+                                              cudaMemcpyHostToDevice, copy_stream_));
+            } else if (inter) {
+                SYLDET_CUDA(cudaMemcpyAsync((char *)staging_.get() + (size_t)s0 * n_channels * esz, (const char *)pcm + (size_t)s0 * n_channels * esz,
+                                            (size_t)ns * n_channels * esz, cudaMemcpyHostToDevice, copy_stream_));
+            } else {
+                SYLDET_CUDA(cudaMemcpy2DAsync((char *)staging_.get() + (size_t)s0 * esz, src_stride * esz, (const char *)pcm + (size_t)s0 * esz,
+                                              src_stride * esz, ns * esz, n_channels, cudaMemcpyHostToDevice, copy_stream_));
+            }
+        }
+        SYLDET_CUDA(cudaEventRecord(ev_copied_[k], copy_stream_));
+        SYLDET_CUDA(cudaStreamWaitEvent(sx, ev_copied_[k], 0));
+        if (!direct && ns > 0) {
+            const char *src = (const char *)staging_.get() + (inter ? (size_t)s0 * n_channels * esz : (size_t)s0 * esz);
+            SYLDET_CUDA(launch_ingest(src, fmt, inter ? 1 : 0, n_channels, ns, src_stride, planar + s0, pitch, sx));
+            launches_ += 1;
+        }
+        st = launch_planar_range(planar, n_channels, n_samples, sb[k + 1], pitch, planar, planar + (size_t)n_channels * pitch, eb[k],
+                                 eb[k + 1] - eb[k], detect_rule, d_all, k == 0, sx);
+        if (st != SYLDET_OK) return st;
+        SYLDET_CUDA(cudaMemcpyAsync(h_counts_ + k, sink_count_.get(), sizeof(unsigned long long), cudaMemcpyDeviceToHost, sx));
+        SYLDET_CUDA(cudaEventRecord(ev_done_[k], sx));
+    }
+
+    // ---- per slice: wait, read its events back, sort them by (channel, evaluation) while later slices are still in flight ----
+    struct Key {
+        uint64_t key;
+        uint32_t idx;
+    };
+    DevEvent *h_ev = static_cast<DevEvent *>(h_events_);
+    float *h_out = reinterpret_cast<float *>(h_ev + sink_capacity_);
+    std::vector<std::vector<Key>> sorted(K);
+    unsigned long long done = 0;
+    bool overflow = false;
+    double t_copied = 0.0;
+    for (int k = 0; k < K; ++k) {
+        SYLDET_CUDA(cudaEventSynchronize(ev_done_[k]));
+        if (k == K - 1) t_copied = now_ms();
+        const unsigned long long n_k = h_counts_[k];
+        if (n_k > sink_capacity_) {
+            overflow = true;
+            break;
+        }
+        const unsigned long long m = n_k - done;
+        if (m == 0) continue;
+        SYLDET_CUDA(cudaMemcpyAsync(h_ev + done, sink_events_.as<DevEvent>() + done, m * sizeof(DevEvent), cudaMemcpyDeviceToHost, d2h_stream_));
+        SYLDET_CUDA(cudaMemcpyAsync(h_out + done * O, sink_outputs_.as<float>() + done * O, m * O * sizeof(float), cudaMemcpyDeviceToHost,
+                                    d2h_stream_));
+        SYLDET_CUDA(cudaStreamSynchronize(d2h_stream_));
+        std::vector<Key> &keys = sorted[k];
+        keys.resize(m);
+        for (unsigned long long i = 0; i < m; ++i) {
+            const DevEvent &e = h_ev[done + i];
+            keys[i] = Key{((uint64_t)(uint32_t)e.channel << 40) | (uint64_t)e.eval, (uint32_t)(done + i)};
+        }
+        std::sort(keys.begin(), keys.end(), [](const Key &a, const Key &b) { return a.key < b.key; });
+        done = n_k;
+    }
+    if (overflow) {
+        // more detections than the event buffer holds: the recording is resident by now, so collect() grows the buffer to the
+        // worst case and replays the launch in one piece
+        SYLDET_CUDA(cudaStreamSynchronize(sx));
+        st = launch_device(planar, n_channels, n_samples, pitch, SYLDET_LAYOUT_PLANAR, detect_rule, d_all, sx);
+        if (st != SYLDET_OK) return st;
+        st = collect(debounce_frames, out);
+        if (st != SYLDET_OK) return st;
+    } else {
+        // ---- merge: slices are consecutive in time, so per channel the slices' groups simply follow each other ---------------
+        const double t_m0 = now_ms();
+        out.outputs_per_event = O;
+        out.rows.resize(done);
+        out.outputs.resize((size_t)done * O);
+        const int64_t first = c.first_output_sample();
+        std::vector<size_t> pos(K, 0);
+        size_t r = 0;
+        for (int ch = 0; ch < n_channels && r < done; ++ch) {
+            const uint64_t ch_end = (uint64_t)(ch + 1) << 40;
+            for (int k = 0; k < K; ++k) {
+                const std::vector<Key> &keys = sorted[k];
+                size_t i = pos[k];
+                for (; i < keys.size() && keys[i].key < ch_end; ++i, ++r) {
+                    const DevEvent &e = h_ev[keys[i].idx];
+                    out.rows[r] = syldet_event{e.channel, 0, first + (int64_t)c.hop * e.eval};  // TrackDetector.swift:39-42,67-68
+                    for (int o = 0; o < O; ++o) out.outputs[r * O + o] = h_out[(size_t)keys[i].idx * O + o];
+                }
+                pos[k] = i;
+            }
+        }
+        const double t_m1 = now_ms();
+        debounce_sorted(c, out.rows, out.outputs, O, debounce_frames);
+        if (e2e_timing())
+            std::fprintf(stderr, "[syldet e2e] %d slices: last slice done %.2f ms after start; tail: sort %.2f ms, merge %.2f ms, debounce %.2f ms (%llu events)\n",
+                         K, t_copied - t_start, t_m0 - t_copied, t_m1 - t_m0, now_ms() - t_m1, done);
+    }
+    if (all_outputs && E > 0) {
+        SYLDET_CUDA(cudaStreamSynchronize(sx));
+        SYLDET_CUDA(cudaMemcpy(all_outputs, d_outs.get(), (size_t)n_channels * E * O * sizeof(float), cudaMemcpyDeviceToHost));
+    }
     return SYLDET_OK;
 }
 

@@ -115,6 +115,7 @@ public:
     syldet_status collect(int64_t debounce_frames, Events &out);
     syldet_status last_detection_count(int64_t *count);
     int64_t launch_count() const { return launches_; }
+    void set_slice_evals(int64_t evals) { slice_evals_ = evals; }
     void set_debug_band(float *d_band, int64_t cols) { debug_band_ = d_band; debug_cols_ = cols; }
     const DeviceModel &model() const { return model_; }
 
@@ -126,12 +127,24 @@ private:
     syldet_status launch_fused_range(const float *d_planar, int n_channels, int64_t ch_stride, const float *valid_begin,
                                      const float *valid_end, int64_t eval_begin, int64_t eval_count, int64_t evals_total,
                                      int detect_rule, float *d_all_outputs, EventSink sink, cudaStream_t stream);
-    syldet_status launch_tc_range(const float *d_planar, int n_channels, int64_t n_samples, int64_t ch_stride, int64_t eval_count,
-                                  int64_t evals_total, int detect_rule, float *d_all_outputs, EventSink sink, cudaStream_t stream);
+    syldet_status launch_tc_range(const float *d_planar, int n_channels, int64_t n_samples, int64_t ch_stride, int64_t eval_offset,
+                                  int64_t eval_count, int64_t evals_total, int detect_rule, float *d_all_outputs, EventSink sink,
+                                  cudaStream_t stream);
+    syldet_status launch_planar_range(const float *d_planar, int n_channels, int64_t n_samples, int64_t n_avail, int64_t ch_stride,
+                                      const float *valid_begin, const float *valid_end, int64_t eval_begin, int64_t eval_count,
+                                      int detect_rule, float *d_all_outputs, bool reset_sink, cudaStream_t stream);
+    syldet_status ensure_pipeline(int slices, size_t event_bytes);
 
     DeviceModel model_;
     int kernel_ = SYLDET_KERNEL_AUTO;
     cudaStream_t own_stream_ = nullptr;
+    // run_host pipeline: time slices are copied on copy_stream_, detected on own_stream_, their events read back on d2h_stream_
+    cudaStream_t copy_stream_ = nullptr, d2h_stream_ = nullptr;
+    std::vector<cudaEvent_t> ev_copied_, ev_done_;
+    unsigned long long *h_counts_ = nullptr;   // pinned, one running event count per slice
+    void *h_events_ = nullptr;                 // pinned: DevEvent[capacity] then float[capacity][outputs]
+    size_t h_events_bytes_ = 0;
+    int64_t slice_evals_ = 256 * 1024;
     DeviceBuffer planar_, feat_, sink_count_, sink_events_, sink_outputs_, staging_;
     unsigned long long sink_capacity_ = 0;
     int64_t launches_ = 0;

@@ -213,6 +213,32 @@ def test_pcm16_and_interleaved_ingest(sd, cfg, synth):
         assert np.array_equal(o, out_ref) and np.array_equal(e.sample, ev_ref.sample) and np.array_equal(e.channel, ev_ref.channel)
 
 
+@pytest.mark.parametrize("kernel_name", ["KERNEL_TENSOR", "KERNEL_FUSED", "KERNEL_GENERIC"])
+def test_run_host_time_slices_are_invisible(sd, cfg, orc, synth, kernel_name):
+    """run() pipelines the recording in time slices (copy of slice k+1 over detection of slice k): events, outputs and the
+    debounce must not depend on the slicing, for every input format; one channel is checked against the oracle."""
+    x = synth.make_audio(3, 44100 * 6 + 77, seed=21) * 4.0
+    s16 = np.clip(np.round(x * 32768.0), -32768, 32767).astype(np.int16)
+    xq = (s16.astype(np.float32) / 32768.0).astype(np.float32)
+    det = sd.BatchDetector(cfg, kernel=getattr(sd, kernel_name))
+    det.set_slice_evals(1 << 40)                       # one slice
+    ev1, out1 = det.run(xq, want_outputs=True, debounce_frames=700)
+    assert len(ev1) > 10
+    _check_channel(orc, xq[1], out1[1], ev1.sample[ev1.channel == 1], 1e-5, debounce=700)
+    for slice_evals in (600, 5000):                    # 16 slices (the cap), then 1 slice per ~5000 evaluations
+        det.set_slice_evals(slice_evals)
+        for pcm, layout in ((xq, sd.LAYOUT_PLANAR), (s16, sd.LAYOUT_PLANAR), (np.ascontiguousarray(xq.T), sd.LAYOUT_INTERLEAVED),
+                            (np.ascontiguousarray(s16.T), sd.LAYOUT_INTERLEAVED)):
+            ev, out = det.run(pcm, want_outputs=True, debounce_frames=700, layout=layout)
+            assert np.array_equal(out, out1)
+            assert np.array_equal(ev.sample, ev1.sample) and np.array_equal(ev.channel, ev1.channel)
+            assert np.array_equal(ev.outputs, ev1.outputs)
+    # a strided planar source (channel_stride > n_samples is what a caller with padded rows passes) and no events at all
+    det.set_slice_evals(600)
+    ev0 = det.run(np.zeros((2, 44100), np.float32))
+    assert len(ev0) == 0
+
+
 def test_syllable_detector_api_matches_oracle(sd, cfg, orc, synth):
     """class SyllableDetector: appendAudioData / processNewValue / lastOutputs / lastDetected with ragged buffers."""
     x = synth.make_audio(1, 44100 * 2, seed=14)[0]

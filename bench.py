@@ -133,6 +133,24 @@ def dram_traffic_per_launch(tensor, alg_bytes):
         return None
 
 
+def stream_latency(args):
+    """BASELINE config 5: 64 live channels, 32-frame buffers, sample.txt network; per-buffer latency (submit -> outputs and
+    `seen` flags host-visible) measured by the C++ driver cli/syldet_stream_bench.cpp through syldet_stream_submit."""
+    import subprocess
+    exe = os.path.join(ROOT, "syllable-detector-swift_b200", "syldet_stream_bench")
+    try:
+        r = subprocess.run([exe, "-n", SAMPLE_TXT, "-c", str(args.stream_channels), "-b", str(args.stream_buffer),
+                            "-s", str(args.stream_seconds), "-p", str(args.stream_paced_seconds),
+                            "-d", os.environ.get("LOCAL_RANK", "0")], capture_output=True, text=True, timeout=600)
+        if r.returncode != 0:
+            return {"error": (r.stderr or r.stdout)[-300:]}
+        d = json.loads(r.stdout)
+        d["api"] = "syldet_stream_submit (one stream_tick_kernel launch per tick that completes an STFT column; samples pulled from and outputs written to pinned host memory by the kernel)"
+        return d
+    except Exception as e:  # noqa: BLE001 - the bench line must still print
+        return {"error": repr(e)[:300]}
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 def run_ours(args):
     import numpy as np
@@ -303,6 +321,8 @@ def run_ours(args):
             cb = cpu_reference(args, steps=1, warmup=0)
             line["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": "port", "sample": cb["sample"],
                                     "frames_per_s": cb["frames_per_s"]}
+        if world == 1 and not args.no_stream:
+            line["stream"] = stream_latency(args)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -338,6 +358,11 @@ if __name__ == "__main__":
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-pcm16", action="store_true")
     ap.add_argument("--kernel", default="auto", choices=["auto", "fused", "tensor"])
+    ap.add_argument("--no-stream", action="store_true")
+    ap.add_argument("--stream-channels", type=int, default=64)
+    ap.add_argument("--stream-buffer", type=int, default=32)
+    ap.add_argument("--stream-seconds", type=float, default=60.0)
+    ap.add_argument("--stream-paced-seconds", type=float, default=5.0)
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     if a.cpu_step_seconds is None:

@@ -60,6 +60,14 @@ def build(force=False, verbose=False):
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd)
+    for name in ("syldet_stream_bench",):
+        src = os.path.join(HERE, "..", "cli", name + ".cpp")
+        out = os.path.join(HERE, name)
+        if force or _stale(out, [src, OUT]):
+            cmd = ["g++", "-O2", "-std=c++17", "-Wall", src, "-o", out, "-L" + HERE, "-lsyldet_cuda", "-Wl,-rpath,$ORIGIN"]
+            if verbose:
+                print(" ".join(cmd), flush=True)
+            subprocess.check_call(cmd)
     return OUT
 
 

@@ -273,6 +273,8 @@ syldet_status DeviceModel::init(const Config &cfg, int device) {
     put_proc(cfg_.input_processing, ixo, ig);
     put_proc(cfg_.output_processing, oxo, og);
 
+    blob.resize((blob.size() + 15) & ~(size_t)15);
+    blob_bytes_ = blob.size();
     st = d_blob_.reserve(blob.size());
     if (st != SYLDET_OK) return st;
     SYLDET_CUDA(cudaMemcpy(d_blob_.get(), blob.data(), blob.size(), cudaMemcpyHostToDevice));

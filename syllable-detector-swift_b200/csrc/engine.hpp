@@ -85,11 +85,14 @@ public:
     const float *wcat_hi() const { return d_dft_.as<float>() + 2 * 128 * (size_t)tc_k_pad(); }
     const float *wcat_lo() const { return wcat_hi() + (size_t)tc_.n0 * 32; }
     int sm_count() const { return sm_count_; }
+    const unsigned char *blob() const { return d_blob_.as<unsigned char>(); }
+    size_t blob_bytes() const { return blob_bytes_; }
 
 private:
     Config cfg_;
     int device_ = -1, max_width_ = 0, sm_count_ = 148;
     DeviceBuffer d_blob_, d_net_, d_dft_;
+    size_t blob_bytes_ = 0;
     TcPlan tc_;
     const float *d_window_ = nullptr;
     const float2 *d_twiddle_ = nullptr;

@@ -16,6 +16,32 @@ cudaError_t launch_nn_generic(const DevNet *d_net, int max_width, const float *f
                               int64_t n_evals, int64_t eval0, int64_t evals_total, int detect_rule, float *all_out,
                               EventSink sink, cudaStream_t stream);
 
+// ---- live tick: kernels_generic.cu (stream_tick_kernel) ------------------------------------------------------------
+enum { STREAM_PHASE_COPY = 1, STREAM_PHASE_COLUMNS = 2, STREAM_PHASE_EVALS = 4, STREAM_PHASE_ALL = 7 };
+struct StreamTick {
+    const float *staged;   // pinned host memory (device-visible) [n_channels][stage_pitch]: samples not yet on the device
+    int stage_pitch, n_staged;
+    float *ring;           // device [n_channels][ring_mask + 1] circular sample history
+    int64_t ring_mask;     // capacity - 1 (power of two)
+    int64_t ring_pos;      // absolute index of the first staged sample
+    float *band;           // device [n_channels][band_mask + 1][band] circular band-feature columns
+    int64_t band_mask;
+    int64_t col0, n_cols;  // STFT columns this tick completes
+    int64_t eval0, n_evals;  // evaluations this tick completes (evaluation j reads columns j .. j+T-1)
+    float *out;            // pinned host memory (device-visible) [n_channels][n_evals][outputs]
+    unsigned *counter;     // device, blocks finished (launches with several blocks per channel)
+    unsigned *flags;       // pinned host memory [n_channels]: receive `seq` when the channel's results are visible (nullptr: no signal)
+    unsigned seq;
+    int phases;            // STREAM_PHASE_* mask; COPY|COLUMNS|EVALS together need one block per channel
+    const unsigned char *blob;  // the configuration's constant blob (DeviceModel): staged in shared memory when it fits
+    int blob_bytes;        // multiple of 16; 0 = read constants through L2
+    int work_bytes;        // set by launch_stream_tick: per-warp work area in front of the staged blob
+};
+constexpr size_t kStreamTickMaxSmem = 200 * 1024;
+size_t stream_tick_smem(int fft_len, int max_width, int *warps_out);
+cudaError_t launch_stream_tick(const DevNet *d_net, int fft_len, int max_width, int n_channels, int blocks_per_channel,
+                               StreamTick t, cudaStream_t stream);
+
 // ---- fused fast path: kernels_fused.cu ---------------------------------------------------------------------------
 constexpr int kFusedMaxW0 = 6144;     // folded layer-0 weights, floats ([inputs][HP])
 constexpr int kFusedMaxHidden = 8;    // widest layer the register epilogue handles

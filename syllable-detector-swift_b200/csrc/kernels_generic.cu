@@ -41,68 +41,82 @@ __global__ void ingest_kernel(const void *__restrict__ src, int format, int inte
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// One warp per STFT column, iterative radix-2 DIT over M = N/2 complex points held in shared memory.
+// One STFT column by one warp: iterative radix-2 DIT over M = N/2 complex points held in shared memory (zr, zi).
+// `load(m)` returns sample m of the frame; the L band magnitudes (scaled) go to dst[0..L).
+template <class LoadSample>
+__device__ __forceinline__ void stft_band_column(const DevNet &net, LoadSample load, float *zr, float *zi, int lane, int bits,
+                                                 float *__restrict__ dst) {
+    const int N = net.fft_len, M = N / 2, W = net.win_len, L = net.band;
+    if (M == 1) {
+        if (lane == 0) {
+            float a = load(0) * net.window[0], b = W > 1 ? load(1) * net.window[1] : 0.0f;
+            dst[0] = scale_value(fabsf(2.0f * (a + b)) / 2.0f, net.scaling);
+        }
+        return;
+    }
+    for (int n = lane; n < M; n += kWarp) {
+        const int r = (int)(__brev((unsigned)n) >> (32 - bits));
+        const int m0 = 2 * n, m1 = 2 * n + 1;
+        zr[r] = m0 < W ? load(m0) * net.window[m0] : 0.0f;
+        zi[r] = m1 < W ? load(m1) * net.window[m1] : 0.0f;
+    }
+    __syncwarp();
+    for (int len = 2; len <= M; len <<= 1) {
+        const int half = len >> 1, step = N / len;
+        for (int idx = lane; idx < (M >> 1); idx += kWarp) {
+            const int j = idx % half, a = (idx / half) * len + j, b = a + half;
+            const float2 w = net.twiddle[j * step];
+            const float tr = zr[b] * w.x - zi[b] * w.y;
+            const float ti = zr[b] * w.y + zi[b] * w.x;
+            const float ar = zr[a], ai = zi[a];
+            zr[b] = ar - tr;
+            zi[b] = ai - ti;
+            zr[a] = ar + tr;
+            zi[a] = ai + ti;
+        }
+        __syncwarp();
+    }
+    for (int f = lane; f < L; f += kWarp) {
+        const int k = net.k0 + f;
+        float mag;
+        if (k == 0) {
+            const float re0 = 2.0f * (zr[0] + zi[0]);
+            mag = sqrtf(re0 * re0 + 0.0f * 0.0f) / 2.0f;
+        } else {
+            const float ar = zr[k], ai = zi[k], br = zr[M - k], bi = -zi[M - k];
+            const float sr = ar + br, si = ai + bi, dr = ar - br, di = ai - bi;
+            const float2 w = net.twiddle[k];
+            const float re = sr + (w.x * di + w.y * dr);
+            const float im = si - (w.x * dr - w.y * di);
+            mag = sqrtf(re * re + im * im) / 2.0f;
+        }
+        dst[f] = scale_value(mag, net.scaling);
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ int log2_ceil(int m) {
+    int bits = 0;
+    while ((1 << bits) < m) ++bits;
+    return bits;
+}
+
+// One warp per STFT column.
 __global__ void stft_band_generic_kernel(const DevNet *__restrict__ netp, const float *__restrict__ pcm, int64_t ch_stride,
                                          int64_t col0, int64_t n_cols, float *__restrict__ feat) {
     extern __shared__ float smem[];
     const DevNet &net = *netp;
-    const int N = net.fft_len, M = N / 2, W = net.win_len, L = net.band;
+    const int N = net.fft_len, M = N / 2, L = net.band;
     const int warps = blockDim.x / kWarp, warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
     float *zr = smem + (size_t)warp * N, *zi = zr + M;
     const int ch = blockIdx.y;
     const float *x_ch = pcm + (int64_t)ch * ch_stride;
     float *feat_ch = feat + (int64_t)ch * n_cols * L;
-    int bits = 0;
-    while ((1 << bits) < M) ++bits;
+    const int bits = log2_ceil(M);
 
     for (int64_t c = (int64_t)blockIdx.x * warps + warp; c < n_cols; c += (int64_t)gridDim.x * warps) {
         const float *fr = x_ch + (col0 + c) * net.hop + net.gap;
-        if (M == 1) {
-            if (lane == 0) {
-                float a = fr[0] * net.window[0], b = W > 1 ? fr[1] * net.window[1] : 0.0f;
-                feat_ch[c * L] = scale_value(fabsf(2.0f * (a + b)) / 2.0f, net.scaling);
-            }
-            continue;
-        }
-        for (int n = lane; n < M; n += kWarp) {
-            const int r = (int)(__brev((unsigned)n) >> (32 - bits));
-            const int m0 = 2 * n, m1 = 2 * n + 1;
-            zr[r] = m0 < W ? fr[m0] * net.window[m0] : 0.0f;
-            zi[r] = m1 < W ? fr[m1] * net.window[m1] : 0.0f;
-        }
-        __syncwarp();
-        for (int len = 2; len <= M; len <<= 1) {
-            const int half = len >> 1, step = N / len;
-            for (int idx = lane; idx < (M >> 1); idx += kWarp) {
-                const int j = idx % half, a = (idx / half) * len + j, b = a + half;
-                const float2 w = net.twiddle[j * step];
-                const float tr = zr[b] * w.x - zi[b] * w.y;
-                const float ti = zr[b] * w.y + zi[b] * w.x;
-                const float ar = zr[a], ai = zi[a];
-                zr[b] = ar - tr;
-                zi[b] = ai - ti;
-                zr[a] = ar + tr;
-                zi[a] = ai + ti;
-            }
-            __syncwarp();
-        }
-        for (int f = lane; f < L; f += kWarp) {
-            const int k = net.k0 + f;
-            float mag;
-            if (k == 0) {
-                const float re0 = 2.0f * (zr[0] + zi[0]);
-                mag = sqrtf(re0 * re0 + 0.0f * 0.0f) / 2.0f;
-            } else {
-                const float ar = zr[k], ai = zi[k], br = zr[M - k], bi = -zi[M - k];
-                const float sr = ar + br, si = ai + bi, dr = ar - br, di = ai - bi;
-                const float2 w = net.twiddle[k];
-                const float re = sr + (w.x * di + w.y * dr);
-                const float im = si - (w.x * dr - w.y * di);
-                mag = sqrtf(re * re + im * im) / 2.0f;
-            }
-            feat_ch[c * L + f] = scale_value(mag, net.scaling);
-        }
-        __syncwarp();
+        stft_band_column(net, [&](int m) { return fr[m]; }, zr, zi, lane, bits, feat_ch + c * L);
     }
 }
 
@@ -174,46 +188,60 @@ __device__ __forceinline__ float apply_transfer(int tf, float v) {
     }
 }
 
+// One evaluation by one warp: `loadf(i)` returns input i (v[t*L+f], oldest column first). Returns the buffer holding the
+// O reverse-mapped outputs (NeuralNet.apply, NeuralNet.swift:294-326).
+template <class LoadFeat>
+__device__ __forceinline__ float *nn_evaluate(const DevNet &net, LoadFeat loadf, float *buf0, float *buf1, int lane) {
+    const int I = net.inputs, O = net.outputs;
+    float *cur = buf0, *nxt = buf1;
+    for (int i = lane; i < I; i += kWarp) cur[i] = loadf(i);
+    __syncwarp();
+    for (int k = 0; k < net.n_ip; ++k) {
+        apply_input_processing(net.ip[k], cur, I, lane);
+        __syncwarp();
+    }
+    for (int l = 0; l < net.n_layers; ++l) {
+        const DevLayer &ly = net.layers[l];
+        for (int o = lane; o < ly.outputs; o += kWarp) {
+            const float *w = ly.w + (size_t)o * ly.inputs;
+            float acc = 0.0f;
+            for (int i = 0; i < ly.inputs; ++i) acc += w[i] * cur[i];
+            nxt[o] = apply_transfer(ly.transfer, acc + ly.b[o]);
+        }
+        __syncwarp();
+        float *t = cur; cur = nxt; nxt = t;
+    }
+    for (int o = lane; o < O; o += kWarp) {
+        float v = cur[o];
+        for (int k = 0; k < net.n_op; ++k) {  // reverse transforms, index order (NeuralNet.swift:316-323)
+            const DevProcessing &p = net.op[k];
+            float t = v + (0 - p.y);
+            t = t / p.gain[o];
+            v = t + p.xoff[o];
+        }
+        cur[o] = v;
+    }
+    __syncwarp();
+    return cur;
+}
+
 __global__ void nn_generic_kernel(const DevNet *__restrict__ netp, const float *__restrict__ feat, int64_t n_cols,
                                   int64_t n_evals, int64_t eval0, int64_t evals_total, int detect_rule,
                                   float *__restrict__ all_out, EventSink sink) {
     extern __shared__ float smem[];
     const DevNet &net = *netp;
     const int warps = blockDim.x / kWarp, warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
-    const int I = net.inputs, O = net.outputs, L = net.band;
+    const int O = net.outputs, L = net.band;
     float *buf0 = smem + (size_t)warp * 2 * net.max_width, *buf1 = buf0 + net.max_width;
     const int ch = blockIdx.y;
     const float *feat_ch = feat + (int64_t)ch * n_cols * L;
 
     for (int64_t j = (int64_t)blockIdx.x * warps + warp; j < n_evals; j += (int64_t)gridDim.x * warps) {
-        float *cur = buf0, *nxt = buf1;
-        for (int i = lane; i < I; i += kWarp) cur[i] = feat_ch[j * L + i];  // v[t*L+f]: contiguous in the column stream
-        __syncwarp();
-        for (int k = 0; k < net.n_ip; ++k) {
-            apply_input_processing(net.ip[k], cur, I, lane);
-            __syncwarp();
-        }
-        for (int l = 0; l < net.n_layers; ++l) {
-            const DevLayer &ly = net.layers[l];
-            for (int o = lane; o < ly.outputs; o += kWarp) {
-                const float *w = ly.w + (size_t)o * ly.inputs;
-                float acc = 0.0f;
-                for (int i = 0; i < ly.inputs; ++i) acc += w[i] * cur[i];
-                nxt[o] = apply_transfer(ly.transfer, acc + ly.b[o]);
-            }
-            __syncwarp();
-            float *t = cur; cur = nxt; nxt = t;
-        }
+        const float *in = feat_ch + j * L;  // v[t*L+f]: contiguous in the column stream
+        float *cur = nn_evaluate(net, [&](int i) { return in[i]; }, buf0, buf1, lane);
         bool hit = false;
         for (int o = lane; o < O; o += kWarp) {
-            float v = cur[o];
-            for (int k = 0; k < net.n_op; ++k) {  // reverse transforms, index order (NeuralNet.swift:316-323)
-                const DevProcessing &p = net.op[k];
-                float t = v + (0 - p.y);
-                t = t / p.gain[o];
-                v = t + p.xoff[o];
-            }
-            cur[o] = v;
+            const float v = cur[o];
             const bool over = (double)v >= net.thresholds[o];  // NaN compares false
             if (detect_rule == SYLDET_DETECT_FIRST_OUTPUT ? (o == 0 && over) : over) hit = true;
             if (all_out) all_out[((int64_t)ch * evals_total + eval0 + j) * O + o] = v;
@@ -222,6 +250,99 @@ __global__ void nn_generic_kernel(const DevNet *__restrict__ netp, const float *
         __syncwarp();
         if (any && lane == 0) sink_push(sink, ch, eval0 + j, cur, O);
         __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Live tick (Processor.swift:102-149 for every channel at once): ONE launch pulls the new samples of every channel
+// straight out of pinned host memory into the channel's device sample ring, computes the STFT columns they complete
+// into the channel's band-feature ring, evaluates the network for every completed feature window and writes the
+// outputs straight into pinned host memory, then raises a host-visible sequence flag. Reference arithmetic order
+// (this file is built with -fmad=false). grid = (blocks per channel, channels); with all three phases in one launch
+// there is one block per channel (block-level barriers order the phases); large ticks run one launch per phase.
+__device__ __forceinline__ const float *relocate(const float *p, const unsigned char *from, const unsigned char *to) {
+    return p ? reinterpret_cast<const float *>(to + (reinterpret_cast<const unsigned char *>(p) - from)) : nullptr;
+}
+
+__global__ void stream_tick_kernel(const DevNet *__restrict__ netp, StreamTick t) {
+    extern __shared__ float smem[];
+    __shared__ DevNet s_net;
+    const int warps = blockDim.x / kWarp, warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+    const int ch = blockIdx.y;
+    const int tid0 = blockIdx.x * blockDim.x + threadIdx.x, tstride = gridDim.x * blockDim.x;
+
+    // (1) the longest-latency loads first: this channel's staged samples, straight out of pinned host memory
+    const float *src = t.staged + (int64_t)ch * t.stage_pitch;
+    float pre[2] = {0.0f, 0.0f};
+    if (t.phases & STREAM_PHASE_COPY) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+            if (tid0 + k * tstride < t.n_staged) pre[k] = src[tid0 + k * tstride];
+    }
+    // (2) while they fly: the configuration (DevNet record + window, twiddles, weights, processing vectors) -> shared
+    // memory, so that the serial left-to-right sums below never wait on L2
+    for (int i = threadIdx.x; i < (int)(sizeof(DevNet) / 4); i += blockDim.x)
+        reinterpret_cast<int *>(&s_net)[i] = reinterpret_cast<const int *>(netp)[i];
+    unsigned char *sblob = reinterpret_cast<unsigned char *>(smem) + t.work_bytes;
+    if (t.blob_bytes) {
+        const int4 *g = reinterpret_cast<const int4 *>(t.blob);
+        int4 *d = reinterpret_cast<int4 *>(sblob);
+        for (int i = threadIdx.x; i < t.blob_bytes / 16; i += blockDim.x) d[i] = g[i];
+    }
+    __syncthreads();
+    if (t.blob_bytes && threadIdx.x == 0) {
+        DevNet &n = s_net;
+        for (int k = 0; k < n.n_ip; ++k) { n.ip[k].xoff = relocate(n.ip[k].xoff, t.blob, sblob); n.ip[k].gain = relocate(n.ip[k].gain, t.blob, sblob); }
+        for (int k = 0; k < n.n_op; ++k) { n.op[k].xoff = relocate(n.op[k].xoff, t.blob, sblob); n.op[k].gain = relocate(n.op[k].gain, t.blob, sblob); }
+        for (int l = 0; l < n.n_layers; ++l) { n.layers[l].w = relocate(n.layers[l].w, t.blob, sblob); n.layers[l].b = relocate(n.layers[l].b, t.blob, sblob); }
+        n.window = relocate(n.window, t.blob, sblob);
+        n.twiddle = reinterpret_cast<const float2 *>(relocate(reinterpret_cast<const float *>(n.twiddle), t.blob, sblob));
+    }
+    const DevNet &net = s_net;
+    float *ring = t.ring + (int64_t)ch * (t.ring_mask + 1);
+
+    if (t.phases & STREAM_PHASE_COPY) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+            if (tid0 + k * tstride < t.n_staged) ring[(t.ring_pos + tid0 + k * tstride) & t.ring_mask] = pre[k];
+        for (int i = tid0 + 2 * tstride; i < t.n_staged; i += tstride) ring[(t.ring_pos + i) & t.ring_mask] = src[i];
+    }
+    __syncthreads();
+    const int L = net.band, O = net.outputs;
+    float *band = t.band + (int64_t)ch * (t.band_mask + 1) * L;
+    if (t.phases & STREAM_PHASE_COLUMNS) {
+        const int N = net.fft_len, M = N / 2;
+        float *zr = smem + (size_t)warp * N, *zi = zr + M;
+        const int bits = log2_ceil(M);
+        for (int64_t c = (int64_t)blockIdx.x * warps + warp; c < t.n_cols; c += (int64_t)gridDim.x * warps) {
+            const int64_t first = (t.col0 + c) * net.hop + net.gap;
+            stft_band_column(net, [&](int m) { return ring[(first + m) & t.ring_mask]; }, zr, zi, lane, bits,
+                             band + ((t.col0 + c) & t.band_mask) * L);
+        }
+        __syncthreads();
+    }
+    if (t.phases & STREAM_PHASE_EVALS) {
+        float *buf0 = smem + (size_t)warp * 2 * net.max_width, *buf1 = buf0 + net.max_width;
+        for (int64_t j = (int64_t)blockIdx.x * warps + warp; j < t.n_evals; j += (int64_t)gridDim.x * warps) {
+            const int64_t c0 = t.eval0 + j;  // oldest column of the window
+            float *cur = nn_evaluate(net, [&](int i) { const int tt = i / L; return band[((c0 + tt) & t.band_mask) * L + (i - tt * L)]; },
+                                     buf0, buf1, lane);
+            for (int o = lane; o < O; o += kWarp) t.out[((int64_t)ch * t.n_evals + j) * O + o] = cur[o];
+            __syncwarp();
+        }
+    }
+    if (t.flags) {  // publish: one flag per channel when the launch has one block per channel, else the last block raises flag 0
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (gridDim.x == 1) {
+                *(volatile unsigned *)(t.flags + ch) = t.seq;
+            } else if (atomicAdd(t.counter, 1u) == gridDim.x * gridDim.y - 1) {
+                *t.counter = 0;
+                __threadfence_system();
+                for (unsigned c = 0; c < gridDim.y; ++c) *(volatile unsigned *)(t.flags + c) = t.seq;
+            }
+        }
     }
 }
 
@@ -269,4 +390,30 @@ cudaError_t launch_nn_generic(const DevNet *d_net, int max_width, const float *f
     return cudaGetLastError();
 }
 
+}  // namespace syldet
+
+namespace syldet {
+size_t stream_tick_smem(int fft_len, int max_width, int *warps_out) {
+    int warps = 4;
+    auto need = [&](int w) { return (size_t)w * std::max<size_t>((size_t)fft_len, 2 * (size_t)max_width) * sizeof(float); };
+    while (warps > 1 && need(warps) > 96 * 1024) warps >>= 1;
+    if (warps_out) *warps_out = warps;
+    return (need(warps) + 15) & ~(size_t)15;
+}
+
+cudaError_t launch_stream_tick(const DevNet *d_net, int fft_len, int max_width, int n_channels, int blocks_per_channel,
+                               StreamTick t, cudaStream_t stream) {
+    int warps = 4;
+    const size_t work = stream_tick_smem(fft_len, max_width, &warps);
+    t.work_bytes = (int)work;
+    if (work + (size_t)t.blob_bytes > kStreamTickMaxSmem) t.blob_bytes = 0;  // too large to stage: read it through L2
+    const size_t smem = work + (size_t)t.blob_bytes;
+    if (smem > 48 * 1024) {  // opt-in size; per device, so not cached here (small configurations never get here)
+        cudaError_t e = cudaFuncSetAttribute(stream_tick_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStreamTickMaxSmem);
+        if (e != cudaSuccess) return e;
+    }
+    dim3 grid((unsigned)blocks_per_channel, (unsigned)n_channels);
+    stream_tick_kernel<<<grid, warps * 32, smem, stream>>>(d_net, t);
+    return cudaGetLastError();
+}
 }  // namespace syldet

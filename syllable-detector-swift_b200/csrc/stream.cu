@@ -4,8 +4,11 @@
 //   Detector     - class SyllableDetector, one stream with appendAudioData / processNewValue / lastOutputs
 //                  (Common/SyllableDetector.swift:13-231)
 //   Resampler    - ResamplerLinear (Common/Resampler.swift:20-70), the index ramp and interpolation run in a kernel
-// Audio lives in a device-resident per-channel buffer; each tick uploads only the new samples, launches the detection
-// kernel over the unconsumed tail of every channel at once and reads back the few new network outputs.
+// Per channel the device keeps a circular sample history and a circular band-feature history, so a tick computes only
+// the STFT columns and evaluations the new samples complete. A tick is ONE kernel launch (stream_tick_kernel): the
+// kernel pulls the new samples from pinned host memory itself, writes the outputs back into pinned host memory and
+// raises a host-visible flag - no memcpy calls and no stream synchronisation on the latency path. Ticks that complete
+// no STFT column (3 of 4 at 32-frame buffers and hop 132) only stage samples on the host.
 #include "stream.hpp"
 
 #include <algorithm>
@@ -14,38 +17,79 @@
 namespace syldet {
 
 // ---------------------------------------------------------------------------------------------------------------
+namespace {
+int64_t pow2_at_least(int64_t v) {
+    int64_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+}  // namespace
+
 syldet_status StreamGroup::init(const Config &cfg, int n_channels, int max_buffer, int device) {
     if (n_channels <= 0 || n_channels > 65535) return set_error(SYLDET_ERR_ARG, "n_channels out of range");
     if (max_buffer <= 0) return set_error(SYLDET_ERR_ARG, "max_buffer must be positive");
-    syldet_status st = batch_.init(cfg, device);
+    syldet_status st = model_.init(cfg, device);
     if (st != SYLDET_OK) return st;
     n_channels_ = n_channels;
     max_buffer_ = max_buffer;
-    const Config &c = batch_.model().config();
-    // room for the retained tail (one full feature window) plus many ticks before a compaction is needed
-    const int64_t tail = c.samples_for_evals(1) + c.hop;
-    const int64_t ticks = std::min<int64_t>(64, std::max<int64_t>(2, 262144 / max_buffer));
-    cap_ = ((tail + ticks * max_buffer + 4095) / 4096) * 4096;
-    st = ring_[0].reserve((size_t)n_channels * cap_ * sizeof(float));
+    const Config &c = model_.config();
+    if (stream_tick_smem(c.fourier_length, model_.max_width(), nullptr) > kStreamTickMaxSmem)
+        return set_error(SYLDET_ERR_CONFIG, "configuration too large for the live tick kernel");
+    // Samples wait in pinned staging until they complete an STFT column: fewer than max(W + gap, hop) can be waiting
+    // when a buffer arrives (see submit), so this never overflows.
+    const int frame = c.gap + c.window_length;
+    stage_cap_ = ((std::max(frame, c.hop) + max_buffer + 31) / 32) * 32;
+    ring_cap_ = pow2_at_least((int64_t)frame + stage_cap_);
+    max_new_ = stage_cap_ / c.hop + 2;
+    band_cols_ = pow2_at_least(c.time_range + max_new_);
+    st = ring_.reserve((size_t)n_channels * ring_cap_ * sizeof(float));
     if (st != SYLDET_OK) return st;
-    st = ring_[1].reserve((size_t)n_channels * cap_ * sizeof(float));
+    st = band_.reserve((size_t)n_channels * band_cols_ * c.band * sizeof(float));
+    if (st != SYLDET_OK) return st;
+    st = counter_.reserve(sizeof(unsigned));
     if (st != SYLDET_OK) return st;
     SYLDET_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
-    SYLDET_CUDA(cudaMallocHost(&h_in_, (size_t)n_channels * max_buffer * sizeof(float)));
-    max_new_ = c.num_evals(tail + max_buffer) + 2;
+    SYLDET_CUDA(cudaMemsetAsync(ring_.get(), 0, ring_.size(), stream_));
+    SYLDET_CUDA(cudaMemsetAsync(band_.get(), 0, band_.size(), stream_));
+    SYLDET_CUDA(cudaMemsetAsync(counter_.get(), 0, sizeof(unsigned), stream_));
+    // cudaMallocHost memory is device-visible at the same address under unified addressing (always on for sm_100)
+    SYLDET_CUDA(cudaMallocHost(&h_stage_, (size_t)n_channels * stage_cap_ * sizeof(float)));
     SYLDET_CUDA(cudaMallocHost(&h_out_, (size_t)n_channels * max_new_ * c.outputs * sizeof(float)));
-    st = d_out_.reserve((size_t)n_channels * max_new_ * c.outputs * sizeof(float));
-    return st;
+    SYLDET_CUDA(cudaMallocHost(&h_flag_, (size_t)n_channels * sizeof(unsigned)));
+    std::memset(h_flag_, 0, (size_t)n_channels * sizeof(unsigned));
+    SYLDET_CUDA(cudaStreamSynchronize(stream_));
+    return SYLDET_OK;
 }
 
 StreamGroup::~StreamGroup() {
     if (stream_) {
-        cudaSetDevice(batch_.model().device());
+        cudaSetDevice(model_.device());
         cudaStreamSynchronize(stream_);
         cudaStreamDestroy(stream_);
     }
-    if (h_in_) cudaFreeHost(h_in_);
+    if (h_stage_) cudaFreeHost(h_stage_);
     if (h_out_) cudaFreeHost(h_out_);
+    if (h_flag_) cudaFreeHost(h_flag_);
+}
+
+// Every channel's block stores the tick's sequence number into its word of pinned host memory once its outputs are
+// visible; polling those words is cheaper than cudaStreamSynchronize and needs no device-side counting. The stream is queried now and then so a failed launch cannot spin forever.
+syldet_status StreamGroup::wait_for_tick() {
+    volatile unsigned *flags = h_flag_;
+    int ch = 0;  // channels [0, ch) have published this tick
+    for (unsigned spins = 0;; ++spins) {
+        while (ch < n_channels_ && flags[ch] == seq_) ++ch;
+        if (ch == n_channels_) return SYLDET_OK;
+        if ((spins & 0x3fff) == 0x3fff) {
+            cudaError_t e = cudaStreamQuery(stream_);
+            if (e == cudaSuccess) {
+                while (ch < n_channels_ && flags[ch] == seq_) ++ch;
+                if (ch == n_channels_) return SYLDET_OK;
+                return set_error(SYLDET_ERR_CUDA, "live tick finished without publishing its results");
+            }
+            if (e != cudaErrorNotReady) return cuda_fail(e, "live tick");
+        }
+    }
 }
 
 syldet_status StreamGroup::submit(const float *const *bufs, int n, const float **outs, int64_t *n_new) {
@@ -53,40 +97,73 @@ syldet_status StreamGroup::submit(const float *const *bufs, int n, const float *
     *outs = h_out_;
     if (n < 0 || n > max_buffer_) return set_error(SYLDET_ERR_ARG, "buffer longer than max_buffer");
     if (n == 0) return SYLDET_OK;
-    syldet_status st = use_device(batch_.model().device());
-    if (st != SYLDET_OK) return st;
-    const Config &c = batch_.model().config();
-    // compaction: keep only samples from the start of the next evaluation's window
-    if (fill_ + n > cap_) {
-        const int64_t keep_from = next_eval_ * c.hop - base_;
-        const int64_t keep = fill_ - keep_from;
-        if (keep + n > cap_) return set_error(SYLDET_ERR_OVERFLOW, "Insufficient space on buffer.");
-        SYLDET_CUDA(cudaMemcpy2DAsync(ring_[cur_ ^ 1].get(), cap_ * sizeof(float), ring_[cur_].as<float>() + keep_from,
-                                      cap_ * sizeof(float), keep * sizeof(float), n_channels_, cudaMemcpyDeviceToDevice, stream_));
-        cur_ ^= 1;
-        base_ += keep_from;
-        fill_ = keep;
-    }
-    for (int ch = 0; ch < n_channels_; ++ch) std::memcpy(h_in_ + (size_t)ch * n, bufs[ch], (size_t)n * sizeof(float));
-    SYLDET_CUDA(cudaMemcpy2DAsync(ring_[cur_].as<float>() + fill_, cap_ * sizeof(float), h_in_, (size_t)n * sizeof(float),
-                                  (size_t)n * sizeof(float), n_channels_, cudaMemcpyHostToDevice, stream_));
-    fill_ += n;
+    const Config &c = model_.config();
+    if (staged_ + n > stage_cap_) return set_error(SYLDET_ERR_OVERFLOW, "Insufficient space on buffer.");
+    for (int ch = 0; ch < n_channels_; ++ch)
+        std::memcpy(h_stage_ + (size_t)ch * stage_cap_ + staged_, bufs[ch], (size_t)n * sizeof(float));
+    staged_ += n;
     total_ += n;
+    const int64_t n_cols = c.num_columns(total_) - cols_done_;
+    if (n_cols <= 0) return SYLDET_OK;  // no column completed: the decision (nothing new) needs no device work
     const int64_t avail = c.num_evals(total_) - next_eval_;
-    if (avail <= 0) {
-        SYLDET_CUDA(cudaStreamSynchronize(stream_));  // h_in_ is reused by the next tick
-        return SYLDET_OK;
-    }
-    if (avail > max_new_) return set_error(SYLDET_ERR_OVERFLOW, "more evaluations pending than the stream was sized for");
-    const int64_t seg0 = next_eval_ * c.hop - base_;
-    st = batch_.launch_device(ring_[cur_].as<float>() + seg0, n_channels_, fill_ - seg0, cap_, SYLDET_LAYOUT_PLANAR,
-                              SYLDET_DETECT_FIRST_OUTPUT, d_out_.as<float>(), stream_);
+    if (avail > max_new_ || n_cols > band_cols_ - c.time_range)
+        return set_error(SYLDET_ERR_OVERFLOW, "more evaluations pending than the stream was sized for");
+    syldet_status st = use_device(model_.device());
     if (st != SYLDET_OK) return st;
-    SYLDET_CUDA(cudaMemcpyAsync(h_out_, d_out_.get(), (size_t)n_channels_ * avail * c.outputs * sizeof(float),
-                                cudaMemcpyDeviceToHost, stream_));
-    SYLDET_CUDA(cudaStreamSynchronize(stream_));
-    next_eval_ += avail;
-    *n_new = avail;
+
+    StreamTick t{};
+    t.staged = h_stage_;
+    t.stage_pitch = stage_cap_;
+    t.n_staged = staged_;
+    t.ring = ring_.as<float>();
+    t.ring_mask = ring_cap_ - 1;
+    t.ring_pos = total_ - staged_;
+    t.band = band_.as<float>();
+    t.band_mask = band_cols_ - 1;
+    t.col0 = cols_done_;
+    t.n_cols = n_cols;
+    t.eval0 = next_eval_;
+    t.n_evals = avail;
+    t.out = h_out_;
+    t.counter = counter_.as<unsigned>();
+    t.seq = ++seq_;
+    t.blob = model_.blob();
+    t.blob_bytes = (int)model_.blob_bytes();
+    int warps = 4;
+    stream_tick_smem(c.fourier_length, model_.max_width(), &warps);
+    const DevNet *net = model_.dev_net();
+    const int64_t cap = std::max<int64_t>(1, (model_.sm_count() * 8) / n_channels_);
+    if (n_cols <= warps) {  // the live shape: one launch, one block per channel
+        t.phases = STREAM_PHASE_COPY | STREAM_PHASE_COLUMNS | (avail > 0 ? STREAM_PHASE_EVALS : 0);
+        t.flags = h_flag_;
+        SYLDET_CUDA(launch_stream_tick(net, c.fourier_length, model_.max_width(), n_channels_, 1, t, stream_));
+        ++launches_;
+    } else {  // a long buffer: one launch per phase so each can spread over many blocks per channel
+        t.phases = STREAM_PHASE_COPY;
+        t.flags = nullptr;
+        int bx = (int)std::min<int64_t>(cap, (staged_ + warps * 32 - 1) / (warps * 32));
+        SYLDET_CUDA(launch_stream_tick(net, c.fourier_length, model_.max_width(), n_channels_, bx, t, stream_));
+        t.phases = STREAM_PHASE_COLUMNS;
+        t.flags = avail > 0 ? nullptr : h_flag_;
+        bx = (int)std::min<int64_t>(cap, (n_cols + warps - 1) / warps);
+        SYLDET_CUDA(launch_stream_tick(net, c.fourier_length, model_.max_width(), n_channels_, bx, t, stream_));
+        launches_ += 2;
+        if (avail > 0) {
+            t.phases = STREAM_PHASE_EVALS;
+            t.flags = h_flag_;
+            bx = (int)std::min<int64_t>(cap, (avail + warps - 1) / warps);
+            SYLDET_CUDA(launch_stream_tick(net, c.fourier_length, model_.max_width(), n_channels_, bx, t, stream_));
+            ++launches_;
+        }
+    }
+    st = wait_for_tick();
+    if (st != SYLDET_OK) return st;
+    staged_ = 0;
+    cols_done_ += n_cols;
+    if (avail > 0) {
+        next_eval_ += avail;
+        *n_new = avail;
+    }
     return SYLDET_OK;
 }
 

@@ -15,22 +15,29 @@ public:
     syldet_status init(const Config &cfg, int n_channels, int max_buffer, int device);
     // One tick. *outs -> pinned host [n_channels][*n_new][outputs], valid until the next call.
     syldet_status submit(const float *const *bufs, int n, const float **outs, int64_t *n_new);
-    const Config &config() const { return batch_.model().config(); }
+    const Config &config() const { return model_.config(); }
     int n_channels() const { return n_channels_; }
-    int64_t launch_count() const { return batch_.launch_count(); }
+    int64_t launch_count() const { return launches_; }
 
 private:
-    Batch batch_;
-    int n_channels_ = 0, max_buffer_ = 0, cur_ = 0;
-    int64_t cap_ = 0;        // floats per channel in each device buffer
-    int64_t base_ = 0;       // absolute sample index of element 0 of the current device buffer
-    int64_t fill_ = 0;       // samples held per channel
-    int64_t total_ = 0;      // samples appended per channel so far
-    int64_t next_eval_ = 0;  // first evaluation not yet produced
-    int64_t max_new_ = 0;
-    DeviceBuffer ring_[2], d_out_;
+    syldet_status wait_for_tick();
+
+    DeviceModel model_;
+    int n_channels_ = 0, max_buffer_ = 0;
+    int stage_cap_ = 0;       // floats per channel in the pinned staging area
+    int staged_ = 0;          // samples per channel staged on the host, not yet pulled by the device
+    int64_t ring_cap_ = 0;    // floats per channel in the device sample ring (power of two)
+    int64_t band_cols_ = 0;   // columns per channel in the device band-feature ring (power of two)
+    int64_t total_ = 0;       // samples appended per channel so far
+    int64_t cols_done_ = 0;   // STFT columns already in the band ring
+    int64_t next_eval_ = 0;   // first evaluation not yet produced
+    int64_t max_new_ = 0;     // most evaluations one tick can complete
+    int64_t launches_ = 0;
+    unsigned seq_ = 0;
+    DeviceBuffer ring_, band_, counter_;
     cudaStream_t stream_ = nullptr;
-    float *h_in_ = nullptr, *h_out_ = nullptr;
+    float *h_stage_ = nullptr, *h_out_ = nullptr;
+    unsigned *h_flag_ = nullptr;
 };
 
 class Detector {

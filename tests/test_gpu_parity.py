@@ -307,6 +307,41 @@ def test_stream_group_matches_batch(sd, cfg, orc, synth):
         assert np.abs(last[ch] - ref[-1]).max() <= TOL_OUT
 
 
+@pytest.mark.parametrize("kw", [
+    dict(fft_len=128, overlap=-7, freq_range=(300.0, 20000.0), time_range=12, hidden=(3,), input_funcs=("normalizestd", "mapminmax")),
+    dict(fft_len=512, overlap=256, freq_range=(1000.0, 9000.0), time_range=5, hidden=(8, 5), outputs=3, input_funcs=("mapstd",), output_funcs=("mapminmax", "mapstd")),
+    dict(fft_len=2048, win_len=1500, overlap=-100, freq_range=(500.0, 5000.0), time_range=2, hidden=(6,), scaling="log", input_funcs=("mapstd", "normalize")),
+])
+def test_stream_group_ragged_ticks_generated_configs(sd, oracle_mod, cw, kw):
+    """The live tick kernel (device sample ring + band-feature ring, one launch per tick) on configurations with a gap, several
+    outputs and long windows, fed ragged buffer lengths (1 sample .. several hops: single-launch and per-phase launches)."""
+    text = cw.random_config(seed=11, threshold=0.3, **kw)
+    c = sd.SyllableDetectorConfig.from_text(text).validate()
+    o = oracle_mod.Oracle(text=text)
+    rng = np.random.default_rng(5)
+    nch, n = 3, 30000
+    x = (0.1 * rng.standard_normal((nch, n))).astype(np.float32)
+    refs = [o.run(x[ch])[0] for ch in range(nch)]
+    scale = max(1.0, max(float(np.nanmax(np.abs(r))) for r in refs))
+    tol = (TOL_OUT if kw.get("scaling", "linear") == "linear" else 2e-4) * scale
+    g = sd.StreamGroup(c, nch, max_buffer=3000)
+    pos, done, launches = 0, 0, 0
+    while pos < n:
+        m = min(int(rng.choice([1, 7, 32, 64, 257, 1000, 3000])), n - pos)
+        seen, n_new = g.submit(x[:, pos:pos + m])
+        pos += m
+        assert np.all(n_new == n_new[0])
+        if n_new[0]:
+            done += int(n_new[0])
+            for ch in range(nch):
+                assert np.abs(g.last_outputs[ch] - refs[ch][done - 1]).max() <= tol
+                flag = bool((refs[ch][done - int(n_new[0]):done, 0].astype(np.float64) >= c.thresholds[0]).any())
+                near = bool((np.abs(refs[ch][done - int(n_new[0]):done, 0].astype(np.float64) - c.thresholds[0]) <= tol).any())
+                assert near or bool(seen[ch]) == flag
+    assert done == o.num_evals(n) > 0
+    assert 0 < g.launch_count
+
+
 def test_resampler_matches_oracle_bit_for_bit(sd, oracle_mod):
     rng = np.random.default_rng(2)
     x = rng.standard_normal(32 * 400).astype(np.float32)

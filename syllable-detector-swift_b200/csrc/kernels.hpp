@@ -31,11 +31,13 @@ struct StreamTick {
     float *out;            // pinned host memory (device-visible) [n_channels][n_evals][outputs]
     unsigned *counter;     // device, blocks finished (launches with several blocks per channel)
     unsigned *flags;       // pinned host memory [n_channels]: receive `seq` when the channel's results are visible (nullptr: no signal)
+    uint4 *packed;         // pinned host memory [n_channels] or nullptr: {out0, out1, out2, seq} in one store (n_evals == 1, outputs <= 3)
     unsigned seq;
     int phases;            // STREAM_PHASE_* mask; COPY|COLUMNS|EVALS together need one block per channel
     const unsigned char *blob;  // the configuration's constant blob (DeviceModel): staged in shared memory when it fits
     int blob_bytes;        // multiple of 16; 0 = read constants through L2
     int work_bytes;        // set by launch_stream_tick: per-warp work area in front of the staged blob
+    long long *stamps;     // optional pinned host [10]: clock64 at the phase boundaries of block (0,0) (SYLDET_STREAM_TIMING=1)
 };
 constexpr size_t kStreamTickMaxSmem = 200 * 1024;
 size_t stream_tick_smem(int fft_len, int max_width, int *warps_out);

@@ -54,18 +54,30 @@ __device__ __forceinline__ void stft_band_column(const DevNet &net, LoadSample l
         }
         return;
     }
-    for (int n = lane; n < M; n += kWarp) {
-        const int r = (int)(__brev((unsigned)n) >> (32 - bits));
-        const int m0 = 2 * n, m1 = 2 * n + 1;
-        zr[r] = m0 < W ? load(m0) * net.window[m0] : 0.0f;
-        zi[r] = m1 < W ? load(m1) * net.window[m1] : 0.0f;
+    for (int n0 = lane; n0 < M; n0 += 4 * kWarp) {  // four points per lane per batch: loads first, then the stores
+        float vr[4], vi[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int n = n0 + k * kWarp, m0 = 2 * n, m1 = 2 * n + 1;
+            vr[k] = (n < M && m0 < W) ? load(m0) * net.window[m0] : 0.0f;
+            vi[k] = (n < M && m1 < W) ? load(m1) * net.window[m1] : 0.0f;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int n = n0 + k * kWarp;
+            if (n < M) {
+                const int r = (int)(__brev((unsigned)n) >> (32 - bits));
+                zr[r] = vr[k];
+                zi[r] = vi[k];
+            }
+        }
     }
     __syncwarp();
-    for (int len = 2; len <= M; len <<= 1) {
-        const int half = len >> 1, step = N / len;
+    for (int lh = 0; (2 << lh) <= M; ++lh) {  // len = 2 << lh (a power of two: index maths by shifts)
+        const int half = 1 << lh, ls = bits - lh;  // twiddle step = N / len = 1 << ls
         for (int idx = lane; idx < (M >> 1); idx += kWarp) {
-            const int j = idx % half, a = (idx / half) * len + j, b = a + half;
-            const float2 w = net.twiddle[j * step];
+            const int j = idx & (half - 1), a = ((idx >> lh) << (lh + 1)) + j, b = a + half;
+            const float2 w = net.twiddle[j << ls];
             const float tr = zr[b] * w.x - zi[b] * w.y;
             const float ti = zr[b] * w.y + zi[b] * w.x;
             const float ar = zr[a], ai = zi[a];
@@ -120,59 +132,139 @@ __global__ void stft_band_generic_kernel(const DevNet *__restrict__ netp, const 
     }
 }
 
+// x[i] = f(i, x[i]) for the lane's elements, eight at a time: all loads of a batch are issued before its first store (the
+// compiler cannot reorder them itself, x may alias whatever f reads).
+template <class F>
+__device__ __forceinline__ void lane_map(float *x, int n, int lane, F f) {
+    for (int i = lane; i < n; i += 8 * kWarp) {
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (i + k * kWarp < n) v[k] = f(i + k * kWarp, x[i + k * kWarp]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (i + k * kWarp < n) x[i + k * kWarp] = v[k];
+    }
+}
+
+// acc = (((0 + t(0)) + t(1)) + ...) + t(n-1): the additions stay in index order (the order vDSP's scalar definition gives and
+// the oracle uses); the terms of the next eight are fetched and formed while the current eight are being added, so the
+// chain costs one FADD per element instead of a load-to-use latency per element.
+template <class Term>
+__device__ __forceinline__ float serial_sum(int n, Term term) {
+    float acc = 0.0f;
+    int i = 0;
+    if (n >= 8) {
+        float cur[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) cur[k] = term(k);
+        for (; i + 16 <= n; i += 8) {
+            float nxt[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) nxt[k] = term(i + 8 + k);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc += cur[k];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) cur[k] = nxt[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc += cur[k];
+        i += 8;
+    }
+    for (; i < n; ++i) acc += term(i);
+    return acc;
+}
+
+// The live tick trades the index-order sums for lane-strided partial sums combined by a shuffle butterfly (every lane ends
+// with the same value): same operations, different association - within the stated 1e-5 output tolerance, and ~5x less
+// latency per evaluation. The batch kernels below keep the index order (kSerial = true).
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+template <class Term>
+__device__ __forceinline__ float strided_sum(int n, int lane, Term term) {
+    float acc = 0.0f;
+    for (int i = lane; i < n; i += 8 * kWarp) {
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = i + k * kWarp < n ? term(i + k * kWarp) : 0.0f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc += v[k];
+    }
+    return warp_sum(acc);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // One warp per evaluation: literal processing chain, lanes own output neurons (each sum is left-to-right in one lane).
+template <bool kSerial>
 __device__ void apply_input_processing(const DevProcessing &p, float *x, int n, int lane) {
     switch (p.function) {
         case SYLDET_PROC_MAPMINMAX:
-            for (int i = lane; i < n; i += kWarp) { float t = (x[i] - p.xoff[i]) * p.gain[i]; x[i] = t + p.y; }
+            lane_map(x, n, lane, [&](int i, float xi) { const float t = (xi - p.xoff[i]) * p.gain[i]; return t + p.y; });
             break;
         case SYLDET_PROC_MAPSTD:
-            for (int i = lane; i < n; i += kWarp) {
-                float t = (x[i] - p.xoff[i]) * p.gain[i];
-                x[i] = (0 != p.y) ? t + p.y : t;
-            }
+            lane_map(x, n, lane, [&](int i, float xi) { const float t = (xi - p.xoff[i]) * p.gain[i]; return (0 != p.y) ? t + p.y : t; });
             break;
         case SYLDET_PROC_L2NORMALIZE: {
             float d = 0.0f;
-            if (lane == 0) {
-                float ss = 0.0f;
-                for (int i = 0; i < n; ++i) ss += x[i] * x[i];
-                d = sqrtf(ss);
+            if constexpr (kSerial) {
+                if (lane == 0) {
+                    const float ss = serial_sum(n, [&](int i) { return x[i] * x[i]; });
+                    d = sqrtf(ss);
+                }
+                d = __shfl_sync(0xffffffffu, d, 0);
+            } else {
+                d = sqrtf(strided_sum(n, lane, [&](int i) { return x[i] * x[i]; }));
             }
-            d = __shfl_sync(0xffffffffu, d, 0);
-            for (int i = lane; i < n; i += kWarp) x[i] = x[i] / d;
+            lane_map(x, n, lane, [&](int, float xi) { return xi / d; });
             break;
         }
         case SYLDET_PROC_NORMALIZE: {
             float mn = 0.0f, mx = 0.0f;
-            if (lane == 0) {
+            if constexpr (kSerial) {
+                if (lane == 0) {
+                    mn = mx = x[0];
+                    for (int i = 1; i < n; ++i) { if (x[i] < mn) mn = x[i]; if (x[i] > mx) mx = x[i]; }
+                }
+                mn = __shfl_sync(0xffffffffu, mn, 0);
+                mx = __shfl_sync(0xffffffffu, mx, 0);
+            } else {
                 mn = mx = x[0];
-                for (int i = 1; i < n; ++i) { if (x[i] < mn) mn = x[i]; if (x[i] > mx) mx = x[i]; }
+                for (int i = lane; i < n; i += kWarp) { const float v = x[i]; if (v < mn) mn = v; if (v > mx) mx = v; }
+#pragma unroll
+                for (int d = 16; d >= 1; d >>= 1) {
+                    const float a = __shfl_xor_sync(0xffffffffu, mn, d), b = __shfl_xor_sync(0xffffffffu, mx, d);
+                    if (a < mn) mn = a;
+                    if (b > mx) mx = b;
+                }
             }
-            mn = __shfl_sync(0xffffffffu, mn, 0);
-            mx = __shfl_sync(0xffffffffu, mx, 0);
             const float range = mx - mn;
             if (0 == range) {
-                for (int i = lane; i < n; i += kWarp) x[i] = -1.0f;
+                lane_map(x, n, lane, [&](int, float) { return -1.0f; });
             } else {
                 const float slope = 2.0f / range, icpt = (0 - mn - mx) / range;
-                for (int i = lane; i < n; i += kWarp) { float t = x[i] * slope; x[i] = t + icpt; }
+                lane_map(x, n, lane, [&](int, float xi) { const float t = xi * slope; return t + icpt; });
             }
             break;
         }
         case SYLDET_PROC_NORMALIZESTD: {
             float mean = 0.0f, sd = 0.0f;
-            if (lane == 0) {
-                float s = 0.0f, v = 0.0f;
-                for (int i = 0; i < n; ++i) s += x[i];
-                mean = s / (float)n;
-                for (int i = 0; i < n; ++i) { float d = x[i] - mean; v += d * d; }
-                sd = sqrtf(v / (float)n);
+            if constexpr (kSerial) {
+                if (lane == 0) {
+                    const float s = serial_sum(n, [&](int i) { return x[i]; });
+                    mean = s / (float)n;
+                    const float v = serial_sum(n, [&](int i) { const float d = x[i] - mean; return d * d; });
+                    sd = sqrtf(v / (float)n);
+                }
+                mean = __shfl_sync(0xffffffffu, mean, 0);
+                sd = __shfl_sync(0xffffffffu, sd, 0);
+            } else {
+                mean = strided_sum(n, lane, [&](int i) { return x[i]; }) / (float)n;
+                sd = sqrtf(strided_sum(n, lane, [&](int i) { const float d = x[i] - mean; return d * d; }) / (float)n);
             }
-            mean = __shfl_sync(0xffffffffu, mean, 0);
-            sd = __shfl_sync(0xffffffffu, sd, 0);
-            for (int i = lane; i < n; i += kWarp) x[i] = (x[i] - mean) / sd;
+            lane_map(x, n, lane, [&](int, float xi) { return (xi - mean) / sd; });
             break;
         }
         default: break;
@@ -190,25 +282,55 @@ __device__ __forceinline__ float apply_transfer(int tf, float v) {
 
 // One evaluation by one warp: `loadf(i)` returns input i (v[t*L+f], oldest column first). Returns the buffer holding the
 // O reverse-mapped outputs (NeuralNet.apply, NeuralNet.swift:294-326).
-template <class LoadFeat>
-__device__ __forceinline__ float *nn_evaluate(const DevNet &net, LoadFeat loadf, float *buf0, float *buf1, int lane) {
+template <bool kSerial, class LoadFeat>
+__device__ __forceinline__ float *nn_evaluate(const DevNet &net, LoadFeat loadf, float *buf0, float *buf1, int lane, long long *dbg = nullptr) {
     const int I = net.inputs, O = net.outputs;
     float *cur = buf0, *nxt = buf1;
-    for (int i = lane; i < I; i += kWarp) cur[i] = loadf(i);
+    for (int i = lane; i < I; i += 12 * kWarp) {  // gather in batches: every load of a batch is in flight before the first store
+        float v[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k)
+            if (i + k * kWarp < I) v[k] = loadf(i + k * kWarp);
+#pragma unroll
+        for (int k = 0; k < 12; ++k)
+            if (i + k * kWarp < I) cur[i + k * kWarp] = v[k];
+    }
     __syncwarp();
+    if (dbg) dbg[0] = clock64();
     for (int k = 0; k < net.n_ip; ++k) {
-        apply_input_processing(net.ip[k], cur, I, lane);
+        apply_input_processing<kSerial>(net.ip[k], cur, I, lane);
         __syncwarp();
+        if (dbg && k < 2) dbg[1 + k] = clock64();
     }
     for (int l = 0; l < net.n_layers; ++l) {
         const DevLayer &ly = net.layers[l];
-        for (int o = lane; o < ly.outputs; o += kWarp) {
-            const float *w = ly.w + (size_t)o * ly.inputs;
-            float acc = 0.0f;
-            for (int i = 0; i < ly.inputs; ++i) acc += w[i] * cur[i];
-            nxt[o] = apply_transfer(ly.transfer, acc + ly.b[o]);
+        if constexpr (kSerial) {
+            for (int o = lane; o < ly.outputs; o += kWarp) {
+                const float *w = ly.w + (size_t)o * ly.inputs;
+                const float acc = serial_sum(ly.inputs, [&](int i) { return w[i] * cur[i]; });
+                nxt[o] = apply_transfer(ly.transfer, acc + ly.b[o]);
+            }
+        } else {  // four neurons at a time: the lanes split the inputs, lane k of the group finishes neuron o0 + k
+            for (int o0 = 0; o0 < ly.outputs; o0 += 4) {
+                float part[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                const float *w = ly.w + (size_t)o0 * ly.inputs;
+                const int rows = min(4, ly.outputs - o0);
+                for (int i = lane; i < ly.inputs; i += kWarp) {
+                    const float xi = cur[i];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (k < rows) part[k] += w[(size_t)k * ly.inputs + i] * xi;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) part[k] = warp_sum(part[k]);
+                if (lane < rows) {
+                    const float acc = lane == 0 ? part[0] : lane == 1 ? part[1] : lane == 2 ? part[2] : part[3];
+                    nxt[o0 + lane] = apply_transfer(ly.transfer, acc + ly.b[o0 + lane]);
+                }
+            }
         }
         __syncwarp();
+        if (dbg && l < 2) dbg[3 + l] = clock64();
         float *t = cur; cur = nxt; nxt = t;
     }
     for (int o = lane; o < O; o += kWarp) {
@@ -238,7 +360,7 @@ __global__ void nn_generic_kernel(const DevNet *__restrict__ netp, const float *
 
     for (int64_t j = (int64_t)blockIdx.x * warps + warp; j < n_evals; j += (int64_t)gridDim.x * warps) {
         const float *in = feat_ch + j * L;  // v[t*L+f]: contiguous in the column stream
-        float *cur = nn_evaluate(net, [&](int i) { return in[i]; }, buf0, buf1, lane);
+        float *cur = nn_evaluate<true>(net, [&](int i) { return in[i]; }, buf0, buf1, lane);
         bool hit = false;
         for (int o = lane; o < O; o += kWarp) {
             const float v = cur[o];
@@ -257,8 +379,8 @@ __global__ void nn_generic_kernel(const DevNet *__restrict__ netp, const float *
 // Live tick (Processor.swift:102-149 for every channel at once): ONE launch pulls the new samples of every channel
 // straight out of pinned host memory into the channel's device sample ring, computes the STFT columns they complete
 // into the channel's band-feature ring, evaluates the network for every completed feature window and writes the
-// outputs straight into pinned host memory, then raises a host-visible sequence flag. Reference arithmetic order
-// (this file is built with -fmad=false). grid = (blocks per channel, channels); with all three phases in one launch
+// outputs straight into pinned host memory, then raises a host-visible sequence flag. Reference operations, unfused
+// (this file is built with -fmad=false); the STFT keeps the reference order, the network's sums are lane-parallel. grid = (blocks per channel, channels); with all three phases in one launch
 // there is one block per channel (block-level barriers order the phases); large ticks run one launch per phase.
 __device__ __forceinline__ const float *relocate(const float *p, const unsigned char *from, const unsigned char *to) {
     return p ? reinterpret_cast<const float *>(to + (reinterpret_cast<const unsigned char *>(p) - from)) : nullptr;
@@ -270,6 +392,9 @@ __global__ void stream_tick_kernel(const DevNet *__restrict__ netp, StreamTick t
     const int warps = blockDim.x / kWarp, warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
     const int ch = blockIdx.y;
     const int tid0 = blockIdx.x * blockDim.x + threadIdx.x, tstride = gridDim.x * blockDim.x;
+    const bool stamp = t.stamps != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;  // SYLDET_STREAM_TIMING
+    long long ts[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (stamp) ts[0] = clock64();
 
     // (1) the longest-latency loads first: this channel's staged samples, straight out of pinned host memory
     const float *src = t.staged + (int64_t)ch * t.stage_pitch;
@@ -300,6 +425,7 @@ __global__ void stream_tick_kernel(const DevNet *__restrict__ netp, StreamTick t
     }
     const DevNet &net = s_net;
     float *ring = t.ring + (int64_t)ch * (t.ring_mask + 1);
+    if (stamp) ts[1] = clock64();
 
     if (t.phases & STREAM_PHASE_COPY) {
 #pragma unroll
@@ -308,6 +434,7 @@ __global__ void stream_tick_kernel(const DevNet *__restrict__ netp, StreamTick t
         for (int i = tid0 + 2 * tstride; i < t.n_staged; i += tstride) ring[(t.ring_pos + i) & t.ring_mask] = src[i];
     }
     __syncthreads();
+    if (stamp) ts[2] = clock64();
     const int L = net.band, O = net.outputs;
     float *band = t.band + (int64_t)ch * (t.band_mask + 1) * L;
     if (t.phases & STREAM_PHASE_COLUMNS) {
@@ -321,19 +448,35 @@ __global__ void stream_tick_kernel(const DevNet *__restrict__ netp, StreamTick t
         }
         __syncthreads();
     }
+    if (stamp) ts[3] = clock64();
     if (t.phases & STREAM_PHASE_EVALS) {
         float *buf0 = smem + (size_t)warp * 2 * net.max_width, *buf1 = buf0 + net.max_width;
         for (int64_t j = (int64_t)blockIdx.x * warps + warp; j < t.n_evals; j += (int64_t)gridDim.x * warps) {
             const int64_t c0 = t.eval0 + j;  // oldest column of the window
-            float *cur = nn_evaluate(net, [&](int i) { const int tt = i / L; return band[((c0 + tt) & t.band_mask) * L + (i - tt * L)]; },
-                                     buf0, buf1, lane);
-            for (int o = lane; o < O; o += kWarp) t.out[((int64_t)ch * t.n_evals + j) * O + o] = cur[o];
+            int tt = 0, f = lane;  // (column, bin) of input i = lane, lane + 32, ... without dividing
+            float *cur = nn_evaluate<false>(net, [&](int) {
+                while (f >= L) { f -= L; ++tt; }
+                const float v = __ldcg(&band[((c0 + tt) & t.band_mask) * L + f]);  // written by earlier ticks or, moments ago, by this block: L2 is the coherent copy
+                f += kWarp;
+                return v;
+            }, buf0, buf1, lane, stamp ? ts + 5 : nullptr);
+            if (t.packed) {  // one evaluation of <= 3 outputs: outputs and sequence number travel in one 16-byte store
+                if (lane == 0)
+                    t.packed[ch] = make_uint4(__float_as_uint(cur[0]), O > 1 ? __float_as_uint(cur[1]) : 0u, O > 2 ? __float_as_uint(cur[2]) : 0u, t.seq);
+            } else {
+                for (int o = lane; o < O; o += kWarp) t.out[((int64_t)ch * t.n_evals + j) * O + o] = cur[o];
+            }
             __syncwarp();
         }
     }
-    if (t.flags) {  // publish: one flag per channel when the launch has one block per channel, else the last block raises flag 0
+    if (stamp) {
+        ts[4] = clock64();
+        for (int k = 0; k < 10; ++k) t.stamps[k] = ts[k];
+    }
+    if (t.flags && !t.packed) {  // publish: one flag per channel when the launch has one block per channel, else the last block raises flag 0
         __threadfence_system();
         __syncthreads();
+
         if (threadIdx.x == 0) {
             if (gridDim.x == 1) {
                 *(volatile unsigned *)(t.flags + ch) = t.seq;

@@ -12,6 +12,9 @@
 #include "stream.hpp"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace syldet {
@@ -57,11 +60,23 @@ syldet_status StreamGroup::init(const Config &cfg, int n_channels, int max_buffe
     SYLDET_CUDA(cudaMallocHost(&h_out_, (size_t)n_channels * max_new_ * c.outputs * sizeof(float)));
     SYLDET_CUDA(cudaMallocHost(&h_flag_, (size_t)n_channels * sizeof(unsigned)));
     std::memset(h_flag_, 0, (size_t)n_channels * sizeof(unsigned));
+    SYLDET_CUDA(cudaMallocHost(&h_packed_, (size_t)n_channels * sizeof(uint4)));
+    std::memset(h_packed_, 0, (size_t)n_channels * sizeof(uint4));
+    if (const char *e = std::getenv("SYLDET_STREAM_TIMING"); e && e[0] == '1') SYLDET_CUDA(cudaMallocHost(&h_stamps_, 128));
     SYLDET_CUDA(cudaStreamSynchronize(stream_));
     return SYLDET_OK;
 }
 
 StreamGroup::~StreamGroup() {
+    if (h_stamps_ && t_ticks_ > 0) {
+        const double n = (double)t_ticks_;
+        std::fprintf(stderr, "[syldet stream timing] %lld single-launch ticks, %d channels; device cycles of block (0,0): preload %.0f, copy %.0f, "
+                             "columns %.0f, evaluations %.0f (gather %.0f, input processing %.0f + %.0f, layers %.0f + %.0f, output %.0f); host us: stage %.2f, launch call %.2f, wait %.2f\n",
+                     (long long)t_ticks_, n_channels_, t_phase_[0] / n, t_phase_[1] / n, t_phase_[2] / n, t_phase_[3] / n,
+                     t_eval_[0] / n, t_eval_[1] / n, t_eval_[2] / n, t_eval_[3] / n, t_eval_[4] / n, t_eval_[5] / n,
+                     t_host_[0] / n, t_host_[1] / n, t_host_[2] / n);
+    }
+    if (h_stamps_) cudaFreeHost(h_stamps_);
     if (stream_) {
         cudaSetDevice(model_.device());
         cudaStreamSynchronize(stream_);
@@ -70,20 +85,22 @@ StreamGroup::~StreamGroup() {
     if (h_stage_) cudaFreeHost(h_stage_);
     if (h_out_) cudaFreeHost(h_out_);
     if (h_flag_) cudaFreeHost(h_flag_);
+    if (h_packed_) cudaFreeHost(h_packed_);
 }
 
-// Every channel's block stores the tick's sequence number into its word of pinned host memory once its outputs are
-// visible; polling those words is cheaper than cudaStreamSynchronize and needs no device-side counting. The stream is queried now and then so a failed launch cannot spin forever.
-syldet_status StreamGroup::wait_for_tick() {
-    volatile unsigned *flags = h_flag_;
+// Every channel's block stores the tick's sequence number into pinned host memory once its outputs are visible (for a
+// single evaluation of <= 3 outputs: in the same 16-byte store as the outputs, so no system-scope fence is needed); polling those words is cheaper than cudaStreamSynchronize and needs no device-side counting. The stream is queried now and then so a failed launch cannot spin forever.
+syldet_status StreamGroup::wait_for_tick(bool packed) {
+    volatile unsigned *flags = packed ? &h_packed_[0].w : h_flag_;
+    const int step = packed ? 4 : 1;  // words between consecutive channels
     int ch = 0;  // channels [0, ch) have published this tick
     for (unsigned spins = 0;; ++spins) {
-        while (ch < n_channels_ && flags[ch] == seq_) ++ch;
+        while (ch < n_channels_ && flags[(size_t)ch * step] == seq_) ++ch;
         if (ch == n_channels_) return SYLDET_OK;
         if ((spins & 0x3fff) == 0x3fff) {
             cudaError_t e = cudaStreamQuery(stream_);
             if (e == cudaSuccess) {
-                while (ch < n_channels_ && flags[ch] == seq_) ++ch;
+                while (ch < n_channels_ && flags[(size_t)ch * step] == seq_) ++ch;
                 if (ch == n_channels_) return SYLDET_OK;
                 return set_error(SYLDET_ERR_CUDA, "live tick finished without publishing its results");
             }
@@ -93,6 +110,7 @@ syldet_status StreamGroup::wait_for_tick() {
 }
 
 syldet_status StreamGroup::submit(const float *const *bufs, int n, const float **outs, int64_t *n_new) {
+    const auto tp0 = std::chrono::steady_clock::now();
     *n_new = 0;
     *outs = h_out_;
     if (n < 0 || n > max_buffer_) return set_error(SYLDET_ERR_ARG, "buffer longer than max_buffer");
@@ -127,15 +145,19 @@ syldet_status StreamGroup::submit(const float *const *bufs, int n, const float *
     t.out = h_out_;
     t.counter = counter_.as<unsigned>();
     t.seq = ++seq_;
+    t.stamps = h_stamps_;
     t.blob = model_.blob();
     t.blob_bytes = (int)model_.blob_bytes();
     int warps = 4;
     stream_tick_smem(c.fourier_length, model_.max_width(), &warps);
     const DevNet *net = model_.dev_net();
     const int64_t cap = std::max<int64_t>(1, (model_.sm_count() * 8) / n_channels_);
-    if (n_cols <= warps) {  // the live shape: one launch, one block per channel
+    const bool single = n_cols <= warps;
+    const auto tp1 = std::chrono::steady_clock::now();
+    if (single) {  // the live shape: one launch, one block per channel
         t.phases = STREAM_PHASE_COPY | STREAM_PHASE_COLUMNS | (avail > 0 ? STREAM_PHASE_EVALS : 0);
         t.flags = h_flag_;
+        if (avail == 1 && c.outputs <= 3) t.packed = h_packed_;
         SYLDET_CUDA(launch_stream_tick(net, c.fourier_length, model_.max_width(), n_channels_, 1, t, stream_));
         ++launches_;
     } else {  // a long buffer: one launch per phase so each can spread over many blocks per channel
@@ -156,8 +178,23 @@ syldet_status StreamGroup::submit(const float *const *bufs, int n, const float *
             ++launches_;
         }
     }
-    st = wait_for_tick();
+    const auto tp2 = std::chrono::steady_clock::now();
+    st = wait_for_tick(t.packed != nullptr);
     if (st != SYLDET_OK) return st;
+    if (t.packed) {  // unpack into the documented [n_channels][n_new][outputs] layout
+        for (int ch = 0; ch < n_channels_; ++ch) std::memcpy(h_out_ + (size_t)ch * c.outputs, &h_packed_[ch], (size_t)c.outputs * sizeof(float));
+    }
+    if (h_stamps_ && single && avail > 0) {
+        const auto tp3 = std::chrono::steady_clock::now();
+        for (int k = 0; k < 4; ++k) t_phase_[k] += (double)(h_stamps_[k + 1] - h_stamps_[k]);
+        t_eval_[0] += (double)(h_stamps_[5] - h_stamps_[3]);   // gather
+        for (int k = 1; k < 5; ++k) t_eval_[k] += (double)(h_stamps_[5 + k] - h_stamps_[4 + k]);  // ip0, ip1, layer0, layer1
+        t_eval_[5] += (double)(h_stamps_[4] - h_stamps_[9]);   // reverse maps + publish
+        t_host_[0] += std::chrono::duration<double, std::micro>(tp1 - tp0).count();
+        t_host_[1] += std::chrono::duration<double, std::micro>(tp2 - tp1).count();
+        t_host_[2] += std::chrono::duration<double, std::micro>(tp3 - tp2).count();
+        ++t_ticks_;
+    }
     staged_ = 0;
     cols_done_ += n_cols;
     if (avail > 0) {

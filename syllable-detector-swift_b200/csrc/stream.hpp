@@ -20,7 +20,7 @@ public:
     int64_t launch_count() const { return launches_; }
 
 private:
-    syldet_status wait_for_tick();
+    syldet_status wait_for_tick(bool packed);
 
     DeviceModel model_;
     int n_channels_ = 0, max_buffer_ = 0;
@@ -38,6 +38,11 @@ private:
     cudaStream_t stream_ = nullptr;
     float *h_stage_ = nullptr, *h_out_ = nullptr;
     unsigned *h_flag_ = nullptr;
+    uint4 *h_packed_ = nullptr;  // [n_channels] {out0, out1, out2, seq}: the single-evaluation tick's result, one store per channel
+    // SYLDET_STREAM_TIMING=1: device cycle stamps per phase and host microseconds per step, reported by the destructor
+    long long *h_stamps_ = nullptr;
+    double t_phase_[4] = {0, 0, 0, 0}, t_eval_[6] = {0, 0, 0, 0, 0, 0}, t_host_[3] = {0, 0, 0};
+    int64_t t_ticks_ = 0;
 };
 
 class Detector {

@@ -72,10 +72,11 @@ bool read_wav(const std::string &path, Wav &w, std::string &err) {
 }
 
 void usage() {
-    std::puts("Usage: syldet -n <net> [-a <audio>]... [-d <seconds>]");
+    std::puts("Usage: syldet -n <net> [-a <audio>]... [-d <seconds>] [-s <trace.wav>]");
     std::puts("  -n, --net <net>          Path to trained network file.");
     std::puts("  -a, --audio <audio>      Path to the audio file to process.");
     std::puts("  -d, --debounce <seconds> Number of seconds to debounce triggers.");
+    std::puts("  -s, --simulate <wav>     Write the simulator trace (output 0 / threshold 0, clamped to [0, 1], 16-bit) instead of events.");
     std::puts("The command line will write a comma-separated list of detection events (when the network has at least one output above threshold) to standard out. For example, it might output:");
     std::puts("");
     std::puts("\t0,1593298,36.1292063492063,0.918557");
@@ -99,6 +100,20 @@ std::string shortest(double v, bool single) {
     return s;
 }
 
+bool write_wav16(const std::string &path, const std::vector<int16_t> &interleaved, int channels, int rate) {
+    FILE *f = std::fopen(path.c_str(), "wb");
+    if (!f) return false;
+    const uint32_t data = (uint32_t)(interleaved.size() * 2), riff = 36 + data, fmt_len = 16, byte_rate = (uint32_t)rate * channels * 2;
+    const uint16_t pcm = 1, ch = (uint16_t)channels, align = (uint16_t)(channels * 2), bits = 16;
+    const uint32_t r = (uint32_t)rate;
+    bool ok = std::fwrite("RIFF", 1, 4, f) == 4 && std::fwrite(&riff, 4, 1, f) == 1 && std::fwrite("WAVEfmt ", 1, 8, f) == 8 &&
+              std::fwrite(&fmt_len, 4, 1, f) == 1 && std::fwrite(&pcm, 2, 1, f) == 1 && std::fwrite(&ch, 2, 1, f) == 1 &&
+              std::fwrite(&r, 4, 1, f) == 1 && std::fwrite(&byte_rate, 4, 1, f) == 1 && std::fwrite(&align, 2, 1, f) == 1 &&
+              std::fwrite(&bits, 2, 1, f) == 1 && std::fwrite("data", 1, 4, f) == 4 && std::fwrite(&data, 4, 1, f) == 1 &&
+              std::fwrite(interleaved.data(), 2, interleaved.size(), f) == interleaved.size();
+    return std::fclose(f) == 0 && ok;
+}
+
 }  // namespace
 
 int main(int argc, char **argv) {
@@ -106,6 +121,7 @@ int main(int argc, char **argv) {
     std::vector<std::string> audio;
     bool have_debounce = false;
     double debounce = 0.0;
+    std::string simulate;  // -s <out.wav>: write the simulator's output track instead of CSV rows
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
         auto value = [&](std::string &dst) { if (i + 1 >= argc) return false; dst = argv[++i]; return true; };
@@ -113,6 +129,7 @@ int main(int argc, char **argv) {
         if (a == "-n" || a == "--net") { if (!value(net)) { usage(); return 64; } }
         else if (a == "-a" || a == "--audio") { if (!value(v)) { usage(); return 64; } audio.push_back(v); }
         else if (a == "-d" || a == "--debounce") { if (!value(v)) { usage(); return 64; } char *e; debounce = std::strtod(v.c_str(), &e); have_debounce = (*e == 0 && !v.empty()); }
+        else if (a == "-s" || a == "--simulate") { if (!value(simulate)) { usage(); return 64; } }
         else { usage(); return 64; }  // EX_USAGE, main.swift:40
     }
     if (net.empty()) { usage(); return 64; }
@@ -140,6 +157,20 @@ int main(int argc, char **argv) {
         }
         if (audio.size() > 1) std::printf("%s\n", path.c_str());  // main.swift:122-124
         if (w.frames <= 0) continue;
+        if (!simulate.empty()) {
+            // the GUI simulator's output (ViewControllerSimulator.swift:135-376): 16-bit PCM, one trace channel per input channel
+            std::vector<int16_t> planar((size_t)w.channels * w.frames), inter((size_t)w.channels * w.frames);
+            if (syldet_batch_simulate_host(batch, w.interleaved.data(), SYLDET_PCM_F32, w.channels, w.frames, 0, SYLDET_LAYOUT_INTERLEAVED,
+                                           SYLDET_PCM_S16, planar.data()) != SYLDET_OK) {
+                std::fprintf(stderr, "Can not simulate %s: %s.\n", path.c_str(), syldet_last_error());
+                continue;
+            }
+            for (int c = 0; c < w.channels; ++c)
+                for (int64_t i = 0; i < w.frames; ++i) inter[(size_t)i * w.channels + c] = planar[(size_t)c * w.frames + i];
+            const std::string out = audio.size() > 1 ? simulate + "." + std::to_string(&path - &audio[0]) + ".wav" : simulate;
+            if (!write_wav16(out, inter, w.channels, w.rate)) std::fprintf(stderr, "Unable to write %s\n", out.c_str());
+            continue;
+        }
         syldet_events *ev = nullptr;
         if (syldet_batch_run_host(batch, w.interleaved.data(), SYLDET_PCM_F32, w.channels, w.frames, 0, SYLDET_LAYOUT_INTERLEAVED,
                                   debounce_frames, SYLDET_DETECT_ANY_OUTPUT, nullptr, &ev) != SYLDET_OK) {

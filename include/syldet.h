@@ -133,6 +133,18 @@ syldet_status syldet_batch_set_slice_evals(syldet_batch *b, int64_t evals);
 syldet_status syldet_batch_run_host(syldet_batch *b, const void *pcm, int pcm_format, int n_channels, int64_t n_samples,
                                     int64_t channel_stride, int layout, int64_t debounce_frames, int detect_rule,
                                     float *all_outputs, syldet_events **events);
+
+/*
+ * Simulator trace: what ViewControllerSimulator.simulateNetwork writes next to the input audio
+ * (SyllableDetector/ViewControllerSimulator.swift:251-254 initial count, :308-344 per-value fill, :203-211 16-bit LPCM writer).
+ * trace is a host buffer [n_channels][n_samples] (planar) of trace_format SYLDET_PCM_F32 or SYLDET_PCM_S16:
+ *   trace[s] = 0                                          for s <  first_output_sample
+ *            = clamp(out0_j / Float(thresholds[0]), 0, 1)  for s >= first_output_sample, j = (s - first_output_sample) / hop
+ *            = 0                                          past the last evaluation's hop (upstream leaves stale buffer contents there)
+ * S16 stores min(32767, rint(v * 32768)) and writes NaN (silence through l2normalize) as 0. pcm arguments as for syldet_batch_run_host.
+ */
+syldet_status syldet_batch_simulate_host(syldet_batch *b, const void *pcm, int pcm_format, int n_channels, int64_t n_samples,
+                                         int64_t channel_stride, int layout, int trace_format, void *trace);
 /*
  * Device-resident variant: d_pcm is a device pointer (float32), d_all_outputs an optional device buffer.
  * `stream` is a cudaStream_t (NULL = legacy default stream).  Launches are asynchronous; nothing is copied to the host.

@@ -197,6 +197,29 @@ class Oracle:
         return s, s / self.samplingRate, outs[j]
 
 
+def simulator_trace(out0, thr0, first, hop, n_samples, s16=False):
+    """Restates the simulator's output track (SyllableDetector/ViewControllerSimulator.swift:251-254 initial silent count,
+    :326-344 value = clamp(lastOutputs[0] / Float(thresholds[0]), 0, 1) repeated for windowLength - windowOverlap samples).
+    Samples past the last evaluation's hop are 0 here (upstream leaves stale buffer contents). Plain loop: small cases only."""
+    tr = np.zeros(n_samples, dtype=np.float32)
+    thr = np.float32(thr0)
+    pos = first
+    for v in np.asarray(out0, dtype=np.float32):
+        if pos >= n_samples:
+            break
+        v = np.float32(v) / thr
+        if v > 1.0:
+            v = np.float32(1.0)
+        elif v < 0.0:
+            v = np.float32(0.0)
+        tr[pos:min(pos + hop, n_samples)] = v
+        pos += hop
+    if not s16:
+        return tr
+    q = np.where(np.isnan(tr), np.float32(0.0), np.rint(tr * np.float32(32768.0)))
+    return np.minimum(q, 32767.0).astype(np.int16)
+
+
 def make_window(kind, n):
     """kind: 0 none, 1 hamming, 2 hann, 3 blackman (vDSP N-denominator forms)."""
     w = np.zeros(n, dtype=np.float32)

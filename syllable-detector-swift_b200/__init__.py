@@ -87,6 +87,7 @@ def _load():
         "syldet_batch_set_slice_evals": (i32, [vp, i64]),
         "syldet_batch_set_kernel": (i32, [vp, i32]), "syldet_batch_active_kernel": (i32, [vp]),
         "syldet_batch_run_host": (i32, [vp, vp, i32, i32, i64, i64, i32, i64, i32, vp, pvp]),
+        "syldet_batch_simulate_host": (i32, [vp, vp, i32, i32, i64, i64, i32, i32, vp]),
         "syldet_batch_launch_device": (i32, [vp, vp, i32, i64, i64, i32, i32, vp, vp]),
         "syldet_batch_collect": (i32, [vp, i64, pvp]), "syldet_batch_launch_count": (i64, [vp]),
         "syldet_batch_last_detection_count": (i32, [vp, C.POINTER(i64)]),
@@ -313,6 +314,20 @@ class BatchDetector:
                                          outs.ctypes.data if want_outputs else None, C.byref(ev)))
         events = Events(ev, self.config.sampling_rate)
         return (events, outs) if want_outputs else events
+
+    def simulate(self, pcm, s16=False, layout=LAYOUT_PLANAR):
+        """Simulator trace (ViewControllerSimulator.swift:251-254, 308-344): clamp(out0 / thr0, 0, 1) held per hop, one value per
+        input sample. -> [n_channels, n_samples] float32 (or int16 as the upstream 16-bit writer stores it)."""
+        a = np.asarray(pcm)
+        if a.ndim == 1:
+            a = a[None, :] if layout == LAYOUT_PLANAR else a[:, None]
+        fmt = PCM_S16 if a.dtype == np.int16 else PCM_F32
+        a = np.ascontiguousarray(a, dtype=np.int16 if fmt == PCM_S16 else np.float32)
+        nch, n = (a.shape if layout == LAYOUT_PLANAR else a.shape[::-1])
+        trace = np.zeros((nch, n), dtype=np.int16 if s16 else np.float32)
+        _check(lib.syldet_batch_simulate_host(self._h, a.ctypes.data, fmt, nch, n, n, layout, PCM_S16 if s16 else PCM_F32,
+                                              trace.ctypes.data))
+        return trace
 
     def launch_device(self, d_pcm_ptr, n_channels, n_samples, channel_stride, detect_rule=DETECT_ANY_OUTPUT, d_outputs_ptr=None,
                       stream=None, layout=LAYOUT_PLANAR):

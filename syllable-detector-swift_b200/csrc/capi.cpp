@@ -178,6 +178,15 @@ syldet_status syldet_batch_run_host(syldet_batch *b, const void *pcm, int pcm_fo
         return SYLDET_OK;
     });
 }
+syldet_status syldet_batch_simulate_host(syldet_batch *b, const void *pcm, int pcm_format, int n_channels, int64_t n_samples,
+                                         int64_t channel_stride, int layout, int trace_format, void *trace) {
+    if (!b || !trace) return set_error(SYLDET_ERR_ARG, "null argument");
+    return guarded([&] {
+        Events ev;
+        return b->b.run_host(pcm, pcm_format, n_channels, n_samples, channel_stride, layout, 0, SYLDET_DETECT_FIRST_OUTPUT, nullptr, ev,
+                             trace_format, trace);
+    });
+}
 syldet_status syldet_batch_launch_device(syldet_batch *b, const float *d_pcm, int n_channels, int64_t n_samples,
                                          int64_t channel_stride, int layout, int detect_rule, float *d_all_outputs, void *stream) {
     if (!b) return set_error(SYLDET_ERR_ARG, "null argument");

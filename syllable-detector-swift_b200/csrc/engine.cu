@@ -730,8 +730,9 @@ syldet_status Batch::ensure_pipeline(int slices, size_t event_bytes) {
 // The recording is cut into time slices: slice k+1 crosses PCIe while slice k is detected and its events are read back and
 // sorted on the host, so everything except the copy itself hides behind the copy.
 syldet_status Batch::run_host(const void *pcm, int fmt, int n_channels, int64_t n_samples, int64_t ch_stride, int layout,
-                              int64_t debounce_frames, int detect_rule, float *all_outputs, Events &out) {
+                              int64_t debounce_frames, int detect_rule, float *all_outputs, Events &out, int trace_format, void *trace) {
     if (!pcm || n_channels <= 0 || n_samples < 0) return set_error(SYLDET_ERR_ARG, "bad pcm arguments");
+    if (trace && trace_format != SYLDET_PCM_F32 && trace_format != SYLDET_PCM_S16) return set_error(SYLDET_ERR_ARG, "unknown trace format");
     if (n_channels > 65535) return set_error(SYLDET_ERR_ARG, "more than 65535 channels in one call");
     if (fmt != SYLDET_PCM_F32 && fmt != SYLDET_PCM_S16) return set_error(SYLDET_ERR_ARG, "unknown pcm format");
     if (layout != SYLDET_LAYOUT_PLANAR && layout != SYLDET_LAYOUT_INTERLEAVED) return set_error(SYLDET_ERR_ARG, "unknown layout");
@@ -760,11 +761,11 @@ syldet_status Batch::run_host(const void *pcm, int fmt, int n_channels, int64_t 
         if (st != SYLDET_OK) return st;
     }
     DeviceBuffer d_outs;
-    if (all_outputs && E > 0) {
+    if ((all_outputs || trace) && E > 0) {
         st = d_outs.reserve((size_t)n_channels * E * O * sizeof(float));
         if (st != SYLDET_OK) return st;
     }
-    float *d_all = all_outputs && E > 0 ? d_outs.as<float>() : nullptr;
+    float *d_all = (all_outputs || trace) && E > 0 ? d_outs.as<float>() : nullptr;
 
     // ---- slices: evaluations [eb[k], eb[k+1]) become launchable once samples [0, sb[k+1]) are on the device ----------------
     int K = (int)std::min<int64_t>(kMaxSlices, std::max<int64_t>(1, (int64_t)total / slice_evals_));
@@ -884,6 +885,17 @@ syldet_status Batch::run_host(const void *pcm, int fmt, int n_channels, int64_t 
     if (all_outputs && E > 0) {
         SYLDET_CUDA(cudaStreamSynchronize(sx));
         SYLDET_CUDA(cudaMemcpy(all_outputs, d_outs.get(), (size_t)n_channels * E * O * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+    if (trace && n_samples > 0) {  // simulator trace (ViewControllerSimulator.swift:251-254, 308-344), built on the device
+        const size_t tsz = trace_format == SYLDET_PCM_S16 ? 2 : 4;
+        DeviceBuffer d_trace;
+        st = d_trace.reserve((size_t)n_channels * n_samples * tsz);
+        if (st != SYLDET_OK) return st;
+        SYLDET_CUDA(launch_simulator_trace(d_all, n_channels, E, O, (float)c.thresholds[0], c.first_output_sample(), c.hop, n_samples,
+                                           trace_format, d_trace.get(), n_samples, sx));
+        launches_ += 1;
+        SYLDET_CUDA(cudaMemcpyAsync(trace, d_trace.get(), (size_t)n_channels * n_samples * tsz, cudaMemcpyDeviceToHost, sx));
+        SYLDET_CUDA(cudaStreamSynchronize(sx));
     }
     return SYLDET_OK;
 }

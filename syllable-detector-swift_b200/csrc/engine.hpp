@@ -112,7 +112,8 @@ public:
     syldet_status set_kernel(int kernel);
     int active_kernel() const;
     syldet_status run_host(const void *pcm, int fmt, int n_channels, int64_t n_samples, int64_t ch_stride, int layout,
-                           int64_t debounce_frames, int detect_rule, float *all_outputs, Events &out);
+                           int64_t debounce_frames, int detect_rule, float *all_outputs, Events &out, int trace_format = 0,
+                           void *trace = nullptr);
     syldet_status launch_device(const float *d_pcm, int n_channels, int64_t n_samples, int64_t ch_stride, int layout,
                                 int detect_rule, float *d_all_outputs, cudaStream_t stream);
     syldet_status collect(int64_t debounce_frames, Events &out);

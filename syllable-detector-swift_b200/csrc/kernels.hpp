@@ -10,6 +10,8 @@ namespace syldet {
 // ---- generic (reference-order) path: kernels_generic.cu ----------------------------------------------------------
 cudaError_t launch_ingest(const void *src, int format, int interleaved, int n_channels, int64_t n_samples, int64_t src_stride,
                           float *dst, int64_t dst_stride, cudaStream_t stream);
+cudaError_t launch_simulator_trace(const float *all_out, int n_channels, int64_t evals, int n_out, float thr0, int64_t first, int hop,
+                                   int64_t n_samples, int format, void *trace, int64_t trace_stride, cudaStream_t stream);
 cudaError_t launch_stft_band_generic(const DevNet *d_net, int fft_len, const float *pcm, int64_t ch_stride, int n_channels,
                                      int64_t col0, int64_t n_cols, float *feat, cudaStream_t stream);
 cudaError_t launch_nn_generic(const DevNet *d_net, int max_width, const float *feat, int n_channels, int64_t n_cols,

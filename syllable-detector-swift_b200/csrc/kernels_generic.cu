@@ -489,6 +489,41 @@ __global__ void stream_tick_kernel(const DevNet *__restrict__ netp, StreamTick t
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Simulator trace (SyllableDetector/ViewControllerSimulator.swift:251-254, 308-344): one value per input sample,
+// 0 until the first evaluation is due, then clamp(out0 / Float(thr0), 0, 1) of evaluation j held for one hop. A pure
+// HBM stream: 4 B of network output per hop read, 2 or 4 B per sample written; a thread writes 8 consecutive samples.
+__global__ void simulator_trace_kernel(const float *__restrict__ all_out, int64_t evals, int n_out, float thr0, int64_t first,
+                                       int hop, int64_t n_samples, int format, void *__restrict__ trace, int64_t trace_stride) {
+    const int ch = blockIdx.y;
+    const float *out_ch = all_out + (int64_t)ch * evals * n_out;
+    for (int64_t s0 = 8 * (blockIdx.x * (int64_t)blockDim.x + threadIdx.x); s0 < n_samples; s0 += 8 * (int64_t)gridDim.x * blockDim.x) {
+        int64_t j = s0 >= first ? (s0 - first) / hop : -1;
+        int64_t next = s0 >= first ? first + (j + 1) * hop : first;  // sample at which evaluation j + 1 takes over
+        float v = 0.0f;
+        bool fresh = true;
+        for (int k = 0; k < 8 && s0 + k < n_samples; ++k) {
+            const int64_t s = s0 + k;
+            if (s >= next) { ++j; next += hop; fresh = true; }
+            if (fresh) {
+                fresh = false;
+                v = 0.0f;
+                if (j >= 0 && j < evals) {
+                    v = out_ch[j * n_out] / thr0;
+                    if (v > 1.0f) v = 1.0f;
+                    else if (v < 0.0f) v = 0.0f;
+                }
+            }
+            if (format == SYLDET_PCM_S16) {  // LPCM 16-bit writer settings (:203-211); NaN (silence through l2normalize) is written as 0
+                const float q = v != v ? 0.0f : rintf(v * 32768.0f);
+                ((int16_t *)trace)[(int64_t)ch * trace_stride + s] = (int16_t)(q > 32767.0f ? 32767.0f : q);
+            } else {
+                ((float *)trace)[(int64_t)ch * trace_stride + s] = v;
+            }
+        }
+    }
+}
+
 }  // namespace
 
 cudaError_t launch_ingest(const void *src, int format, int interleaved, int n_channels, int64_t n_samples, int64_t src_stride,
@@ -497,6 +532,16 @@ cudaError_t launch_ingest(const void *src, int format, int interleaved, int n_ch
     if (total <= 0) return cudaSuccess;
     int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
     ingest_kernel<<<blocks, 256, 0, stream>>>(src, format, interleaved, n_channels, n_samples, src_stride, dst, dst_stride);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_simulator_trace(const float *all_out, int n_channels, int64_t evals, int n_out, float thr0, int64_t first, int hop,
+                                   int64_t n_samples, int format, void *trace, int64_t trace_stride, cudaStream_t stream) {
+    if (n_samples <= 0 || n_channels <= 0) return cudaSuccess;
+    const int64_t threads = (n_samples + 7) / 8;
+    const int bx = (int)std::min<int64_t>((threads + 255) / 256, std::max<int64_t>(1, (148 * 16) / n_channels));
+    dim3 grid((unsigned)bx, (unsigned)n_channels);
+    simulator_trace_kernel<<<grid, 256, 0, stream>>>(all_out, evals, n_out, thr0, first, hop, n_samples, format, trace, trace_stride);
     return cudaGetLastError();
 }
 

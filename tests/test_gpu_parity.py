@@ -126,6 +126,29 @@ def test_generated_configs_fused_and_generic(sd, oracle_mod, cw, kw):
             _check_channel(o, x[ch], outs[ch], ev.sample[ev.channel == ch], tol)
 
 
+def test_high_overlap_wide_hidden_config(sd, oracle_mod, cw):
+    """BASELINE config 4 shape: FFT 1024, hop 4, band 1-8 kHz (L = 162), T = 8 (1296 inputs), 256 tansig units, 2 outputs.
+    Too wide for the fused kernels: the reference-order kernels take it. Left-to-right sums over 1296 terms: same order in
+    the oracle, so the usual tolerance holds."""
+    text = cw.random_config(seed=21, fft_len=1024, overlap=1020, freq_range=(1000.0, 8000.0), time_range=8, hidden=(256,),
+                            outputs=2, threshold=0.2)
+    c = sd.SyllableDetectorConfig.from_text(text).validate()
+    assert (c.hop, c.net_inputs) == (4, 1296)
+    o = oracle_mod.Oracle(text=text)
+    rng = np.random.default_rng(3)
+    n = 1024 + 4 * 7 + 4 * 700
+    t = np.arange(n)
+    x = np.stack([(0.05 * rng.standard_normal(n) + 0.3 * np.sin(2 * np.pi * f0 * t / 44100)).astype(np.float32) for f0 in (3000.0, 6100.0)])
+    det = sd.BatchDetector(c)
+    assert det.active_kernel == sd.KERNEL_GENERIC
+    ev, outs = det.run(x, want_outputs=True)
+    assert outs.shape[1] == 701
+    for ch in range(2):
+        ref = o.run(x[ch])[0]
+        scale = max(1.0, float(np.nanmax(np.abs(ref))))
+        _check_channel(o, x[ch], outs[ch], ev.sample[ev.channel == ch], TOL_OUT * scale)
+
+
 @pytest.mark.parametrize("kernel_name", ["KERNEL_FUSED", "KERNEL_TENSOR", "KERNEL_GENERIC"])
 def test_chunk_and_batch_invariance(sd, cfg, synth, kernel_name):
     """Any split of the work gives identical results: channels together or alone, long or short recordings.
@@ -340,6 +363,31 @@ def test_stream_group_ragged_ticks_generated_configs(sd, oracle_mod, cw, kw):
                 assert near or bool(seen[ch]) == flag
     assert done == o.num_evals(n) > 0
     assert 0 < g.launch_count
+
+
+def test_simulator_trace_matches_oracle(sd, cfg, orc, oracle_mod, synth):
+    """Simulator output track (ViewControllerSimulator.swift:251-254, 308-344): float trace within TOL_OUT / thr0 of the oracle's,
+    16-bit trace within one quantisation step; exact structure (leading zeros, hop-long plateaus, zero tail)."""
+    n = 44100 * 3 + 77
+    x = synth.make_audio(2, n, seed=23)
+    det = sd.BatchDetector(cfg)
+    tr = det.simulate(x)
+    tr16 = det.simulate(x, s16=True)
+    first, hop, thr0 = cfg.first_output_sample, cfg.hop, cfg.thresholds[0]
+    assert tr.shape == (2, n) and tr16.dtype == np.int16
+    for ch in range(2):
+        ref_out = orc.run(x[ch])[0][:, 0]
+        ref = oracle_mod.simulator_trace(ref_out, thr0, first, hop, n)
+        ref16 = oracle_mod.simulator_trace(ref_out, thr0, first, hop, n, s16=True)
+        assert np.all(tr[ch, :first] == 0.0) and np.abs(tr[ch] - ref).max() <= TOL_OUT / thr0 * 1.01
+        E = orc.num_evals(n)
+        body = tr[ch, first:first + E * hop].reshape(E, hop)
+        assert np.all(body == body[:, :1]) and np.all(tr[ch, first + E * hop:] == 0.0)
+        assert tr[ch].min() >= 0.0 and tr[ch].max() == 1.0   # the synthetic syllables saturate the trace
+        assert np.abs(tr16[ch].astype(np.int32) - ref16.astype(np.int32)).max() <= 2 and tr16[ch].max() == 32767
+    # silence: l2normalize gives NaN outputs; the float trace keeps them, the 16-bit trace stores 0
+    z = np.zeros((1, 4000), dtype=np.float32)
+    assert np.isnan(det.simulate(z)[0, first:first + hop]).all() and np.all(det.simulate(z, s16=True) == 0)
 
 
 def test_resampler_matches_oracle_bit_for_bit(sd, oracle_mod):

@@ -150,3 +150,16 @@ def test_resampler_oracle(oracle_mod):
     assert 0.955 < n_out / ideal < 0.98
     st = r.state()
     assert abs(st[0] - step) == 0 and -1.0 <= st[2] <= 1.0
+
+
+def test_simulator_trace_known_answer():
+    """ViewControllerSimulator.swift:251-254, 326-344: silent until the first evaluation is due, then clamp(out0 / thr0, 0, 1)
+    held for one hop; the 16-bit form saturates at 32767 and stores NaN as 0."""
+    import oracle
+    tr = oracle.simulator_trace([0.25, 1.0, -0.1, np.nan], 0.5, first=5, hop=3, n_samples=16)
+    exp = np.array([0, 0, 0, 0, 0, .5, .5, .5, 1, 1, 1, 0, 0, 0, np.nan, np.nan], dtype=np.float32)
+    assert np.array_equal(tr, exp, equal_nan=True)
+    tr16 = oracle.simulator_trace([0.25, 1.0, -0.1, np.nan], 0.5, first=5, hop=3, n_samples=16, s16=True)
+    assert tr16.tolist() == [0] * 5 + [16384] * 3 + [32767] * 3 + [0] * 5
+    # more evaluations than the recording has room for: the trace stops at n_samples
+    assert oracle.simulator_trace([1.0] * 10, 1.0, first=2, hop=4, n_samples=9).tolist() == [0, 0, 1, 1, 1, 1, 1, 1, 1]

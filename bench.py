@@ -51,7 +51,8 @@ def cpu_reference(args, steps, warmup, calibrate_s=0.0):
     oracle.build()
     synth = importlib.import_module("syllable-detector-swift_b200.synth")
     orc = oracle.Oracle(SAMPLE_TXT)
-    threads = orc.max_threads()
+    # every host core this process may run on - not omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 to its workers
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     sec = 120
     x = synth.make_audio(threads, sec * FS, seed=123)
     t0 = time.perf_counter()

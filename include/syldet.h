@@ -187,6 +187,21 @@ void syldet_stream_destroy(syldet_stream *s);
 syldet_status syldet_stream_submit(syldet_stream *s, const float *const *bufs, int n, uint8_t *seen, int32_t *n_new,
                                    float *last_out);
 int64_t syldet_stream_launch_count(const syldet_stream *s);
+/*
+ * Level meters of the live view: getInputForChannel / getOutputForChannel for every channel (Processor.swift:158-184, StatMax in
+ * SummaryStat.swift:39-62). input_rms[c] = sqrt(max over the buffers submitted since the last call of sum(x^2)/n, :110-113),
+ * output_max[c] = max over the evaluations since the last call of Double(lastOutputs[0]) (:138); NaN where upstream returns nil.
+ * Reads and resets (readStatAndReset). Both maxima are kept on the device by the tick kernel. Either array may be NULL.
+ */
+syldet_status syldet_stream_read_levels(syldet_stream *s, double *input_rms, double *output_max);
+/*
+ * TTL-style pulses (ProcessorAudio: Processor.swift:187-221; AudioOutputInterface: AudioInterface.swift:13-40, 442-445).
+ * After set_pulse(high_seconds = 0.001 upstream, output_rate), every submit whose `seen` flag is set for a channel arms
+ * Int(high_seconds * output_rate) high frames for it; render_pulses fills the next n_frames of every channel's output buffer
+ * with 1.0 while armed frames remain and 0.0 after, exactly as the output device's render callback does.
+ */
+syldet_status syldet_stream_set_pulse(syldet_stream *s, double high_seconds, double output_rate);
+syldet_status syldet_stream_render_pulses(syldet_stream *s, float *const *out, int n_frames);
 
 /* ---- ResamplerLinear (Common/Resampler.swift:20-70), bit-faithful including per-buffer state ------------------------ */
 syldet_status syldet_resampler_linear_create(double rate_in, double rate_out, syldet_resampler **out);

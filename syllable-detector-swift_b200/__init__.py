@@ -100,6 +100,8 @@ def _load():
         "syldet_detector_seen_syllable": (i32, [vp]),
         "syldet_stream_create": (i32, [vp, i32, i32, i32, pvp]), "syldet_stream_destroy": (None, [vp]),
         "syldet_stream_submit": (i32, [vp, vp, i32, vp, vp, vp]), "syldet_stream_launch_count": (i64, [vp]),
+        "syldet_stream_read_levels": (i32, [vp, vp, vp]), "syldet_stream_set_pulse": (i32, [vp, dbl, dbl]),
+        "syldet_stream_render_pulses": (i32, [vp, vp, i32]),
         "syldet_resampler_linear_create": (i32, [dbl, dbl, pvp]), "syldet_resampler_destroy": (None, [vp]),
         "syldet_resampler_process": (i32, [vp, vp, i64, vp, i64, C.POINTER(i64)]),
         "syldet_resampler_max_output": (i64, [vp, i64]),
@@ -456,6 +458,25 @@ class StreamGroup:
     @property
     def launch_count(self):
         return lib.syldet_stream_launch_count(self._h)
+
+    def read_levels(self):
+        """-> (input_rms[n_channels], output_max[n_channels]) since the last call, NaN = upstream's nil
+        (getInputForChannel / getOutputForChannel, Processor.swift:158-184); resets both."""
+        a = np.zeros(self.n_channels, dtype=np.float64)
+        b = np.zeros(self.n_channels, dtype=np.float64)
+        _check(lib.syldet_stream_read_levels(self._h, a.ctypes.data, b.ctypes.data))
+        return a, b
+
+    def set_pulse(self, high_seconds=0.001, output_rate=44100.0):
+        """ProcessorAudio.highDuration (Processor.swift:192): arm TTL pulses on detection."""
+        _check(lib.syldet_stream_set_pulse(self._h, float(high_seconds), float(output_rate)))
+
+    def render_pulses(self, n_frames):
+        """The output device's render callback (AudioInterface.swift:13-40). -> float32 [n_channels, n_frames] of 1.0 / 0.0"""
+        out = np.zeros((self.n_channels, n_frames), dtype=np.float32)
+        ptrs = (C.c_void_p * self.n_channels)(*[out.ctypes.data + ch * n_frames * 4 for ch in range(self.n_channels)])
+        _check(lib.syldet_stream_render_pulses(self._h, ptrs, n_frames))
+        return out
 
     def submit(self, bufs):
         """bufs: float32 [n_channels, n]. -> (seen[n_channels] bool, n_new[n_channels])"""

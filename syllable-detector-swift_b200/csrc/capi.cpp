@@ -3,6 +3,8 @@
 #include <new>
 
 #include "engine.hpp"
+#include <algorithm>
+
 #include "stream.hpp"
 
 using namespace syldet;
@@ -287,6 +289,7 @@ syldet_status syldet_stream_submit(syldet_stream *s, const float *const *bufs, i
             for (int64_t j = 0; j < fresh; ++j)  // lastDetected for every new value (Processor.swift:136-144)
                 if ((double)outs[((size_t)ch * fresh + j) * O] >= c.thresholds[0]) any = true;
             if (seen) seen[ch] = any ? 1 : 0;
+            if (any && s->high_frames > 0) s->high_for[ch] = s->high_frames;  // createHighOutput (AudioInterface.swift:442-445)
             if (n_new) n_new[ch] = (int32_t)fresh;
             if (last_out && fresh > 0) std::memcpy(last_out + (size_t)ch * O, outs + ((size_t)ch * fresh + fresh - 1) * O, O * sizeof(float));
         }
@@ -294,6 +297,29 @@ syldet_status syldet_stream_submit(syldet_stream *s, const float *const *bufs, i
     });
 }
 int64_t syldet_stream_launch_count(const syldet_stream *s) { return s ? s->g.launch_count() : 0; }
+syldet_status syldet_stream_read_levels(syldet_stream *s, double *input_rms, double *output_max) {
+    if (!s) return set_error(SYLDET_ERR_ARG, "null argument");
+    return guarded([&] { return s->g.read_levels(input_rms, output_max); });
+}
+syldet_status syldet_stream_set_pulse(syldet_stream *s, double high_seconds, double output_rate) {
+    if (!s || !(high_seconds >= 0.0) || !(output_rate > 0.0)) return set_error(SYLDET_ERR_ARG, "bad pulse arguments");
+    return guarded([&] {
+        s->high_frames = (int64_t)(high_seconds * output_rate);  // Int(duration * outputFormat.mSampleRate)
+        s->high_for.assign(s->g.n_channels(), 0);
+        return SYLDET_OK;
+    });
+}
+syldet_status syldet_stream_render_pulses(syldet_stream *s, float *const *out, int n_frames) {
+    if (!s || !out || n_frames < 0) return set_error(SYLDET_ERR_ARG, "bad render arguments");
+    if (s->high_for.empty()) return set_error(SYLDET_ERR_ARG, "syldet_stream_set_pulse has not been called");
+    for (int ch = 0; ch < s->g.n_channels(); ++ch) {  // renderOutput (AudioInterface.swift:23-36)
+        const int64_t high = s->high_for[ch];
+        if (0 < high) s->high_for[ch] = high - std::min<int64_t>(high, n_frames);
+        if (out[ch])
+            for (int i = 0; i < n_frames; ++i) out[ch][i] = i < high ? 1.0f : 0.0f;
+    }
+    return SYLDET_OK;
+}
 
 // ---- resampler -------------------------------------------------------------------------------------------------------
 syldet_status syldet_resampler_linear_create(double rate_in, double rate_out, syldet_resampler **out) {

@@ -39,9 +39,14 @@ struct StreamTick {
     const unsigned char *blob;  // the configuration's constant blob (DeviceModel): staged in shared memory when it fits
     int blob_bytes;        // multiple of 16; 0 = read constants through L2
     int work_bytes;        // set by launch_stream_tick: per-warp work area in front of the staged blob
+    unsigned long long *level_in;  // device [n_channels]: max over buffers of the mean square (bits of a non-negative double); nullptr = off
+    int *level_out;        // device [n_channels]: max over evaluations of output 0 (order-preserving int image of the float)
+    int n_marks;           // staged buffers in this launch (<= kStreamMaxMarks)
+    int marks[8];          // end of each staged buffer, in samples from the start of the staging area
     long long *stamps;     // optional pinned host [10]: clock64 at the phase boundaries of block (0,0) (SYLDET_STREAM_TIMING=1)
 };
 constexpr size_t kStreamTickMaxSmem = 200 * 1024;
+constexpr int kStreamMaxMarks = 8;
 size_t stream_tick_smem(int fft_len, int max_width, int *warps_out);
 cudaError_t launch_stream_tick(const DevNet *d_net, int fft_len, int max_width, int n_channels, int blocks_per_channel,
                                StreamTick t, cudaStream_t stream);

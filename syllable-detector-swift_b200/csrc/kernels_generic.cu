@@ -435,6 +435,23 @@ __global__ void stream_tick_kernel(const DevNet *__restrict__ netp, StreamTick t
     }
     __syncthreads();
     if (stamp) ts[2] = clock64();
+    // Input level meter (Processor.swift:110-113, StatMax of the buffer's mean square): one warp per staged buffer, taken from the
+    // back so that the warps the STFT columns do not need do it. Single-block launches read the samples back from the ring
+    // (L2), the others from the staging area.
+    if ((t.phases & STREAM_PHASE_COPY) && t.level_in && blockIdx.x == 0) {
+        for (int b = 0; b < t.n_marks; ++b) {
+            if (warps - 1 - (b % warps) != warp) continue;
+            const int lo = b ? t.marks[b - 1] : 0, hi = t.marks[b];
+            float part = 0.0f;
+            for (int i = lo + lane; i < hi; i += kWarp) {
+                const float v = gridDim.x == 1 ? ring[(t.ring_pos + i) & t.ring_mask] : src[i];
+                part += v * v;
+            }
+            part = warp_sum(part);                                  // vDSP_svesq: summation order unspecified
+            const double ms = (double)part / (double)(hi - lo);     // Double(sum) / Double(length)
+            if (lane == 0 && hi > lo && ms == ms) atomicMax(t.level_in + ch, (unsigned long long)__double_as_longlong(ms));  // ms >= 0: bit order = value order
+        }
+    }
     const int L = net.band, O = net.outputs;
     float *band = t.band + (int64_t)ch * (t.band_mask + 1) * L;
     if (t.phases & STREAM_PHASE_COLUMNS) {
@@ -460,6 +477,11 @@ __global__ void stream_tick_kernel(const DevNet *__restrict__ netp, StreamTick t
                 f += kWarp;
                 return v;
             }, buf0, buf1, lane, stamp ? ts + 5 : nullptr);
+            if (t.level_out && lane == 0) {  // output meter (Processor.swift:138, StatMax of Double(lastOutputs[0])); NaN never wins upstream either
+                const float v0 = cur[0];
+                const int bits = __float_as_int(v0);
+                if (v0 == v0) atomicMax(t.level_out + ch, bits >= 0 ? bits : bits ^ 0x7fffffff);  // order-preserving map float -> int
+            }
             if (t.packed) {  // one evaluation of <= 3 outputs: outputs and sequence number travel in one 16-byte store
                 if (lane == 0)
                     t.packed[ch] = make_uint4(__float_as_uint(cur[0]), O > 1 ? __float_as_uint(cur[1]) : 0u, O > 2 ? __float_as_uint(cur[2]) : 0u, t.seq);

@@ -15,6 +15,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 
 namespace syldet {
@@ -51,10 +52,16 @@ syldet_status StreamGroup::init(const Config &cfg, int n_channels, int max_buffe
     if (st != SYLDET_OK) return st;
     st = counter_.reserve(sizeof(unsigned));
     if (st != SYLDET_OK) return st;
+    st = level_in_.reserve((size_t)n_channels * sizeof(unsigned long long));
+    if (st != SYLDET_OK) return st;
+    st = level_out_.reserve((size_t)n_channels * sizeof(int));
+    if (st != SYLDET_OK) return st;
     SYLDET_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     SYLDET_CUDA(cudaMemsetAsync(ring_.get(), 0, ring_.size(), stream_));
     SYLDET_CUDA(cudaMemsetAsync(band_.get(), 0, band_.size(), stream_));
     SYLDET_CUDA(cudaMemsetAsync(counter_.get(), 0, sizeof(unsigned), stream_));
+    SYLDET_CUDA(cudaMemsetAsync(level_in_.get(), 0, level_in_.size(), stream_));
+    SYLDET_CUDA(cudaMemsetAsync(level_out_.get(), 0x80, level_out_.size(), stream_));  // 0x80808080: below the image of every finite float
     // cudaMallocHost memory is device-visible at the same address under unified addressing (always on for sm_100)
     SYLDET_CUDA(cudaMallocHost(&h_stage_, (size_t)n_channels * stage_cap_ * sizeof(float)));
     SYLDET_CUDA(cudaMallocHost(&h_out_, (size_t)n_channels * max_new_ * c.outputs * sizeof(float)));
@@ -110,7 +117,7 @@ syldet_status StreamGroup::wait_for_tick(bool packed) {
 }
 
 syldet_status StreamGroup::submit(const float *const *bufs, int n, const float **outs, int64_t *n_new) {
-    const auto tp0 = std::chrono::steady_clock::now();
+    t_submit_ = std::chrono::steady_clock::now();
     *n_new = 0;
     *outs = h_out_;
     if (n < 0 || n > max_buffer_) return set_error(SYLDET_ERR_ARG, "buffer longer than max_buffer");
@@ -121,14 +128,26 @@ syldet_status StreamGroup::submit(const float *const *bufs, int n, const float *
         std::memcpy(h_stage_ + (size_t)ch * stage_cap_ + staged_, bufs[ch], (size_t)n * sizeof(float));
     staged_ += n;
     total_ += n;
+    marks_.push_back(staged_);
+    ++buffers_seen_;
     const int64_t n_cols = c.num_columns(total_) - cols_done_;
-    if (n_cols <= 0) return SYLDET_OK;  // no column completed: the decision (nothing new) needs no device work
+    // no column completed: the decision (nothing new) needs no device work; the samples wait in the staging area
+    if (n_cols <= 0 && (int)marks_.size() < kStreamMaxMarks) return SYLDET_OK;
     const int64_t avail = c.num_evals(total_) - next_eval_;
     if (avail > max_new_ || n_cols > band_cols_ - c.time_range)
         return set_error(SYLDET_ERR_OVERFLOW, "more evaluations pending than the stream was sized for");
+    syldet_status st = launch_tick(n_cols, avail);
+    if (st != SYLDET_OK) return st;
+    *n_new = avail;
+    return SYLDET_OK;
+}
+
+// Sends everything in the staging area through the device: copy into the sample rings (+ level meter), the n_cols STFT columns
+// and the `avail` evaluations it completes; returns when the results are host-visible.
+syldet_status StreamGroup::launch_tick(int64_t n_cols, int64_t avail) {
+    const Config &c = model_.config();
     syldet_status st = use_device(model_.device());
     if (st != SYLDET_OK) return st;
-
     StreamTick t{};
     t.staged = h_stage_;
     t.stage_pitch = stage_cap_;
@@ -148,6 +167,10 @@ syldet_status StreamGroup::submit(const float *const *bufs, int n, const float *
     t.stamps = h_stamps_;
     t.blob = model_.blob();
     t.blob_bytes = (int)model_.blob_bytes();
+    t.level_in = level_in_.as<unsigned long long>();
+    t.level_out = level_out_.as<int>();
+    t.n_marks = (int)marks_.size();
+    for (int k = 0; k < t.n_marks; ++k) t.marks[k] = marks_[k];
     int warps = 4;
     stream_tick_smem(c.fourier_length, model_.max_width(), &warps);
     const DevNet *net = model_.dev_net();
@@ -190,17 +213,50 @@ syldet_status StreamGroup::submit(const float *const *bufs, int n, const float *
         t_eval_[0] += (double)(h_stamps_[5] - h_stamps_[3]);   // gather
         for (int k = 1; k < 5; ++k) t_eval_[k] += (double)(h_stamps_[5 + k] - h_stamps_[4 + k]);  // ip0, ip1, layer0, layer1
         t_eval_[5] += (double)(h_stamps_[4] - h_stamps_[9]);   // reverse maps + publish
-        t_host_[0] += std::chrono::duration<double, std::micro>(tp1 - tp0).count();
+        t_host_[0] += std::chrono::duration<double, std::micro>(tp1 - t_submit_).count();
         t_host_[1] += std::chrono::duration<double, std::micro>(tp2 - tp1).count();
         t_host_[2] += std::chrono::duration<double, std::micro>(tp3 - tp2).count();
         ++t_ticks_;
     }
     staged_ = 0;
+    marks_.clear();
     cols_done_ += n_cols;
-    if (avail > 0) {
-        next_eval_ += avail;
-        *n_new = avail;
+    next_eval_ += avail;
+    evals_seen_ += avail;
+    return SYLDET_OK;
+}
+
+syldet_status StreamGroup::read_levels(double *input_rms, double *output_max) {
+    if (staged_ > 0) {  // buffers still waiting on the host count too
+        syldet_status st = launch_tick(0, 0);
+        if (st != SYLDET_OK) return st;
     }
+    syldet_status st = use_device(model_.device());
+    if (st != SYLDET_OK) return st;
+    std::vector<unsigned long long> in(n_channels_);
+    std::vector<int> out(n_channels_);
+    SYLDET_CUDA(cudaMemcpyAsync(in.data(), level_in_.get(), in.size() * sizeof(in[0]), cudaMemcpyDeviceToHost, stream_));
+    SYLDET_CUDA(cudaMemcpyAsync(out.data(), level_out_.get(), out.size() * sizeof(out[0]), cudaMemcpyDeviceToHost, stream_));
+    SYLDET_CUDA(cudaMemsetAsync(level_in_.get(), 0, level_in_.size(), stream_));
+    SYLDET_CUDA(cudaMemsetAsync(level_out_.get(), 0x80, level_out_.size(), stream_));
+    SYLDET_CUDA(cudaStreamSynchronize(stream_));
+    const double nil = std::nan("");
+    for (int ch = 0; ch < n_channels_; ++ch) {
+        if (input_rms) {
+            double ms;
+            std::memcpy(&ms, &in[ch], sizeof ms);
+            input_rms[ch] = buffers_seen_ > 0 ? std::sqrt(ms) : nil;  // sqrt(meanSquareLevel), Processor.swift:168-170
+        }
+        if (output_max) {
+            const int img = out[ch];
+            const int bits = img >= 0 ? img : img ^ 0x7fffffff;
+            float v;
+            std::memcpy(&v, &bits, sizeof v);
+            output_max[ch] = (evals_seen_ > 0 && img != (int)0x80808080) ? (double)v : nil;
+        }
+    }
+    buffers_seen_ = 0;
+    evals_seen_ = 0;
     return SYLDET_OK;
 }
 

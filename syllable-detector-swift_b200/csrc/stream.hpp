@@ -1,5 +1,7 @@
 // Streaming front-ends (see stream.cu).
 #pragma once
+#include <chrono>
+
 #include "engine.hpp"
 
 namespace syldet {
@@ -18,9 +20,13 @@ public:
     const Config &config() const { return model_.config(); }
     int n_channels() const { return n_channels_; }
     int64_t launch_count() const { return launches_; }
+    // getInputForChannel / getOutputForChannel for every channel (Processor.swift:158-184): RMS of the loudest buffer and the
+    // largest output 0 since the last call, NaN where upstream returns nil; resets both (readStatAndReset).
+    syldet_status read_levels(double *input_rms, double *output_max);
 
 private:
     syldet_status wait_for_tick(bool packed);
+    syldet_status launch_tick(int64_t n_cols, int64_t avail);
 
     DeviceModel model_;
     int n_channels_ = 0, max_buffer_ = 0;
@@ -34,7 +40,9 @@ private:
     int64_t max_new_ = 0;     // most evaluations one tick can complete
     int64_t launches_ = 0;
     unsigned seq_ = 0;
-    DeviceBuffer ring_, band_, counter_;
+    DeviceBuffer ring_, band_, counter_, level_in_, level_out_;
+    std::vector<int> marks_;  // ends of the buffers waiting in the staging area
+    int64_t buffers_seen_ = 0, evals_seen_ = 0;  // since the last read_levels
     cudaStream_t stream_ = nullptr;
     float *h_stage_ = nullptr, *h_out_ = nullptr;
     unsigned *h_flag_ = nullptr;
@@ -43,6 +51,7 @@ private:
     long long *h_stamps_ = nullptr;
     double t_phase_[4] = {0, 0, 0, 0}, t_eval_[6] = {0, 0, 0, 0, 0, 0}, t_host_[3] = {0, 0, 0};
     int64_t t_ticks_ = 0;
+    std::chrono::steady_clock::time_point t_submit_{};
 };
 
 class Detector {
@@ -84,6 +93,9 @@ private:
 
 struct syldet_stream {
     syldet::StreamGroup g;
+    // TTL pulses (ProcessorAudio.prepareOutputFor, Processor.swift:212-221; AudioOutputInterface, AudioInterface.swift:13-40, 442-445)
+    int64_t high_frames = 0;         // Int(highDuration * output sample rate); 0 = pulses off
+    std::vector<int64_t> high_for;   // outputHighFor[channel]
 };
 struct syldet_detector {
     syldet::Detector d;

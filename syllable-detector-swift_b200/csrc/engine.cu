@@ -523,17 +523,31 @@ syldet_status Batch::launch_tc_range(const float *d_planar, int n_channels, int6
         SYLDET_CUDA(cudaMemsetAsync(d_timing.get(), 0, (size_t)grid * 32 * sizeof(long long), stream));
         w.debug_timing = d_timing.as<long long>();
     }
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (timing) {
+        SYLDET_CUDA(cudaEventCreate(&ev0));
+        SYLDET_CUDA(cudaEventCreate(&ev1));
+        SYLDET_CUDA(cudaEventRecord(ev0, stream));
+    }
     SYLDET_CUDA(launch_tc(tp.hp, grid, tp.smem, tp.params, w, &tm_main, &tm_tail, stream));
     launches_ += 1;
     if (timing) {
         std::vector<long long> h((size_t)grid * 32);
+        SYLDET_CUDA(cudaEventRecord(ev1, stream));
         SYLDET_CUDA(cudaStreamSynchronize(stream));
+        float ms = 0.0f;
+        SYLDET_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+        cudaEventDestroy(ev0);
+        cudaEventDestroy(ev1);
         SYLDET_CUDA(cudaMemcpy(h.data(), d_timing.get(), h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
         static const char *names[30] = {"tma.hi_free", "", "", "", "", "tma.total", "mma.full", "mma.tmem_empty", "mma.lo_ready", "mma.a_ready",
                                         "mma.p_empty", "mma.total", "F.p_full", "F.bar1", "F.bar2", "F.tmem_ld", "F.sums+l0", "F.total", "D.tmem_full", "D.bar1",
                                         "D.a_free", "D.bar2", "D.tmem_ld", "D.total", "S.full", "S.lo_free", "", "", "", "S.total"};
         const double tiles = (double)n_channels * w.chunks_per_channel * ((w.chunk_evals + c.time_range - 1 + tc_tile_frames() - 1) / tc_tile_frames()) / grid;
-        std::fprintf(stderr, "[syldet tc timing] grid %d, ~%.0f tiles per CTA; mean cycles per tile:\n", grid, tiles);
+        long long max_cycles = 0;   // slot 5 = whole role loop of the TMA warp
+        for (int b = 0; b < grid; ++b) max_cycles = std::max(max_cycles, h[(size_t)b * 32 + 5]);
+        std::fprintf(stderr, "[syldet tc timing] grid %d, ~%.0f tiles per CTA; launch %.3f ms, longest CTA %lld cycles => SM clock ~%.0f MHz; mean cycles per tile:\n",
+                     grid, tiles, ms, max_cycles, ms > 0 ? (double)max_cycles / ms * 1e-3 : 0.0);
         for (int k = 0; k < 30; ++k) {
             if (!names[k][0]) continue;
             double sum = 0;

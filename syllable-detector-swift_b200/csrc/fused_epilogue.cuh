@@ -49,6 +49,12 @@ __device__ __forceinline__ float sqrt_fast(float x) {  // MUFU.SQRT, max relativ
     return r;
 }
 
+__device__ __forceinline__ float sqrt_fast_ftz(float x) {  // as sqrt_fast, denormal inputs read as zero (no scaling fix-up code)
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // ---- epilogue: one thread = one evaluation -----------------------------------------------------------------------
 template <int HP, int STAT>
 __device__ __forceinline__ void gather_layer0(const FusedParams &p, const float *ring, int slot, float (&acc)[HP], float &s0,

@@ -17,17 +17,19 @@
 //  (3) epilogue (SIMT): diagonal sum over a shared-memory ring of product rows, window statistic from per-column
 //      partials, transfer functions, remaining layers, reverse output maps, threshold test, event append.
 //
-// Roles (18 warps, one CTA per SM, persistent over (channel, chunk) units; every role walks the same tile sequence):
+// Roles (26 warps, one CTA per SM, persistent over (channel, chunk) units; every role walks the same tile sequence):
 //   warp 0        TMA producer                      full[s] <- hi_free[s]
 //   warp 1        MMA issuer + TMEM allocator       DFT(it): full, tmem_empty, lo_ready -> hi_free, tmem_full, lo_free
 //                                                   layer0(it-1): a_ready, p_empty -> p_full, a_free
-//   warps 2-9     evaluators (F): two groups of four warps (one per TMEM lane quadrant) that take alternate tiles:
+//   warps 2-13    evaluators (F): three groups of four warps (one per TMEM lane quadrant) that take tiles in turn:
 //                                                   p_full, ring_ready[other] -> product ring -> p_empty, ring_ready[own];
 //                                                   diagonal sum (T x LDS.128), window statistic, network tail, events
-//   warps 10-17   spectrum warps (D)                tmem_full -> D -> xbuf -> tmem_empty; |X| -> layer-0 A operand -> a_ready
-//   warps 18-21   splitters (S)                     full, lo_free -> lo tile -> lo_ready, hi_free
+//   warps 14-21   spectrum warps (D)                tmem_full -> D -> registers -> tmem_empty; two shuffle rounds -> |X| ->
+//                                                   layer-0 A operand + per-column statistic partials -> a_ready
+//   warps 22-25   splitters (S)                     full, lo_free -> lo tile -> lo_ready, hi_free
 // Every role is a serial chain per tile and runs at ~0.1 IPC per warp (profiles/): the roles overlap through double buffers, and
-// the longest chain (the evaluators') is split over two groups so that no role needs more than one tile period per tile.
+// the longest chain (the evaluators': ~530 dependent warp instructions per tile) is split over three groups so that no role
+// needs more than one tile period per tile.
 #include <cuda.h>
 
 #include "fused_epilogue.cuh"
@@ -37,9 +39,14 @@ namespace syldet {
 
 namespace {
 
-constexpr int kWarpTma = 0, kWarpMma = 1, kWarpF0 = 2, kNumF = 8, kWarpD0 = 10, kNumD = 8, kWarpS0 = 18, kNumS = 4;
 constexpr int kFGroup = 4;                     // warps per evaluator group (one per TMEM lane quadrant)
-constexpr int kTcThreads = (kWarpS0 + kNumS) * 32;  // 704
+#ifndef TC_GROUPS
+#define TC_GROUPS 2
+#endif
+constexpr int kNumGroups = TC_GROUPS;          // evaluator groups; group g takes the tiles with it % kNumGroups == g
+constexpr int kWarpTma = 0, kWarpMma = 1, kWarpF0 = 2, kNumF = kFGroup * kNumGroups, kWarpD0 = kWarpF0 + kNumF, kNumD = 8,
+              kWarpS0 = kWarpD0 + kNumD, kNumS = 4;
+constexpr int kTcThreads = (kWarpS0 + kNumS) * 32;  // 832
 static_assert(kWarpF0 % 4 == 2 && kWarpD0 % 4 == 2, "quadrant / half assignment below assumes these starts");
 constexpr int kTileRows = 64;                  // rows of Y per tile = N of the DFT MMA
 constexpr int kTileFrames = kTileRows - 1;     // frames completed per tile
@@ -53,30 +60,29 @@ constexpr int kMaxN0 = 56;                     // widest layer-0 product row (T 
 constexpr int kTmemCols = 512;
 constexpr int kColAhi = 0, kColAlo = kKPad, kColD0 = 2 * kKPad, kColP0 = kColD0 + 2 * kTileRows;
 static_assert(kColP0 + 2 * kMaxN0 <= kTmemCols, "TMEM budget");
-constexpr int kXPitch = 36;                    // floats per xbuf row: 16-byte aligned, conflict-free for LDS.128 by column
-constexpr int kPRing = 160;                    // product-row ring (rows = columns): two tiles in flight + the T-1 rows before them
-constexpr int kStatRing = 512;                 // per-column statistic ring
-constexpr int kBarD = 1, kBarF = 2;            // named barriers: D group; F groups use kBarF and kBarF + 1
+constexpr int kPRing = 208;                    // product-row ring (rows = columns): one tile per group in flight + the T-1 rows before them
+constexpr int kStatRing = 512;                 // per-column statistic ring: [2 planes][kStatRing][4 bin quarters] float
+constexpr int kBarF = 2;                       // named barriers of the F groups: kBarF and kBarF + 1
 constexpr int kEvCap = 96;                     // shared-memory event buffer per F group (flushed with one global atomic)
+static_assert(kBarF + kNumGroups <= 16 && kNumGroups <= 4, "named barriers / barrier block layout");
 
 struct TcSmem {  // byte offsets from the 1024-byte aligned base
     static constexpr int hi0 = 0, hi1 = 35840, lo = 71680;          // audio tiles (34 816 rounded up to 1024)
     static constexpr int abuf = 107520;                             // [2 buffers][hi, lo][64 rows x 128 B]
     static constexpr int wcat = abuf + 4 * 8192;                    // [hi, lo][<= 56 rows x 128 B]
-    static constexpr int xbuf = wcat + 2 * kMaxN0 * 128;            // [4 parts][64 rows][kXPitch] float
-    static constexpr int pbuf = xbuf + 4 * kTileRows * kXPitch * 4; // [kPRing][ppitch] float; everything after it is placed at run time
-    // then: float2 colstat[kStatRing] | event meta int4[2][kEvCap] | event outputs float[2][kEvCap][n_out] | barriers (256 B)
+    static constexpr int pbuf = wcat + 2 * kMaxN0 * 128;            // [kPRing][ppitch] float; everything after it is placed at run time
+    // then: float4 colstat[2][kStatRing] | event meta int4[groups][kEvCap] | event outputs float[groups][kEvCap][n_out] | barriers (256 B)
     __host__ __device__ static constexpr int ppitch(int np) { return ((((np + 7) >> 3) << 1) | 1) << 2; }  // whole 8-float chunks + 1: an odd number of float4
     __host__ __device__ static constexpr int colstat(int np) { return pbuf + kPRing * ppitch(np) * 4; }
-    __host__ __device__ static constexpr int evmeta(int np) { return colstat(np) + kStatRing * 8; }
-    __host__ __device__ static constexpr int evout(int np) { return evmeta(np) + 2 * kEvCap * 16; }
-    __host__ __device__ static constexpr int bars(int np, int n_out) { return evout(np) + 2 * kEvCap * n_out * 4; }
+    __host__ __device__ static constexpr int evmeta(int np) { return colstat(np) + 2 * kStatRing * 16; }
+    __host__ __device__ static constexpr int evout(int np) { return evmeta(np) + kNumGroups * kEvCap * 16; }
+    __host__ __device__ static constexpr int bars(int np, int n_out) { return evout(np) + kNumGroups * kEvCap * n_out * 4; }
     __host__ __device__ static constexpr int total(int np, int n_out) { return bars(np, n_out) + 256; }
     __host__ __device__ static constexpr int hi(int stage) { return stage ? hi1 : hi0; }
     __host__ __device__ static constexpr int a(int buf, int part) { return abuf + (buf * 2 + part) * 8192; }
 };
 static_assert(TcSmem::abuf % 1024 == 0 && TcSmem::wcat % 1024 == 0 && (kMaxN0 * 128) % 1024 == 0, "swizzle atoms need 1024-byte alignment");
-static_assert(TcSmem::xbuf % 16 == 0 && TcSmem::pbuf % 16 == 0, "alignment");
+static_assert(TcSmem::pbuf % 16 == 0, "alignment");
 
 // Linear walk over (unit, tile) pairs owned by this CTA; every role iterates the identical sequence.
 struct TileWalk {
@@ -132,7 +138,8 @@ struct RoleTimer {
     long long *dst;
     long long acc[6];
     long long t_start;
-    __device__ RoleTimer(long long *base, int first_slot) : dst(nullptr), acc{0, 0, 0, 0, 0, 0}, t_start(0) {
+    bool relaxed;   // this role has slack: its waits may back off (ptx::mbar_wait_relaxed)
+    __device__ RoleTimer(long long *base, int first_slot, bool relaxed_waits = true) : dst(nullptr), acc{0, 0, 0, 0, 0, 0}, t_start(0), relaxed(relaxed_waits) {
         if constexpr (kOn) {
             dst = base + blockIdx.x * 32 + first_slot;
             t_start = clock64();
@@ -147,7 +154,8 @@ struct RoleTimer {
     }
     __device__ __forceinline__ void wait(uint64_t *bar, uint32_t parity, int k) {
         const long long t0 = now();
-        ptx::mbar_wait(bar, parity);
+        if (relaxed) ptx::mbar_wait_relaxed(bar, parity);
+        else ptx::mbar_wait(bar, parity);
         add(k, t0);
     }
     __device__ __forceinline__ void sync(int id, int n, int k) {
@@ -165,7 +173,33 @@ struct RoleTimer {
     }
 };
 
-template <int HP, bool kScaled, bool kTiming>
+// An evaluator group empties its shared-memory event buffer: all threads of the group; one global atomic for the whole batch.
+// Out of line (one copy, away from the hot loop).
+__device__ __noinline__ void flush_group_events(EventSink sink, const int4 *ev_meta, const float *ev_out, int *ev_count,
+                                                unsigned long long *ev_base, int n_ev, int ft, int bar_f, int n_out) {
+    if (ft == 0) *ev_base = atomicAdd(sink.count, (unsigned long long)n_ev);
+    bar_sync(bar_f, kFGroup * 32);
+    const unsigned long long base = *ev_base;
+    for (int e = ft; e < n_ev; e += kFGroup * 32) {
+        const unsigned long long idx = base + e;
+        if (idx < sink.capacity) {
+            const int4 m = ev_meta[e];
+            sink.events[idx] = DevEvent{m.x, 0, (int64_t)(((unsigned long long)(unsigned)m.w << 32) | (unsigned)m.z)};
+            for (int k = 0; k < n_out; ++k) sink.outputs[idx * n_out + k] = ev_out[e * n_out + k];
+        }
+    }
+    bar_sync(bar_f, kFGroup * 32);
+    if (ft == 0) *ev_count = 0;
+}
+
+// Rare shapes (more than two layers, several outputs): kept out of line so that the evaluators' hot loop stays compact.
+__device__ __noinline__ bool network_tail_cold(const FusedParams &p, int detect_rule, float (&a)[kFusedMaxHidden], float (&out)[kFusedMaxOut]) {
+    return network_tail(p, detect_rule, a, out);
+}
+
+// kFast: the shape of the reference's sample network is known at compile time (l2normalize window statistic, tansig hidden
+// layer, one purelin output, one reverse output map), which strips the run-time dispatch from the evaluators' dependent chain.
+template <int HP, bool kScaled, bool kTiming, bool kFast>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __grid_constant__ CUtensorMap tmap_main,
                  const __grid_constant__ CUtensorMap tmap_tail) {
@@ -173,19 +207,22 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
     // 1024-byte aligned base (swizzle atoms); plain pointer arithmetic so that the compiler keeps the shared address space
     unsigned char *smem = smem_dyn + ((1024u - (ptx::smem_addr(smem_dyn) & 1023u)) & 1023u);
     const int L = p.band, T = p.time_range;
+    const int window_stat = kFast ? (int)FUSED_STAT_L2 : p.window_stat;
+    const int tf0 = kFast ? (int)SYLDET_TF_TANSIG : p.tf[0], tf1 = kFast ? (int)SYLDET_TF_PURELIN : p.tf[1];
+    const int n_op = kFast ? 1 : p.n_op, n_out = kFast ? 1 : p.n_out;
+    const bool one_output_tail = kFast || (p.n_layers == 2 && p.n_out == 1);
     const int n0 = w.n0;                           // layer-0 product row length (multiple of 16)
     const int np = T * HP;                         // its meaningful prefix
     const int ppitch = TcSmem::ppitch(np);         // product ring pitch in floats
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TcSmem::bars(np, p.n_out));
     uint64_t *full = bars, *hi_free = bars + 2, *lo_ready = bars + 4, *lo_free = bars + 5, *tmem_full = bars + 6, *tmem_empty = bars + 8;
     uint64_t *a_ready = bars + 10, *a_free = bars + 12, *p_full = bars + 14, *p_empty = bars + 16;
-    uint64_t *ring_ready = bars + 18;                                         // [2]: an F group has written its tile's product rows
-    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 20);
-    int *ev_counts = reinterpret_cast<int *>(bars + 21);                      // [2] events waiting in shared memory, per F group
-    unsigned long long *ev_bases = reinterpret_cast<unsigned long long *>(bars + 22);  // [2]
-    float *xbuf = reinterpret_cast<float *>(smem + TcSmem::xbuf);
+    uint64_t *ring_ready = bars + 18;                                         // [groups <= 4]: an F group has written its tile's product rows
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 22);
+    int *ev_counts = reinterpret_cast<int *>(bars + 23);                      // [groups <= 4] events waiting in shared memory, per F group
+    unsigned long long *ev_bases = reinterpret_cast<unsigned long long *>(bars + 25);  // [groups <= 4]
     float *pbuf = reinterpret_cast<float *>(smem + TcSmem::pbuf);
-    float2 *colstat = reinterpret_cast<float2 *>(smem + TcSmem::colstat(np));
+    float *colstat = reinterpret_cast<float *>(smem + TcSmem::colstat(np));   // sum of squares | minimum, then the maximum plane
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -199,12 +236,13 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
             ptx::mbar_init(&a_free[i], 1);
             ptx::mbar_init(&p_full[i], 1);
             ptx::mbar_init(&p_empty[i], kFGroup);
+        }
+        for (int i = 0; i < kNumGroups; ++i) {
             ptx::mbar_init(&ring_ready[i], kFGroup);
+            ev_counts[i] = 0;
         }
         ptx::mbar_init(lo_ready, kNumS);
         ptx::mbar_init(lo_free, 1);
-        ev_counts[0] = 0;
-        ev_counts[1] = 0;
         ptx::fence_mbar_init();
     }
     if (warp == kWarpMma) {
@@ -224,10 +262,11 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
-    // DFT matrix -> TMEM (A operand of the first contraction): lane m = matrix row, column = k, hi | lo
+    // DFT matrix -> TMEM (A operand of the first contraction): column = k, hi | lo; lane 32*quad + lane takes the row of
+    // (part = lane >> 3, bin = 8*quad + (lane & 7)), which puts the four parts of a bin into one warp of the spectrum role
     if (warp >= kWarpF0 && warp < kWarpF0 + 4) {
         const int quad = warp & 3;
-        const int m = quad * 32 + lane;
+        const int m = (lane >> 3) * 32 + quad * 8 + (lane & 7);
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
         for (int part = 0; part < 2; ++part) {
             const float *src = (part ? w.dft_lo : w.dft_hi) + (size_t)m * kKPad;
@@ -285,7 +324,7 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
                 }
                 ptx::mma_tf32_ts(d, a, ptx::smem_desc_kmajor(b + kMainChunks * kMainBytes, 256, 6), idesc_dft, 1);
             };
-            RoleTimer<kTiming> tm(w.debug_timing, 6);
+            RoleTimer<kTiming> tm(w.debug_timing, 6, false);   // the MMA issuer is the pacemaker: it polls
             auto issue_l0 = [&](uint32_t jt) {  // per-column layer-0 products of tile jt
                 const int ab = jt & 1;
                 const uint32_t ph = (jt >> 1) & 1;
@@ -336,18 +375,17 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
         }
     } else if (warp < kWarpD0) {
         // ================================ evaluators (F) ==============================================================
-        // Two groups of four warps (one warp per TMEM lane quadrant); group g takes the tiles with it % 2 == g, i.e. always the
-        // layer-0 accumulator P[g]. The accumulator is an M = 64 tile: product row c (= column c of the tile) sits in lane
+        // Groups of four warps (one warp per TMEM lane quadrant); group g takes the tiles with it % groups == g, reading the
+        // layer-0 accumulator P[it & 1]. The accumulator is an M = 64 tile: product row c (= column c of the tile) sits in lane
         // 32*(c/16) + c%16, so lanes 0-15 of a warp own one row each: they move it to the product ring and then evaluate the
-        // network whose newest column is c. The ring is shared by the groups: ring_ready[g] says "group g wrote its tile's rows",
-        // which also proves it finished the evaluations of its previous tile (whose rows the writer of tile it + 1 may reuse).
+        // network whose newest column is c. The ring is shared by the groups: ring_ready[g] says "group g wrote its tile's rows".
         const int quad = warp & 3, grp = (warp - kWarpF0) >> 2;
         const int ft = (warp - kWarpF0 - grp * kFGroup) * 32 + lane;   // thread index inside the group
         const int bar_f = kBarF + grp;
         int *ev_count = ev_counts + grp;
         unsigned long long *ev_base = ev_bases + grp;
         int4 *ev_meta = reinterpret_cast<int4 *>(smem + TcSmem::evmeta(np)) + grp * kEvCap;   // (channel, -, eval lo, eval hi)
-        float *ev_out = reinterpret_cast<float *>(smem + TcSmem::evout(np)) + grp * kEvCap * p.n_out;
+        float *ev_out = reinterpret_cast<float *>(smem + TcSmem::evout(np)) + grp * kEvCap * n_out;
         const int c = quad * 16 + (lane & 15);              // column of the tile this thread owns
         const bool owner = lane < 16;
         const int nchunks = (np + 7) >> 3;                  // 8-column chunks of a product row
@@ -356,33 +394,23 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
         int gcol = 0;                                       // product-ring position of the tile's first column (mod kPRing)
         uint32_t scol = 0;                                  // columns seen so far, all units (statistic ring position)
         RoleTimer<kTiming> tm(w.debug_timing, 12);
-        auto flush_events = [&](int n_ev) {                 // all threads of the group; one global atomic for the whole batch
-            if (ft == 0) *ev_base = atomicAdd(w.sink.count, (unsigned long long)n_ev);
-            bar_sync(bar_f, kFGroup * 32);
-            const unsigned long long base = *ev_base;
-            for (int e = ft; e < n_ev; e += kFGroup * 32) {
-                const unsigned long long idx = base + e;
-                if (idx < w.sink.capacity) {
-                    const int4 m = ev_meta[e];
-                    w.sink.events[idx] = DevEvent{m.x, 0, (int64_t)(((unsigned long long)(unsigned)m.w << 32) | (unsigned)m.z)};
-                    for (int k = 0; k < p.n_out; ++k) w.sink.outputs[idx * p.n_out + k] = ev_out[e * p.n_out + k];
-                }
-            }
-            bar_sync(bar_f, kFGroup * 32);
-            if (ft == 0) *ev_count = 0;
-        };
-        for (uint32_t it = 0; tw.valid(); ++it, tw.next(w, T)) {
-            const int ab = it & 1;
+        auto flush_events = [&](int n_ev) { flush_group_events(w.sink, ev_meta, ev_out, ev_count, ev_base, n_ev, ft, bar_f, n_out); };
+        int turn = 0;                                       // it % kNumGroups
+        for (uint32_t it = 0; tw.valid(); ++it, tw.next(w, T), turn = turn + 1 == kNumGroups ? 0 : turn + 1) {
+            const int ab = it & 1;                          // layer-0 accumulator of this tile
             const int frames = tw.frames();
-            if (ab != grp) {                                // the other group's tile: only keep the ring positions in step
+            if (turn != grp) {                              // another group's tile: only keep the ring positions in step
                 gcol += frames;
                 if (gcol >= kPRing) gcol -= kPRing;
                 scol += frames;
                 continue;
             }
+            // the group of tile it-1 has written that tile (history rows), which also proves it finished the evaluations of tile
+            // it-1-groups, the newest tile whose ring rows this tile may reuse (this group's own tile it-groups is done as well)
+            if (it > 0) tm.wait(&ring_ready[grp == 0 ? kNumGroups - 1 : grp - 1], ((it - 1) / kNumGroups) & 1, 0);
+            // only now: a group sees every other use of an accumulator, and a parity wait is only meaningful for the phase that
+            // is pending; tile it-1 copied => tile it-2 (the previous use of P[ab]) copied => the pending phase is this tile's
             tm.wait(&p_full[ab], (it >> 1) & 1, 0);
-            // the other group has written tile it-1 (history rows) and is done with tile it-3 (whose ring rows this tile reuses)
-            if (it > 0) tm.wait(&ring_ready[grp ^ 1], ((it - 1) >> 1) & 1, 0);
             ptx::tc_fence_after();
             const long long t_f0 = tm.now();
             {   // P row -> product ring, four 8-column chunks at a time: loads in flight, one wait, then the stores
@@ -434,7 +462,7 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
                 float acc[HP];
 #pragma unroll
                 for (int h = 0; h < HP; ++h) acc[h] = 0.0f;
-                float s0 = p.window_stat == FUSED_STAT_L2 ? 0.0f : INFINITY, s1 = -INFINITY;
+                float s0 = window_stat == FUSED_STAT_L2 ? 0.0f : INFINITY, s1 = -INFINITY;
                 if (valid) {
                     const int th = (T + 1) >> 1, t0 = owner ? 0 : th, t1 = owner ? th : T;
                     int row = gcol + c - (T - 1) + t0;                     // ring position of this lane's first column
@@ -453,22 +481,27 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
                             const float4 v1 = prow[1];
                             acc[4] += v1.x; acc[5] += v1.y; acc[6] += v1.z; acc[7] += v1.w;
                         }
-                        const float2 cs = colstat[col & (kStatRing - 1)];
-                        if (p.window_stat == FUSED_STAT_L2) s0 += cs.x;
-                        else { s0 = fminf(s0, cs.x); s1 = fmaxf(s1, cs.y); }
+                        const float4 *cs = reinterpret_cast<const float4 *>(colstat) + (col & (kStatRing - 1));
+                        const float4 ca = cs[0];            // the four bin quarters of the column
+                        if (window_stat == FUSED_STAT_L2) s0 += (ca.x + ca.y) + (ca.z + ca.w);
+                        else if (window_stat == FUSED_STAT_MINMAX) {
+                            const float4 cb = cs[kStatRing];
+                            s0 = fminf(s0, fminf(fminf(ca.x, ca.y), fminf(ca.z, ca.w)));
+                            s1 = fmaxf(s1, fmaxf(fmaxf(cb.x, cb.y), fmaxf(cb.z, cb.w)));
+                        }
                     }
                 }
 #pragma unroll
                 for (int h = 0; h < HP; ++h) acc[h] += __shfl_xor_sync(0xffffffffu, acc[h], 16);
                 {
                     const float o0 = __shfl_xor_sync(0xffffffffu, s0, 16), o1 = __shfl_xor_sync(0xffffffffu, s1, 16);
-                    if (p.window_stat == FUSED_STAT_L2) s0 += o0;
+                    if (window_stat == FUSED_STAT_L2) s0 += o0;
                     else { s0 = fminf(s0, o0); s1 = fmaxf(s1, o1); }
                 }
                 float inv = 1.0f, beta = 0.0f;  // z = acc * inv + beta * V + B'
-                if (p.window_stat == FUSED_STAT_L2) {            // x / sqrt(sum x^2)  (NeuralNet.swift:47-59); silence: 0 * inf = NaN
+                if (window_stat == FUSED_STAT_L2) {            // x / sqrt(sum x^2)  (NeuralNet.swift:47-59); silence: 0 * inf = NaN
                     inv = rcp_fast(sqrt_fast(s0));
-                } else if (p.window_stat == FUSED_STAT_MINMAX) {  // x * 2/range + (-mn-mx)/range  (NeuralNet.swift:69-96)
+                } else if (window_stat == FUSED_STAT_MINMAX) {  // x * 2/range + (-mn-mx)/range  (NeuralNet.swift:69-96)
                     const float range = s1 - s0;
                     if (0 == range) { inv = 0.0f; beta = -1.0f; }  // flat window: every input becomes -1
                     else { inv = 2.0f / range; beta = (0 - s0 - s1) / range; }
@@ -476,25 +509,31 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
                 float a[kFusedMaxHidden];
 #pragma unroll
                 for (int h = 0; h < kFusedMaxHidden; ++h)
-                    a[h] = h < HP ? transfer_fast(p.tf[0], fmaf(acc[h < HP ? h : 0], inv, fmaf(beta, p.v[h], p.bprime[h]))) : 0.0f;
+                    a[h] = h < HP ? transfer_fast(tf0, fmaf(acc[h < HP ? h : 0], inv, fmaf(beta, p.v[h], p.bprime[h]))) : 0.0f;
                 tm.add(4, t_f1);
-                float *o = w.all_out + ((int64_t)tw.ch * w.out_evals_per_channel + w.eval_offset + tw.e0 + j) * p.n_out;
+                float *o = w.all_out + ((int64_t)tw.ch * w.out_evals_per_channel + w.eval_offset + tw.e0 + j) * n_out;
                 const bool store = valid && owner && w.all_out != nullptr;
-                if (p.n_layers == 2 && p.n_out == 1) {   // the common shape: hidden layer -> one output (NeuralNet.swift:310-323)
+                if (one_output_tail) {   // the common shape: hidden layer -> one output (NeuralNet.swift:310-323)
                     float sacc = p.rest_b[0];
 #pragma unroll
                     for (int h = 0; h < HP; ++h) sacc = fmaf(p.rest_w[h], a[h], sacc);
-                    float v = transfer_fast(p.tf[1], sacc);
-                    for (int k = 0; k < p.n_op; ++k)  // reverse maps in index order
+                    float v = transfer_fast(tf1, sacc);
+#pragma unroll 1
+                    for (int k = 0; k < n_op; ++k)  // reverse maps in index order
                         v = (v + (0 - p.op_y[k])) / p.op_gain[k * kFusedMaxOut] + p.op_xoff[k * kFusedMaxOut];
                     hit = v >= p.thr_f[0];            // == (double)v >= thr (TrackDetector.swift:72); NaN -> false
                     out[0] = v;
                     if (store) o[0] = v;
                 } else {
-                    hit = network_tail(p, w.detect_rule, a, out);
+                    float a_mem[kFusedMaxHidden], out_mem[kFusedMaxOut];   // copies: only this branch touches local memory
+#pragma unroll
+                    for (int h = 0; h < kFusedMaxHidden; ++h) a_mem[h] = a[h];
+                    hit = network_tail_cold(p, w.detect_rule, a_mem, out_mem);
+#pragma unroll
+                    for (int k = 0; k < kFusedMaxOut; ++k) out[k] = out_mem[k];
                     if (store) {
 #pragma unroll 1
-                        for (int k = 0; k < p.n_out; ++k) o[k] = pick(out, k);
+                        for (int k = 0; k < n_out; ++k) o[k] = pick(out, k);
                     }
                 }
                 hit = hit && valid && owner;
@@ -509,7 +548,7 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
                     const int64_t ev = w.eval_offset + tw.e0 + j;
                     ev_meta[e] = make_int4(tw.ch, 0, (int)(unsigned)(ev & 0xffffffffll), (int)(ev >> 32));
 #pragma unroll 1
-                    for (int k = 0; k < p.n_out; ++k) ev_out[e * p.n_out + k] = pick(out, k);
+                    for (int k = 0; k < n_out; ++k) ev_out[e * n_out + k] = pick(out, k);
                 }
             }
             tm.sync(bar_f, kFGroup * 32, 2);  // this group's next tile overwrites ring rows that this tile's evaluations read
@@ -526,13 +565,22 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
         tm.flush(ft == 0 && grp == 0);
     } else if (warp < kWarpS0) {
         // ================================ spectrum warps (D) ===========================================================
+        // TMEM lane 32*quad + lane holds DFT-matrix row (part = lane >> 3: Re B1 | Im B1 | Re B2 | Im B2, bin = 8*quad + (lane & 7)),
+        // so the four parts of a bin sit in one warp and combine through two shuffle rounds; nothing goes through shared memory:
+        //   (1) X[c] = P1[c] + P2[c+1]: B1 lanes (bit 4 clear) take columns 4g, 4g+1, B2 lanes take 4g+2, 4g+3 (xor 16)
+        //   (2) re^2 + im^2: Re lanes (bit 3 clear) keep the columns of even g, Im lanes those of odd g           (xor 8)
+        // after which every lane owns 8 magnitudes of its bin: columns col0 + 8*i + u. A store instruction then covers rows
+        // r, r+2, r+4, r+6 x 8 bins = all 32 banks of the SWIZZLE_128B operand.
         const int quad = warp & 3, dw = warp - kWarpD0, half = dw >> 2;
-        const int dt = dw * 32 + lane;
-        const int c = dt >> 2, qq = dt & 3;                 // column of the tile, quarter of its 32 bins
-        const float *x_re1 = xbuf + (0 * kTileRows + c) * kXPitch + qq * 8, *x_im1 = xbuf + (1 * kTileRows + c) * kXPitch + qq * 8;
-        const float *x_re2 = xbuf + (2 * kTileRows + c + 1) * kXPitch + qq * 8, *x_im2 = xbuf + (3 * kTileRows + c + 1) * kXPitch + qq * 8;
-        float *x_dst = xbuf + (quad * kTileRows + half * 32) * kXPitch + lane;
-        const int a_off0 = c * 128 + ((((2 * qq) ^ c) & 7) << 4), a_off1 = c * 128 + ((((2 * qq + 1) ^ c) & 7) << 4);
+        const bool up = (lane & 16) != 0, im = (lane & 8) != 0;
+        const int bin = quad * 8 + (lane & 7);
+        const bool in_band = bin < L;
+        const int col0 = half * 32 + (up ? 2 : 0) + (im ? 4 : 0);
+        int a_off[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) a_off[u] = (col0 + u) * 128 + ((((bin >> 2) ^ (col0 + u)) & 7) << 4) + ((bin & 3) << 2);
+        const int stat_col = col0 + 8 * ((lane & 7) >> 1) + (lane & 1);   // the column whose statistic ends up in this lane
+        const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + kColD0 + half * 32;
         TileWalk tw;
         tw.init(w, T);
         uint32_t gcol = 0;
@@ -543,66 +591,102 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
             const int frames = tw.frames();
             tm.wait(&tmem_full[s], ph, 0);
             ptx::tc_fence_after();
-            uint32_t r[32];
+            // One load of the warp's 32 (+1) columns, then straight-line code: the shuffle chains of the eight column groups are
+            // independent, and a warp needs that many in flight to hide the latency of the (busy) shared-memory/shuffle pipe.
+            uint32_t r[33];
             const long long t_d0 = tm.now();
-            ptx::tmem_ld_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + kColD0 + s * kTileRows + half * 32, r);
-            ptx::tc_wait_ld();
+            {
+                uint32_t r32[32];
+                ptx::tmem_ld_x32(taddr0 + s * kTileRows, r32);
+                r[32] = 0;                                      // column 64 does not exist: frame 63 is never complete in this tile
+                if (half == 0) ptx::tmem_ld_x1(taddr0 + s * kTileRows + 32, r[32]);
+                ptx::tc_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) r[j] = r32[j];
+            }
             tm.add(4, t_d0);
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tmem_empty[s]);
-            tm.sync(kBarD, kNumD * 32, 1);                  // everyone is done reading the previous tile's xbuf
+            // ---- (1) X_c = (Re1[c] + Re2[c+1]) + i (Im1[c] + Im2[c+1]) ------------------------------------------------------
+            float x[8][2];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) x_dst[j * kXPitch] = __uint_as_float(r[j]);
-            tm.wait(&a_free[s], ph ^ 1, 2);                 // layer 0 of tile it-2 has read this A buffer
-            tm.sync(kBarD, kNumD * 32, 3);
-            // ---- X_c = (Re1[c] + Re2[c+1]) + i (Im1[c] + Im2[c+1]); |X| of the band -> layer-0 A operand (hi, lo) ----------
-            float s0 = p.window_stat == FUSED_STAT_L2 ? 0.0f : INFINITY, s1 = -INFINITY;
-            if (c < frames) {
-                unsigned char *a_hi = smem + TcSmem::a(s, 0), *a_lo = smem + TcSmem::a(s, 1);
+            for (int g = 0; g < 8; ++g)
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
-                    const float4 r1 = *reinterpret_cast<const float4 *>(x_re1 + 4 * u), r2 = *reinterpret_cast<const float4 *>(x_re2 + 4 * u);
-                    const float4 i1 = *reinterpret_cast<const float4 *>(x_im1 + 4 * u), i2 = *reinterpret_cast<const float4 *>(x_im2 + 4 * u);
-                    const float re[4] = {r1.x + r2.x, r1.y + r2.y, r1.z + r2.z, r1.w + r2.w};
-                    const float im[4] = {i1.x + i2.x, i1.y + i2.y, i1.z + i2.z, i1.w + i2.w};
-                    float m[4], mh[4];
+                    const float send = __uint_as_float(up ? r[4 * g + u + 1] : r[4 * g + 2 + u]);
+                    const float own = __uint_as_float(up ? r[4 * g + 3 + u] : r[4 * g + u]);
+                    x[g][u] = own + __shfl_xor_sync(0xffffffffu, send, 16);
+                }
+            // ---- (2) |X| of the band (plain multiplies and add, as the reference computes it) -------------------------------
+            float mag[8];                                       // e = 2*i + u: column col0 + 8*i + u
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        float v = sqrt_fast(re[k] * re[k] + im[k] * im[k]);
-                        if constexpr (kScaled) v = scale_value_nl(v, p.scaling);
-                        if (qq * 8 + u * 4 + k >= L) v = 0.0f;
-                        else if (p.window_stat == FUSED_STAT_L2) s0 = fmaf(v, v, s0);
-                        else if (p.window_stat == FUSED_STAT_MINMAX) { s0 = fminf(s0, v); s1 = fmaxf(s1, v); }
-                        m[k] = v;
-                        mh[k] = tf32_trunc(v);
-                    }
-                    const int off = u ? a_off1 : a_off0;
-                    *reinterpret_cast<float4 *>(a_hi + off) = make_float4(mh[0], mh[1], mh[2], mh[3]);
-                    *reinterpret_cast<float4 *>(a_lo + off) = make_float4(m[0] - mh[0], m[1] - mh[1], m[2] - mh[2], m[3] - mh[3]);
-                    if (w.debug_band) {
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            if (qq * 8 + u * 4 + k < L)
-                                w.debug_band[((int64_t)tw.ch * w.debug_cols + tw.e0 + tw.cols_before() + c) * L + qq * 8 + u * 4 + k] = m[k];
+                for (int u = 0; u < 2; ++u) {
+                    const float sq_a = __fmul_rn(x[2 * i][u], x[2 * i][u]), sq_b = __fmul_rn(x[2 * i + 1][u], x[2 * i + 1][u]);
+                    const float other = __shfl_xor_sync(0xffffffffu, im ? sq_a : sq_b, 8);
+                    float v;
+                    if constexpr (kScaled) v = scale_value_nl(sqrt_fast(__fadd_rn(im ? sq_b : sq_a, other)), p.scaling);
+                    else v = sqrt_fast_ftz(__fadd_rn(im ? sq_b : sq_a, other));
+                    mag[2 * i + u] = in_band ? v : 0.0f;
+                }
+            // ---- window statistic: per-column partial over this warp's 8 bins; the evaluators combine the four quadrants -----
+            if (window_stat != FUSED_STAT_NONE) {
+                // eight values x eight lanes -> lane b holds the total of value b: exchange half of the values per round
+                auto reduce8 = [&](float (&q)[8], auto op) {
+                    const bool b4 = (lane & 4) != 0, b2 = (lane & 2) != 0, b1 = (lane & 1) != 0;
+                    float h4[4], h2[2];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) h4[k] = op(b4 ? q[k + 4] : q[k], __shfl_xor_sync(0xffffffffu, b4 ? q[k] : q[k + 4], 4));
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) h2[k] = op(b2 ? h4[k + 2] : h4[k], __shfl_xor_sync(0xffffffffu, b2 ? h4[k] : h4[k + 2], 2));
+                    return op(b1 ? h2[1] : h2[0], __shfl_xor_sync(0xffffffffu, b1 ? h2[0] : h2[1], 1));
+                };
+                float q[8];
+                float *cs = colstat + (((gcol + (uint32_t)stat_col) & (kStatRing - 1)) << 2) + quad;
+                if (window_stat == FUSED_STAT_L2) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) q[e] = mag[e] * mag[e];
+                    const float tot = reduce8(q, [](float a, float b) { return a + b; });
+                    if (stat_col < frames) cs[0] = tot;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) q[e] = in_band ? mag[e] : INFINITY;
+                    const float mn = reduce8(q, [](float a, float b) { return fminf(a, b); });
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) q[e] = in_band ? mag[e] : -INFINITY;
+                    const float mx = reduce8(q, [](float a, float b) { return fmaxf(a, b); });
+                    if (stat_col < frames) {
+                        cs[0] = mn;
+                        cs[kStatRing * 4] = mx;
                     }
                 }
             }
-            if (p.window_stat != FUSED_STAT_NONE) {         // combine the four bin quarters of the column
+            // ---- magnitudes -> layer-0 A operand (hi, lo) -----------------------------------------------------------------------
+            tm.wait(&a_free[s], ph ^ 1, 2);                 // layer 0 of tile it-2 has read this A buffer
+            {
+                unsigned char *a_hi = smem + TcSmem::a(s, 0), *a_lo = smem + TcSmem::a(s, 1);
 #pragma unroll
-                for (int d = 1; d <= 2; d <<= 1) {
-                    const float o0 = __shfl_xor_sync(0xffffffffu, s0, d), o1 = __shfl_xor_sync(0xffffffffu, s1, d);
-                    if (p.window_stat == FUSED_STAT_L2) s0 += o0;
-                    else { s0 = fminf(s0, o0); s1 = fmaxf(s1, o1); }
-                }
-                if (qq == 0 && c < frames) colstat[(gcol + c) & (kStatRing - 1)] = make_float2(s0, s1);
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int col = col0 + 8 * i + u;
+                        if (col < frames) {
+                            const float v = mag[2 * i + u], vh = tf32_trunc(v);
+                            *reinterpret_cast<float *>(a_hi + a_off[u] + i * 1024) = vh;
+                            *reinterpret_cast<float *>(a_lo + a_off[u] + i * 1024) = v - vh;
+                            if (w.debug_band && in_band)
+                                w.debug_band[((int64_t)tw.ch * w.debug_cols + tw.e0 + tw.cols_before() + col) * L + bin] = v;
+                        }
+                    }
             }
             ptx::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&a_ready[s]);
             gcol += frames;
         }
-        tm.flush(dt == 0);
+        tm.flush(dw == 0 && lane == 0);
     } else {
         // ================================ splitters (S) ================================================================
         const int st = (warp - kWarpS0) * 32 + lane;
@@ -653,11 +737,12 @@ int tc_tile_frames() { return kTileFrames; }
 int tc_k_pad() { return kKPad; }
 int tc_max_n0() { return kMaxN0; }
 bool tc_layout_fits(int time_range, int n0) {
-    // product ring: a tile's rows plus the T-1 before them; statistic ring: the spectrum warps run at most 4 tiles ahead
-    // product ring: the writer of tile it+2 must not touch what the evaluations of tile it+1 read (rows of it+1 and the last T-1
-    // of it): 3 * tile - 1 - ring < tile - (T - 1); statistic ring: the spectrum warps run at most 5 tiles ahead
-    return n0 <= kMaxN0 && 3 * kTileFrames - 1 - kPRing < kTileFrames - (time_range - 1) && 2 * kTileFrames + time_range <= kPRing &&
-           6 * kTileFrames + time_range <= kStatRing;
+    // product ring: tile it (start b) reuses the positions of tile it - groups (start b + ring - groups * tile), whose last T-1
+    // rows the evaluations of tile it - groups + 1 may still read: ring - groups * tile >= T - 1.
+    // statistic ring: the MMA warp cannot pass the DFT of tile it before the copy of tile it-3 is done, the spectrum warps are
+    // at most at tile it, the slowest group at tile it - 2 - groups: (groups + 3) * tile + T columns.
+    return n0 <= kMaxN0 && kNumGroups * kTileFrames + time_range <= kPRing &&
+           (kNumGroups + 3) * kTileFrames + time_range <= kStatRing;
 }
 
 cudaError_t launch_tc(int hp, int grid, size_t smem, const FusedParams &p, const TcWork &w, const void *tmap_main, const void *tmap_tail,
@@ -670,13 +755,16 @@ cudaError_t launch_tc(int hp, int grid, size_t smem, const FusedParams &p, const
         if (e == cudaSuccess) kern<<<grid, kTcThreads, smem, stream>>>(p, w, tm, tt);
     };
     const bool scaled = p.scaling != SYLDET_SCALING_LINEAR;
+    const bool fast = hp == 4 && !scaled && p.window_stat == FUSED_STAT_L2 && p.tf[0] == SYLDET_TF_TANSIG && p.n_layers == 2 && p.n_out == 1 &&
+                      p.tf[1] == SYLDET_TF_PURELIN && p.n_op == 1;
     if (w.debug_timing) {   // SYLDET_TC_TIMING: instrumented build of the common shape only
-        if (hp == 4 && !scaled) go(tc_detect_kernel<4, false, true>);
+        if (fast) go(tc_detect_kernel<4, false, true, true>);
         else return cudaErrorNotSupported;
-    } else if (hp == 4 && !scaled) go(tc_detect_kernel<4, false, false>);
-    else if (hp == 4) go(tc_detect_kernel<4, true, false>);
-    else if (!scaled) go(tc_detect_kernel<8, false, false>);
-    else go(tc_detect_kernel<8, true, false>);
+    } else if (fast) go(tc_detect_kernel<4, false, false, true>);
+    else if (hp == 4 && !scaled) go(tc_detect_kernel<4, false, false, false>);
+    else if (hp == 4) go(tc_detect_kernel<4, true, false, false>);
+    else if (!scaled) go(tc_detect_kernel<8, false, false, false>);
+    else go(tc_detect_kernel<8, true, false, false>);
     if (e != cudaSuccess) return e;
     return cudaGetLastError();
 }

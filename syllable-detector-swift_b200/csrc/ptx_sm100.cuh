@@ -61,6 +61,32 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     } while (!done);
 }
 
+// Same wait for roles with slack: back off between polls so that a waiting warp does not compete for issue slots and
+// instruction fetch with the warps that are working (SYLDET_MBAR_SLEEP ns; 0 = plain polling).
+#ifndef SYLDET_MBAR_SLEEP
+#define SYLDET_MBAR_SLEEP 0
+#endif
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity) {
+#if SYLDET_MBAR_SLEEP > 0
+    uint32_t done;
+    for (;;) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_addr(bar)), "r"(parity)
+            : "memory");
+        if (done) break;
+        asm volatile("nanosleep.u32 %0;" ::"r"((uint32_t)SYLDET_MBAR_SLEEP));
+    }
+#else
+    mbar_wait(bar, parity);
+#endif
+}
+
 // ---- TMA ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
@@ -147,6 +173,9 @@ __device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t (&r)[8]) {
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                  : "r"(taddr)
                  : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x1(uint32_t taddr, uint32_t &r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t (&r)[8]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),

@@ -126,6 +126,33 @@ def test_generated_configs_fused_and_generic(sd, oracle_mod, cw, kw):
             _check_channel(o, x[ch], outs[ch], ev.sample[ev.channel == ch], tol)
 
 
+@pytest.mark.parametrize("kw", [
+    # every instantiation / run-time branch of the tensor-core kernel besides the sample.txt shape (kFast):
+    dict(overlap=124, hidden=(4,), input_funcs=("normalize", "mapminmax"), transfer="LogSig"),                  # min/max statistic partials
+    dict(overlap=124, hidden=(4,), scaling="db", input_funcs=("mapminmax",)),                                    # kScaled, no statistic
+    dict(overlap=128, hidden=(8,), time_range=6, outputs=2, input_funcs=("l2normalize",), output_funcs=("mapminmax", "mapstd")),  # HP = 8, several outputs
+    dict(overlap=120, hidden=(4, 3), time_range=3, scaling="log", input_funcs=("l2normalize", "mapminmax")),     # three layers, hop 136, short window
+    dict(overlap=124, hidden=(3,), time_range=12, freq_range=(500.0, 5900.0), input_funcs=("l2normalize", "mapminmax"), out_transfer="LogSig"),  # 32 bins, T = 12
+    dict(overlap=124, hidden=(4,), input_funcs=("l2normalize", "mapminmax"), output_funcs=()),                  # sample shape without the reverse map
+])
+def test_tensor_kernel_shape_variants(sd, oracle_mod, cw, kw):
+    text = cw.random_config(seed=11, threshold=0.3, fft_len=256, **kw)
+    c = sd.SyllableDetectorConfig.from_text(text).validate()
+    assert sd.KERNEL_TENSOR in sd.BatchDetector.available_kernels(c), "shape must be eligible for the tensor-core kernel"
+    o = oracle_mod.Oracle(text=text)
+    rng = np.random.default_rng(13)
+    n = 60000   # several tiles per unit, a ragged last tile
+    t = np.arange(n)
+    x = np.stack([(0.05 * rng.standard_normal(n) + 0.4 * np.sin(2 * np.pi * f0 * t / 44100 + 3 * np.sin(2 * np.pi * 2 * t / 44100))).astype(np.float32)
+                  for f0 in (2500.0, 5200.0, 3900.0)])
+    ev, outs = sd.BatchDetector(c, kernel=sd.KERNEL_TENSOR).run(x, want_outputs=True)
+    for ch in range(x.shape[0]):
+        ref = o.run(x[ch])[0]
+        scale = max(1.0, float(np.nanmax(np.abs(ref))))
+        tol = (TOL_OUT if kw.get("scaling", "linear") == "linear" else 2e-4) * scale
+        _check_channel(o, x[ch], outs[ch], ev.sample[ev.channel == ch], tol)
+
+
 def test_high_overlap_wide_hidden_config(sd, oracle_mod, cw):
     """BASELINE config 4 shape: FFT 1024, hop 4, band 1-8 kHz (L = 162), T = 8 (1296 inputs), 256 tansig units, 2 outputs.
     Too wide for the fused kernels: the reference-order kernels take it. Left-to-right sums over 1296 terms: same order in

@@ -541,8 +541,8 @@ syldet_status Batch::launch_tc_range(const float *d_planar, int n_channels, int6
         cudaEventDestroy(ev1);
         SYLDET_CUDA(cudaMemcpy(h.data(), d_timing.get(), h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
         static const char *names[30] = {"tma.hi_free", "", "", "", "", "tma.total", "mma.full", "mma.tmem_empty", "mma.lo_ready", "mma.a_ready",
-                                        "mma.p_empty", "mma.total", "F.p_full", "F.bar1", "F.bar2", "F.tmem_ld", "F.sums+l0", "F.total", "D.tmem_full", "D.bar1",
-                                        "D.a_free", "D.bar2", "D.tmem_ld", "D.total", "S.full", "S.lo_free", "", "", "", "S.total"};
+                                        "mma.p_empty", "mma.total", "F.p_full", "F.bar1", "F.bar2", "F.tmem_ld", "F.sums+l0", "F.total", "D.tmem_full", "",
+                                        "D.a_free", "", "D.tmem_ld", "D.total", "S.full", "S.lo_free", "", "", "", "S.total"};
         const double tiles = (double)n_channels * w.chunks_per_channel * ((w.chunk_evals + c.time_range - 1 + tc_tile_frames() - 1) / tc_tile_frames()) / grid;
         long long max_cycles = 0;   // slot 5 = whole role loop of the TMA warp
         for (int b = 0; b < grid; ++b) max_cycles = std::max(max_cycles, h[(size_t)b * 32 + 5]);

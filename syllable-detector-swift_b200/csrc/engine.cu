@@ -511,6 +511,7 @@ syldet_status Batch::launch_tc_range(const float *d_planar, int n_channels, int6
     w.wcat_hi = model_.wcat_hi();
     w.wcat_lo = model_.wcat_lo();
     w.n0 = tp.n0;
+    w.lo_stages = tc_lo_stages(tp.params, tp.hp);
     w.debug_band = debug_band_;
     w.debug_cols = debug_cols_;
     const int64_t units = (int64_t)n_channels * w.chunks_per_channel;

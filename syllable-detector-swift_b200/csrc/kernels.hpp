@@ -127,11 +127,13 @@ struct TcWork {
     const float *dft_hi, *dft_lo;   // [128][k_pad] windowed DFT matrix, tf32 hi / lo parts
     const float *wcat_hi, *wcat_lo; // [n0][32] folded layer-0 weights, row (t*HP + h), column = band bin
     int n0;                         // T*HP rounded up to a multiple of 16
+    int lo_stages;                  // 1 or 2 lo tiles in shared memory (tc_lo_stages)
     float *debug_band;              // optional [n_channels][debug_cols][band] band magnitudes (tests)
     int64_t debug_cols;
     long long *debug_timing;        // optional [grid][32] cycle counters per role (SYLDET_TC_TIMING=1)
 };
 size_t tc_smem_bytes(const FusedParams &p, int hp);
+int tc_lo_stages(const FusedParams &p, int hp);
 int tc_tile_frames();
 int tc_k_pad();
 int tc_max_n0();

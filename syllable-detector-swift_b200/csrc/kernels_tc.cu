@@ -17,18 +17,18 @@
 //  (3) epilogue (SIMT): diagonal sum over a shared-memory ring of product rows, window statistic from per-column
 //      partials, transfer functions, remaining layers, reverse output maps, threshold test, event append.
 //
-// Roles (26 warps, one CTA per SM, persistent over (channel, chunk) units; every role walks the same tile sequence):
+// Roles (22 warps with two evaluator groups, one CTA per SM, persistent over (channel, chunk) units; every role walks the same tile sequence):
 //   warp 0        TMA producer                      full[s] <- hi_free[s]
 //   warp 1        MMA issuer + TMEM allocator       DFT(it): full, tmem_empty, lo_ready -> hi_free, tmem_full, lo_free
 //                                                   layer0(it-1): a_ready, p_empty -> p_full, a_free
-//   warps 2-13    evaluators (F): three groups of four warps (one per TMEM lane quadrant) that take tiles in turn:
+//   then          evaluators (F): TC_GROUPS (2) groups of four warps (one per TMEM lane quadrant) that take tiles in turn:
 //                                                   p_full, ring_ready[other] -> product ring -> p_empty, ring_ready[own];
 //                                                   diagonal sum (T x LDS.128), window statistic, network tail, events
-//   warps 14-21   spectrum warps (D)                tmem_full -> D -> registers -> tmem_empty; two shuffle rounds -> |X| ->
+//   then 8        spectrum warps (D)                tmem_full -> D -> registers -> tmem_empty; two shuffle rounds -> |X| ->
 //                                                   layer-0 A operand + per-column statistic partials -> a_ready
-//   warps 22-25   splitters (S)                     full, lo_free -> lo tile -> lo_ready, hi_free
+//   then 4        splitters (S)                     full, lo_free -> lo tile -> lo_ready, hi_free
 // Every role is a serial chain per tile and runs at ~0.1 IPC per warp (profiles/): the roles overlap through double buffers, and
-// the longest chain (the evaluators': ~530 dependent warp instructions per tile) is split over three groups so that no role
+// the longest chain (the evaluators': ~530 dependent warp instructions per tile) is split over the groups so that no role
 // needs more than one tile period per tile.
 #include <cuda.h>
 
@@ -67,20 +67,26 @@ constexpr int kEvCap = 96;                     // shared-memory event buffer per
 static_assert(kBarF + kNumGroups <= 16 && kNumGroups <= 4, "named barriers / barrier block layout");
 
 struct TcSmem {  // byte offsets from the 1024-byte aligned base
-    static constexpr int hi0 = 0, hi1 = 35840, lo = 71680;          // audio tiles (34 816 rounded up to 1024)
-    static constexpr int abuf = 107520;                             // [2 buffers][hi, lo][64 rows x 128 B]
+    static constexpr int hi0 = 0, hi1 = kTileBytes, lo = 2 * kTileBytes;   // audio tiles (34 816 B = 34 swizzle atoms each)
+    static constexpr int abuf = 3 * kTileBytes;                     // [2 buffers][hi, lo][64 rows x 128 B]
     static constexpr int wcat = abuf + 4 * 8192;                    // [hi, lo][<= 56 rows x 128 B]
     static constexpr int pbuf = wcat + 2 * kMaxN0 * 128;            // [kPRing][ppitch] float; everything after it is placed at run time
-    // then: float4 colstat[2][kStatRing] | event meta int4[groups][kEvCap] | event outputs float[groups][kEvCap][n_out] | barriers (256 B)
+    // then: float4 colstat[planes][kStatRing] | event meta int4[groups][kEvCap] | event outputs float[groups][kEvCap][n_out] |
+    //       barriers (256 B) | optionally the second lo tile (1024-byte aligned) when it fits
+    // planes: 1 (sum of squares), 2 for the min/max statistic
     __host__ __device__ static constexpr int ppitch(int np) { return ((((np + 7) >> 3) << 1) | 1) << 2; }  // whole 8-float chunks + 1: an odd number of float4
     __host__ __device__ static constexpr int colstat(int np) { return pbuf + kPRing * ppitch(np) * 4; }
-    __host__ __device__ static constexpr int evmeta(int np) { return colstat(np) + 2 * kStatRing * 16; }
-    __host__ __device__ static constexpr int evout(int np) { return evmeta(np) + kNumGroups * kEvCap * 16; }
-    __host__ __device__ static constexpr int bars(int np, int n_out) { return evout(np) + kNumGroups * kEvCap * n_out * 4; }
-    __host__ __device__ static constexpr int total(int np, int n_out) { return bars(np, n_out) + 256; }
+    __host__ __device__ static constexpr int evmeta(int np, int planes) { return colstat(np) + planes * kStatRing * 16; }
+    __host__ __device__ static constexpr int evout(int np, int planes) { return evmeta(np, planes) + kNumGroups * kEvCap * 16; }
+    __host__ __device__ static constexpr int bars(int np, int n_out, int planes) { return evout(np, planes) + kNumGroups * kEvCap * n_out * 4; }
+    __host__ __device__ static constexpr int lo1(int np, int n_out, int planes) { return (bars(np, n_out, planes) + 256 + 1023) & ~1023; }
+    __host__ __device__ static constexpr int total(int np, int n_out, int planes, int lo_stages) {
+        return lo_stages == 2 ? lo1(np, n_out, planes) + kTileBytes : bars(np, n_out, planes) + 256;
+    }
     __host__ __device__ static constexpr int hi(int stage) { return stage ? hi1 : hi0; }
     __host__ __device__ static constexpr int a(int buf, int part) { return abuf + (buf * 2 + part) * 8192; }
 };
+static_assert(kTileBytes % 1024 == 0, "tiles are whole swizzle atoms");
 static_assert(TcSmem::abuf % 1024 == 0 && TcSmem::wcat % 1024 == 0 && (kMaxN0 * 128) % 1024 == 0, "swizzle atoms need 1024-byte alignment");
 static_assert(TcSmem::pbuf % 16 == 0, "alignment");
 
@@ -214,8 +220,12 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
     const int n0 = w.n0;                           // layer-0 product row length (multiple of 16)
     const int np = T * HP;                         // its meaningful prefix
     const int ppitch = TcSmem::ppitch(np);         // product ring pitch in floats
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TcSmem::bars(np, p.n_out));
-    uint64_t *full = bars, *hi_free = bars + 2, *lo_ready = bars + 4, *lo_free = bars + 5, *tmem_full = bars + 6, *tmem_empty = bars + 8;
+    const int planes = window_stat == FUSED_STAT_MINMAX ? 2 : 1;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TcSmem::bars(np, p.n_out, planes));
+    uint64_t *full = bars, *hi_free = bars + 2, *lo_ready = bars + 4, *lo_free = bars + 29, *tmem_full = bars + 6, *tmem_empty = bars + 8;   // lo_*: [2]
+    // lo tile(s): with two, stage = it & 1 like the hi tiles and the splitters never wait for pass 3 of the previous tile
+    const int lo_stages = w.lo_stages;
+    const int lo1_off = TcSmem::lo1(np, p.n_out, planes);
     uint64_t *a_ready = bars + 10, *a_free = bars + 12, *p_full = bars + 14, *p_empty = bars + 16;
     uint64_t *ring_ready = bars + 18;                                         // [groups <= 4]: an F group has written its tile's product rows
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 22);
@@ -241,8 +251,10 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
             ptx::mbar_init(&ring_ready[i], kFGroup);
             ev_counts[i] = 0;
         }
-        ptx::mbar_init(lo_ready, kNumS);
-        ptx::mbar_init(lo_free, 1);
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&lo_ready[i], kNumS);
+            ptx::mbar_init(&lo_free[i], 1);
+        }
         ptx::fence_mbar_init();
     }
     if (warp == kWarpMma) {
@@ -308,7 +320,7 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
         if (ptx::elect_one()) {
             constexpr uint32_t idesc_dft = ptx::idesc_tf32(128, kTileRows);
             const uint32_t idesc_l0 = ptx::idesc_tf32(64, n0);
-            const uint32_t lo = ptx::smem_addr(smem + TcSmem::lo);
+            const uint32_t lo_a = ptx::smem_addr(smem + TcSmem::lo), lo_b = ptx::smem_addr(smem + lo1_off);
             const uint32_t wc_hi = ptx::smem_addr(smem + TcSmem::wcat), wc_lo = wc_hi + kMaxN0 * 128;
             // one K sweep of the band DFT: 4 SWIZZLE_128B chunks of 4 k-steps + the 8-column SWIZZLE_32B tail (rolled: the
             // instruction stream of every role has to stay small, the roles share the instruction cache)
@@ -363,11 +375,13 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
                 dft_pass(d, tmem_base + kColAhi, hi, 0);
                 dft_pass(d, tmem_base + kColAlo, hi, 1);
                 ptx::mma_commit(&hi_free[s]);             // the MMA side is done with hi[s]
-                tm.wait(lo_ready, it & 1, 2);         // lo written (splitters)
+                const int ls = lo_stages == 2 ? s : 0;
+                const uint32_t lo_use = lo_stages == 2 ? (it >> 1) : it;   // uses of this lo buffer so far
+                tm.wait(&lo_ready[ls], lo_use & 1, 2);   // lo written (splitters)
                 ptx::tc_fence_after();
-                dft_pass(d, tmem_base + kColAhi, lo, 1);
+                dft_pass(d, tmem_base + kColAhi, ls ? lo_b : lo_a, 1);
                 ptx::mma_commit(&tmem_full[s]);
-                ptx::mma_commit(lo_free);
+                ptx::mma_commit(&lo_free[ls]);
                 if (it > 0) issue_l0(it - 1);             // its magnitudes were written while this tile's DFT was queued
             }
             if (it > 0) issue_l0(it - 1);
@@ -384,8 +398,8 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
         const int bar_f = kBarF + grp;
         int *ev_count = ev_counts + grp;
         unsigned long long *ev_base = ev_bases + grp;
-        int4 *ev_meta = reinterpret_cast<int4 *>(smem + TcSmem::evmeta(np)) + grp * kEvCap;   // (channel, -, eval lo, eval hi)
-        float *ev_out = reinterpret_cast<float *>(smem + TcSmem::evout(np)) + grp * kEvCap * n_out;
+        int4 *ev_meta = reinterpret_cast<int4 *>(smem + TcSmem::evmeta(np, planes)) + grp * kEvCap;   // (channel, -, eval lo, eval hi)
+        float *ev_out = reinterpret_cast<float *>(smem + TcSmem::evout(np, planes)) + grp * kEvCap * n_out;
         const int c = quad * 16 + (lane & 15);              // column of the tile this thread owns
         const bool owner = lane < 16;
         const int nchunks = (np + 7) >> 3;                  // 8-column chunks of a product row
@@ -698,9 +712,11 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
         for (uint32_t it = 0; tw.valid(); ++it, tw.next(w, T)) {
             const int s = it & 1;
             tm.wait(&full[s], (it >> 1) & 1, 0);
-            tm.wait(lo_free, (it & 1) ^ 1, 1);          // pass 3 of the previous tile has read the lo buffer
+            const int ls = lo_stages == 2 ? s : 0;
+            const uint32_t lo_use = lo_stages == 2 ? (it >> 1) : it;
+            tm.wait(&lo_free[ls], (lo_use & 1) ^ 1, 1);  // pass 3 of the previous user of this lo buffer has read it
             const float4 *hi4 = reinterpret_cast<const float4 *>(smem + TcSmem::hi(s)) + st;
-            float4 *lo4 = reinterpret_cast<float4 *>(smem + TcSmem::lo) + st;
+            float4 *lo4 = reinterpret_cast<float4 *>(smem + (ls ? lo1_off : TcSmem::lo)) + st;
             // lo = x - tf32_trunc(x); layout-agnostic: same offsets in both buffers. Two batches, loads in flight before stores.
             constexpr int kBatch = (kPerThread + 1) / 2;
 #pragma unroll
@@ -718,7 +734,7 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
             ptx::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-                ptx::mbar_arrive(lo_ready);
+                ptx::mbar_arrive(&lo_ready[ls]);
                 ptx::mbar_arrive(&hi_free[s]);
             }
         }
@@ -732,7 +748,14 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
 
 }  // namespace
 
-size_t tc_smem_bytes(const FusedParams &p, int hp) { return 1024 + TcSmem::total(p.time_range * hp, p.n_out); }
+static int tc_planes(const FusedParams &p) { return p.window_stat == FUSED_STAT_MINMAX ? 2 : 1; }
+// two lo tiles when they fit into the 227 KB a CTA can have
+int tc_lo_stages(const FusedParams &p, int hp) {
+    return 1024 + TcSmem::total(p.time_range * hp, p.n_out, tc_planes(p), 2) <= 227 * 1024 ? 2 : 1;
+}
+size_t tc_smem_bytes(const FusedParams &p, int hp) {
+    return 1024 + TcSmem::total(p.time_range * hp, p.n_out, tc_planes(p), tc_lo_stages(p, hp));
+}
 int tc_tile_frames() { return kTileFrames; }
 int tc_k_pad() { return kKPad; }
 int tc_max_n0() { return kMaxN0; }

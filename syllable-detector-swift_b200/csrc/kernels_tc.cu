@@ -368,7 +368,11 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
                 const int s = it & 1;
                 const uint32_t ph = (it >> 1) & 1;
                 tm.wait(&full[s], ph, 0);             // hi landed (TMA)
-                tm.wait(&tmem_empty[s], ph ^ 1, 1);   // accumulator s drained by the spectrum warps
+                // accumulator s is free: the spectrum warps read it for tile it-2 before they arrived on a_ready(it-2), which
+                // this thread waited for when it issued layer 0 of that tile (previous iteration) - no separate wait needed
+#ifdef TC_WAIT_TMEM_EMPTY
+                tm.wait(&tmem_empty[s], ph ^ 1, 1);
+#endif
                 ptx::tc_fence_after();
                 const uint32_t d = tmem_base + kColD0 + s * kTileRows;
                 const uint32_t hi = ptx::smem_addr(smem + TcSmem::hi(s));

@@ -60,7 +60,7 @@ constexpr int kMaxN0 = 56;                     // widest layer-0 product row (T 
 constexpr int kTmemCols = 512;
 constexpr int kColAhi = 0, kColAlo = kKPad, kColD0 = 2 * kKPad, kColP0 = kColD0 + 2 * kTileRows;
 static_assert(kColP0 + 2 * kMaxN0 <= kTmemCols, "TMEM budget");
-constexpr int kPRing = 208;                    // product-row ring (rows = columns): one tile per group in flight + the T-1 rows before them
+constexpr int kPRing = kNumGroups * kTileFrames + 22;   // product-row ring (rows = columns): one tile per group in flight + the T-1 (<= 21) rows before them
 constexpr int kStatRing = 512;                 // per-column statistic ring: [2 planes][kStatRing][4 bin quarters] float
 constexpr int kBarF = 2;                       // named barriers of the F groups: kBarF and kBarF + 1
 constexpr int kEvCap = 96;                     // shared-memory event buffer per F group (flushed with one global atomic)

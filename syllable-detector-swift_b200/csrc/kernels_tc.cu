@@ -19,7 +19,7 @@
 //
 // Roles (22 warps with two evaluator groups, one CTA per SM, persistent over (channel, chunk) units; every role walks the same tile sequence):
 //   warp 0        TMA producer                      full[s] <- hi_free[s]
-//   warp 1        MMA issuer + TMEM allocator       DFT(it): full, tmem_empty, lo_ready -> hi_free, tmem_full, lo_free
+//   warp 1        MMA issuer + TMEM allocator       DFT(it): full, (tmem_empty: implied), lo_ready -> hi_free, tmem_full, lo_free
 //                                                   layer0(it-1): a_ready, p_empty -> p_full, a_free
 //   then          evaluators (F): TC_GROUPS (2) groups of four warps (one per TMEM lane quadrant) that take tiles in turn:
 //                                                   p_full, ring_ready[other] -> product ring -> p_empty, ring_ready[own];

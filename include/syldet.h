@@ -50,7 +50,7 @@ enum { SYLDET_LAYOUT_PLANAR = 0, SYLDET_LAYOUT_INTERLEAVED = 1 };
 enum { SYLDET_DETECT_ANY_OUTPUT = 0,   /* TrackDetector.swift:71-77 (CLI rule)  */
        SYLDET_DETECT_FIRST_OUTPUT = 1  /* SyllableDetector.lastDetected :27-31 (live rule) */ };
 enum { SYLDET_PCM_F32 = 0, SYLDET_PCM_S16 = 1 };
-enum { SYLDET_KERNEL_AUTO = 0, SYLDET_KERNEL_GENERIC = 1, SYLDET_KERNEL_FUSED = 2, SYLDET_KERNEL_TENSOR = 3 };
+enum { SYLDET_KERNEL_AUTO = 0, SYLDET_KERNEL_GENERIC = 1, SYLDET_KERNEL_FUSED = 2, SYLDET_KERNEL_TENSOR = 3, SYLDET_KERNEL_TENSOR_TF32 = 4 };
 
 typedef struct syldet_config syldet_config;     /* SyllableDetectorConfig + NeuralNet                    */
 typedef struct syldet_batch syldet_batch;       /* TrackDetector + main.swift loop, many channels at once */
@@ -115,7 +115,11 @@ int64_t syldet_config_debounce_frames(const syldet_config *cfg, double seconds);
 syldet_status syldet_batch_create(const syldet_config *cfg, int device, syldet_batch **out);
 void syldet_batch_destroy(syldet_batch *b);
 /* SYLDET_KERNEL_AUTO picks the fastest kernel the configuration qualifies for: TENSOR (tcgen05 band DFT + fused epilogue),
- * FUSED (SIMT FFT + fused epilogue), else the GENERIC reference-order path. */
+ * FUSED (SIMT FFT + fused epilogue), else the GENERIC reference-order path.
+ * TENSOR computes the two correction products of its 3xTF32 band DFT in fp16 for the reference's sample network shape: results
+ * are at float32 level (same error as TENSOR_TF32) while the audio has an RMS above ~1e-5 and peaks below 65504 - any PCM-derived
+ * signal; below that the error grows as ~1e-11 / rms. TENSOR_TF32 keeps all three products in TF32 (amplitude-invariant like the
+ * reference, ~10 % slower). The environment variable SYLDET_TC_TF32_CORR=1 makes TENSOR behave like TENSOR_TF32. */
 syldet_status syldet_batch_set_kernel(syldet_batch *b, int kernel);
 int syldet_batch_active_kernel(const syldet_batch *b);
 /* syldet_batch_run_host cuts a recording into up to 16 time slices so that the PCIe copy of slice k+1 overlaps the detection and

@@ -31,6 +31,7 @@ LAYOUT_PLANAR, LAYOUT_INTERLEAVED = 0, 1
 DETECT_ANY_OUTPUT, DETECT_FIRST_OUTPUT = 0, 1
 PCM_F32, PCM_S16 = 0, 1
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_FUSED, KERNEL_TENSOR = 0, 1, 2, 3
+KERNEL_TENSOR_TF32 = 4   # tensor kernel with all three DFT products in TF32 (amplitude-invariant; see include/syldet.h)
 KERNEL_NAMES = {1: "generic", 2: "fused", 3: "tensor"}
 
 _STATUS = {1: "unableToOpenPath", 2: "missingValue", 3: "invalidValue", 4: "mismatchedLength", 5: "invalidConfiguration",

@@ -166,6 +166,23 @@ float tf32_round(double v) {  // round to nearest, ties away (cvt.rna.tf32.f32):
     std::memcpy(&f, &u, 4);
     return f;
 }
+uint16_t f32_to_f16_rn(float f) {  // round to nearest even, subnormals kept (cvt.rn.f16.f32)
+    uint32_t x;
+    std::memcpy(&x, &f, 4);
+    const uint16_t sign = (uint16_t)((x >> 16) & 0x8000u);
+    x &= 0x7FFFFFFFu;
+    if (x >= 0x47800000u) return (uint16_t)(sign | 0x7C00u);   // >= 65536 (not reached: |values| <= 1)
+    if (x < 0x38800000u) {                                      // below the smallest normal 2^-14: count units of 2^-24
+        float a;
+        std::memcpy(&a, &x, 4);
+        return (uint16_t)(sign | (uint32_t)std::lrint((double)a * 16777216.0));
+    }
+    const uint32_t mant = x & 0x7FFFFFu, exp = (x >> 23) - 127 + 15;
+    uint32_t half = (exp << 10) | (mant >> 13);
+    const uint32_t rem = mant & 0x1FFFu;
+    if (rem > 0x1000u || (rem == 0x1000u && (half & 1u))) ++half;   // a carry moves into the exponent
+    return (uint16_t)(sign | half);
+}
 }  // namespace
 
 TcPlan plan_tc(const Config &c, const FusedPlan &fused) {
@@ -199,6 +216,15 @@ TcPlan plan_tc(const Config &c, const FusedPlan &fused) {
     // rows: [0,32) Re B1 | [32,64) Im B1 | [64,96) Re B2 | [96,128) Im B2 ; B1 = samples [0,hop), B2 = samples [hop,W)
     plan.dft_hi.assign((size_t)128 * kpad, 0.0f);
     plan.dft_lo.assign((size_t)128 * kpad, 0.0f);
+    // fp16 correction operand (TC_F16_CORR): K order [lo(n < 128) | hi * 2^-11 (n < 128) | lo(n >= 128) | hi * 2^-11 (n >= 128)],
+    // two k per 32-bit word (low half first); lo = value - tf32(value), paired with fp16(x) and fp16((x - tf32(x)) * 2^11)
+    std::vector<uint16_t> a16((size_t)128 * 2 * kpad, 0);
+    auto put16 = [&](size_t row, int n, double full, float hi) {
+        const int main = n < 128, k = n & 127;
+        const size_t j_lo = main ? (size_t)k : (size_t)256 + k, j_hi = main ? (size_t)128 + k : (size_t)264 + k;
+        a16[row * 2 * kpad + j_lo] = f32_to_f16_rn((float)(full - (double)hi));
+        a16[row * 2 * kpad + j_hi] = f32_to_f16_rn(hi * (1.0f / 2048.0f));
+    };
     for (int b = 0; b < c.band; ++b) {
         const int k = c.k0 + b;
         for (int half = 0; half < 2; ++half)
@@ -213,8 +239,12 @@ TcPlan plan_tc(const Config &c, const FusedPlan &fused) {
                 plan.dft_lo[ire] = tf32_round(re - (double)plan.dft_hi[ire]);
                 plan.dft_hi[iim] = tf32_round(im);
                 plan.dft_lo[iim] = tf32_round(im - (double)plan.dft_hi[iim]);
+                put16((size_t)(half * 64 + b), n, re, plan.dft_hi[ire]);
+                put16((size_t)(half * 64 + 32 + b), n, im, plan.dft_hi[iim]);
             }
     }
+    plan.dft16.assign((size_t)128 * kpad, 0u);
+    for (size_t i = 0; i < plan.dft16.size(); ++i) plan.dft16[i] = (uint32_t)a16[2 * i] | ((uint32_t)a16[2 * i + 1] << 16);
     plan.ok = true;
     return plan;
 }
@@ -336,12 +366,13 @@ syldet_status DeviceModel::init(const Config &cfg, int device) {
     tc_ = plan_tc(cfg_, fused_);
     if (tc_.ok) {
         const size_t n = tc_.dft_hi.size(), nw = tc_.wcat_hi.size();
-        st = d_dft_.reserve((2 * n + 2 * nw) * sizeof(float));
+        st = d_dft_.reserve((3 * n + 2 * nw) * sizeof(float));
         if (st != SYLDET_OK) return st;
         SYLDET_CUDA(cudaMemcpy(d_dft_.get(), tc_.dft_hi.data(), n * sizeof(float), cudaMemcpyHostToDevice));
         SYLDET_CUDA(cudaMemcpy(d_dft_.as<float>() + n, tc_.dft_lo.data(), n * sizeof(float), cudaMemcpyHostToDevice));
         SYLDET_CUDA(cudaMemcpy(d_dft_.as<float>() + 2 * n, tc_.wcat_hi.data(), nw * sizeof(float), cudaMemcpyHostToDevice));
         SYLDET_CUDA(cudaMemcpy(d_dft_.as<float>() + 2 * n + nw, tc_.wcat_lo.data(), nw * sizeof(float), cudaMemcpyHostToDevice));
+        SYLDET_CUDA(cudaMemcpy(d_dft_.as<float>() + 2 * n + 2 * nw, tc_.dft16.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice));
     }
     return SYLDET_OK;
 }
@@ -391,9 +422,10 @@ Batch::~Batch() {
 }
 
 syldet_status Batch::set_kernel(int kernel) {
-    if (kernel != SYLDET_KERNEL_AUTO && kernel != SYLDET_KERNEL_GENERIC && kernel != SYLDET_KERNEL_FUSED && kernel != SYLDET_KERNEL_TENSOR)
+    if (kernel != SYLDET_KERNEL_AUTO && kernel != SYLDET_KERNEL_GENERIC && kernel != SYLDET_KERNEL_FUSED && kernel != SYLDET_KERNEL_TENSOR &&
+        kernel != SYLDET_KERNEL_TENSOR_TF32)
         return set_error(SYLDET_ERR_ARG, "unknown kernel selector");
-    if (kernel == SYLDET_KERNEL_TENSOR && !model_.tc().ok)
+    if ((kernel == SYLDET_KERNEL_TENSOR || kernel == SYLDET_KERNEL_TENSOR_TF32) && !model_.tc().ok)
         return set_error(SYLDET_ERR_UNSUPPORTED, "tensor-core kernel not available for this configuration: " + model_.tc().why);
     if (kernel == SYLDET_KERNEL_FUSED && !model_.fused().ok)
         return set_error(SYLDET_ERR_UNSUPPORTED, "fused kernel not available for this configuration: " + model_.fused().why);
@@ -510,8 +542,11 @@ syldet_status Batch::launch_tc_range(const float *d_planar, int n_channels, int6
     w.dft_lo = model_.dft_lo();
     w.wcat_hi = model_.wcat_hi();
     w.wcat_lo = model_.wcat_lo();
+    w.dft16 = model_.dft16();
     w.n0 = tp.n0;
     w.lo_stages = tc_lo_stages(tp.params, tp.hp);
+    static const bool tf32_corr = std::getenv("SYLDET_TC_TF32_CORR") != nullptr;   // all three products in TF32 (amplitude-invariant)
+    w.f16_corr = (tf32_corr || kernel_ == SYLDET_KERNEL_TENSOR_TF32) ? 0 : 1;
     w.debug_band = debug_band_;
     w.debug_cols = debug_cols_;
     const int64_t units = (int64_t)n_channels * w.chunks_per_channel;
@@ -579,7 +614,7 @@ syldet_status Batch::launch_planar_range(const float *d_planar, int n_channels, 
     EventSink sink{sink_count_.as<unsigned long long>(), sink_events_.as<DevEvent>(), sink_outputs_.as<float>(), sink_capacity_};
 
     const int kernel = active_kernel();
-    if (kernel == SYLDET_KERNEL_TENSOR) {
+    if (kernel == SYLDET_KERNEL_TENSOR || kernel == SYLDET_KERNEL_TENSOR_TF32) {
         // evaluations whose rows [e, e+T] are all complete hop-rows go to the tensor-core kernel; the last few (and inputs
         // whose base/pitch are not 16-byte aligned) go to the SIMT fused kernel
         const float *base = d_planar + eval_begin * c.hop;

@@ -60,6 +60,7 @@ struct TcPlan {
     int hp = 0;
     size_t smem = 0;
     std::vector<float> dft_hi, dft_lo;  // [128][k_pad]
+    std::vector<uint32_t> dft16;        // [128][k_pad] fp16 pairs: the two correction operands of the TC_F16_CORR build (kernels_tc.cu)
     std::vector<float> wcat_hi, wcat_lo;  // [n0][32]
     int n0 = 0;
 };
@@ -84,6 +85,7 @@ public:
     const float *dft_lo() const { return d_dft_.as<float>() + 128 * (size_t)tc_k_pad(); }
     const float *wcat_hi() const { return d_dft_.as<float>() + 2 * 128 * (size_t)tc_k_pad(); }
     const float *wcat_lo() const { return wcat_hi() + (size_t)tc_.n0 * 32; }
+    const uint32_t *dft16() const { return reinterpret_cast<const uint32_t *>(wcat_lo() + (size_t)tc_.n0 * 32); }
     int sm_count() const { return sm_count_; }
     const unsigned char *blob() const { return d_blob_.as<unsigned char>(); }
     size_t blob_bytes() const { return blob_bytes_; }

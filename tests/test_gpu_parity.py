@@ -153,6 +153,19 @@ def test_tensor_kernel_shape_variants(sd, oracle_mod, cw, kw):
         _check_channel(o, x[ch], outs[ch], ev.sample[ev.channel == ch], tol)
 
 
+def test_tensor_kernel_amplitude_range(sd, cfg, orc, synth):
+    """The default tensor kernel computes the two DFT correction products in fp16: float32-level results while the samples are
+    fp16 normals (rms >~ 1e-5, |x| < 65504), checked here from rms 50 down to 5e-5. KERNEL_TENSOR_TF32 keeps everything in TF32
+    and stays within the tolerance for any amplitude (rms 2e-9 here), like the reference's float32 arithmetic."""
+    x0 = synth.make_audio(2, 44100 * 2, seed=5)
+    for kernel, exps in ((sd.KERNEL_TENSOR, (12, 0, -8)), (sd.KERNEL_TENSOR_TF32, (12, 0, -8, -16, -22))):
+        for e in exps:
+            x = (x0 * np.float32(2.0 ** e)).astype(np.float32)
+            ev, outs = sd.BatchDetector(cfg, kernel=kernel).run(x, want_outputs=True)
+            for ch in range(x.shape[0]):
+                _check_channel(orc, x[ch], outs[ch], ev.sample[ev.channel == ch], TOL_OUT)
+
+
 def test_high_overlap_wide_hidden_config(sd, oracle_mod, cw):
     """BASELINE config 4 shape: FFT 1024, hop 4, band 1-8 kHz (L = 162), T = 8 (1296 inputs), 256 tansig units, 2 outputs.
     Too wide for the fused kernels: the reference-order kernels take it. Left-to-right sums over 1296 terms: same order in

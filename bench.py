@@ -184,7 +184,8 @@ def run_ours(args):
     d_out = torch.empty((nch, E, cfg.net_outputs), dtype=torch.float32, device=dev)
     det = sd.BatchDetector(cfg, device=local, kernel=getattr(sd, "KERNEL_" + args.kernel.upper()))
     assert det.active_kernel in (sd.KERNEL_FUSED, sd.KERNEL_TENSOR), "sample.txt must take a fused kernel"
-    kernel_name = {sd.KERNEL_FUSED: "fused_detect_kernel<256,4> (SIMT FFT)", sd.KERNEL_TENSOR: "tc_detect_kernel<4> (tcgen05 3xTF32 band DFT)"}[det.active_kernel]
+    kernel_name = {sd.KERNEL_FUSED: "fused_detect_kernel<256,4> (SIMT FFT)", sd.KERNEL_TENSOR: ("tc_detect_kernel<4> (tcgen05 3xTF32 band DFT)" if os.environ.get("SYLDET_TC_TF32_CORR") else
+                                         "tc_detect_kernel<4,kFast,kF16> (tcgen05 band DFT: TF32 product + one fp16 correction pass)")}[det.active_kernel]
     stream = torch.cuda.current_stream(dev)
 
     def launch():

@@ -26,6 +26,23 @@ def test_library_exports_every_declared_symbol(sd):
     assert set(names) == set(sd.EXPORTED_SYMBOLS)
 
 
+def test_python_constants_mirror_the_header_enums(sd):
+    """Every SYLDET_* enumerator the header defines with an explicit value has the same value in the Python mirror (the
+    mirror drops the SYLDET_ prefix)."""
+    text = open(os.path.join(ROOT, "include", "syldet.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    pairs = re.findall(r"\bSYLDET_([A-Z0-9_]+)\s*=\s*(-?\d+)", text)
+    assert ("KERNEL_TENSOR_TF32", "4") in pairs and len(pairs) > 15
+    checked = 0
+    for name, value in pairs:
+        if hasattr(sd, name):
+            assert getattr(sd, name) == int(value), name
+            checked += 1
+    assert checked >= 10
+    for name in ("KERNEL_AUTO", "KERNEL_GENERIC", "KERNEL_FUSED", "KERNEL_TENSOR", "KERNEL_TENSOR_TF32"):
+        assert hasattr(sd, name), name
+
+
 def test_sample_txt_fields(sd):
     c = sd.SyllableDetectorConfig(SAMPLE_TXT).validate()
     assert (c.sampling_rate, c.fourier_length, c.window_length, c.window_overlap, c.time_range) == (44100.0, 256, 256, 124, 10)

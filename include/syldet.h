@@ -116,10 +116,14 @@ syldet_status syldet_batch_create(const syldet_config *cfg, int device, syldet_b
 void syldet_batch_destroy(syldet_batch *b);
 /* SYLDET_KERNEL_AUTO picks the fastest kernel the configuration qualifies for: TENSOR (tcgen05 band DFT + fused epilogue),
  * FUSED (SIMT FFT + fused epilogue), else the GENERIC reference-order path.
- * TENSOR computes the two correction products of its 3xTF32 band DFT in fp16 for the reference's sample network shape: results
- * are at float32 level (same error as TENSOR_TF32) while the audio has an RMS above ~1e-5 and peaks below 65504 - any PCM-derived
- * signal; below that the error grows as ~1e-11 / rms. TENSOR_TF32 keeps all three products in TF32 (amplitude-invariant like the
- * reference, ~10 % slower). The environment variable SYLDET_TC_TF32_CORR=1 makes TENSOR behave like TENSOR_TF32. */
+ * TENSOR computes the two correction products of its 3xTF32 band DFT in fp16 for the reference's sample network shape (l2normalize
+ * first). That pass is at float32 level inside an amplitude window (no sample beyond +-32752; norm of the band-magnitude window
+ * >= 2^-8, i.e. audio rms >~ 2e-5; any 16-bit PCM input qualifies by construction). The kernel checks the window on every
+ * evaluation; when audio falls outside it, syldet_batch_collect / _last_detection_count / _run_host transparently repeat the launch
+ * with the all-TF32 variant and the handle keeps using that variant (syldet_batch_range_fallbacks counts the switch). Results are
+ * therefore amplitude-invariant like the reference's float32 arithmetic; dense device outputs of syldet_batch_launch_device are final
+ * once one of those calls has returned. TENSOR_TF32 selects the all-TF32 variant up front (~10 % slower); the environment variable
+ * SYLDET_TC_TF32_CORR=1 does the same for every handle. */
 syldet_status syldet_batch_set_kernel(syldet_batch *b, int kernel);
 int syldet_batch_active_kernel(const syldet_batch *b);
 /* syldet_batch_run_host cuts a recording into up to 16 time slices so that the PCIe copy of slice k+1 overlaps the detection and
@@ -160,6 +164,18 @@ syldet_status syldet_batch_launch_device(syldet_batch *b, const float *d_pcm, in
 syldet_status syldet_batch_collect(syldet_batch *b, int64_t debounce_frames, syldet_events **events);
 /* Kernels launched by this handle since creation (for bench.py's gpu_launches). */
 int64_t syldet_batch_launch_count(const syldet_batch *b);
+/* 1 once this handle has switched its tensor kernel to the all-TF32 variant because audio left the fp16 window (see above), else 0. */
+int64_t syldet_batch_range_fallbacks(const syldet_batch *b);
+/*
+ * CircularShortTimeFourierTransform.extractPower()[f0 ..< f1] (CSTFT.swift:280-337 = |X[k]|, band slice of SyllableDetector.swift:136-148)
+ * as the ACTIVE kernel computes it on the detection path, before the spectrogram scaling: band receives [n_channels][n_columns][L]
+ * float32 with L = freq_index_range width and *n_columns = num_evals + time_range - 1 (every column that feeds an evaluation; 0 when
+ * the recording is shorter than one feature window). Call with band = NULL to query *n_columns. pcm arguments as for
+ * syldet_batch_run_host. Inspection / parity-test entry point: the band magnitudes never leave the chip in normal operation.
+ * (extractMagnitude(), :221-278, is the square of these values; upstream's detector never calls it.)
+ */
+syldet_status syldet_batch_spectra_host(syldet_batch *b, const void *pcm, int pcm_format, int n_channels, int64_t n_samples,
+                                        int64_t channel_stride, int layout, float *band, int64_t *n_columns);
 /* Raw detection count of the last launch before debounce (synchronises). */
 syldet_status syldet_batch_last_detection_count(syldet_batch *b, int64_t *count);
 

@@ -25,16 +25,37 @@ def build(force=False):
     return out
 
 
-_lib = None
+def build_fast():
+    """Timing-only build (-O3 -march=native, oracle/Makefile target `fast`) for bench.py's CPU legs. Compiled on the box that runs
+    it, into a per-host file under the system temp directory (a library built for another CPU must not travel)."""
+    import hashlib
+    import platform
+    import tempfile
+    try:
+        with open("/proc/cpuinfo") as f:
+            cpu = next((l for l in f if l.startswith("flags")), platform.processor())
+    except OSError:
+        cpu = platform.processor()
+    tag = hashlib.sha1((cpu + open(os.path.join(_HERE, "oracle.c")).read()).encode()).hexdigest()[:12]
+    out = os.path.join(tempfile.gettempdir(), "liboracle_fast_%s.so" % tag)
+    if not os.path.exists(out):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "fast", "FAST_OUT=" + out])
+    return out
 
 
-def _load():
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(lib_path()):
-        build()
-    L = C.CDLL(lib_path())
+_libs = {}
+
+
+def _load(fast=False):
+    if fast in _libs:
+        return _libs[fast]
+    if fast:
+        path = build_fast()
+    else:
+        if not os.path.exists(lib_path()):
+            build()
+        path = lib_path()
+    L = C.CDLL(path)
     vp, cp, ip, lg, db = C.c_void_p, C.c_char_p, C.POINTER(C.c_int), C.c_long, C.c_double
     L.orc_config_parse.argtypes = [cp, C.c_size_t, C.POINTER(vp), ip, cp, C.c_int]
     L.orc_config_load.argtypes = [cp, C.POINTER(vp), ip, cp, C.c_int]
@@ -66,7 +87,7 @@ def _load():
     L.orc_resampler_process.argtypes = [vp, vp, lg, vp, lg]
     L.orc_resampler_process.restype = lg
     L.orc_resampler_state.argtypes = [vp, vp, vp, vp]
-    _lib = L
+    _libs[fast] = L
     return L
 
 
@@ -84,8 +105,9 @@ def _f32(a):
 
 
 class Oracle:
-    def __init__(self, path=None, text=None):
-        L = _load()
+    def __init__(self, path=None, text=None, fast=False):
+        """fast=True: the timing-only -O3 -march=native build (bench.py's CPU legs); parity checks use the default build."""
+        L = _load(fast)
         h = C.c_void_p()
         code = C.c_int(0)
         key = C.create_string_buffer(256)

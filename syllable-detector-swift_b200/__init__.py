@@ -92,6 +92,8 @@ def _load():
         "syldet_batch_launch_device": (i32, [vp, vp, i32, i64, i64, i32, i32, vp, vp]),
         "syldet_batch_collect": (i32, [vp, i64, pvp]), "syldet_batch_launch_count": (i64, [vp]),
         "syldet_batch_last_detection_count": (i32, [vp, C.POINTER(i64)]),
+        "syldet_batch_range_fallbacks": (i64, [vp]),
+        "syldet_batch_spectra_host": (i32, [vp, vp, i32, i32, i64, i64, i32, vp, C.POINTER(i64)]),
         "syldet_events_count": (i64, [vp]), "syldet_events_outputs_per_event": (i32, [vp]),
         "syldet_events_data": (C.POINTER(Event), [vp]), "syldet_events_outputs": (C.POINTER(C.c_float), [vp]),
         "syldet_events_free": (None, [vp]),
@@ -331,6 +333,28 @@ class BatchDetector:
         _check(lib.syldet_batch_simulate_host(self._h, a.ctypes.data, fmt, nch, n, n, layout, PCM_S16 if s16 else PCM_F32,
                                               trace.ctypes.data))
         return trace
+
+    @property
+    def range_fallbacks(self):
+        """1 once the tensor kernel of this handle switched to its all-TF32 variant (audio outside the fp16 window), else 0."""
+        return lib.syldet_batch_range_fallbacks(self._h)
+
+    def spectra(self, pcm, layout=LAYOUT_PLANAR):
+        """extractPower()[f0 ..< f1] (CSTFT.swift:280-337) of every column that feeds an evaluation, as the active kernel computes it
+        on the detection path. -> float32 [n_channels, num_evals + time_range - 1, band]"""
+        a = np.asarray(pcm)
+        if a.ndim == 1:
+            a = a[None, :] if layout == LAYOUT_PLANAR else a[:, None]
+        fmt = PCM_S16 if a.dtype == np.int16 else PCM_F32
+        a = np.ascontiguousarray(a, dtype=np.int16 if fmt == PCM_S16 else np.float32)
+        nch, n = (a.shape if layout == LAYOUT_PLANAR else a.shape[::-1])
+        cols = C.c_int64()
+        _check(lib.syldet_batch_spectra_host(self._h, a.ctypes.data, fmt, nch, n, n, layout, None, C.byref(cols)))
+        k0, k1 = self.config.freq_indices
+        band = np.zeros((nch, cols.value, k1 - k0), dtype=np.float32)
+        if cols.value:
+            _check(lib.syldet_batch_spectra_host(self._h, a.ctypes.data, fmt, nch, n, n, layout, band.ctypes.data, C.byref(cols)))
+        return band
 
     def launch_device(self, d_pcm_ptr, n_channels, n_samples, channel_stride, detect_rule=DETECT_ANY_OUTPUT, d_outputs_ptr=None,
                       stream=None, layout=LAYOUT_PLANAR):

@@ -209,6 +209,12 @@ syldet_status syldet_batch_collect(syldet_batch *b, int64_t debounce_frames, syl
     });
 }
 int64_t syldet_batch_launch_count(const syldet_batch *b) { return b ? b->b.launch_count() : 0; }
+int64_t syldet_batch_range_fallbacks(const syldet_batch *b) { return b ? b->b.range_fallbacks() : 0; }
+syldet_status syldet_batch_spectra_host(syldet_batch *b, const void *pcm, int pcm_format, int n_channels, int64_t n_samples,
+                                        int64_t channel_stride, int layout, float *band, int64_t *n_columns) {
+    if (!b) return set_error(SYLDET_ERR_ARG, "null argument");
+    return guarded([&] { return b->b.spectra_host(pcm, pcm_format, n_channels, n_samples, channel_stride, layout, band, n_columns); });
+}
 syldet_status syldet_batch_last_detection_count(syldet_batch *b, int64_t *count) {
     if (!b || !count) return set_error(SYLDET_ERR_ARG, "null argument");
     return b->b.last_detection_count(count);

@@ -404,7 +404,7 @@ syldet_status Batch::init(const Config &cfg, int device) {
     syldet_status st = model_.init(cfg, device);
     if (st != SYLDET_OK) return st;
     SYLDET_CUDA(cudaStreamCreateWithFlags(&own_stream_, cudaStreamNonBlocking));
-    st = sink_count_.reserve(sizeof(unsigned long long));
+    st = sink_count_.reserve(kSinkHeaderBytes);   // [0, 8): detection count, [8, 12): range flag of the fp16 correction pass
     return st;
 }
 
@@ -490,6 +490,8 @@ syldet_status Batch::launch_fused_range(const float *d_planar, int n_channels, i
     w.sink = sink;
     w.window = model_.window();
     w.twiddle = model_.twiddle();
+    w.debug_band = debug_band_;
+    w.debug_cols = debug_cols_;
     FusedLaunch l = fp.launch;
     const int64_t units = (int64_t)n_channels * w.chunks_per_channel;
     l.grid = (int)std::min<int64_t>(units, resident);
@@ -546,7 +548,11 @@ syldet_status Batch::launch_tc_range(const float *d_planar, int n_channels, int6
     w.n0 = tp.n0;
     w.lo_stages = tc_lo_stages(tp.params, tp.hp);
     static const bool tf32_corr = std::getenv("SYLDET_TC_TF32_CORR") != nullptr;   // all three products in TF32 (amplitude-invariant)
-    w.f16_corr = (tf32_corr || kernel_ == SYLDET_KERNEL_TENSOR_TF32) ? 0 : 1;
+    w.f16_corr = (tf32_corr || kernel_ == SYLDET_KERNEL_TENSOR_TF32 || !f16_ok_) ? 0 : 1;
+    // int16-derived samples k / 32768 are exact fp16 operands (x: at most one rounding in the normal range; its tf32 residual times
+    // 2^11 is a multiple of 2^-4 below 2): no lower bound needed there. Float input: see kTcGuardLo.
+    w.guard_lo = pcm_exact_ ? 0.0f : kTcGuardLo;
+    w.range_flag = reinterpret_cast<int *>(sink_count_.as<unsigned char>() + 8);
     w.debug_band = debug_band_;
     w.debug_cols = debug_cols_;
     const int64_t units = (int64_t)n_channels * w.chunks_per_channel;
@@ -609,7 +615,7 @@ syldet_status Batch::launch_planar_range(const float *d_planar, int n_channels, 
                                          int detect_rule, float *d_all_outputs, bool reset_sink, cudaStream_t stream) {
     const Config &c = model_.config();
     const int64_t E = c.num_evals(n_samples);
-    if (reset_sink) SYLDET_CUDA(cudaMemsetAsync(sink_count_.get(), 0, sizeof(unsigned long long), stream));
+    if (reset_sink) SYLDET_CUDA(cudaMemsetAsync(sink_count_.get(), 0, kSinkHeaderBytes, stream));
     if (eval_count <= 0) return SYLDET_OK;
     EventSink sink{sink_count_.as<unsigned long long>(), sink_events_.as<DevEvent>(), sink_outputs_.as<float>(), sink_capacity_};
 
@@ -644,7 +650,12 @@ syldet_status Batch::launch_planar_range(const float *d_planar, int n_channels, 
         syldet_status st = feat_.reserve((size_t)n_channels * ncols * L * sizeof(float));
         if (st != SYLDET_OK) return st;
         SYLDET_CUDA(launch_stft_band_generic(model_.dev_net(), c.fourier_length, d_planar, ch_stride, n_channels, e0, ncols,
-                                             feat_.as<float>(), stream));
+                                             feat_.as<float>(), ncols * L, -1, stream));
+        if (debug_band_) {   // extractPower() values before the scaling, straight into the caller's [channel][column][bin] buffer
+            SYLDET_CUDA(launch_stft_band_generic(model_.dev_net(), c.fourier_length, d_planar, ch_stride, n_channels, e0, ncols,
+                                                 debug_band_ + e0 * L, debug_cols_ * L, SYLDET_SCALING_LINEAR, stream));
+            launches_ += 1;
+        }
         SYLDET_CUDA(launch_nn_generic(model_.dev_net(), model_.max_width(), feat_.as<float>(), n_channels, ncols, ne, e0, E,
                                       detect_rule, d_all_outputs, sink, stream));
         launches_ += 2;
@@ -653,7 +664,7 @@ syldet_status Batch::launch_planar_range(const float *d_planar, int n_channels, 
 }
 
 syldet_status Batch::launch_device(const float *d_pcm, int n_channels, int64_t n_samples, int64_t ch_stride, int layout,
-                                   int detect_rule, float *d_all_outputs, cudaStream_t stream) {
+                                   int detect_rule, float *d_all_outputs, cudaStream_t stream, bool pcm_exact) {
     if (!d_pcm || n_channels <= 0 || n_samples < 0) return set_error(SYLDET_ERR_ARG, "bad pcm arguments");
     if (n_channels > 65535) return set_error(SYLDET_ERR_ARG, "more than 65535 channels in one call");
     if (layout == SYLDET_LAYOUT_PLANAR && n_channels > 1 && ch_stride < n_samples) return set_error(SYLDET_ERR_ARG, "channel_stride < n_samples");
@@ -666,7 +677,8 @@ syldet_status Batch::launch_device(const float *d_pcm, int n_channels, int64_t n
         st = ensure_sink(std::max<unsigned long long>(1, std::min<unsigned long long>(total, std::max<unsigned long long>(1ull << 20, total / 8))));
         if (st != SYLDET_OK) return st;
     }
-    last_ = Last{true, d_pcm, n_channels, n_samples, ch_stride, layout, detect_rule, d_all_outputs, stream};
+    last_ = Last{true, d_pcm, n_channels, n_samples, ch_stride, layout, detect_rule, d_all_outputs, stream, pcm_exact};
+    pcm_exact_ = pcm_exact;
     if (layout == SYLDET_LAYOUT_INTERLEAVED && n_channels > 1) {
         const int64_t pitch = (n_samples + 3) & ~(int64_t)3;
         st = planar_.reserve((size_t)n_channels * pitch * sizeof(float));
@@ -681,13 +693,45 @@ syldet_status Batch::launch_device(const float *d_pcm, int n_channels, int64_t n
                          detect_rule, d_all_outputs, stream);
 }
 
-syldet_status Batch::last_detection_count(int64_t *count) {
+// Waits for the last launch and makes its results final. Two things can ask for a repeat of the launch: more detections than the
+// event buffer holds (grow it to the worst case), and the range flag of the tensor kernel's fp16 correction pass (audio outside the
+// window in which that pass is at float32 level: this handle switches to the all-TF32 variant for good). Dense outputs the caller
+// asked for are rewritten by the repeat, on the same stream.
+syldet_status Batch::settle(unsigned long long *n_events) {
     if (!last_.valid) return set_error(SYLDET_ERR_ARG, "no launch to inspect");
     syldet_status st = use_device(model_.device());
     if (st != SYLDET_OK) return st;
-    SYLDET_CUDA(cudaStreamSynchronize(last_.stream));
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        SYLDET_CUDA(cudaStreamSynchronize(last_.stream));
+        SinkHeader h{};
+        SYLDET_CUDA(cudaMemcpy(&h, sink_count_.get(), sizeof h, cudaMemcpyDeviceToHost));
+        bool replay = false;
+        if (h.range_flag != 0 && f16_ok_) {
+            f16_ok_ = false;
+            ++range_fallbacks_;
+            replay = true;
+        }
+        if (h.count > sink_capacity_) {
+            const unsigned long long total = (unsigned long long)model_.config().num_evals(last_.n_samples) * last_.n_channels;
+            st = ensure_sink(total);
+            if (st != SYLDET_OK) return st;
+            replay = true;
+        }
+        if (!replay) {
+            *n_events = h.count;
+            return SYLDET_OK;
+        }
+        const Last l = last_;
+        st = launch_device(l.d_pcm, l.n_channels, l.n_samples, l.ch_stride, l.layout, l.detect_rule, l.d_all_outputs, l.stream, l.pcm_exact);
+        if (st != SYLDET_OK) return st;
+    }
+    return set_error(SYLDET_ERR_OVERFLOW, "event buffer overflow after replay");
+}
+
+syldet_status Batch::last_detection_count(int64_t *count) {
     unsigned long long n = 0;
-    SYLDET_CUDA(cudaMemcpy(&n, sink_count_.get(), sizeof n, cudaMemcpyDeviceToHost));
+    syldet_status st = settle(&n);
+    if (st != SYLDET_OK) return st;
     *count = (int64_t)n;
     return SYLDET_OK;
 }
@@ -704,26 +748,13 @@ double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::
 syldet_status Batch::collect(int64_t debounce_frames, Events &out) {
     if (!last_.valid) return set_error(SYLDET_ERR_ARG, "collect without a launch");
     if (debounce_frames < 0) return set_error(SYLDET_ERR_ARG, "negative debounce");
-    syldet_status st = use_device(model_.device());
-    if (st != SYLDET_OK) return st;
     const Config &c = model_.config();
     const int O = c.outputs;
     const double t_c0 = now_ms();
-    SYLDET_CUDA(cudaStreamSynchronize(last_.stream));
-    const double t_c1 = now_ms();
     unsigned long long n = 0;
-    SYLDET_CUDA(cudaMemcpy(&n, sink_count_.get(), sizeof n, cudaMemcpyDeviceToHost));
-    if (n > sink_capacity_) {  // more detections than the event buffer holds: grow to the worst case and replay
-        const unsigned long long total = (unsigned long long)c.num_evals(last_.n_samples) * last_.n_channels;
-        st = ensure_sink(total);
-        if (st != SYLDET_OK) return st;
-        Last l = last_;
-        st = launch_device(l.d_pcm, l.n_channels, l.n_samples, l.ch_stride, l.layout, l.detect_rule, l.d_all_outputs, l.stream);
-        if (st != SYLDET_OK) return st;
-        SYLDET_CUDA(cudaStreamSynchronize(last_.stream));
-        SYLDET_CUDA(cudaMemcpy(&n, sink_count_.get(), sizeof n, cudaMemcpyDeviceToHost));
-        if (n > sink_capacity_) return set_error(SYLDET_ERR_OVERFLOW, "event buffer overflow after replay");
-    }
+    syldet_status st = settle(&n);
+    if (st != SYLDET_OK) return st;
+    const double t_c1 = now_ms();
     std::vector<DevEvent> ev(n);
     std::vector<float> outs((size_t)n * O);
     if (n) {
@@ -765,7 +796,7 @@ syldet_status Batch::ensure_pipeline(int slices, size_t event_bytes) {
         SYLDET_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
         ev_done_.push_back(b);
     }
-    if (!h_counts_) SYLDET_CUDA(cudaMallocHost(&h_counts_, kMaxSlices * sizeof(unsigned long long)));
+    if (!h_counts_) SYLDET_CUDA(cudaMallocHost(&h_counts_, kMaxSlices * sizeof(SinkHeader)));
     if (event_bytes > h_events_bytes_) {
         if (h_events_) cudaFreeHost(h_events_);
         h_events_ = nullptr;
@@ -831,35 +862,50 @@ syldet_status Batch::run_host(const void *pcm, int fmt, int n_channels, int64_t 
     st = ensure_pipeline(K, (size_t)sink_capacity_ * (sizeof(DevEvent) + sizeof(float) * O));
     if (st != SYLDET_OK) return st;
     cudaStream_t sx = own_stream_;
-    last_ = Last{true, planar_.as<float>(), n_channels, n_samples, pitch, SYLDET_LAYOUT_PLANAR, detect_rule, d_all, sx};
+    pcm_exact_ = fmt == SYLDET_PCM_S16;   // k / 32768: exact operands for the tensor kernel's fp16 correction pass
+    last_ = Last{true, planar_.as<float>(), n_channels, n_samples, pitch, SYLDET_LAYOUT_PLANAR, detect_rule, d_all, sx, pcm_exact_};
     const double t_start = now_ms();
     float *planar = planar_.as<float>();
+    // Errors inside the pipeline: nothing may stay in flight that reads the caller's buffer when control returns.
+    auto drain = [&](syldet_status status) {
+        cudaStreamSynchronize(copy_stream_);
+        cudaStreamSynchronize(sx);
+        cudaGetLastError();
+        return status;
+    };
+#define SYLDET_CUDA_DRAIN(expr)                                                        \
+    do {                                                                               \
+        cudaError_t _e = (expr);                                                       \
+        if (_e != cudaSuccess) return drain(::syldet::cuda_fail(_e, #expr));           \
+    } while (0)
     for (int k = 0; k < K; ++k) {
         const int64_t s0 = sb[k], ns = sb[k + 1] - sb[k];
         if (ns > 0) {
-            if (direct) {
-                SYLDET_CUDA(cudaMemcpy2DAsync(planar + s0, pitch * 4, (const float *)pcm + s0, src_stride * 4, ns * 4, n_channels,
-                                              cudaMemcpyHostToDevice, copy_stream_));
-            } else if (inter) {
-                SYLDET_CUDA(cudaMemcpyAsync((char *)staging_.get() + (size_t)s0 * n_channels * esz, (const char *)pcm + (size_t)s0 * n_channels * esz,
-                                            (size_t)ns * n_channels * esz, cudaMemcpyHostToDevice, copy_stream_));
+            // one plain copy per channel row: cudaMemcpy2D rejects pitches above cudaDeviceProp::memPitch (2 GiB - 1), which a
+            // recording of more than ~3.4 hours per channel would exceed
+            if (inter) {
+                SYLDET_CUDA_DRAIN(cudaMemcpyAsync((char *)staging_.get() + (size_t)s0 * n_channels * esz, (const char *)pcm + (size_t)s0 * n_channels * esz,
+                                                  (size_t)ns * n_channels * esz, cudaMemcpyHostToDevice, copy_stream_));
             } else {
-                SYLDET_CUDA(cudaMemcpy2DAsync((char *)staging_.get() + (size_t)s0 * esz, src_stride * esz, (const char *)pcm + (size_t)s0 * esz,
-                                              src_stride * esz, ns * esz, n_channels, cudaMemcpyHostToDevice, copy_stream_));
+                for (int ch = 0; ch < n_channels; ++ch) {
+                    char *dst = direct ? (char *)(planar + (size_t)ch * pitch + s0) : (char *)staging_.get() + ((size_t)ch * src_stride + s0) * esz;
+                    SYLDET_CUDA_DRAIN(cudaMemcpyAsync(dst, (const char *)pcm + ((size_t)ch * src_stride + s0) * esz, (size_t)ns * esz,
+                                                      cudaMemcpyHostToDevice, copy_stream_));
+                }
             }
         }
-        SYLDET_CUDA(cudaEventRecord(ev_copied_[k], copy_stream_));
-        SYLDET_CUDA(cudaStreamWaitEvent(sx, ev_copied_[k], 0));
+        SYLDET_CUDA_DRAIN(cudaEventRecord(ev_copied_[k], copy_stream_));
+        SYLDET_CUDA_DRAIN(cudaStreamWaitEvent(sx, ev_copied_[k], 0));
         if (!direct && ns > 0) {
             const char *src = (const char *)staging_.get() + (inter ? (size_t)s0 * n_channels * esz : (size_t)s0 * esz);
-            SYLDET_CUDA(launch_ingest(src, fmt, inter ? 1 : 0, n_channels, ns, src_stride, planar + s0, pitch, sx));
+            SYLDET_CUDA_DRAIN(launch_ingest(src, fmt, inter ? 1 : 0, n_channels, ns, src_stride, planar + s0, pitch, sx));
             launches_ += 1;
         }
         st = launch_planar_range(planar, n_channels, n_samples, sb[k + 1], pitch, planar, planar + (size_t)n_channels * pitch, eb[k],
                                  eb[k + 1] - eb[k], detect_rule, d_all, k == 0, sx);
-        if (st != SYLDET_OK) return st;
-        SYLDET_CUDA(cudaMemcpyAsync(h_counts_ + k, sink_count_.get(), sizeof(unsigned long long), cudaMemcpyDeviceToHost, sx));
-        SYLDET_CUDA(cudaEventRecord(ev_done_[k], sx));
+        if (st != SYLDET_OK) return drain(st);
+        SYLDET_CUDA_DRAIN(cudaMemcpyAsync(h_counts_ + k, sink_count_.get(), sizeof(SinkHeader), cudaMemcpyDeviceToHost, sx));
+        SYLDET_CUDA_DRAIN(cudaEventRecord(ev_done_[k], sx));
     }
 
     // ---- per slice: wait, read its events back, sort them by (channel, evaluation) while later slices are still in flight ----
@@ -871,22 +917,22 @@ syldet_status Batch::run_host(const void *pcm, int fmt, int n_channels, int64_t 
     float *h_out = reinterpret_cast<float *>(h_ev + sink_capacity_);
     std::vector<std::vector<Key>> sorted(K);
     unsigned long long done = 0;
-    bool overflow = false;
+    bool redo = false;   // the event buffer overflowed or the fp16 range flag went up: collect() repeats the launch (see settle)
     double t_copied = 0.0;
     for (int k = 0; k < K; ++k) {
-        SYLDET_CUDA(cudaEventSynchronize(ev_done_[k]));
+        SYLDET_CUDA_DRAIN(cudaEventSynchronize(ev_done_[k]));
         if (k == K - 1) t_copied = now_ms();
-        const unsigned long long n_k = h_counts_[k];
-        if (n_k > sink_capacity_) {
-            overflow = true;
+        const unsigned long long n_k = h_counts_[k].count;
+        if (n_k > sink_capacity_ || (h_counts_[k].range_flag != 0 && f16_ok_)) {
+            redo = true;
             break;
         }
         const unsigned long long m = n_k - done;
         if (m == 0) continue;
-        SYLDET_CUDA(cudaMemcpyAsync(h_ev + done, sink_events_.as<DevEvent>() + done, m * sizeof(DevEvent), cudaMemcpyDeviceToHost, d2h_stream_));
-        SYLDET_CUDA(cudaMemcpyAsync(h_out + done * O, sink_outputs_.as<float>() + done * O, m * O * sizeof(float), cudaMemcpyDeviceToHost,
-                                    d2h_stream_));
-        SYLDET_CUDA(cudaStreamSynchronize(d2h_stream_));
+        SYLDET_CUDA_DRAIN(cudaMemcpyAsync(h_ev + done, sink_events_.as<DevEvent>() + done, m * sizeof(DevEvent), cudaMemcpyDeviceToHost, d2h_stream_));
+        SYLDET_CUDA_DRAIN(cudaMemcpyAsync(h_out + done * O, sink_outputs_.as<float>() + done * O, m * O * sizeof(float), cudaMemcpyDeviceToHost,
+                                          d2h_stream_));
+        SYLDET_CUDA_DRAIN(cudaStreamSynchronize(d2h_stream_));
         std::vector<Key> &keys = sorted[k];
         keys.resize(m);
         for (unsigned long long i = 0; i < m; ++i) {
@@ -896,12 +942,11 @@ syldet_status Batch::run_host(const void *pcm, int fmt, int n_channels, int64_t 
         std::sort(keys.begin(), keys.end(), [](const Key &a, const Key &b) { return a.key < b.key; });
         done = n_k;
     }
-    if (overflow) {
-        // more detections than the event buffer holds: the recording is resident by now, so collect() grows the buffer to the
-        // worst case and replays the launch in one piece
+    if (redo) {
+        // the recording is resident once the pipeline has drained: collect() sees the same condition in the device-side header
+        // and repeats the launch in one piece (larger event buffer / all-TF32 variant)
+        SYLDET_CUDA(cudaStreamSynchronize(copy_stream_));
         SYLDET_CUDA(cudaStreamSynchronize(sx));
-        st = launch_device(planar, n_channels, n_samples, pitch, SYLDET_LAYOUT_PLANAR, detect_rule, d_all, sx);
-        if (st != SYLDET_OK) return st;
         st = collect(debounce_frames, out);
         if (st != SYLDET_OK) return st;
     } else {
@@ -947,6 +992,35 @@ syldet_status Batch::run_host(const void *pcm, int fmt, int n_channels, int64_t 
         SYLDET_CUDA(cudaMemcpyAsync(trace, d_trace.get(), (size_t)n_channels * n_samples * tsz, cudaMemcpyDeviceToHost, sx));
         SYLDET_CUDA(cudaStreamSynchronize(sx));
     }
+    return SYLDET_OK;
+#undef SYLDET_CUDA_DRAIN
+}
+
+// extractPower()[f0 ..< f1] (CSTFT.swift:280-337, SyllableDetector.swift:134-151) as the active kernel computes it: the detection
+// path runs with a tap on its band magnitudes (before the spectrogram scaling). Test / inspection entry point, not a fast path.
+syldet_status Batch::spectra_host(const void *pcm, int fmt, int n_channels, int64_t n_samples, int64_t ch_stride, int layout, float *band,
+                                  int64_t *n_columns) {
+    const Config &c = model_.config();
+    const int64_t E = c.num_evals(n_samples);
+    const int64_t cols = E > 0 ? E + c.time_range - 1 : 0;
+    if (n_columns) *n_columns = cols;
+    if (!band || cols == 0) return SYLDET_OK;   // query of *n_columns, or nothing to compute
+    syldet_status st = use_device(model_.device());
+    if (st != SYLDET_OK) return st;
+    DeviceBuffer d_band;
+    const size_t bytes = (size_t)n_channels * cols * c.band * sizeof(float);
+    st = d_band.reserve(bytes);
+    if (st != SYLDET_OK) return st;
+    SYLDET_CUDA(cudaMemset(d_band.get(), 0, bytes));
+    debug_band_ = d_band.as<float>();
+    debug_cols_ = cols;
+    Events ev;
+    st = run_host(pcm, fmt, n_channels, n_samples, ch_stride, layout, 0, SYLDET_DETECT_ANY_OUTPUT, nullptr, ev);
+    debug_band_ = nullptr;
+    debug_cols_ = 0;
+    if (st != SYLDET_OK) return st;
+    SYLDET_CUDA(cudaStreamSynchronize(own_stream_));
+    SYLDET_CUDA(cudaMemcpy(band, d_band.get(), bytes, cudaMemcpyDeviceToHost));
     return SYLDET_OK;
 }
 

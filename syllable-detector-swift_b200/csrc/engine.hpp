@@ -101,6 +101,19 @@ private:
     FusedPlan fused_;
 };
 
+// Header of the device-side event sink: detection count (may exceed the capacity) and the range flag the tensor kernel raises when
+// its fp16 correction pass meets audio outside the window in which it is at float32 level (kernels_tc.cu).
+struct SinkHeader {
+    unsigned long long count;
+    int range_flag;
+    int reserved;
+};
+constexpr size_t kSinkHeaderBytes = sizeof(SinkHeader);
+// Lower bound of the window's band energy sum |X|^2 (= squared norm of the network input before l2normalize) for the fp16 correction
+// pass: its absolute operand errors (2^-25 per subnormal sample, x |A_lo| <= 2^-12) add ~6e-11 per band magnitude, i.e. less than 1e-6
+// to a network output while the norm is >= 2^-8 (audio rms >~ 2e-5). Quieter float audio takes the all-TF32 variant.
+constexpr float kTcGuardLo = 1.52587890625e-05f;   // 2^-16
+
 struct Events {
     int outputs_per_event = 0;
     std::vector<syldet_event> rows;
@@ -117,9 +130,14 @@ public:
                            int64_t debounce_frames, int detect_rule, float *all_outputs, Events &out, int trace_format = 0,
                            void *trace = nullptr);
     syldet_status launch_device(const float *d_pcm, int n_channels, int64_t n_samples, int64_t ch_stride, int layout,
-                                int detect_rule, float *d_all_outputs, cudaStream_t stream);
+                                int detect_rule, float *d_all_outputs, cudaStream_t stream, bool pcm_exact = false);
     syldet_status collect(int64_t debounce_frames, Events &out);
     syldet_status last_detection_count(int64_t *count);
+    // launches repeated with the all-TF32 variant because the fp16 range flag went up (at most 1: the switch is permanent)
+    int64_t range_fallbacks() const { return range_fallbacks_; }
+    // band magnitudes extractPower()[f0 ..< f1] of every column that feeds an evaluation, from the active kernel: [n_channels][E + T - 1][band]
+    syldet_status spectra_host(const void *pcm, int fmt, int n_channels, int64_t n_samples, int64_t ch_stride, int layout, float *band,
+                               int64_t *n_columns);
     int64_t launch_count() const { return launches_; }
     void set_slice_evals(int64_t evals) { slice_evals_ = evals; }
     void set_debug_band(float *d_band, int64_t cols) { debug_band_ = d_band; debug_cols_ = cols; }
@@ -140,6 +158,7 @@ private:
                                       const float *valid_begin, const float *valid_end, int64_t eval_begin, int64_t eval_count,
                                       int detect_rule, float *d_all_outputs, bool reset_sink, cudaStream_t stream);
     syldet_status ensure_pipeline(int slices, size_t event_bytes);
+    syldet_status settle(unsigned long long *n_events);
 
     DeviceModel model_;
     int kernel_ = SYLDET_KERNEL_AUTO;
@@ -147,7 +166,10 @@ private:
     // run_host pipeline: time slices are copied on copy_stream_, detected on own_stream_, their events read back on d2h_stream_
     cudaStream_t copy_stream_ = nullptr, d2h_stream_ = nullptr;
     std::vector<cudaEvent_t> ev_copied_, ev_done_;
-    unsigned long long *h_counts_ = nullptr;   // pinned, one running event count per slice
+    SinkHeader *h_counts_ = nullptr;           // pinned, one snapshot of the sink header (running event count, range flag) per slice
+    bool f16_ok_ = true;                       // false once the range flag went up: the tensor kernel runs all-TF32 from then on
+    bool pcm_exact_ = false;                   // the current input came from 16-bit PCM (exact fp16 operands)
+    int64_t range_fallbacks_ = 0;
     void *h_events_ = nullptr;                 // pinned: DevEvent[capacity] then float[capacity][outputs]
     size_t h_events_bytes_ = 0;
     int64_t slice_evals_ = 256 * 1024;
@@ -165,6 +187,7 @@ private:
         int layout = 0, detect_rule = 0;
         float *d_all_outputs = nullptr;
         cudaStream_t stream = nullptr;
+        bool pcm_exact = false;
     } last_;
 };
 

@@ -12,8 +12,11 @@ cudaError_t launch_ingest(const void *src, int format, int interleaved, int n_ch
                           float *dst, int64_t dst_stride, cudaStream_t stream);
 cudaError_t launch_simulator_trace(const float *all_out, int n_channels, int64_t evals, int n_out, float thr0, int64_t first, int hop,
                                    int64_t n_samples, int format, void *trace, int64_t trace_stride, cudaStream_t stream);
+// feat: [channel][n_cols][band] with `feat_ch_pitch` floats between channels; scaling_override >= 0 replaces the configuration's
+// spectrogram scaling (SYLDET_SCALING_LINEAR = raw extractPower() values)
 cudaError_t launch_stft_band_generic(const DevNet *d_net, int fft_len, const float *pcm, int64_t ch_stride, int n_channels,
-                                     int64_t col0, int64_t n_cols, float *feat, cudaStream_t stream);
+                                     int64_t col0, int64_t n_cols, float *feat, int64_t feat_ch_pitch, int scaling_override,
+                                     cudaStream_t stream);
 cudaError_t launch_nn_generic(const DevNet *d_net, int max_width, const float *feat, int n_channels, int64_t n_cols,
                               int64_t n_evals, int64_t eval0, int64_t evals_total, int detect_rule, float *all_out,
                               EventSink sink, cudaStream_t stream);
@@ -99,6 +102,8 @@ struct FusedWork {
     EventSink sink;
     const float *window;   // [win_len]
     const float2 *twiddle; // [fft_len/2]
+    float *debug_band;     // optional [n_channels][debug_cols][band] band magnitudes before the scaling (tests / spectra API)
+    int64_t debug_cols;
 };
 
 struct FusedLaunch {
@@ -133,6 +138,10 @@ struct TcWork {
     float *debug_band;              // optional [n_channels][debug_cols][band] band magnitudes (tests)
     int64_t debug_cols;
     long long *debug_timing;        // optional [grid][32] cycle counters per role (SYLDET_TC_TIMING=1)
+    // range guard of the fp16 correction pass (f16_corr = 1): an evaluation whose window energy sum |X|^2 is outside
+    // [guard_lo, FLT_MAX] (and not exactly 0) sets *range_flag; the host then repeats the launch with f16_corr = 0
+    float guard_lo;
+    int *range_flag;
 };
 size_t tc_smem_bytes(const FusedParams &p, int hp);
 int tc_lo_stages(const FusedParams &p, int hp);

@@ -291,6 +291,8 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_detect_kernel(const __
                         const float re = sr + (t.x * di + t.y * dr);
                         const float im = si - (t.x * dr - t.y * di);
                         float mag = 0.5f * sqrt_fast(re * re + im * im);
+                        if (w.debug_band && f < L)   // extractPower() values, before the scaling (column index == evaluation index)
+                            w.debug_band[((int64_t)ch * w.debug_cols + w.eval_offset + e0 + r * RC + warp * G + g) * L + f] = mag;
                         if (p.scaling != SYLDET_SCALING_LINEAR) mag = scale_value(mag, p.scaling);
                         if (f < L) dst[f] = mag;
                     }

@@ -45,12 +45,12 @@ __global__ void ingest_kernel(const void *__restrict__ src, int format, int inte
 // `load(m)` returns sample m of the frame; the L band magnitudes (scaled) go to dst[0..L).
 template <class LoadSample>
 __device__ __forceinline__ void stft_band_column(const DevNet &net, LoadSample load, float *zr, float *zi, int lane, int bits,
-                                                 float *__restrict__ dst) {
+                                                 float *__restrict__ dst, int scaling) {
     const int N = net.fft_len, M = N / 2, W = net.win_len, L = net.band;
     if (M == 1) {
         if (lane == 0) {
             float a = load(0) * net.window[0], b = W > 1 ? load(1) * net.window[1] : 0.0f;
-            dst[0] = scale_value(fabsf(2.0f * (a + b)) / 2.0f, net.scaling);
+            dst[0] = scale_value(fabsf(2.0f * (a + b)) / 2.0f, scaling);
         }
         return;
     }
@@ -102,7 +102,7 @@ __device__ __forceinline__ void stft_band_column(const DevNet &net, LoadSample l
             const float im = si - (w.x * dr - w.y * di);
             mag = sqrtf(re * re + im * im) / 2.0f;
         }
-        dst[f] = scale_value(mag, net.scaling);
+        dst[f] = scale_value(mag, scaling);
     }
     __syncwarp();
 }
@@ -115,7 +115,8 @@ __device__ __forceinline__ int log2_ceil(int m) {
 
 // One warp per STFT column.
 __global__ void stft_band_generic_kernel(const DevNet *__restrict__ netp, const float *__restrict__ pcm, int64_t ch_stride,
-                                         int64_t col0, int64_t n_cols, float *__restrict__ feat) {
+                                         int64_t col0, int64_t n_cols, float *__restrict__ feat, int64_t feat_ch_pitch,
+                                         int scaling_override) {
     extern __shared__ float smem[];
     const DevNet &net = *netp;
     const int N = net.fft_len, M = N / 2, L = net.band;
@@ -123,12 +124,13 @@ __global__ void stft_band_generic_kernel(const DevNet *__restrict__ netp, const 
     float *zr = smem + (size_t)warp * N, *zi = zr + M;
     const int ch = blockIdx.y;
     const float *x_ch = pcm + (int64_t)ch * ch_stride;
-    float *feat_ch = feat + (int64_t)ch * n_cols * L;
+    float *feat_ch = feat + (int64_t)ch * feat_ch_pitch;
     const int bits = log2_ceil(M);
+    const int scaling = scaling_override >= 0 ? scaling_override : net.scaling;
 
     for (int64_t c = (int64_t)blockIdx.x * warps + warp; c < n_cols; c += (int64_t)gridDim.x * warps) {
         const float *fr = x_ch + (col0 + c) * net.hop + net.gap;
-        stft_band_column(net, [&](int m) { return fr[m]; }, zr, zi, lane, bits, feat_ch + c * L);
+        stft_band_column(net, [&](int m) { return fr[m]; }, zr, zi, lane, bits, feat_ch + c * L, scaling);
     }
 }
 
@@ -461,7 +463,7 @@ __global__ void stream_tick_kernel(const DevNet *__restrict__ netp, StreamTick t
         for (int64_t c = (int64_t)blockIdx.x * warps + warp; c < t.n_cols; c += (int64_t)gridDim.x * warps) {
             const int64_t first = (t.col0 + c) * net.hop + net.gap;
             stft_band_column(net, [&](int m) { return ring[(first + m) & t.ring_mask]; }, zr, zi, lane, bits,
-                             band + ((t.col0 + c) & t.band_mask) * L);
+                             band + ((t.col0 + c) & t.band_mask) * L, net.scaling);
         }
         __syncthreads();
     }
@@ -568,7 +570,8 @@ cudaError_t launch_simulator_trace(const float *all_out, int n_channels, int64_t
 }
 
 cudaError_t launch_stft_band_generic(const DevNet *d_net, int fft_len, const float *pcm, int64_t ch_stride, int n_channels,
-                                     int64_t col0, int64_t n_cols, float *feat, cudaStream_t stream) {
+                                     int64_t col0, int64_t n_cols, float *feat, int64_t feat_ch_pitch, int scaling_override,
+                                     cudaStream_t stream) {
     if (n_cols <= 0 || n_channels <= 0) return cudaSuccess;
     int warps = 8;
     while (warps > 1 && (size_t)warps * fft_len * sizeof(float) > 96 * 1024) warps >>= 1;
@@ -579,7 +582,7 @@ cudaError_t launch_stft_band_generic(const DevNet *d_net, int fft_len, const flo
     const int64_t cap = std::max<int64_t>(1, (148 * 8) / n_channels);
     if (bx > cap) bx = cap;
     dim3 grid((unsigned)bx, (unsigned)n_channels);
-    stft_band_generic_kernel<<<grid, warps * 32, smem, stream>>>(d_net, pcm, ch_stride, col0, n_cols, feat);
+    stft_band_generic_kernel<<<grid, warps * 32, smem, stream>>>(d_net, pcm, ch_stride, col0, n_cols, feat, feat_ch_pitch, scaling_override);
     return cudaGetLastError();
 }
 

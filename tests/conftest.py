@@ -41,7 +41,7 @@ def cw():
 
 @pytest.fixture(scope="session")
 def synth():
-    return importlib.import_module("syllable-detector-swift_b200.synth")
+    return importlib.import_module("tools.synth")
 
 
 @pytest.fixture(scope="session")

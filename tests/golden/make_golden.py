@@ -15,7 +15,7 @@ sys.path.insert(0, ROOT)
 from oracle import Oracle  # noqa: E402
 
 cw = importlib.import_module("syllable-detector-swift_b200.config_writer")
-synth = importlib.import_module("syllable-detector-swift_b200.synth")
+synth = importlib.import_module("tools.synth")
 
 
 def cases():

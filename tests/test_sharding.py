@@ -27,7 +27,7 @@ def _worker(rank, world, port, mode, out_path):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     sh = importlib.import_module("syllable-detector-swift_b200.sharding")
-    synth = importlib.import_module("syllable-detector-swift_b200.synth")
+    synth = importlib.import_module("tools.synth")
     from oracle import Oracle
     orc = Oracle(SAMPLE_TXT)
     rows = []

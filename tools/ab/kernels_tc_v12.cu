@@ -17,21 +17,19 @@
 //  (3) epilogue (SIMT): diagonal sum over a shared-memory ring of product rows, window statistic from per-column
 //      partials, transfer functions, remaining layers, reverse output maps, threshold test, event append.
 //
-// Roles (18 warps, one CTA per SM, persistent over (channel, chunk) units; every role walks the same tile sequence):
+// Roles (22 warps with two evaluator groups, one CTA per SM, persistent over (channel, chunk) units; every role walks the same tile sequence):
 //   warp 0        TMA producer                      full[s] <- hi_free[s]
-//   warp 1        MMA issuer + TMEM allocator       DFT(it): full, tmem_empty (even it; implied for odd it), lo_ready -> hi_free, tmem_full, lo_free
-//                                                   layer0(pair k = tiles 2k, 2k+1), issued after DFT(2k+2): a_ready, p_empty -> p_full, a_free
-//   then 4        evaluators (F), one warp per TMEM lane quadrant: layer 0 is ONE M = 128 contraction per PAIR of tiles (rows 0-63:
-//                                                   tile 2k, rows 64-127: tile 2k+1), so every lane owns one product row = one evaluation:
-//                                                   p_full -> product ring -> p_empty; diagonal sum (T x LDS.128), window statistic,
-//                                                   network tail, events
+//   warp 1        MMA issuer + TMEM allocator       DFT(it): full, (tmem_empty: implied), lo_ready -> hi_free, tmem_full, lo_free
+//                                                   layer0(it-1): a_ready, p_empty -> p_full, a_free
+//   then          evaluators (F): TC_GROUPS (2) groups of four warps (one per TMEM lane quadrant) that take tiles in turn:
+//                                                   p_full, ring_ready[other] -> product ring -> p_empty, ring_ready[own];
+//                                                   diagonal sum (T x LDS.128), window statistic, network tail, events
 //   then 8        spectrum warps (D)                tmem_full -> D -> registers -> tmem_empty; two shuffle rounds -> |X| ->
-//                                                   layer-0 A operand (half of the pair's 128 rows) + per-column statistic partials -> a_ready
+//                                                   layer-0 A operand + per-column statistic partials -> a_ready
 //   then 4        splitters (S)                     full, lo_free -> lo tile -> lo_ready, hi_free
-// Every role is a serial chain per tile and runs at ~0.1 IPC per warp (profiles/): the roles overlap through double buffers.
-// Round 1 ran layer 0 per tile (M = 64: half-rate tensor pipe, 16 of 32 lanes per evaluator warp, two evaluator groups of four
-// warps taking tiles in turn); the pair scheme halves the evaluators' instruction count per evaluation and the weight-operand
-// reads, and frees four warps (registers: 112 per thread instead of 80).
+// Every role is a serial chain per tile and runs at ~0.1 IPC per warp (profiles/): the roles overlap through double buffers, and
+// the longest chain (the evaluators': ~530 dependent warp instructions per tile) is split over the groups so that no role
+// needs more than one tile period per tile.
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -42,15 +40,19 @@ namespace syldet {
 
 namespace {
 
-constexpr int kFGroup = 4;                     // evaluator warps (one per TMEM lane quadrant)
+constexpr int kFGroup = 4;                     // warps per evaluator group (one per TMEM lane quadrant)
 // kF16: the two correction products of the 3xTF32 band DFT (Alo*Bhi + Ahi*Blo) as ONE K-concatenated kind::f16 pass
 //   [fp16(Alo) | fp16(Ahi * 2^-11)] * [fp16(x) ; fp16((x - tf32(x)) * 2^11)]       (17 MMAs instead of 34 per tile)
 // The fp16 tile has the byte geometry of the fp32 one (4 x [64 rows x 128 B] + [64 rows x 32 B]); K order: x(n < 128) |
 // lo(n < 128) | x(n >= 128) | lo(n >= 128). Error terms are scaled by 2^-11, so fp16's 11 bits keep the sum at fp32 level
 // for |x| in [6e-5, 65504]; quieter samples carry an absolute error of 2^-25 * 2^-11 each (documented in DESIGN.md).
-constexpr int kWarpTma = 0, kWarpMma = 1, kWarpF0 = 2, kNumF = kFGroup, kWarpD0 = kWarpF0 + kNumF, kNumD = 8,
+#ifndef TC_GROUPS
+#define TC_GROUPS 2
+#endif
+constexpr int kNumGroups = TC_GROUPS;          // evaluator groups; group g takes the tiles with it % kNumGroups == g
+constexpr int kWarpTma = 0, kWarpMma = 1, kWarpF0 = 2, kNumF = kFGroup * kNumGroups, kWarpD0 = kWarpF0 + kNumF, kNumD = 8,
               kWarpS0 = kWarpD0 + kNumD, kNumS = 4;
-constexpr int kTcThreads = (kWarpS0 + kNumS) * 32;  // 576
+constexpr int kTcThreads = (kWarpS0 + kNumS) * 32;  // 832
 static_assert(kWarpF0 % 4 == 2 && kWarpD0 % 4 == 2, "quadrant / half assignment below assumes these starts");
 constexpr int kTileRows = 64;                  // rows of Y per tile = N of the DFT MMA
 constexpr int kTileFrames = kTileRows - 1;     // frames completed per tile
@@ -64,32 +66,31 @@ constexpr int kMaxN0 = 56;                     // widest layer-0 product row (T 
 constexpr int kTmemCols = 512;
 constexpr int kColAhi = 0, kColAlo = kKPad, kColD0 = 2 * kKPad, kColP0 = kColD0 + 2 * kTileRows;
 static_assert(kColP0 + 2 * kMaxN0 <= kTmemCols, "TMEM budget");
-constexpr int kPairFrames = 2 * kTileFrames;   // evaluations the evaluators finish per pass (one pair of tiles)
-constexpr int kPRing = kPairFrames + 22;       // product-row ring (rows = columns): the pair in flight + the T-1 (<= 22) rows before it
-constexpr int kStatRing = 640;                 // per-column statistic ring: [2 planes][kStatRing][4 bin quarters] float (see tc_layout_fits)
-constexpr int kBarF = 2;                       // named barrier of the evaluators
-constexpr int kEvCap = 192;                    // shared-memory event buffer of the evaluators (flushed with one global atomic)
-static_assert(kEvCap >= kPairFrames + 32, "the event buffer must take one pair after every flush check");
+constexpr int kPRing = kNumGroups * kTileFrames + 22;   // product-row ring (rows = columns): one tile per group in flight + the T-1 (<= 21) rows before them
+constexpr int kStatRing = 512;                 // per-column statistic ring: [2 planes][kStatRing][4 bin quarters] float
+constexpr int kBarF = 2;                       // named barriers of the F groups: kBarF and kBarF + 1
+constexpr int kEvCap = 96;                     // shared-memory event buffer per F group (flushed with one global atomic)
+static_assert(kBarF + kNumGroups <= 16 && kNumGroups <= 4, "named barriers / barrier block layout");
 
 struct TcSmem {  // byte offsets from the 1024-byte aligned base
     static constexpr int hi0 = 0, hi1 = kTileBytes, lo = 2 * kTileBytes;   // audio tiles (34 816 B = 34 swizzle atoms each)
-    static constexpr int abuf = 3 * kTileBytes;                     // [hi, lo][128 rows x 128 B]: rows 0-63 even tile, 64-127 odd tile of a pair
+    static constexpr int abuf = 3 * kTileBytes;                     // [2 buffers][hi, lo][64 rows x 128 B]
     static constexpr int wcat = abuf + 4 * 8192;                    // [hi, lo][<= 56 rows x 128 B]
     static constexpr int pbuf = wcat + 2 * kMaxN0 * 128;            // [kPRing][ppitch] float; everything after it is placed at run time
-    // then: float4 colstat[planes][kStatRing] | event meta int4[kEvCap] | event outputs float[kEvCap][n_out] |
+    // then: float4 colstat[planes][kStatRing] | event meta int4[groups][kEvCap] | event outputs float[groups][kEvCap][n_out] |
     //       barriers (256 B) | optionally the second lo tile (1024-byte aligned) when it fits
     // planes: 1 (sum of squares), 2 for the min/max statistic
     __host__ __device__ static constexpr int ppitch(int np) { return ((((np + 7) >> 3) << 1) | 1) << 2; }  // whole 8-float chunks + 1: an odd number of float4
     __host__ __device__ static constexpr int colstat(int np) { return pbuf + kPRing * ppitch(np) * 4; }
     __host__ __device__ static constexpr int evmeta(int np, int planes) { return colstat(np) + planes * kStatRing * 16; }
-    __host__ __device__ static constexpr int evout(int np, int planes) { return evmeta(np, planes) + kEvCap * 16; }
-    __host__ __device__ static constexpr int bars(int np, int n_out, int planes) { return evout(np, planes) + kEvCap * n_out * 4; }
+    __host__ __device__ static constexpr int evout(int np, int planes) { return evmeta(np, planes) + kNumGroups * kEvCap * 16; }
+    __host__ __device__ static constexpr int bars(int np, int n_out, int planes) { return evout(np, planes) + kNumGroups * kEvCap * n_out * 4; }
     __host__ __device__ static constexpr int lo1(int np, int n_out, int planes) { return (bars(np, n_out, planes) + 256 + 1023) & ~1023; }
     __host__ __device__ static constexpr int total(int np, int n_out, int planes, int lo_stages) {
         return lo_stages == 2 ? lo1(np, n_out, planes) + kTileBytes : bars(np, n_out, planes) + 256;
     }
     __host__ __device__ static constexpr int hi(int stage) { return stage ? hi1 : hi0; }
-    __host__ __device__ static constexpr int a(int half, int part) { return abuf + part * 16384 + half * 8192; }
+    __host__ __device__ static constexpr int a(int buf, int part) { return abuf + (buf * 2 + part) * 8192; }
 };
 static_assert(kTileBytes % 1024 == 0, "tiles are whole swizzle atoms");
 static_assert(TcSmem::abuf % 1024 == 0 && TcSmem::wcat % 1024 == 0 && (kMaxN0 * 128) % 1024 == 0, "swizzle atoms need 1024-byte alignment");
@@ -227,15 +228,15 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
     const int ppitch = TcSmem::ppitch(np);         // product ring pitch in floats
     const int planes = window_stat == FUSED_STAT_MINMAX ? 2 : 1;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TcSmem::bars(np, p.n_out, planes));
-    uint64_t *full = bars, *hi_free = bars + 2, *lo_ready = bars + 4, *tmem_full = bars + 6, *tmem_empty = bars + 8;   // [2] each
-    uint64_t *p_full = bars + 10, *p_empty = bars + 12, *lo_free = bars + 14;                                           // [2] each
-    uint64_t *a_ready = bars + 16, *a_free = bars + 17;                       // one A operand (128 rows), refilled pair by pair
+    uint64_t *full = bars, *hi_free = bars + 2, *lo_ready = bars + 4, *lo_free = bars + 29, *tmem_full = bars + 6, *tmem_empty = bars + 8;   // lo_*: [2]
     // lo tile(s): with two, stage = it & 1 like the hi tiles and the splitters never wait for pass 3 of the previous tile
     const int lo_stages = w.lo_stages;
     const int lo1_off = TcSmem::lo1(np, p.n_out, planes);
-    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 18);
-    int *ev_count = reinterpret_cast<int *>(bars + 19);                       // events waiting in shared memory
-    unsigned long long *ev_base = reinterpret_cast<unsigned long long *>(bars + 20);
+    uint64_t *a_ready = bars + 10, *a_free = bars + 12, *p_full = bars + 14, *p_empty = bars + 16;
+    uint64_t *ring_ready = bars + 18;                                         // [groups <= 4]: an F group has written its tile's product rows
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 22);
+    int *ev_counts = reinterpret_cast<int *>(bars + 23);                      // [groups <= 4] events waiting in shared memory, per F group
+    unsigned long long *ev_bases = reinterpret_cast<unsigned long long *>(bars + 25);  // [groups <= 4]
     float *pbuf = reinterpret_cast<float *>(smem + TcSmem::pbuf);
     float *colstat = reinterpret_cast<float *>(smem + TcSmem::colstat(np));   // sum of squares | minimum, then the maximum plane
 
@@ -247,14 +248,19 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
             ptx::mbar_init(&hi_free[i], 1 + kNumS);
             ptx::mbar_init(&tmem_full[i], 1);
             ptx::mbar_init(&tmem_empty[i], kNumD);
+            ptx::mbar_init(&a_ready[i], kNumD);
+            ptx::mbar_init(&a_free[i], 1);
             ptx::mbar_init(&p_full[i], 1);
             ptx::mbar_init(&p_empty[i], kFGroup);
+        }
+        for (int i = 0; i < kNumGroups; ++i) {
+            ptx::mbar_init(&ring_ready[i], kFGroup);
+            ev_counts[i] = 0;
+        }
+        for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&lo_ready[i], kNumS);
             ptx::mbar_init(&lo_free[i], 1);
         }
-        ptx::mbar_init(a_ready, 2 * kNumD);   // both tiles of a pair
-        ptx::mbar_init(a_free, 1);
-        *ev_count = 0;
         ptx::fence_mbar_init();
     }
     if (warp == kWarpMma) {
@@ -319,6 +325,7 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
         // ================================ MMA issuer ==================================================================
         if (ptx::elect_one()) {
             constexpr uint32_t idesc_dft = ptx::idesc_tf32(128, kTileRows);
+            const uint32_t idesc_l0 = ptx::idesc_tf32(64, n0);
             const uint32_t lo_a = ptx::smem_addr(smem + TcSmem::lo), lo_b = ptx::smem_addr(smem + lo1_off);
             const uint32_t wc_hi = ptx::smem_addr(smem + TcSmem::wcat), wc_lo = wc_hi + kMaxN0 * 128;
             // one K sweep of the band DFT: 4 SWIZZLE_128B chunks of 4 k-steps + the 8-column SWIZZLE_32B tail (rolled: the
@@ -347,14 +354,14 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
                 ptx::mma_f16_ts(d, a, ptx::smem_desc_kmajor(b + kMainChunks * kMainBytes, 256, 6), idesc_f16, 1);
             };
             RoleTimer<kTiming> tm(w.debug_timing, 6, false);   // the MMA issuer is the pacemaker: it polls
-            const uint32_t idesc_l0 = ptx::idesc_tf32(128, n0);
-            const uint32_t a_hi = ptx::smem_addr(smem + TcSmem::a(0, 0)), a_lo = ptx::smem_addr(smem + TcSmem::a(0, 1));
-            auto issue_l0 = [&](uint32_t pk) {  // per-column layer-0 products of the pair pk = tiles 2pk, 2pk+1 (M = 128)
-                const int pb = pk & 1;
-                tm.wait(a_ready, pk & 1, 3);                      // both tiles' magnitudes written and fenced
-                tm.wait(&p_empty[pb], ((pk >> 1) & 1) ^ 1, 4);    // product buffer drained by the evaluators
+            auto issue_l0 = [&](uint32_t jt) {  // per-column layer-0 products of tile jt
+                const int ab = jt & 1;
+                const uint32_t ph = (jt >> 1) & 1;
+                tm.wait(&a_ready[ab], ph, 3);       // magnitudes written and fenced
+                tm.wait(&p_empty[ab], ph ^ 1, 4);   // product buffer drained by the evaluators
                 ptx::tc_fence_after();
-                const uint32_t d = tmem_base + kColP0 + pb * kMaxN0;
+                const uint32_t d = tmem_base + kColP0 + ab * kMaxN0;
+                const uint32_t a_hi = ptx::smem_addr(smem + TcSmem::a(ab, 0)), a_lo = ptx::smem_addr(smem + TcSmem::a(ab, 1));
                 uint32_t acc = 0;
 #pragma unroll 1
                 for (int pass = 0; pass < 3; ++pass) {
@@ -365,20 +372,24 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
                         acc = 1;
                     }
                 }
-                ptx::mma_commit(&p_full[pb]);
-                ptx::mma_commit(a_free);
+                ptx::mma_commit(&p_full[ab]);
+                ptx::mma_commit(&a_free[ab]);
+#ifdef TC_EXP_SERIAL_P   // experiment: no MMA queued while the evaluators read P
+                ptx::mbar_wait(&p_empty[ab], ph);
+#endif
             };
             TileWalk tw;
             tw.init(w, T);
-            uint32_t it = 0, next_pair = 0;
+            uint32_t it = 0;
             for (; tw.valid(); ++it, tw.next(w, T)) {
                 const int s = it & 1;
                 const uint32_t ph = (it >> 1) & 1;
                 tm.wait(&full[s], ph, 0);             // hi landed (TMA)
-                // accumulator s is free once the spectrum warps have read tile it-2. For odd it that is implied: they arrived on
-                // a_ready for the pair (it-3, it-2) after their TMEM loads, and this thread waited for it in the previous iteration.
-                // For even it the pair (it-2, it-1) is only waited for below, after this tile's DFT is queued.
-                if (s == 0) tm.wait(&tmem_empty[0], ph ^ 1, 1);
+                // accumulator s is free: the spectrum warps read it for tile it-2 before they arrived on a_ready(it-2), which
+                // this thread waited for when it issued layer 0 of that tile (previous iteration) - no separate wait needed
+#ifdef TC_WAIT_TMEM_EMPTY
+                tm.wait(&tmem_empty[s], ph ^ 1, 1);
+#endif
                 ptx::tc_fence_after();
                 const uint32_t d = tmem_base + kColD0 + s * kTileRows;
                 const uint32_t hi = ptx::smem_addr(smem + TcSmem::hi(s));
@@ -393,55 +404,57 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
                 else dft_pass(d, tmem_base + kColAhi, ls ? lo_b : lo_a, 1);
                 ptx::mma_commit(&tmem_full[s]);
                 ptx::mma_commit(&lo_free[ls]);
-                if (s == 0 && it >= 2) issue_l0(next_pair++);   // tiles it-2, it-1: their magnitudes were written while DFTs were queued
+                if (it > 0) issue_l0(it - 1);             // its magnitudes were written while this tile's DFT was queued
             }
-            while (next_pair < (it + 1) / 2) issue_l0(next_pair++);
+            if (it > 0) issue_l0(it - 1);
             tm.flush(true);
         }
     } else if (warp < kWarpD0) {
         // ================================ evaluators (F) ==============================================================
-        // Four warps, one per TMEM lane quadrant. The layer-0 accumulator P[pk & 1] of pair pk is an M = 128 tile: product row r sits
-        // in lane r; rows 0-63 are the columns of tile 2pk, rows 64-127 those of tile 2pk+1. So quadrants 0/1 own tile 2pk (columns
-        // 0-31 / 32-63) and quadrants 2/3 tile 2pk+1, and every lane owns one row: it moves the row to the product ring and then
-        // evaluates the network whose newest column is that row.
-        const int quad = warp & 3;
-        const int ft = (warp - kWarpF0) * 32 + lane;        // thread index inside the role
-        const int sel = quad >> 1;                          // which tile of the pair
-        const int c = (quad & 1) * 32 + lane;               // column of that tile this thread owns
-        int4 *ev_meta = reinterpret_cast<int4 *>(smem + TcSmem::evmeta(np, planes));   // (channel, -, eval lo, eval hi)
-        float *ev_out = reinterpret_cast<float *>(smem + TcSmem::evout(np, planes));
+        // Groups of four warps (one warp per TMEM lane quadrant); group g takes the tiles with it % groups == g, reading the
+        // layer-0 accumulator P[it & 1]. The accumulator is an M = 64 tile: product row c (= column c of the tile) sits in lane
+        // 32*(c/16) + c%16, so lanes 0-15 of a warp own one row each: they move it to the product ring and then evaluate the
+        // network whose newest column is c. The ring is shared by the groups: ring_ready[g] says "group g wrote its tile's rows".
+        const int quad = warp & 3, grp = (warp - kWarpF0) >> 2;
+        const int ft = (warp - kWarpF0 - grp * kFGroup) * 32 + lane;   // thread index inside the group
+        const int bar_f = kBarF + grp;
+        int *ev_count = ev_counts + grp;
+        unsigned long long *ev_base = ev_bases + grp;
+        int4 *ev_meta = reinterpret_cast<int4 *>(smem + TcSmem::evmeta(np, planes)) + grp * kEvCap;   // (channel, -, eval lo, eval hi)
+        float *ev_out = reinterpret_cast<float *>(smem + TcSmem::evout(np, planes)) + grp * kEvCap * n_out;
+        const int c = quad * 16 + (lane & 15);              // column of the tile this thread owns
+        const bool owner = lane < 16;
         const int nchunks = (np + 7) >> 3;                  // 8-column chunks of a product row
         TileWalk tw;
         tw.init(w, T);
-        int gcol = 0;                                       // product-ring position of the pair's first column (mod kPRing)
-        int scol = 0;                                       // statistic-ring position of the same column (mod kStatRing)
+        int gcol = 0;                                       // product-ring position of the tile's first column (mod kPRing)
+        uint32_t scol = 0;                                  // columns seen so far, all units (statistic ring position)
         RoleTimer<kTiming> tm(w.debug_timing, 12);
-        auto flush_events = [&](int n_ev) { flush_group_events(w.sink, ev_meta, ev_out, ev_count, ev_base, n_ev, ft, kBarF, n_out); };
-        for (uint32_t pk = 0; tw.valid(); ++pk) {
-            // this thread's tile of the pair: unit position, frame count, ring positions
-            TileWalk mine = tw;
-            const int frames_a = tw.frames();
-            tw.next(w, T);
-            int frames_b = 0;
-            if (tw.valid()) {
-                frames_b = tw.frames();
-                if (sel) mine = tw;
-                tw.next(w, T);
+        auto flush_events = [&](int n_ev) { flush_group_events(w.sink, ev_meta, ev_out, ev_count, ev_base, n_ev, ft, bar_f, n_out); };
+        int turn = 0;                                       // it % kNumGroups
+        for (uint32_t it = 0; tw.valid(); ++it, tw.next(w, T), turn = turn + 1 == kNumGroups ? 0 : turn + 1) {
+            const int ab = it & 1;                          // layer-0 accumulator of this tile
+            const int frames = tw.frames();
+            if (turn != grp) {                              // another group's tile: only keep the ring positions in step
+                gcol += frames;
+                if (gcol >= kPRing) gcol -= kPRing;
+                scol += frames;
+                continue;
             }
-            const int frames = sel ? frames_b : frames_a;   // 0: the last pair has no second tile
-            int g_mine = gcol + (sel ? frames_a : 0), s_mine = scol + (sel ? frames_a : 0);
-            if (g_mine >= kPRing) g_mine -= kPRing;
-            if (s_mine >= kStatRing) s_mine -= kStatRing;
-            const int pb = pk & 1;
-            tm.wait(&p_full[pb], (pk >> 1) & 1, 0);
+            // the group of tile it-1 has written that tile (history rows), which also proves it finished the evaluations of tile
+            // it-1-groups, the newest tile whose ring rows this tile may reuse (this group's own tile it-groups is done as well)
+            if (it > 0) tm.wait(&ring_ready[grp == 0 ? kNumGroups - 1 : grp - 1], ((it - 1) / kNumGroups) & 1, 0);
+            // only now: a group sees every other use of an accumulator, and a parity wait is only meaningful for the phase that
+            // is pending; tile it-1 copied => tile it-2 (the previous use of P[ab]) copied => the pending phase is this tile's
+            tm.wait(&p_full[ab], (it >> 1) & 1, 0);
             ptx::tc_fence_after();
             const long long t_f0 = tm.now();
             {   // P row -> product ring, four 8-column chunks at a time: loads in flight, one wait, then the stores
-                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + kColP0 + pb * kMaxN0;
-                int row = g_mine + c;
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + kColP0 + ab * kMaxN0;
+                int row = gcol + c;
                 if (row >= kPRing) row -= kPRing;
                 float4 *dst = reinterpret_cast<float4 *>(pbuf + row * ppitch);
-                const bool store = c < frames;
+                const bool store = owner && c < frames;
 #pragma unroll
                 for (int q0 = 0; q0 < kMaxN0 / 8; q0 += 4) {
                     if (q0 < nchunks) {
@@ -463,17 +476,22 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
                 tm.add(3, t_f0);
                 ptx::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&p_empty[pb]);
+                if (lane == 0) {
+                    ptx::mbar_arrive(&p_empty[ab]);
+                    ptx::mbar_arrive(&ring_ready[grp]);
+                }
             }
-            tm.sync(kBarF, kFGroup * 32, 1);   // the pair's rows (and, from the previous pass, the T-1 rows before them) are in the ring
+            tm.sync(bar_f, kFGroup * 32, 1);
             const long long t_f1 = tm.now();
-            // evaluation whose newest column is column c of this thread's tile: unit-local index j
-            const int j = mine.cols_before() - (T - 1) + c;
+            // evaluation whose newest column is column c of this tile: unit-local index j
+            const int j = tw.cols_before() - (T - 1) + c;
 #ifdef TC_EXP_SKIP_EVAL
             const bool valid = false;
 #else
             const bool valid = c < frames && j >= 0;
 #endif
+            // Lanes l and l + 16 share evaluation c: each sums half of the T columns, one shuffle round combines them, both run
+            // the (cheap) network tail and lane l stores.
             bool hit = false;
             float out[kFusedMaxOut];
             {
@@ -482,16 +500,14 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
                 for (int h = 0; h < HP; ++h) acc[h] = 0.0f;
                 float s0 = window_stat == FUSED_STAT_L2 ? 0.0f : INFINITY, s1 = -INFINITY;
                 if (valid) {
-                    int row = g_mine + c - (T - 1);                        // ring position of the window's oldest column
+                    const int th = (T + 1) >> 1, t0 = owner ? 0 : th, t1 = owner ? th : T;
+                    int row = gcol + c - (T - 1) + t0;                     // ring position of this lane's first column
                     if (row < 0) row += kPRing;
                     else if (row >= kPRing) row -= kPRing;
-                    int col = s_mine + c - (T - 1);                        // same column in the statistic ring
-                    if (col < 0) col += kStatRing;
-                    else if (col >= kStatRing) col -= kStatRing;
-                    const float *pt = pbuf + row * ppitch;                 // advances by one ring row and one (t, :) block per step
-                    const float4 *cs = reinterpret_cast<const float4 *>(colstat) + col;
+                    uint32_t col = scol + (uint32_t)(c - (T - 1) + t0);    // same column in the statistic ring
+                    const float *pt = pbuf + t0 * HP + row * ppitch;       // advances by one ring row and one (t, :) block per step
 #pragma unroll 2
-                    for (int t = 0; t < T; ++t) {
+                    for (int t = t0; t < t1; ++t, ++col) {
                         const float4 *prow = reinterpret_cast<const float4 *>(pt);
                         pt += ppitch + HP;
                         if (++row == kPRing) { row = 0; pt -= kPRing * ppitch; }
@@ -501,6 +517,7 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
                             const float4 v1 = prow[1];
                             acc[4] += v1.x; acc[5] += v1.y; acc[6] += v1.z; acc[7] += v1.w;
                         }
+                        const float4 *cs = reinterpret_cast<const float4 *>(colstat) + (col & (kStatRing - 1));
                         const float4 ca = cs[0];            // the four bin quarters of the column
                         if (window_stat == FUSED_STAT_L2) s0 += (ca.x + ca.y) + (ca.z + ca.w);
                         else if (window_stat == FUSED_STAT_MINMAX) {
@@ -508,16 +525,14 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
                             s0 = fminf(s0, fminf(fminf(ca.x, ca.y), fminf(ca.z, ca.w)));
                             s1 = fmaxf(s1, fmaxf(fmaxf(cb.x, cb.y), fmaxf(cb.z, cb.w)));
                         }
-                        ++cs;
-                        if (++col == kStatRing) { col = 0; cs -= kStatRing; }
                     }
                 }
-                if constexpr (kF16) {
-                    // Range guard of the fp16 correction pass: the pass is at float32 level while the window's band
-                    // energy sum |X|^2 is at least guard_lo (absolute operand errors of 2^-25 stay below 1e-6 of the normalised
-                    // features) and no sample overflowed fp16 (inf / NaN energy otherwise). An exactly silent window (energy 0) is
-                    // exact in both variants. Anything else raises the flag; the host then repeats the launch with the all-TF32 variant.
-                    if (valid && !(s0 >= w.guard_lo && s0 <= 3.0e38f) && s0 != 0.0f) *w.range_flag = 1;
+#pragma unroll
+                for (int h = 0; h < HP; ++h) acc[h] += __shfl_xor_sync(0xffffffffu, acc[h], 16);
+                {
+                    const float o0 = __shfl_xor_sync(0xffffffffu, s0, 16), o1 = __shfl_xor_sync(0xffffffffu, s1, 16);
+                    if (window_stat == FUSED_STAT_L2) s0 += o0;
+                    else { s0 = fminf(s0, o0); s1 = fmaxf(s1, o1); }
                 }
                 float inv = 1.0f, beta = 0.0f;  // z = acc * inv + beta * V + B'
                 if (window_stat == FUSED_STAT_L2) {            // x / sqrt(sum x^2)  (NeuralNet.swift:47-59); silence: 0 * inf = NaN
@@ -532,8 +547,8 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
                 for (int h = 0; h < kFusedMaxHidden; ++h)
                     a[h] = h < HP ? transfer_fast(tf0, fmaf(acc[h < HP ? h : 0], inv, fmaf(beta, p.v[h], p.bprime[h]))) : 0.0f;
                 tm.add(4, t_f1);
-                float *o = w.all_out + ((int64_t)mine.ch * w.out_evals_per_channel + w.eval_offset + mine.e0 + j) * n_out;
-                const bool store = valid && w.all_out != nullptr;
+                float *o = w.all_out + ((int64_t)tw.ch * w.out_evals_per_channel + w.eval_offset + tw.e0 + j) * n_out;
+                const bool store = valid && owner && w.all_out != nullptr;
                 if (one_output_tail) {   // the common shape: hidden layer -> one output (NeuralNet.swift:310-323)
                     float sacc = p.rest_b[0];
 #pragma unroll
@@ -557,34 +572,33 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
                         for (int k = 0; k < n_out; ++k) o[k] = pick(out, k);
                     }
                 }
-                hit = hit && valid;
+                hit = hit && valid && owner;
             }
             const unsigned hits = __ballot_sync(0xffffffffu, hit);
-            if (hits) {   // append to the shared-memory event buffer (room for a whole pair is guaranteed by the flush rule)
+            if (hits) {   // append to the shared-memory event buffer (room for a whole tile is guaranteed by the flush rule)
                 int base = 0;
                 if (lane == 0) base = atomicAdd(ev_count, __popc(hits));
                 base = __shfl_sync(0xffffffffu, base, 0);
                 if (hit) {
                     const int e = base + __popc(hits & ((1u << lane) - 1));
-                    const int64_t ev = w.eval_offset + mine.e0 + j;
-                    ev_meta[e] = make_int4(mine.ch, 0, (int)(unsigned)(ev & 0xffffffffll), (int)(ev >> 32));
+                    const int64_t ev = w.eval_offset + tw.e0 + j;
+                    ev_meta[e] = make_int4(tw.ch, 0, (int)(unsigned)(ev & 0xffffffffll), (int)(ev >> 32));
 #pragma unroll 1
                     for (int k = 0; k < n_out; ++k) ev_out[e * n_out + k] = pick(out, k);
                 }
             }
-            tm.sync(kBarF, kFGroup * 32, 2);  // the next pair overwrites ring rows that this pair's evaluations read
+            tm.sync(bar_f, kFGroup * 32, 2);  // this group's next tile overwrites ring rows that this tile's evaluations read
             const int n_ev = *ev_count;
-            if (n_ev > kEvCap - kPairFrames) flush_events(n_ev);
-            gcol += frames_a + frames_b;
+            if (n_ev > kEvCap - kTileFrames) flush_events(n_ev);
+            gcol += frames;
             if (gcol >= kPRing) gcol -= kPRing;
-            scol += frames_a + frames_b;
-            if (scol >= kStatRing) scol -= kStatRing;
+            scol += frames;
         }
         {
             const int n_ev = *ev_count;
             if (n_ev > 0) flush_events(n_ev);
         }
-        tm.flush(ft == 0);
+        tm.flush(ft == 0 && grp == 0);
     } else if (warp < kWarpS0) {
         // ================================ spectrum warps (D) ===========================================================
         // TMEM lane 32*quad + lane holds DFT-matrix row (part = lane >> 3: Re B1 | Im B1 | Re B2 | Im B2, bin = 8*quad + (lane & 7)),
@@ -605,10 +619,9 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
         const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + kColD0 + half * 32;
         TileWalk tw;
         tw.init(w, T);
-        int gcol = 0;                                       // statistic-ring position of the tile's first column (mod kStatRing)
+        uint32_t gcol = 0;
         RoleTimer<kTiming> tm(w.debug_timing, 18);
-        uint32_t it = 0;
-        for (; tw.valid(); ++it, tw.next(w, T)) {
+        for (uint32_t it = 0; tw.valid(); ++it, tw.next(w, T)) {
             const int s = it & 1;
             const uint32_t ph = (it >> 1) & 1;
             const int frames = tw.frames();
@@ -650,12 +663,8 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
                     const float sq_a = __fmul_rn(x[2 * i][u], x[2 * i][u]), sq_b = __fmul_rn(x[2 * i + 1][u], x[2 * i + 1][u]);
                     const float other = __shfl_xor_sync(0xffffffffu, im ? sq_a : sq_b, 8);
                     float v;
-                    if constexpr (kScaled) {
-                        const float raw = sqrt_fast(__fadd_rn(im ? sq_b : sq_a, other));
-                        if (w.debug_band && in_band && col0 + 8 * i + u < frames)   // extractPower() values, before the scaling
-                            w.debug_band[((int64_t)tw.ch * w.debug_cols + w.eval_offset + tw.e0 + tw.cols_before() + col0 + 8 * i + u) * L + bin] = raw;
-                        v = scale_value_nl(raw, p.scaling);
-                    } else v = sqrt_fast_ftz(__fadd_rn(im ? sq_b : sq_a, other));
+                    if constexpr (kScaled) v = scale_value_nl(sqrt_fast(__fadd_rn(im ? sq_b : sq_a, other)), p.scaling);
+                    else v = sqrt_fast_ftz(__fadd_rn(im ? sq_b : sq_a, other));
                     mag[2 * i + u] = in_band ? v : 0.0f;
                 }
             // ---- window statistic: per-column partial over this warp's 8 bins; the evaluators combine the four quadrants -----
@@ -671,9 +680,7 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
                     return op(b1 ? h2[1] : h2[0], __shfl_xor_sync(0xffffffffu, b1 ? h2[0] : h2[1], 1));
                 };
                 float q[8];
-                int sidx = gcol + stat_col;
-                if (sidx >= kStatRing) sidx -= kStatRing;
-                float *cs = colstat + (sidx << 2) + quad;
+                float *cs = colstat + (((gcol + (uint32_t)stat_col) & (kStatRing - 1)) << 2) + quad;
                 if (window_stat == FUSED_STAT_L2) {
 #pragma unroll
                     for (int e = 0; e < 8; ++e) q[e] = mag[e] * mag[e];
@@ -693,9 +700,9 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
                 }
             }
             // ---- magnitudes -> layer-0 A operand (hi, lo) -----------------------------------------------------------------------
-            tm.wait(a_free, ph ^ 1, 2);                     // layer 0 of the previous pair has read the A operand
+            tm.wait(&a_free[s], ph ^ 1, 2);                 // layer 0 of tile it-2 has read this A buffer
             {
-                unsigned char *a_hi = smem + TcSmem::a(s, 0), *a_lo = smem + TcSmem::a(s, 1);   // this tile's half of the 128 rows
+                unsigned char *a_hi = smem + TcSmem::a(s, 0), *a_lo = smem + TcSmem::a(s, 1);
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -705,20 +712,16 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
                             const float v = mag[2 * i + u], vh = tf32_trunc(v);
                             *reinterpret_cast<float *>(a_hi + a_off[u] + i * 1024) = vh;
                             *reinterpret_cast<float *>(a_lo + a_off[u] + i * 1024) = v - vh;
-                            if constexpr (!kScaled) {
-                                if (w.debug_band && in_band)
-                                    w.debug_band[((int64_t)tw.ch * w.debug_cols + w.eval_offset + tw.e0 + tw.cols_before() + col) * L + bin] = v;
-                            }
+                            if (w.debug_band && in_band)
+                                w.debug_band[((int64_t)tw.ch * w.debug_cols + tw.e0 + tw.cols_before() + col) * L + bin] = v;
                         }
                     }
             }
             ptx::fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(a_ready);
+            if (lane == 0) ptx::mbar_arrive(&a_ready[s]);
             gcol += frames;
-            if (gcol >= kStatRing) gcol -= kStatRing;
         }
-        if ((it & 1) && lane == 0) ptx::mbar_arrive(a_ready);   // odd tile count: the last pair has no second tile
         tm.flush(dw == 0 && lane == 0);
     } else {
         // ================================ splitters (S) ================================================================
@@ -822,12 +825,12 @@ int tc_tile_frames() { return kTileFrames; }
 int tc_k_pad() { return kKPad; }
 int tc_max_n0() { return kMaxN0; }
 bool tc_layout_fits(int time_range, int n0) {
-    // product ring: a pair (start b) reuses the positions of the previous pair except its last ring - pair rows, which this pair's
-    // evaluations still read: ring - pair >= T - 1.
-    // statistic ring: when the spectrum warps write tile it (even), the MMA warp has passed issue_l0(pair it/2 - 1), i.e. the
-    // evaluators have copied pair it/2 - 3 (tiles it-6, it-5) and may still read the T-1 columns before it; the spectrum warps can
-    // run two more tiles ahead before the next such wait: 9 tiles + T columns.
-    return n0 <= kMaxN0 && kPairFrames + time_range - 1 <= kPRing && 9 * kTileFrames + time_range <= kStatRing;
+    // product ring: tile it (start b) reuses the positions of tile it - groups (start b + ring - groups * tile), whose last T-1
+    // rows the evaluations of tile it - groups + 1 may still read: ring - groups * tile >= T - 1.
+    // statistic ring: the MMA warp cannot pass the DFT of tile it before the copy of tile it-3 is done, the spectrum warps are
+    // at most at tile it, the slowest group at tile it - 2 - groups: (groups + 3) * tile + T columns.
+    return n0 <= kMaxN0 && kNumGroups * kTileFrames + time_range <= kPRing &&
+           (kNumGroups + 3) * kTileFrames + time_range <= kStatRing;
 }
 
 cudaError_t launch_tc(int hp, int grid, size_t smem, const FusedParams &p, const TcWork &w, const void *tmap_main, const void *tmap_tail,

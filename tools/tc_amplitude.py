@@ -9,7 +9,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sd = importlib.import_module("syldet_b200")
-synth = importlib.import_module("syllable-detector-swift_b200.synth")
+synth = importlib.import_module("tools.synth")
 from oracle import Oracle
 
 path = os.path.join(ROOT, "tests", "golden", "sample.txt")

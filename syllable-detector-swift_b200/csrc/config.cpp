@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
+#include <locale.h>
 #include <sstream>
 #include <string_view>
 #include <unordered_map>
@@ -60,6 +61,13 @@ Dict read_pairs(std::string_view text) {
     return d;
 }
 
+// Swift's Double(String) / Float(String) do not depend on the process locale: parse under the "C" locale whatever LC_NUMERIC says
+// (a host application running with e.g. de_DE would otherwise read "0.5" as 0).
+locale_t c_locale() {
+    static locale_t loc = newlocale(LC_ALL_MASK, "C", (locale_t)0);
+    return loc;
+}
+
 template <typename T>
 bool whole_number(const std::string &s, T &out);
 
@@ -67,14 +75,14 @@ template <>
 bool whole_number<double>(const std::string &s, double &out) {
     if (s.empty() || is_space(s.front())) return false;
     char *end = nullptr;
-    out = std::strtod(s.c_str(), &end);
+    out = strtod_l(s.c_str(), &end, c_locale());
     return end != s.c_str() && *end == '\0';
 }
 template <>
 bool whole_number<float>(const std::string &s, float &out) {
     if (s.empty() || is_space(s.front())) return false;
     char *end = nullptr;
-    out = std::strtof(s.c_str(), &end);
+    out = strtof_l(s.c_str(), &end, c_locale());
     return end != s.c_str() && *end == '\0';
 }
 template <>

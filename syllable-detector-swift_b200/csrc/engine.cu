@@ -183,6 +183,17 @@ uint16_t f32_to_f16_rn(float f) {  // round to nearest even, subnormals kept (cv
     if (rem > 0x1000u || (rem == 0x1000u && (half & 1u))) ++half;   // a carry moves into the exponent
     return (uint16_t)(sign | half);
 }
+float f16_to_f32(uint16_t h) {
+    const uint32_t sign = (uint32_t)(h & 0x8000u) << 16, exp = (h >> 10) & 0x1Fu, mant = h & 0x3FFu;
+    float f;
+    if (exp == 0) {
+        f = (float)mant * (1.0f / 16777216.0f);   // subnormal: mant * 2^-24
+        return sign ? -f : f;
+    }
+    const uint32_t u = sign | ((exp - 15 + 127) << 23) | (mant << 13);   // inf / NaN do not occur (|A| <= 1.08)
+    std::memcpy(&f, &u, 4);
+    return f;
+}
 }  // namespace
 
 TcPlan plan_tc(const Config &c, const FusedPlan &fused) {
@@ -216,14 +227,20 @@ TcPlan plan_tc(const Config &c, const FusedPlan &fused) {
     // rows: [0,32) Re B1 | [32,64) Im B1 | [64,96) Re B2 | [96,128) Im B2 ; B1 = samples [0,hop), B2 = samples [hop,W)
     plan.dft_hi.assign((size_t)128 * kpad, 0.0f);
     plan.dft_lo.assign((size_t)128 * kpad, 0.0f);
-    // fp16 correction operand (TC_F16_CORR): K order [lo(n < 128) | hi * 2^-11 (n < 128) | lo(n >= 128) | hi * 2^-11 (n >= 128)],
-    // two k per 32-bit word (low half first); lo = value - tf32(value), paired with fp16(x) and fp16((x - tf32(x)) * 2^11)
-    std::vector<uint16_t> a16((size_t)128 * 2 * kpad, 0);
-    auto put16 = [&](size_t row, int n, double full, float hi) {
-        const int main = n < 128, k = n & 127;
-        const size_t j_lo = main ? (size_t)k : (size_t)256 + k, j_hi = main ? (size_t)128 + k : (size_t)264 + k;
-        a16[row * 2 * kpad + j_lo] = f32_to_f16_rn((float)(full - (double)hi));
-        a16[row * 2 * kpad + j_hi] = f32_to_f16_rn(hi * (1.0f / 2048.0f));
+    // fp16 A operand of the kF16 variant (kernels_tc.cu): per row 416 fp16 = 208 words, K order
+    //   [a1(n < 128) | a1 2^-11 (n < 128) | a1(n >= 128) (8) | a1 2^-11 (n >= 128) (8) | a2(n < 128) | a2(n >= 128) (8) | 0 (8)]
+    // with a1 = fp16(A), a2 = fp16(A - a1); two k per 32-bit word (low half first)
+    const int a16_halves = tc_a16_cols() * 2;
+    std::vector<uint16_t> a16((size_t)128 * a16_halves, 0);
+    auto put16 = [&](size_t row, int n, double full) {
+        const uint16_t h1 = f32_to_f16_rn((float)full);
+        const float a1 = f16_to_f32(h1);
+        const bool main = n < 128;
+        const int k = n & 127;
+        uint16_t *dst = a16.data() + row * a16_halves;
+        dst[main ? k : 256 + k] = h1;
+        dst[main ? 128 + k : 264 + k] = f32_to_f16_rn(a1 * (1.0f / 2048.0f));
+        dst[main ? 272 + k : 400 + k] = f32_to_f16_rn((float)(full - (double)a1));
     };
     for (int b = 0; b < c.band; ++b) {
         const int k = c.k0 + b;
@@ -239,11 +256,11 @@ TcPlan plan_tc(const Config &c, const FusedPlan &fused) {
                 plan.dft_lo[ire] = tf32_round(re - (double)plan.dft_hi[ire]);
                 plan.dft_hi[iim] = tf32_round(im);
                 plan.dft_lo[iim] = tf32_round(im - (double)plan.dft_hi[iim]);
-                put16((size_t)(half * 64 + b), n, re, plan.dft_hi[ire]);
-                put16((size_t)(half * 64 + 32 + b), n, im, plan.dft_hi[iim]);
+                put16((size_t)(half * 64 + b), n, re);
+                put16((size_t)(half * 64 + 32 + b), n, im);
             }
     }
-    plan.dft16.assign((size_t)128 * kpad, 0u);
+    plan.dft16.assign((size_t)128 * tc_a16_cols(), 0u);
     for (size_t i = 0; i < plan.dft16.size(); ++i) plan.dft16[i] = (uint32_t)a16[2 * i] | ((uint32_t)a16[2 * i + 1] << 16);
     plan.ok = true;
     return plan;
@@ -366,13 +383,13 @@ syldet_status DeviceModel::init(const Config &cfg, int device) {
     tc_ = plan_tc(cfg_, fused_);
     if (tc_.ok) {
         const size_t n = tc_.dft_hi.size(), nw = tc_.wcat_hi.size();
-        st = d_dft_.reserve((3 * n + 2 * nw) * sizeof(float));
+        st = d_dft_.reserve((2 * n + 2 * nw + tc_.dft16.size()) * sizeof(float));
         if (st != SYLDET_OK) return st;
         SYLDET_CUDA(cudaMemcpy(d_dft_.get(), tc_.dft_hi.data(), n * sizeof(float), cudaMemcpyHostToDevice));
         SYLDET_CUDA(cudaMemcpy(d_dft_.as<float>() + n, tc_.dft_lo.data(), n * sizeof(float), cudaMemcpyHostToDevice));
         SYLDET_CUDA(cudaMemcpy(d_dft_.as<float>() + 2 * n, tc_.wcat_hi.data(), nw * sizeof(float), cudaMemcpyHostToDevice));
         SYLDET_CUDA(cudaMemcpy(d_dft_.as<float>() + 2 * n + nw, tc_.wcat_lo.data(), nw * sizeof(float), cudaMemcpyHostToDevice));
-        SYLDET_CUDA(cudaMemcpy(d_dft_.as<float>() + 2 * n + 2 * nw, tc_.dft16.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        SYLDET_CUDA(cudaMemcpy(d_dft_.as<float>() + 2 * n + 2 * nw, tc_.dft16.data(), tc_.dft16.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     }
     return SYLDET_OK;
 }

@@ -60,7 +60,7 @@ struct TcPlan {
     int hp = 0;
     size_t smem = 0;
     std::vector<float> dft_hi, dft_lo;  // [128][k_pad]
-    std::vector<uint32_t> dft16;        // [128][k_pad] fp16 pairs: the two correction operands of the TC_F16_CORR build (kernels_tc.cu)
+    std::vector<uint32_t> dft16;        // [128][tc_a16_cols()] fp16 pairs: two-term fp16 split of the DFT matrix (kF16 variant, kernels_tc.cu)
     std::vector<float> wcat_hi, wcat_lo;  // [n0][32]
     int n0 = 0;
 };

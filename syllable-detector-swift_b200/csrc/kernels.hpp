@@ -131,10 +131,10 @@ struct TcWork {
     EventSink sink;
     const float *dft_hi, *dft_lo;   // [128][k_pad] windowed DFT matrix, tf32 hi / lo parts
     const float *wcat_hi, *wcat_lo; // [n0][32] folded layer-0 weights, row (t*HP + h), column = band bin
-    const uint32_t *dft16;          // [128][k_pad] fp16 pairs (TC_F16_CORR build): lo part | hi part * 2^-11, see plan_tc
+    const uint32_t *dft16;          // [128][tc_a16_cols()] fp16 pairs: the two-term split of the DFT matrix (kF16 variant), see plan_tc
     int n0;                         // T*HP rounded up to a multiple of 16
     int lo_stages;                  // 1 or 2 lo tiles in shared memory (tc_lo_stages)
-    int f16_corr;                   // 1: correction products of the band DFT as one fp16 pass (sample shape; SYLDET_TC_TF32_CORR=1 turns it off)
+    int f16_corr;                   // 1: band DFT on fp16 splits (sample shape; range-guarded); 0: 3xTF32 (SYLDET_KERNEL_TENSOR_TF32, SYLDET_TC_TF32_CORR=1)
     float *debug_band;              // optional [n_channels][debug_cols][band] band magnitudes (tests)
     int64_t debug_cols;
     long long *debug_timing;        // optional [grid][32] cycle counters per role (SYLDET_TC_TIMING=1)
@@ -147,6 +147,7 @@ size_t tc_smem_bytes(const FusedParams &p, int hp);
 int tc_lo_stages(const FusedParams &p, int hp);
 int tc_tile_frames();
 int tc_k_pad();
+int tc_a16_cols();                  // 32-bit words per row of the fp16 A operand (TcWork::dft16)
 int tc_max_n0();
 bool tc_layout_fits(int time_range, int n0);
 cudaError_t launch_tc(int hp, int grid, size_t smem, const FusedParams &p, const TcWork &w, const void *tmap_main,

@@ -43,11 +43,16 @@ namespace syldet {
 namespace {
 
 constexpr int kFGroup = 4;                     // evaluator warps (one per TMEM lane quadrant)
-// kF16: the two correction products of the 3xTF32 band DFT (Alo*Bhi + Ahi*Blo) as ONE K-concatenated kind::f16 pass
-//   [fp16(Alo) | fp16(Ahi * 2^-11)] * [fp16(x) ; fp16((x - tf32(x)) * 2^11)]       (17 MMAs instead of 34 per tile)
-// The fp16 tile has the byte geometry of the fp32 one (4 x [64 rows x 128 B] + [64 rows x 32 B]); K order: x(n < 128) |
-// lo(n < 128) | x(n >= 128) | lo(n >= 128). Error terms are scaled by 2^-11, so fp16's 11 bits keep the sum at fp32 level
-// for |x| in [6e-5, 65504]; quieter samples carry an absolute error of 2^-25 * 2^-11 each (documented in DESIGN.md).
+// kF16: the whole band DFT as kind::f16 MMAs on two-term fp16 splits of both operands (the sample shape):
+//   A = a1 + a2, a1 = fp16(A), a2 = fp16(A - a1);   x = h1 + h2 * 2^-11, h1 = fp16(x), h2 = fp16((x - h1) * 2^11)
+//   A x ~= a1 h1 + (a1 2^-11) h2 + a2 h1            (the dropped term a2 (x - h1) is <= 2^-24 |A| |x|)
+// as ONE K-concatenated pass [a1 | a1 2^-11 | a2] * [h1 ; h2 ; h1]: 26 MMAs with K = 16 per tile, where round 1 ran 17 kind::tf32
+// MMAs on the raw audio plus 17 kind::f16 correction MMAs (a tf32 MMA takes as long as an f16 one and moves as many operand bytes
+// for half the K). The splitters write the fp16 tile with the byte geometry of the fp32 one (4 x [64 rows x 128 B] + [64 rows x 32 B]):
+// chunks 0,1 = h1(n < 128), chunks 2,3 = h2(n < 128), tail = h1(n >= 128) | h2(n >= 128); the third product re-reads chunks 0,1 and
+// the tail (against a zero A block for its h2 half). The raw fp32 tile is then read by the splitters only.
+// fp16's 11 bits per term keep the sum at float32 level for |x| in [6e-5, 32752]; quieter samples carry an absolute error of
+// ~2^-36 each, which the evaluators' range guard bounds against the window's energy.
 constexpr int kWarpTma = 0, kWarpMma = 1, kWarpF0 = 2, kNumF = kFGroup, kWarpD0 = kWarpF0 + kNumF, kNumD = 8,
               kWarpS0 = kWarpD0 + kNumD, kNumS = 4;
 constexpr int kTcThreads = (kWarpS0 + kNumS) * 32;  // 576
@@ -63,6 +68,9 @@ constexpr int kTileBytes = kMainChunks * kMainBytes + kTailBytes;  // 34 816 per
 constexpr int kMaxN0 = 56;                     // widest layer-0 product row (T * HP, padded to 16) with P double buffered
 constexpr int kTmemCols = 512;
 constexpr int kColAhi = 0, kColAlo = kKPad, kColD0 = 2 * kKPad, kColP0 = kColD0 + 2 * kTileRows;
+// kF16: the A operand [a1(128) | a1 2^-11 (128) | a1(8) a1 2^-11 (8) | a2(128) | a2(8) 0(8)] in fp16 pairs, from kColAhi
+constexpr int kA16Cols = 64 + 64 + 8 + 64 + 8;
+static_assert(kA16Cols <= 2 * kKPad, "the fp16 A operand fits where the tf32 hi / lo parts go");
 static_assert(kColP0 + 2 * kMaxN0 <= kTmemCols, "TMEM budget");
 constexpr int kPairFrames = 2 * kTileFrames;   // evaluations the evaluators finish per pass (one pair of tiles)
 constexpr int kPRing = kPairFrames + 22;       // product-row ring (rows = columns): the pair in flight + the T-1 (<= 22) rows before it
@@ -244,7 +252,7 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&full[i], 1);
-            ptx::mbar_init(&hi_free[i], 1 + kNumS);
+            ptx::mbar_init(&hi_free[i], kF16 ? kNumS : 1 + kNumS);   // kF16: the tensor core never reads the raw tile
             ptx::mbar_init(&tmem_full[i], 1);
             ptx::mbar_init(&tmem_empty[i], kNumD);
             ptx::mbar_init(&p_full[i], 1);
@@ -280,13 +288,23 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
         const int quad = warp & 3;
         const int m = (lane >> 3) * 32 + quad * 8 + (lane & 7);
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
-        for (int part = 0; part < 2; ++part) {
-            const float *src = (part ? (kF16 ? reinterpret_cast<const float *>(w.dft16) : w.dft_lo) : w.dft_hi) + (size_t)m * kKPad;
-            for (int kb = 0; kb < kKPad / 8; ++kb) {
+        if constexpr (kF16) {
+            const uint32_t *src = w.dft16 + (size_t)m * kA16Cols;
+            for (int kb = 0; kb < kA16Cols / 8; ++kb) {
                 uint32_t r[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) r[i] = __float_as_uint(__ldg(src + kb * 8 + i));
-                ptx::tmem_st_x8(lane_addr + (part ? kColAlo : kColAhi) + kb * 8, r);
+                for (int i = 0; i < 8; ++i) r[i] = __ldg(src + kb * 8 + i);
+                ptx::tmem_st_x8(lane_addr + kColAhi + kb * 8, r);
+            }
+        } else {
+            for (int part = 0; part < 2; ++part) {
+                const float *src = (part ? w.dft_lo : w.dft_hi) + (size_t)m * kKPad;
+                for (int kb = 0; kb < kKPad / 8; ++kb) {
+                    uint32_t r[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) r[i] = __float_as_uint(__ldg(src + kb * 8 + i));
+                    ptx::tmem_st_x8(lane_addr + (part ? kColAlo : kColAhi) + kb * 8, r);
+                }
             }
         }
         ptx::tc_wait_st();
@@ -335,16 +353,26 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
                 }
                 ptx::mma_tf32_ts(d, a, ptx::smem_desc_kmajor(b + kMainChunks * kMainBytes, 256, 6), idesc_dft, 1);
             };
-            // the fp16 correction pass: same descriptors and column steps (32 B of K per instruction), 16 k each
+            // kF16: the fp16 band DFT, same descriptors and column steps (32 B of K per instruction = 16 k = 8 TMEM columns).
+            // Segments of the A operand (TMEM columns from kColAhi): [0, 128) a1 | a1 2^-11 against chunks 0..3 (h1, h2), [128, 136)
+            // against the tail, [136, 200) a2 against chunks 0,1 (h1 again), [200, 208) a2 | 0 against the tail.
             constexpr uint32_t idesc_f16 = ptx::idesc_f16(128, kTileRows);
-            auto corr_pass = [&](uint32_t d, uint32_t a, uint32_t b) {
-                uint64_t desc = ptx::smem_desc_kmajor(b, 1024, 2);
+            auto f16_pass = [&](uint32_t d, uint32_t a, uint32_t b) {
+                const uint64_t desc0 = ptx::smem_desc_kmajor(b, 1024, 2), desc_tail = ptx::smem_desc_kmajor(b + kMainChunks * kMainBytes, 256, 6);
+                uint32_t acc = 0;
 #pragma unroll 1
-                for (int j = 0; j < kMainChunks; ++j, a += 32, desc += kMainBytes >> 4) {
+                for (int j = 0; j < kMainChunks + 2; ++j) {        // chunks 0, 1, 2, 3, then 0, 1 again
+                    const int chunk = j < kMainChunks ? j : j - kMainChunks;
+                    const uint32_t aj = a + (j < kMainChunks ? j * 32 : 136 + (j - kMainChunks) * 32);
+                    const uint64_t desc = desc0 + (uint64_t)(chunk * (kMainBytes >> 4));
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) ptx::mma_f16_ts(d, a + ks * 8, desc + ks * 2, idesc_f16, 1);
+                    for (int ks = 0; ks < 4; ++ks) {
+                        ptx::mma_f16_ts(d, aj + ks * 8, desc + ks * 2, idesc_f16, acc);
+                        acc = 1;
+                    }
                 }
-                ptx::mma_f16_ts(d, a, ptx::smem_desc_kmajor(b + kMainChunks * kMainBytes, 256, 6), idesc_f16, 1);
+                ptx::mma_f16_ts(d, a + 128, desc_tail, idesc_f16, 1);
+                ptx::mma_f16_ts(d, a + 200, desc_tail, idesc_f16, 1);
             };
             RoleTimer<kTiming> tm(w.debug_timing, 6, false);   // the MMA issuer is the pacemaker: it polls
             const uint32_t idesc_l0 = ptx::idesc_tf32(128, n0);
@@ -374,7 +402,7 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
             for (; tw.valid(); ++it, tw.next(w, T)) {
                 const int s = it & 1;
                 const uint32_t ph = (it >> 1) & 1;
-                tm.wait(&full[s], ph, 0);             // hi landed (TMA)
+                if constexpr (!kF16) tm.wait(&full[s], ph, 0);   // hi landed (TMA); kF16 reads only what the splitters wrote
                 // accumulator s is free once the spectrum warps have read tile it-2. For odd it that is implied: they arrived on
                 // a_ready for the pair (it-3, it-2) after their TMEM loads, and this thread waited for it in the previous iteration.
                 // For even it the pair (it-2, it-1) is only waited for below, after this tile's DFT is queued.
@@ -382,14 +410,16 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
                 ptx::tc_fence_after();
                 const uint32_t d = tmem_base + kColD0 + s * kTileRows;
                 const uint32_t hi = ptx::smem_addr(smem + TcSmem::hi(s));
-                dft_pass(d, tmem_base + kColAhi, hi, 0);
-                if constexpr (!kF16) dft_pass(d, tmem_base + kColAlo, hi, 1);
-                ptx::mma_commit(&hi_free[s]);             // the MMA side is done with hi[s]
+                if constexpr (!kF16) {
+                    dft_pass(d, tmem_base + kColAhi, hi, 0);
+                    dft_pass(d, tmem_base + kColAlo, hi, 1);
+                    ptx::mma_commit(&hi_free[s]);         // the MMA side is done with hi[s]
+                }
                 const int ls = lo_stages == 2 ? s : 0;
                 const uint32_t lo_use = lo_stages == 2 ? (it >> 1) : it;   // uses of this lo buffer so far
                 tm.wait(&lo_ready[ls], lo_use & 1, 2);   // lo written (splitters)
                 ptx::tc_fence_after();
-                if constexpr (kF16) corr_pass(d, tmem_base + kColAlo, ls ? lo_b : lo_a);
+                if constexpr (kF16) f16_pass(d, tmem_base + kColAhi, ls ? lo_b : lo_a);
                 else dft_pass(d, tmem_base + kColAhi, ls ? lo_b : lo_a, 1);
                 ptx::mma_commit(&tmem_full[s]);
                 ptx::mma_commit(&lo_free[ls]);
@@ -734,15 +764,16 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
             const int ls = lo_stages == 2 ? s : 0;
             const uint32_t lo_use = lo_stages == 2 ? (it >> 1) : it;
             tm.wait(&lo_free[ls], (lo_use & 1) ^ 1, 1);  // pass 3 of the previous user of this lo buffer has read it
-            if constexpr (kF16) {   // fp32 tile -> fp16 tile [x | (x - tf32(x)) * 2^11]. A warp instruction takes rows r0, r0+4, r0+8, r0+12 (one 128 B row
+            if constexpr (kF16) {   // fp32 tile -> fp16 tile [h1 = fp16(x) | h2 = fp16((x - h1) * 2^11)]. A warp instruction takes rows r0, r0+4, r0+8, r0+12 (one 128 B row
                 // per quarter warp): the loads are whole rows and the 8-byte stores of the four rows fall on disjoint banks.
                 const unsigned char *hi_b = smem + TcSmem::hi(s);
                 unsigned char *b16 = smem + (ls ? lo1_off : TcSmem::lo);
                 const int sw = st >> 5, phys = lane & 7, rq = sw + 4 * (lane >> 3);   // row = rq + 16 * (kk & 3), chunk = kk >> 2
                 auto convert = [](const float4 &v, uint2 &hx, uint2 &hl) {
                     const __half2 x01 = __floats2half2_rn(v.x, v.y), x23 = __floats2half2_rn(v.z, v.w);
-                    const __half2 l01 = __floats2half2_rn((v.x - tf32_trunc(v.x)) * 2048.0f, (v.y - tf32_trunc(v.y)) * 2048.0f);
-                    const __half2 l23 = __floats2half2_rn((v.z - tf32_trunc(v.z)) * 2048.0f, (v.w - tf32_trunc(v.w)) * 2048.0f);
+                    const float2 f01 = __half22float2(x01), f23 = __half22float2(x23);
+                    const __half2 l01 = __floats2half2_rn((v.x - f01.x) * 2048.0f, (v.y - f01.y) * 2048.0f);
+                    const __half2 l23 = __floats2half2_rn((v.z - f23.x) * 2048.0f, (v.w - f23.y) * 2048.0f);
                     hx = make_uint2(*reinterpret_cast<const uint32_t *>(&x01), *reinterpret_cast<const uint32_t *>(&x23));
                     hl = make_uint2(*reinterpret_cast<const uint32_t *>(&l01), *reinterpret_cast<const uint32_t *>(&l23));
                 };
@@ -820,6 +851,7 @@ size_t tc_smem_bytes(const FusedParams &p, int hp) {
 }
 int tc_tile_frames() { return kTileFrames; }
 int tc_k_pad() { return kKPad; }
+int tc_a16_cols() { return kA16Cols; }
 int tc_max_n0() { return kMaxN0; }
 bool tc_layout_fits(int time_range, int n0) {
     // product ring: a pair (start b) reuses the positions of the previous pair except its last ring - pair rows, which this pair's

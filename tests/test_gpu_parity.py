@@ -214,11 +214,15 @@ def test_amplitude_int16_input_is_exact_for_the_fp16_pass(sd, cfg, orc, synth):
 
 def test_amplitude_range_non_normalised_configs(sd, oracle_mod, cw):
     """Configurations without a per-window normaliser (mapminmax only; db scaling) are not scale-invariant: the tensor kernel keeps all
-    three DFT products in TF32 for them, so any amplitude stays at float32 level."""
+    three DFT products in TF32 for them, so no amplitude triggers a fallback and the error stays at float32 level. "float32 level" is
+    amplitude-dependent here (magnitudes of ~30 against offsets of ~5e-4 make the hidden pre-activations ill-conditioned): the bound is
+    the larger of the usual tolerance and 4x the distance between the float32 oracle and its float64 twin on the same input."""
+    from oracle import twin64
     for kw in (dict(hidden=(4,), input_funcs=("mapminmax",)), dict(hidden=(4,), scaling="db", input_funcs=("mapminmax",))):
         text = cw.random_config(seed=17, threshold=0.3, fft_len=256, overlap=124, **kw)
         c = sd.SyllableDetectorConfig.from_text(text).validate()
         o = oracle_mod.Oracle(text=text)
+        tw = twin64.Twin64(text=text)
         rng = np.random.default_rng(4)
         n = 50000
         t = np.arange(n)
@@ -228,8 +232,11 @@ def test_amplitude_range_non_normalised_configs(sd, oracle_mod, cw):
             det = sd.BatchDetector(c, kernel=sd.KERNEL_TENSOR)
             ev, outs = det.run(x, want_outputs=True)
             ref = o.run(x)[0]
+            r64 = tw.run(x)
+            r64 = r64[0] if isinstance(r64, tuple) else r64
             scale = max(1.0, float(np.nanmax(np.abs(ref))))
             tol = (TOL_OUT if kw.get("scaling", "linear") == "linear" else TOL_NONLINEAR) * scale
+            tol = max(tol, 4.0 * float(np.nanmax(np.abs(ref - r64))))
             _check_channel(o, x, outs[0], ev.sample, tol)
             assert det.range_fallbacks == 0
 

@@ -1,9 +1,10 @@
 """CPU model of the operand rounding in the tensor-core band DFT (csrc/kernels_tc.cu): the exact float64 product
-sum_n A[n] x[n] against (a) the 3xTF32 split Ahi*xhi + Alo*xhi + Ahi*xlo and (b) the production variant for the sample
-shape, Ahi*xhi in TF32 plus ONE fp16 pass [fp16(Alo) | fp16(Ahi 2^-11)] . [fp16(x) ; fp16((x - xhi) 2^11)].
+sum_n A[n] x[n] against (a) the 3xTF32 split Ahi*xhi + Alo*xhi + Ahi*xlo (SYLDET_KERNEL_TENSOR_TF32) and (b) the production
+variant for the sample shape: two-term fp16 splits of both operands, a1 = fp16(A), a2 = fp16(A - a1), h1 = fp16(x),
+h2 = fp16((x - h1) 2^11), as one K-concatenated pass [a1 | a1 2^-11 | a2] . [h1 ; h2 ; h1].
 Sums are taken in float64, so only the operand roundings are modelled (the tensor core adds float32 accumulation on top,
-which the GPU parity tests cover). The model pins the documented validity range of (b): float32-level down to rms ~1e-5,
-degrading as ~1e-11 / rms below, while (a) is amplitude-invariant."""
+which the GPU parity tests cover). The model pins the validity range of (b): float32-level down to rms ~1e-5, degrading as
+~1e-11 / rms below (where the kernel's range guard hands the launch to (a)), while (a) is amplitude-invariant."""
 import numpy as np
 import pytest
 
@@ -35,13 +36,14 @@ def _errors(a, x):
     # (a) 3xTF32: Alo rounded to tf32, xlo exact in fp32 (<= 13 significant bits, truncated to tf32 by the tensor core)
     a_lo32 = _tf32_round((a - a_hi).astype(np.float32)).astype(np.float64)
     tf32 = (a_hi * x_hi + a_lo32 * x_hi + a_hi * _tf32_trunc(x_lo.astype(np.float32)).astype(np.float64)).sum(axis=1)
-    # (b) TF32 + one fp16 pass
-    a_lo16 = (a - a_hi).astype(np.float32).astype(np.float16).astype(np.float64)
-    a_hi16 = (a_hi.astype(np.float32) * np.float32(2.0 ** -11)).astype(np.float16).astype(np.float64)
+    # (b) two-term fp16 splits (plan_tc put16 / the splitters' convert())
+    a1 = a.astype(np.float32).astype(np.float16)
+    a1s = (a1.astype(np.float32) * np.float32(2.0 ** -11)).astype(np.float16).astype(np.float64)
+    a2 = (a - a1.astype(np.float64)).astype(np.float32).astype(np.float16).astype(np.float64)
     with np.errstate(over="ignore", invalid="ignore"):
-        x16 = x.astype(np.float16).astype(np.float64)
-        xl16 = (x_lo.astype(np.float32) * np.float32(2048.0)).astype(np.float16).astype(np.float64)
-        f16 = (a_hi * x_hi + a_lo16 * x16 + a_hi16 * xl16).sum(axis=1)
+        h1 = x.astype(np.float16)
+        h2 = ((x - h1.astype(np.float32)) * np.float32(2048.0)).astype(np.float16).astype(np.float64)
+        f16 = (a1.astype(np.float64) * h1.astype(np.float64) + a1s * h2 + a2 * h1.astype(np.float64)).sum(axis=1)
     scale = np.sqrt((a * a).sum(axis=1) * (x.astype(np.float64) ** 2).sum(axis=1))   # |A| |x|: what the error terms scale with
     return np.abs(tf32 - exact) / scale, np.abs(f16 - exact) / scale
 

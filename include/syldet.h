@@ -50,7 +50,8 @@ enum { SYLDET_LAYOUT_PLANAR = 0, SYLDET_LAYOUT_INTERLEAVED = 1 };
 enum { SYLDET_DETECT_ANY_OUTPUT = 0,   /* TrackDetector.swift:71-77 (CLI rule)  */
        SYLDET_DETECT_FIRST_OUTPUT = 1  /* SyllableDetector.lastDetected :27-31 (live rule) */ };
 enum { SYLDET_PCM_F32 = 0, SYLDET_PCM_S16 = 1 };
-enum { SYLDET_KERNEL_AUTO = 0, SYLDET_KERNEL_GENERIC = 1, SYLDET_KERNEL_FUSED = 2, SYLDET_KERNEL_TENSOR = 3, SYLDET_KERNEL_TENSOR_TF32 = 4 };
+enum { SYLDET_KERNEL_AUTO = 0, SYLDET_KERNEL_GENERIC = 1, SYLDET_KERNEL_FUSED = 2, SYLDET_KERNEL_TENSOR = 3, SYLDET_KERNEL_TENSOR_TF32 = 4,
+       SYLDET_KERNEL_WIDE = 5 /* wide hidden layer as a 3xTF32 tcgen05 contraction over a high-overlap STFT (hop 4) */ };
 
 typedef struct syldet_config syldet_config;     /* SyllableDetectorConfig + NeuralNet                    */
 typedef struct syldet_batch syldet_batch;       /* TrackDetector + main.swift loop, many channels at once */
@@ -115,7 +116,8 @@ int64_t syldet_config_debounce_frames(const syldet_config *cfg, double seconds);
 syldet_status syldet_batch_create(const syldet_config *cfg, int device, syldet_batch **out);
 void syldet_batch_destroy(syldet_batch *b);
 /* SYLDET_KERNEL_AUTO picks the fastest kernel the configuration qualifies for: TENSOR (tcgen05 band DFT + fused epilogue),
- * FUSED (SIMT FFT + fused epilogue), else the GENERIC reference-order path.
+ * FUSED (SIMT FFT + fused epilogue), WIDE (two-layer networks with up to 1024 hidden units on a hop-4 STFT: the hidden layer as a
+ * 3xTF32 tcgen05 contraction), else the GENERIC reference-order path.
  * TENSOR computes the two correction products of its 3xTF32 band DFT in fp16 for the reference's sample network shape (l2normalize
  * first). That pass is at float32 level inside an amplitude window (no sample beyond +-32752; norm of the band-magnitude window
  * >= 2^-8, i.e. audio rms >~ 2e-5; any 16-bit PCM input qualifies by construction). The kernel checks the window on every

@@ -32,7 +32,8 @@ DETECT_ANY_OUTPUT, DETECT_FIRST_OUTPUT = 0, 1
 PCM_F32, PCM_S16 = 0, 1
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_FUSED, KERNEL_TENSOR = 0, 1, 2, 3
 KERNEL_TENSOR_TF32 = 4   # tensor kernel with all three DFT products in TF32 (amplitude-invariant; see include/syldet.h)
-KERNEL_NAMES = {1: "generic", 2: "fused", 3: "tensor"}
+KERNEL_WIDE = 5          # two-layer networks with a wide hidden layer on a hop-4 STFT: 3xTF32 tcgen05 contraction (kernels_wide.cu)
+KERNEL_NAMES = {1: "generic", 2: "fused", 3: "tensor", 4: "tensor_tf32", 5: "wide"}
 
 _STATUS = {1: "unableToOpenPath", 2: "missingValue", 3: "invalidValue", 4: "mismatchedLength", 5: "invalidConfiguration",
            6: "badArgument", 7: "cuda", 8: "outOfMemory", 9: "bufferOverflow", 10: "unsupported"}
@@ -286,7 +287,7 @@ class BatchDetector:
     def available_kernels(config, device=0):
         """Kernel selectors this configuration qualifies for, fastest first."""
         out = []
-        for k in (KERNEL_TENSOR, KERNEL_FUSED, KERNEL_GENERIC):
+        for k in (KERNEL_TENSOR, KERNEL_FUSED, KERNEL_WIDE, KERNEL_GENERIC):
             try:
                 BatchDetector(config, device, kernel=k)
                 out.append(k)

@@ -20,6 +20,7 @@ SOURCES = [
     ("kernels_generic.cu", ["-fmad=false"]),
     ("kernels_fused.cu", ["-Xptxas", "-v"]),
     ("kernels_tc.cu", ["-Xptxas", "-v"] + os.environ.get("SYLDET_TC_DEFS", "").split()),
+    ("kernels_wide.cu", ["-Xptxas", "-v"] + os.environ.get("SYLDET_WIDE_DEFS", "").split()),
 ]
 
 

@@ -267,6 +267,108 @@ TcPlan plan_tc(const Config &c, const FusedPlan &fused) {
 }
 
 // -----------------------------------------------------------------------------------------------------------------
+WidePlan plan_wide(const Config &c) {
+    WidePlan plan;
+    auto no = [&](const std::string &why) { plan.ok = false; plan.why = why; return plan; };
+    if (c.gap != 0 || c.hop != 4) return no("hop is not 4 samples (the sliding A operand needs 16-byte rows)");
+    if (c.layers.size() != 2) return no("not a two-layer network");
+    const int H = c.layers[0].outputs, I = c.inputs, O = c.outputs, T = c.time_range, L = c.band;
+    if (H < 16 || H > 1024) return no("hidden width outside [16, 1024]");
+    if (O > kFusedMaxOut) return no("more than 8 outputs");
+    if (T > wide_max_time_range()) return no("time range above 17");
+    if ((int)c.output_processing.size() > kMaxProcessing) return no("too many output processing functions");
+    if (c.fourier_length > 4096) return no("fourierLength above 4096 (shared-memory staging of stft_planes_kernel)");
+    WideParams &p = plan.params;
+    std::memset(&p, 0, sizeof p);
+    // input chain: [one per-window statistic]? followed by per-position affine maps: y_i = A_i (alpha x_i + beta) + C_i (as plan_fused)
+    p.window_stat = FUSED_STAT_NONE;
+    std::vector<double> A(I, 1.0), C(I, 0.0);
+    for (size_t k = 0; k < c.input_processing.size(); ++k) {
+        const Processing &pr = c.input_processing[k];
+        if (pr.function == SYLDET_PROC_MAPMINMAX || pr.function == SYLDET_PROC_MAPSTD) {
+            for (int i = 0; i < I; ++i) {
+                A[i] = A[i] * (double)pr.gains[i];
+                C[i] = (C[i] - (double)pr.x_offsets[i]) * (double)pr.gains[i] + (double)pr.y;
+            }
+        } else {
+            if (k != 0) return no("a per-window normaliser after another processing function");
+            if (pr.function == SYLDET_PROC_NORMALIZESTD) return no("normalizestd needs a second pass over the window");
+            p.window_stat = pr.function == SYLDET_PROC_L2NORMALIZE ? FUSED_STAT_L2 : FUSED_STAT_MINMAX;
+        }
+    }
+    p.time_range = T;
+    p.band = L;
+    const int planes = (L + 3) / 4;
+    p.n_planes = ((planes + kWidePL - 1) / kWidePL) * kWidePL;
+    p.hidden = H;
+    p.h_pad = ((H + 255) / 256) * 256;
+    p.n_out = O;
+    p.n_op = (int)c.output_processing.size();
+    p.tf0 = c.layers[0].transfer;
+    p.tf1 = c.layers[1].transfer;
+    for (int o = 0; o < O; ++o) p.b1[o] = c.layers[1].biases[o];
+    for (int k = 0; k < p.n_op; ++k) {
+        const Processing &pr = c.output_processing[k];
+        p.op_y[k] = pr.y;
+        for (int o = 0; o < O; ++o) {
+            p.op_gain[k * kFusedMaxOut + o] = pr.gains[o];
+            p.op_xoff[k * kFusedMaxOut + o] = pr.x_offsets[o];
+        }
+    }
+    for (int o = 0; o < O; ++o) {
+        float t = (float)c.thresholds[o];
+        if ((double)t < c.thresholds[o]) t = std::nextafterf(t, INFINITY);
+        p.thr_f[o] = t;
+    }
+    if (wide_smem_bytes(p.h_pad) > 227 * 1024) return no("shared-memory working set too large");
+    // folded constants
+    const Layer &l0 = c.layers[0], &l1 = c.layers[1];
+    plan.v.assign(p.h_pad, 0.0f);
+    plan.bprime.assign(p.h_pad, 0.0f);
+    std::vector<double> wf((size_t)H * I);
+    for (int h = 0; h < H; ++h) {
+        double v = 0.0, b = (double)l0.biases[h];
+        for (int i = 0; i < I; ++i) {
+            const double w = (double)l0.weights[(size_t)h * I + i];
+            wf[(size_t)h * I + i] = w * A[i];
+            v += w * A[i];
+            b += w * C[i];
+        }
+        plan.v[h] = (float)v;
+        plan.bprime[h] = (float)b;
+    }
+    plan.w1.assign((size_t)O * p.h_pad, 0.0f);
+    for (int o = 0; o < O; ++o)
+        for (int h = 0; h < H; ++h) plan.w1[(size_t)o * p.h_pad + h] = l1.weights[(size_t)o * H + h];
+    // weight blocks in streaming order: [pass nc][chunk c][t][hi | lo][plane q][n < 256][e < 4], input index i = t*L + f,
+    // f = (c*kWidePL + q)*4 + e (zero for f >= L and for padded hidden units)
+    const int n_nc = p.h_pad / 256, n_chunks = p.n_planes / kWidePL;
+    const size_t blk = wide_weight_block_bytes() / sizeof(float), half = blk / 2;
+    plan.weights.assign((size_t)n_nc * n_chunks * T * blk, 0.0f);
+    for (int nc = 0; nc < n_nc; ++nc)
+        for (int cch = 0; cch < n_chunks; ++cch)
+            for (int t = 0; t < T; ++t) {
+                float *dst = plan.weights.data() + ((size_t)(nc * n_chunks + cch) * T + t) * blk;
+                for (int q = 0; q < kWidePL; ++q)
+                    for (int n = 0; n < 256; ++n) {
+                        const int h = nc * 256 + n;
+                        if (h >= H) continue;
+                        for (int e = 0; e < 4; ++e) {
+                            const int f = (cch * kWidePL + q) * 4 + e;
+                            if (f >= L) continue;
+                            const double w = wf[(size_t)h * I + (size_t)t * L + f];
+                            const float hi = tf32_round(w);
+                            const size_t idx = ((size_t)q * 256 + n) * 4 + e;
+                            dst[idx] = hi;
+                            dst[half + idx] = tf32_round(w - (double)hi);
+                        }
+                    }
+            }
+    plan.ok = true;
+    return plan;
+}
+
+// -----------------------------------------------------------------------------------------------------------------
 syldet_status DeviceModel::init(const Config &cfg, int device) {
     cfg_ = cfg;
     if (!cfg_.valid) {
@@ -380,6 +482,17 @@ syldet_status DeviceModel::init(const Config &cfg, int device) {
             fused_.blocks_per_sm = blocks;
         }
     }
+    wide_ = plan_wide(cfg_);
+    if (wide_.ok) {
+        const size_t nw = wide_.weights.size(), nh = wide_.v.size(), n1 = wide_.w1.size();
+        st = d_wide_.reserve((nw + 2 * nh + n1) * sizeof(float));
+        if (st != SYLDET_OK) return st;
+        float *d = d_wide_.as<float>();
+        SYLDET_CUDA(cudaMemcpy(d, wide_.weights.data(), nw * sizeof(float), cudaMemcpyHostToDevice));
+        SYLDET_CUDA(cudaMemcpy(d + nw, wide_.v.data(), nh * sizeof(float), cudaMemcpyHostToDevice));
+        SYLDET_CUDA(cudaMemcpy(d + nw + nh, wide_.bprime.data(), nh * sizeof(float), cudaMemcpyHostToDevice));
+        SYLDET_CUDA(cudaMemcpy(d + nw + 2 * nh, wide_.w1.data(), n1 * sizeof(float), cudaMemcpyHostToDevice));
+    }
     tc_ = plan_tc(cfg_, fused_);
     if (tc_.ok) {
         const size_t n = tc_.dft_hi.size(), nw = tc_.wcat_hi.size();
@@ -440,8 +553,10 @@ Batch::~Batch() {
 
 syldet_status Batch::set_kernel(int kernel) {
     if (kernel != SYLDET_KERNEL_AUTO && kernel != SYLDET_KERNEL_GENERIC && kernel != SYLDET_KERNEL_FUSED && kernel != SYLDET_KERNEL_TENSOR &&
-        kernel != SYLDET_KERNEL_TENSOR_TF32)
+        kernel != SYLDET_KERNEL_TENSOR_TF32 && kernel != SYLDET_KERNEL_WIDE)
         return set_error(SYLDET_ERR_ARG, "unknown kernel selector");
+    if (kernel == SYLDET_KERNEL_WIDE && !model_.wide().ok)
+        return set_error(SYLDET_ERR_UNSUPPORTED, "wide-hidden tensor kernel not available for this configuration: " + model_.wide().why);
     if ((kernel == SYLDET_KERNEL_TENSOR || kernel == SYLDET_KERNEL_TENSOR_TF32) && !model_.tc().ok)
         return set_error(SYLDET_ERR_UNSUPPORTED, "tensor-core kernel not available for this configuration: " + model_.tc().why);
     if (kernel == SYLDET_KERNEL_FUSED && !model_.fused().ok)
@@ -451,7 +566,8 @@ syldet_status Batch::set_kernel(int kernel) {
 }
 
 int Batch::active_kernel() const {
-    if (kernel_ == SYLDET_KERNEL_AUTO) return model_.tc().ok ? SYLDET_KERNEL_TENSOR : model_.fused().ok ? SYLDET_KERNEL_FUSED : SYLDET_KERNEL_GENERIC;
+    if (kernel_ == SYLDET_KERNEL_AUTO)
+        return model_.tc().ok ? SYLDET_KERNEL_TENSOR : model_.fused().ok ? SYLDET_KERNEL_FUSED : model_.wide().ok ? SYLDET_KERNEL_WIDE : SYLDET_KERNEL_GENERIC;
     return kernel_;
 }
 
@@ -617,6 +733,56 @@ syldet_status Batch::launch_tc_range(const float *d_planar, int n_channels, int6
     return SYLDET_OK;
 }
 
+// Wide-hidden path: per time segment, stft_planes_kernel (band magnitudes as A-operand planes + column statistics) and then
+// wide_l0_kernel (3xTF32 tcgen05 contraction + the rest of the network + detection). The segment bounds the plane buffers.
+syldet_status Batch::launch_wide_range(const float *d_planar, int n_channels, int64_t ch_stride, int64_t eval_begin, int64_t eval_count,
+                                       int64_t evals_total, int detect_rule, float *d_all_outputs, EventSink sink, cudaStream_t stream) {
+    const Config &c = model_.config();
+    const WidePlan &wp = model_.wide();
+    const int T = c.time_range, P = wp.params.n_planes, tile = wide_tile_rows();
+    const int64_t budget = (int64_t)1 << 30;   // bytes of raw + lo planes per segment
+    int64_t seg = std::max<int64_t>(tile, budget / ((int64_t)n_channels * P * 16 * 2));
+    seg = (seg / tile) * tile;
+    for (int64_t e0 = eval_begin; e0 < eval_begin + eval_count; e0 += seg) {
+        const int64_t ne = std::min(seg, eval_begin + eval_count - e0), ncols = ne + T - 1;
+        const int64_t rows_alloc = ((ncols + kWideStftCols - 1) / kWideStftCols) * kWideStftCols + 4;
+        syldet_status st = wide_hi_.reserve((size_t)n_channels * P * rows_alloc * 16);
+        if (st != SYLDET_OK) return st;
+        st = wide_lo_.reserve((size_t)n_channels * P * rows_alloc * 16);
+        if (st != SYLDET_OK) return st;
+        st = wide_stats_.reserve((size_t)n_channels * rows_alloc * sizeof(float4));
+        if (st != SYLDET_OK) return st;
+        SYLDET_CUDA(launch_stft_planes(model_.dev_net(), c.fourier_length, c.window_length, c.hop, d_planar, ch_stride, n_channels, e0, ncols,
+                                       wide_hi_.as<float>(), wide_lo_.as<float>(), wide_stats_.as<float4>(), P, rows_alloc, stream));
+        if (debug_band_) {   // extractPower() values before the scaling: the same reference-order FFT, straight into the caller's buffer
+            SYLDET_CUDA(launch_stft_band_generic(model_.dev_net(), c.fourier_length, d_planar, ch_stride, n_channels, e0, ncols,
+                                                 debug_band_ + e0 * c.band, debug_cols_ * c.band, SYLDET_SCALING_LINEAR, stream));
+            launches_ += 1;
+        }
+        WideWork w{};
+        w.planes_hi = wide_hi_.as<float>();
+        w.planes_lo = wide_lo_.as<float>();
+        w.stats = wide_stats_.as<float4>();
+        w.rows_alloc = rows_alloc;
+        w.n_cols = ncols;
+        w.n_evals = ne;
+        w.n_channels = n_channels;
+        w.detect_rule = detect_rule;
+        w.eval_offset = e0;
+        w.out_evals_per_channel = evals_total;
+        w.all_out = d_all_outputs;
+        w.sink = sink;
+        w.weights = model_.wide_weights();
+        w.v = model_.wide_v();
+        w.bprime = model_.wide_bprime();
+        w.w1 = model_.wide_w1();
+        const int64_t tiles = (int64_t)n_channels * ((ne + tile - 1) / tile);
+        SYLDET_CUDA(launch_wide((int)std::min<int64_t>(tiles, model_.sm_count()), wp.params, w, stream));
+        launches_ += 2;
+    }
+    return SYLDET_OK;
+}
+
 syldet_status Batch::launch_planar(const float *d_planar, int n_channels, int64_t n_samples, int64_t ch_stride,
                                    const float *valid_begin, const float *valid_end, int detect_rule, float *d_all_outputs,
                                    cudaStream_t stream) {
@@ -657,6 +823,8 @@ syldet_status Batch::launch_planar_range(const float *d_planar, int n_channels, 
     if (kernel == SYLDET_KERNEL_FUSED)
         return launch_fused_range(d_planar, n_channels, ch_stride, valid_begin, valid_end, eval_begin, eval_count, E, detect_rule,
                                   d_all_outputs, sink, stream);
+    if (kernel == SYLDET_KERNEL_WIDE)
+        return launch_wide_range(d_planar, n_channels, ch_stride, eval_begin, eval_count, E, detect_rule, d_all_outputs, sink, stream);
 
     // generic two-kernel path, segmented in time so the band-feature buffer stays bounded
     const int L = c.band, T = c.time_range;

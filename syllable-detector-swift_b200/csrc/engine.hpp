@@ -66,6 +66,17 @@ struct TcPlan {
 };
 TcPlan plan_tc(const Config &cfg, const FusedPlan &fused);
 
+// Wide-hidden tensor path (kernels_wide.cu): two-layer networks on a hop-4 STFT; layer 0 as a 3xTF32 tcgen05 contraction.
+struct WidePlan {
+    bool ok = false;
+    std::string why;
+    WideParams params{};
+    std::vector<float> weights;   // blocks [pass][chunk][t][hi | lo][plane][256][4] of the folded layer-0 weights (tf32 hi / lo)
+    std::vector<float> v, bprime; // [h_pad]
+    std::vector<float> w1;        // [n_out][h_pad]
+};
+WidePlan plan_wide(const Config &cfg);
+
 // Device-resident copy of one configuration (weights, window, twiddles, DevNet record).
 class DeviceModel {
 public:
@@ -81,6 +92,11 @@ public:
     int max_width() const { return max_width_; }
     const FusedPlan &fused() const { return fused_; }
     const TcPlan &tc() const { return tc_; }
+    const WidePlan &wide() const { return wide_; }
+    const float *wide_weights() const { return d_wide_.as<float>(); }
+    const float *wide_v() const { return d_wide_.as<float>() + wide_.weights.size(); }
+    const float *wide_bprime() const { return wide_v() + wide_.v.size(); }
+    const float *wide_w1() const { return wide_bprime() + wide_.bprime.size(); }
     const float *dft_hi() const { return d_dft_.as<float>(); }
     const float *dft_lo() const { return d_dft_.as<float>() + 128 * (size_t)tc_k_pad(); }
     const float *wcat_hi() const { return d_dft_.as<float>() + 2 * 128 * (size_t)tc_k_pad(); }
@@ -93,7 +109,8 @@ public:
 private:
     Config cfg_;
     int device_ = -1, max_width_ = 0, sm_count_ = 148;
-    DeviceBuffer d_blob_, d_net_, d_dft_;
+    DeviceBuffer d_blob_, d_net_, d_dft_, d_wide_;
+    WidePlan wide_;
     size_t blob_bytes_ = 0;
     TcPlan tc_;
     const float *d_window_ = nullptr;
@@ -159,6 +176,8 @@ private:
                                       int detect_rule, float *d_all_outputs, bool reset_sink, cudaStream_t stream);
     syldet_status ensure_pipeline(int slices, size_t event_bytes);
     syldet_status settle(unsigned long long *n_events);
+    syldet_status launch_wide_range(const float *d_planar, int n_channels, int64_t ch_stride, int64_t eval_begin, int64_t eval_count,
+                                    int64_t evals_total, int detect_rule, float *d_all_outputs, EventSink sink, cudaStream_t stream);
 
     DeviceModel model_;
     int kernel_ = SYLDET_KERNEL_AUTO;
@@ -174,6 +193,7 @@ private:
     size_t h_events_bytes_ = 0;
     int64_t slice_evals_ = 256 * 1024;
     DeviceBuffer planar_, feat_, sink_count_, sink_events_, sink_outputs_, staging_;
+    DeviceBuffer wide_hi_, wide_lo_, wide_stats_;   // band-magnitude planes + column statistics of one time segment (wide path)
     unsigned long long sink_capacity_ = 0;
     int64_t launches_ = 0;
     float *debug_band_ = nullptr;

@@ -153,6 +153,48 @@ bool tc_layout_fits(int time_range, int n0);
 cudaError_t launch_tc(int hp, int grid, size_t smem, const FusedParams &p, const TcWork &w, const void *tmap_main,
                       const void *tmap_tail, cudaStream_t stream);
 
+// ---- wide-hidden tensor path: kernels_wide.cu (+ stft_planes_kernel in kernels_generic.cu) -----------------------------------
+constexpr int kWidePL = 6;           // planes (of 4 bins) per K chunk: 24 inputs per (chunk, column offset) step
+constexpr int kWideStftCols = 64;    // STFT columns per CTA of stft_planes_kernel (they share one staged audio span)
+
+// Passed by value in kernel parameter space.
+struct alignas(16) WideParams {
+    int time_range, band, n_planes;  // n_planes = ceil(band / 4) rounded up to a multiple of kWidePL
+    int hidden, h_pad;               // h_pad = hidden rounded up to a multiple of 256 (accumulator passes of 256 columns)
+    int n_out, n_op, window_stat;    // FUSED_STAT_NONE / _L2 / _MINMAX
+    int tf0, tf1, reserved0, reserved1;
+    float b1[kFusedMaxOut];          // output-layer biases
+    float op_y[kMaxProcessing];
+    float op_gain[kMaxProcessing * kFusedMaxOut];
+    float op_xoff[kMaxProcessing * kFusedMaxOut];
+    float thr_f[kFusedMaxOut];       // smallest float >= threshold
+};
+
+struct WideWork {
+    const float *planes_hi, *planes_lo;  // [n_channels][n_planes][rows_alloc][4]: band magnitudes, raw and (v - tf32(v))
+    const float4 *stats;                 // [n_channels][rows_alloc]: per column {sum x^2, min, max, -}
+    int64_t rows_alloc;                  // row pitch of the planes / statistics
+    int64_t n_cols;                      // magnitude rows that exist (n_evals + T - 1)
+    int64_t n_evals;                     // evaluations of this launch per channel
+    int n_channels;
+    int detect_rule;
+    int64_t eval_offset, out_evals_per_channel;
+    float *all_out;
+    EventSink sink;
+    const float *weights;                // pre-arranged blocks, see plan_wide: [pass of 256 hidden units][chunk][t][hi | lo][plane][256][4]
+    const float *v, *bprime;             // [h_pad] folded layer-0 constants: z = acc * alpha + beta * V + B'
+    const float *w1;                     // [n_out][h_pad] output-layer weights
+};
+size_t wide_smem_bytes(int h_pad);
+int wide_tile_rows();
+int wide_max_time_range();
+size_t wide_weight_block_bytes();
+cudaError_t launch_wide(int grid, const WideParams &p, const WideWork &w, cudaStream_t stream);
+size_t stft_planes_smem(int fft_len, int win_len, int hop, int n_planes);
+cudaError_t launch_stft_planes(const DevNet *d_net, int fft_len, int win_len, int hop, const float *pcm, int64_t ch_stride, int n_channels,
+                               int64_t col0, int64_t n_cols, float *hi, float *lo, float4 *stats, int n_planes, int64_t rows_alloc,
+                               cudaStream_t stream);
+
 bool fused_supports_fft(int fft_len);
 size_t fused_smem_bytes(int fft_len, const FusedParams &p);
 cudaError_t launch_fused(const FusedLaunch &cfg, const FusedParams &p, const FusedWork &w, cudaStream_t stream);

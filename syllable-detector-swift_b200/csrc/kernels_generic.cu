@@ -134,6 +134,71 @@ __global__ void stft_band_generic_kernel(const DevNet *__restrict__ netp, const 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// High-overlap STFT for the wide-hidden tensor path (kernels_wide.cu): a CTA stages the audio span of kWideStftCols consecutive
+// columns in shared memory ONCE (with hop 4 and a 1024-sample window, 64 columns share 1276 samples instead of reading 65 536), each
+// warp then runs the reference-order FFT (stft_band_column) on frames of that span. The band magnitudes (after the spectrogram
+// scaling) leave the kernel in the layout the tensor kernel's A operand wants: planes of 4 bins, [plane][row][4] float32, as a raw
+// part (the tensor core truncates it to tf32) and a lo part (v - tf32(v)); plus per-column statistics for the per-window normalisers.
+__device__ __forceinline__ float tf32_trunc_g(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+__global__ void __launch_bounds__(256) stft_planes_kernel(const DevNet *__restrict__ netp, const float *__restrict__ pcm, int64_t ch_stride,
+                                                          int64_t col0, int64_t n_cols, float *__restrict__ hi, float *__restrict__ lo,
+                                                          float4 *__restrict__ stats, int n_planes, int64_t rows_alloc) {
+    extern __shared__ float smem[];
+    const DevNet &net = *netp;
+    const int N = net.fft_len, M = N / 2, L = net.band, W = net.win_len, hop = net.hop;
+    const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+    const int pitch = n_planes * 4 + 1;                       // output tile row pitch (odd: conflict-free column reads)
+    const int span = (kWideStftCols - 1) * hop + W;
+    float *audio = smem;                                       // [span]
+    float *tile = audio + ((span + 3) & ~3);                   // [kWideStftCols][pitch]
+    float *fft = tile + kWideStftCols * pitch;                 // [8 warps][N]
+    float *zr = fft + (size_t)warp * N, *zi = zr + M;
+    const int ch = blockIdx.y;
+    const int64_t c_first = (int64_t)blockIdx.x * kWideStftCols;
+    const int cols = (int)min((int64_t)kWideStftCols, n_cols - c_first);
+    const float *src = pcm + (int64_t)ch * ch_stride + (col0 + c_first) * hop + net.gap;
+    const int need = (cols - 1) * hop + W;
+    for (int i = threadIdx.x; i < need; i += blockDim.x) audio[i] = src[i];
+    for (int i = threadIdx.x; i < kWideStftCols * pitch; i += blockDim.x) tile[i] = 0.0f;   // padding bins and missing columns read as 0
+    __syncthreads();
+    const int bits = log2_ceil(M);
+    for (int c = warp; c < cols; c += blockDim.x / kWarp) {
+        const float *fr = audio + c * hop;
+        float *row = tile + c * pitch;
+        stft_band_column(net, [&](int m) { return fr[m]; }, zr, zi, lane, bits, row, net.scaling);
+        __syncwarp();
+        float ss = 0.0f, mn = INFINITY, mx = -INFINITY;
+        for (int f = lane; f < L; f += kWarp) {
+            const float v = row[f];
+            ss += v * v;
+            mn = fminf(mn, v);
+            mx = fmaxf(mx, v);
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            ss += __shfl_xor_sync(0xffffffffu, ss, d);
+            mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, d));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+        }
+        if (lane == 0) stats[(int64_t)ch * rows_alloc + c_first + c] = make_float4(ss, mn, mx, 0.0f);
+    }
+    __syncthreads();
+    float4 *hi4 = reinterpret_cast<float4 *>(hi) + (int64_t)ch * n_planes * rows_alloc + c_first;
+    float4 *lo4 = reinterpret_cast<float4 *>(lo) + (int64_t)ch * n_planes * rows_alloc + c_first;
+    for (int i = threadIdx.x; i < n_planes * kWideStftCols; i += blockDim.x) {
+        const int pl = i / kWideStftCols, r = i % kWideStftCols;   // consecutive threads: consecutive rows of one plane (16 B each)
+        if (r < cols) {
+            const float *v = tile + r * pitch + pl * 4;
+            const float4 raw = make_float4(v[0], v[1], v[2], v[3]);
+            hi4[(int64_t)pl * rows_alloc + r] = raw;
+            lo4[(int64_t)pl * rows_alloc + r] = make_float4(raw.x - tf32_trunc_g(raw.x), raw.y - tf32_trunc_g(raw.y), raw.z - tf32_trunc_g(raw.z),
+                                                            raw.w - tf32_trunc_g(raw.w));
+        }
+    }
+}
+
 // x[i] = f(i, x[i]) for the lane's elements, eight at a time: all loads of a batch are issued before its first store (the
 // compiler cannot reorder them itself, x may alias whatever f reads).
 template <class F>
@@ -583,6 +648,23 @@ cudaError_t launch_stft_band_generic(const DevNet *d_net, int fft_len, const flo
     if (bx > cap) bx = cap;
     dim3 grid((unsigned)bx, (unsigned)n_channels);
     stft_band_generic_kernel<<<grid, warps * 32, smem, stream>>>(d_net, pcm, ch_stride, col0, n_cols, feat, feat_ch_pitch, scaling_override);
+    return cudaGetLastError();
+}
+
+size_t stft_planes_smem(int fft_len, int win_len, int hop, int n_planes) {
+    const int span = (kWideStftCols - 1) * hop + win_len;
+    return sizeof(float) * ((size_t)((span + 3) & ~3) + (size_t)kWideStftCols * (n_planes * 4 + 1) + (size_t)8 * fft_len);
+}
+
+cudaError_t launch_stft_planes(const DevNet *d_net, int fft_len, int win_len, int hop, const float *pcm, int64_t ch_stride, int n_channels,
+                               int64_t col0, int64_t n_cols, float *hi, float *lo, float4 *stats, int n_planes, int64_t rows_alloc,
+                               cudaStream_t stream) {
+    if (n_cols <= 0 || n_channels <= 0) return cudaSuccess;
+    const size_t smem = stft_planes_smem(fft_len, win_len, hop, n_planes);
+    cudaError_t e = cudaFuncSetAttribute(stft_planes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid((unsigned)((n_cols + kWideStftCols - 1) / kWideStftCols), (unsigned)n_channels);
+    stft_planes_kernel<<<grid, 256, smem, stream>>>(d_net, pcm, ch_stride, col0, n_cols, hi, lo, stats, n_planes, rows_alloc);
     return cudaGetLastError();
 }
 

@@ -1,0 +1,292 @@
+// Wide-hidden tensor path (sm_100a): NeuralNetLayer.apply of layer 0 (Common/NeuralNet.swift:366-377) for networks whose hidden
+// layer makes it a real dense contraction - BASELINE config 4: FFT 1024, hop 4, 162 bins x 8 columns = 1296 inputs -> 256..1024
+// hidden units - as a 3xTF32 tcgen05 GEMM with the accumulator in TMEM, followed in the same kernel by the rest of
+// NeuralNet.apply (:294-326: window normaliser folded into a per-row scale / offset, transfer function, output layer, reverse output
+// maps) and the threshold test of TrackDetector.process (SyllableDetectorCLI/TrackDetector.swift:71-77).
+//
+//   Z[j][h] = sum_{t < T} sum_{f < L} m[j + t][f] * W'[h][t*L + f]          m = band magnitudes (stft_planes_kernel), W' = folded weights
+//
+// The A operand is never materialised: row j of the [evaluations x T*L] input matrix is T consecutive rows of the magnitude matrix
+// (the sliding feature window of SyllableDetector.processNewValue, Common/SyllableDetector.swift:153-217). The magnitudes sit in
+// shared memory as planes of 4 bins, [plane][row][16 B] - the canonical no-swizzle K-major UMMA layout (core matrix = 8 rows x 16 B,
+// contiguous) - so the operand of column offset t is the SAME bytes with the start address advanced by t rows (16 t bytes): an
+// implicit im2col along time at zero cost. K runs over (chunk of kWidePL planes, t, plane); the magnitudes of a chunk are loaded once
+// per tile and used by all T offsets, the weights stream through a two-stage ring of pre-arranged blocks (one cp.async.bulk each).
+//   per tile: 256 evaluations (two M = 128 accumulators of N = 256 columns: all 512 TMEM columns), so that every weight block that
+//   crosses L2 -> shared memory feeds 2 x 128 rows (the weight stream is what bounds this kernel after the tensor pipe).
+// Roles: warp 0 loader (cp.async.bulk), warp 1 MMA issuer + TMEM, warps 2-5 epilogue (one per TMEM lane quadrant; a thread owns one
+// row of each accumulator, i.e. two evaluations, so the output layer needs no cross-lane reduction).
+#include <cuda.h>
+
+#include "fused_epilogue.cuh"
+#include "ptx_sm100.cuh"
+
+namespace syldet {
+
+namespace {
+
+constexpr int kWThreads = 6 * 32;
+constexpr int kWTileRows = 256;                     // evaluations per tile (2 accumulators x 128 TMEM lanes)
+constexpr int kWRowsPad = kWTileRows + 16;          // magnitude rows in shared memory: tile + T - 1 (T <= 17)
+constexpr int kWN = 256;                            // hidden units per accumulator pass
+constexpr int kWPlaneA = kWRowsPad * 16;            // bytes of one A plane
+constexpr int kWPlaneW = kWN * 16;                  // bytes of one weight plane
+constexpr int kWABytes = 2 * kWidePL * kWPlaneA;    // one A buffer: raw | lo
+constexpr int kWWBytes = 2 * kWidePL * kWPlaneW;    // one weight stage: hi | lo
+constexpr int kWTmemCols = 512;
+
+struct WideSmem {
+    static constexpr int a0 = 0, a1 = kWABytes, w0 = 2 * kWABytes, w1 = w0 + kWWBytes, vb = w1 + kWWBytes;   // then float2 vb[h_pad], barriers
+    __host__ __device__ static constexpr int bars(int h_pad) { return vb + h_pad * 8; }
+    __host__ __device__ static constexpr int total(int h_pad) { return bars(h_pad) + 128; }
+};
+static_assert(kWABytes % 128 == 0 && kWWBytes % 128 == 0, "alignment of the operand buffers");
+
+// Shared-memory matrix descriptor, K-major, no swizzle (cute::UMMA canonical layout ((8,n),2):((1,SBO),LBO) in 16-byte units):
+// core matrix = 8 rows x 16 B contiguous; lbo = bytes between the two core matrices of a K step, sbo = bytes between 8-row groups.
+__device__ __forceinline__ uint64_t smem_desc_nosw(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
+           ((uint64_t)1 << 46);
+}
+
+__global__ void __launch_bounds__(kWThreads, 1) wide_l0_kernel(const __grid_constant__ WideParams p, const WideWork w) {
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    unsigned char *smem = smem_dyn + ((128u - (ptx::smem_addr(smem_dyn) & 127u)) & 127u);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int T = p.time_range, n_nc = p.h_pad / kWN, n_chunks = p.n_planes / kWidePL;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + WideSmem::bars(p.h_pad));
+    uint64_t *a_full = bars, *a_empty = bars + 2, *w_full = bars + 4, *w_empty = bars + 6, *acc_full = bars + 8, *acc_empty = bars + 9;
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 10);
+    float2 *vb = reinterpret_cast<float2 *>(smem + WideSmem::vb);
+
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&a_full[i], 1);
+            ptx::mbar_init(&a_empty[i], 1);
+            ptx::mbar_init(&w_full[i], 1);
+            ptx::mbar_init(&w_empty[i], 1);
+        }
+        ptx::mbar_init(acc_full, 1);
+        ptx::mbar_init(acc_empty, 4);
+        ptx::fence_mbar_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(tmem_ptr, kWTmemCols);
+        ptx::tmem_relinquish();
+    }
+    for (int h = tid; h < p.h_pad; h += kWThreads) vb[h] = make_float2(__ldg(w.v + h), __ldg(w.bprime + h));
+    // rows of the A buffers that no copy fills (the tail of the last tile of a channel) must hold finite values
+    for (int i = tid; i < 2 * kWABytes / 16; i += kWThreads) reinterpret_cast<float4 *>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ptx::fence_proxy_async_smem();
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    const int tiles_per_ch = (int)((w.n_evals + kWTileRows - 1) / kWTileRows);
+    const int n_tiles = tiles_per_ch * w.n_channels;
+
+    if (warp == 0) {
+        // ================================ loader ======================================================================
+        if (ptx::elect_one()) {
+            uint32_t a_use = 0, w_use = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int ch = tile / tiles_per_ch;
+                const int64_t j0 = (int64_t)(tile - ch * tiles_per_ch) * kWTileRows;
+                const int64_t rows_left = w.n_cols - j0;                       // magnitude rows that exist from j0 on
+                const int rows = (int)min((int64_t)(kWTileRows + T - 1), rows_left);
+                const float *hi = w.planes_hi + ((int64_t)ch * p.n_planes * w.rows_alloc + j0) * 4;
+                const float *lo = w.planes_lo + ((int64_t)ch * p.n_planes * w.rows_alloc + j0) * 4;
+                for (int nc = 0; nc < n_nc; ++nc) {
+                    for (int c = 0; c < n_chunks; ++c, ++a_use) {
+                        const int ab = a_use & 1;
+                        ptx::mbar_wait(&a_empty[ab], ((a_use >> 1) & 1) ^ 1);
+                        unsigned char *dst = smem + (ab ? WideSmem::a1 : WideSmem::a0);
+                        ptx::mbar_expect_tx(&a_full[ab], 2u * kWidePL * (uint32_t)rows * 16u);
+                        for (int q = 0; q < kWidePL; ++q) {
+                            const int64_t off = (int64_t)(c * kWidePL + q) * w.rows_alloc * 4;
+                            ptx::bulk_copy_g2s(dst + q * kWPlaneA, hi + off, (uint32_t)rows * 16u, &a_full[ab]);
+                            ptx::bulk_copy_g2s(dst + (kWidePL + q) * kWPlaneA, lo + off, (uint32_t)rows * 16u, &a_full[ab]);
+                        }
+                        for (int t = 0; t < T; ++t, ++w_use) {
+                            const int ws = w_use & 1;
+                            ptx::mbar_wait(&w_empty[ws], ((w_use >> 1) & 1) ^ 1);
+                            ptx::mbar_expect_tx(&w_full[ws], kWWBytes);
+                            const unsigned char *blk = reinterpret_cast<const unsigned char *>(w.weights) +
+                                                       (size_t)((nc * n_chunks + c) * T + t) * kWWBytes;
+                            ptx::bulk_copy_g2s(smem + (ws ? WideSmem::w1 : WideSmem::w0), blk, kWWBytes, &w_full[ws]);
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ==================================================================
+        if (ptx::elect_one()) {
+            constexpr uint32_t idesc = ptx::idesc_tf32(128, kWN);
+            const uint32_t a_base0 = ptx::smem_addr(smem + WideSmem::a0), a_base1 = ptx::smem_addr(smem + WideSmem::a1);
+            const uint32_t w_base0 = ptx::smem_addr(smem + WideSmem::w0), w_base1 = ptx::smem_addr(smem + WideSmem::w1);
+            uint32_t a_use = 0, w_use = 0, acc_use = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int nc = 0; nc < n_nc; ++nc, ++acc_use) {
+                    ptx::mbar_wait(acc_empty, (acc_use & 1) ^ 1);       // the epilogue has read the previous accumulators
+                    ptx::tc_fence_after();
+                    uint32_t acc = 0;
+                    for (int c = 0; c < n_chunks; ++c, ++a_use) {
+                        const int ab = a_use & 1;
+                        ptx::mbar_wait(&a_full[ab], (a_use >> 1) & 1);
+                        for (int t = 0; t < T; ++t, ++w_use) {
+                            const int ws = w_use & 1;
+                            ptx::mbar_wait(&w_full[ws], (w_use >> 1) & 1);
+                            ptx::tc_fence_after();
+#pragma unroll 1
+                            for (int half = 0; half < 2; ++half) {
+                                const uint32_t d = tmem_base + half * kWN;
+                                const uint32_t a_row = (ab ? a_base1 : a_base0) + (uint32_t)(half * 128 + t) * 16u;
+                                uint32_t accf = acc;
+#pragma unroll 1
+                                for (int pass = 0; pass < 3; ++pass) {      // raw x hi | lo x hi | raw x lo   (3xTF32)
+                                    const uint32_t a_part = a_row + (pass == 1 ? kWidePL * kWPlaneA : 0);
+                                    const uint32_t w_part = (ws ? w_base1 : w_base0) + (pass == 2 ? kWidePL * kWPlaneW : 0);
+#pragma unroll
+                                    for (int ks = 0; ks < kWidePL / 2; ++ks) {
+                                        ptx::mma_tf32_ss(d, smem_desc_nosw(a_part + 2 * ks * kWPlaneA, kWPlaneA, 128),
+                                                         smem_desc_nosw(w_part + 2 * ks * kWPlaneW, kWPlaneW, 128), idesc, accf);
+                                        accf = 1;
+                                    }
+                                }
+                            }
+                            acc = 1;
+                            ptx::mma_commit(&w_empty[ws]);
+                        }
+                        ptx::mma_commit(&a_empty[ab]);
+                    }
+                    ptx::mma_commit(acc_full);
+                }
+            }
+        }
+    } else {
+        // ================================ epilogue ====================================================================
+        const int quad = warp & 3;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+        const int n_out = p.n_out;
+        uint32_t acc_use = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int ch = tile / tiles_per_ch;
+            const int64_t j0 = (int64_t)(tile - ch * tiles_per_ch) * kWTileRows;
+            // this thread's two evaluations: rows quad*32 + lane of each accumulator
+            float inv[2], beta[2], out[2][kFusedMaxOut];
+            bool valid[2];
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int64_t j = j0 + half * 128 + quad * 32 + lane;
+                valid[half] = j < w.n_evals;
+                inv[half] = 1.0f;
+                beta[half] = 0.0f;
+                if (valid[half] && p.window_stat != FUSED_STAT_NONE) {      // window statistic from the per-column partials
+                    const float4 *st = w.stats + (int64_t)ch * w.rows_alloc + j;
+                    float s0 = p.window_stat == FUSED_STAT_L2 ? 0.0f : INFINITY, s1 = -INFINITY;
+                    for (int t = 0; t < T; ++t) {
+                        const float4 c4 = __ldg(st + t);
+                        if (p.window_stat == FUSED_STAT_L2) s0 += c4.x;
+                        else { s0 = fminf(s0, c4.y); s1 = fmaxf(s1, c4.z); }
+                    }
+                    if (p.window_stat == FUSED_STAT_L2) inv[half] = rcp_fast(sqrt_fast(s0));   // silence: 0 * inf = NaN (NeuralNet.swift:47-59)
+                    else {
+                        const float range = s1 - s0;
+                        if (0 == range) { inv[half] = 0.0f; beta[half] = -1.0f; }               // flat window (NeuralNet.swift:84-88)
+                        else { inv[half] = 2.0f / range; beta[half] = (0 - s0 - s1) / range; }
+                    }
+                }
+#pragma unroll
+                for (int o = 0; o < kFusedMaxOut; ++o) out[half][o] = o < n_out ? p.b1[o] : 0.0f;
+            }
+            for (int nc = 0; nc < n_nc; ++nc, ++acc_use) {
+                ptx::mbar_wait(acc_full, acc_use & 1);
+                ptx::tc_fence_after();
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+#pragma unroll 1
+                    for (int cb = 0; cb < kWN / 32; ++cb) {
+                        uint32_t r[32];
+                        ptx::tmem_ld_x32(lane_addr + half * kWN + cb * 32, r);
+                        ptx::tc_wait_ld();
+                        const int h0 = nc * kWN + cb * 32;
+                        if (h0 < p.hidden) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) {
+                                const int h = h0 + i;
+                                const float2 c2 = vb[h];
+                                const float a = transfer_fast(p.tf0, fmaf(__uint_as_float(r[i]), inv[half], fmaf(beta[half], c2.x, c2.y)));
+                                const float *w1 = w.w1 + h;                  // [n_out][h_pad]; padded hidden units have zero weights
+#pragma unroll
+                                for (int o = 0; o < kFusedMaxOut; ++o)
+                                    if (o < n_out) out[half][o] = fmaf(__ldg(w1 + (size_t)o * p.h_pad), a, out[half][o]);
+                            }
+                        }
+                    }
+                }
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(acc_empty);
+            }
+            // output transfer, reverse maps in index order (NeuralNet.swift:316-323), threshold test, events
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                bool hit = false;
+                const int64_t j = j0 + half * 128 + quad * 32 + lane;
+#pragma unroll
+                for (int o = 0; o < kFusedMaxOut; ++o) {
+                    if (o < n_out) {
+                        float v = transfer_fast(p.tf1, out[half][o]);
+                        for (int k = 0; k < p.n_op; ++k) v = (v + (0 - p.op_y[k])) / p.op_gain[k * kFusedMaxOut + o] + p.op_xoff[k * kFusedMaxOut + o];
+                        out[half][o] = v;
+                        if (v >= p.thr_f[o] && (w.detect_rule == SYLDET_DETECT_ANY_OUTPUT || o == 0)) hit = true;   // NaN -> false
+                    }
+                }
+                hit = hit && valid[half];
+                if (valid[half] && w.all_out) {
+                    float *dst = w.all_out + ((int64_t)ch * w.out_evals_per_channel + w.eval_offset + j) * n_out;
+#pragma unroll
+                    for (int o = 0; o < kFusedMaxOut; ++o)
+                        if (o < n_out) dst[o] = out[half][o];
+                }
+                const unsigned hits = __ballot_sync(0xffffffffu, hit);
+                if (hits) {
+                    unsigned long long base = 0;
+                    if (lane == 0) base = atomicAdd(w.sink.count, (unsigned long long)__popc(hits));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (hit) {
+                        const unsigned long long idx = base + __popc(hits & ((1u << lane) - 1));
+                        if (idx < w.sink.capacity) {
+                            w.sink.events[idx] = DevEvent{ch, 0, w.eval_offset + j};
+#pragma unroll
+                            for (int o = 0; o < kFusedMaxOut; ++o)
+                                if (o < n_out) w.sink.outputs[idx * n_out + o] = out[half][o];
+                        }
+                    }
+                }
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) ptx::tmem_dealloc(tmem_base, kWTmemCols);
+}
+
+}  // namespace
+
+size_t wide_smem_bytes(int h_pad) { return 128 + WideSmem::total(h_pad); }
+int wide_tile_rows() { return kWTileRows; }
+int wide_max_time_range() { return kWRowsPad - kWTileRows + 1; }
+size_t wide_weight_block_bytes() { return kWWBytes; }
+
+cudaError_t launch_wide(int grid, const WideParams &p, const WideWork &w, cudaStream_t stream) {
+    const size_t smem = wide_smem_bytes(p.h_pad);
+    cudaError_t e = cudaFuncSetAttribute(wide_l0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    wide_l0_kernel<<<grid, kWThreads, smem, stream>>>(p, w);
+    return cudaGetLastError();
+}
+
+}  // namespace syldet

@@ -39,7 +39,7 @@ def test_python_constants_mirror_the_header_enums(sd):
             assert getattr(sd, name) == int(value), name
             checked += 1
     assert checked >= 10
-    for name in ("KERNEL_AUTO", "KERNEL_GENERIC", "KERNEL_FUSED", "KERNEL_TENSOR", "KERNEL_TENSOR_TF32"):
+    for name in ("KERNEL_AUTO", "KERNEL_GENERIC", "KERNEL_FUSED", "KERNEL_TENSOR", "KERNEL_TENSOR_TF32", "KERNEL_WIDE"):
         assert hasattr(sd, name), name
 
 

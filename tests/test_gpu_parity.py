@@ -287,8 +287,8 @@ def test_spectra_generated_configs(sd, oracle_mod, cw, kw):
 
 def test_high_overlap_wide_hidden_config(sd, oracle_mod, cw):
     """BASELINE config 4 shape: FFT 1024, hop 4, band 1-8 kHz (L = 162), T = 8 (1296 inputs), 256 tansig units, 2 outputs.
-    Too wide for the fused kernels: the reference-order kernels take it. Left-to-right sums over 1296 terms: same order in
-    the oracle, so the usual tolerance holds."""
+    Too wide for the fused kernels: AUTO takes the wide-hidden tensor path (layer 0 as a 3xTF32 tcgen05 contraction over the sliding
+    feature window, kernels_wide.cu); the reference-order kernels remain selectable and agree with it."""
     text = cw.random_config(seed=21, fft_len=1024, overlap=1020, freq_range=(1000.0, 8000.0), time_range=8, hidden=(256,),
                             outputs=2, threshold=0.2)
     c = sd.SyllableDetectorConfig.from_text(text).validate()
@@ -299,13 +299,43 @@ def test_high_overlap_wide_hidden_config(sd, oracle_mod, cw):
     t = np.arange(n)
     x = np.stack([(0.05 * rng.standard_normal(n) + 0.3 * np.sin(2 * np.pi * f0 * t / 44100)).astype(np.float32) for f0 in (3000.0, 6100.0)])
     det = sd.BatchDetector(c)
-    assert det.active_kernel == sd.KERNEL_GENERIC
-    ev, outs = det.run(x, want_outputs=True)
-    assert outs.shape[1] == 701
-    for ch in range(2):
+    assert det.active_kernel == sd.KERNEL_WIDE
+    assert sd.BatchDetector.available_kernels(c) == [sd.KERNEL_WIDE, sd.KERNEL_GENERIC]
+    for kernel in (sd.KERNEL_WIDE, sd.KERNEL_GENERIC):
+        ev, outs = sd.BatchDetector(c, kernel=kernel).run(x, want_outputs=True)
+        assert outs.shape[1] == 701
+        for ch in range(2):
+            ref = o.run(x[ch])[0]
+            scale = max(1.0, float(np.nanmax(np.abs(ref))))
+            _check_channel(o, x[ch], outs[ch], ev.sample[ev.channel == ch], TOL_OUT * scale)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(fft_len=1024, overlap=1020, freq_range=(1000.0, 8000.0), time_range=8, hidden=(600,), outputs=1, input_funcs=("normalize", "mapminmax"), transfer="LogSig"),   # 3 accumulator passes, min/max statistic
+    dict(fft_len=512, win_len=400, overlap=396, freq_range=(500.0, 9000.0), time_range=5, hidden=(64,), outputs=4, scaling="db", input_funcs=("mapminmax",), output_funcs=("mapminmax", "mapstd")),   # zero padding, no statistic, 4 outputs
+    dict(fft_len=256, overlap=252, freq_range=(2000.0, 7000.0), time_range=17, hidden=(1024,), outputs=2, input_funcs=("l2normalize",), out_transfer="TanSig"),   # T at the limit, 4 passes, 29 bins (2 chunks, padded)
+])
+def test_wide_kernel_shape_variants(sd, oracle_mod, cw, kw):
+    """Every branch of the wide-hidden tensor path: several accumulator passes (hidden > 256), each window statistic, spectrogram
+    scaling, plane padding, ragged tiles (evaluation counts that are no multiple of 256) and several channels."""
+    text = cw.random_config(seed=31, threshold=0.3, **kw)
+    c = sd.SyllableDetectorConfig.from_text(text).validate()
+    assert c.hop == 4 and sd.KERNEL_WIDE in sd.BatchDetector.available_kernels(c)
+    o = oracle_mod.Oracle(text=text)
+    rng = np.random.default_rng(17)
+    n = kw.get("win_len", kw["fft_len"]) + 4 * (kw["time_range"] - 1) + 4 * 1100 + 3
+    t = np.arange(n)
+    x = np.stack([(0.05 * rng.standard_normal(n) + 0.3 * np.sin(2 * np.pi * f0 * t / 44100 + 2 * np.sin(2 * np.pi * 5 * t / 44100))).astype(np.float32)
+                  for f0 in (3000.0, 6100.0, 4400.0)])
+    ev, outs = sd.BatchDetector(c, kernel=sd.KERNEL_WIDE).run(x, want_outputs=True)
+    assert outs.shape[1] == 1101
+    for ch in range(x.shape[0]):
         ref = o.run(x[ch])[0]
         scale = max(1.0, float(np.nanmax(np.abs(ref))))
-        _check_channel(o, x[ch], outs[ch], ev.sample[ev.channel == ch], TOL_OUT * scale)
+        tol = (TOL_OUT if kw.get("scaling", "linear") == "linear" else TOL_NONLINEAR) * scale
+        _check_channel(o, x[ch], outs[ch], ev.sample[ev.channel == ch], tol)
+    band = sd.BatchDetector(c, kernel=sd.KERNEL_WIDE).spectra(x[:1])
+    assert band.shape == (1, 1101 + kw["time_range"] - 1, o.L)
 
 
 @pytest.mark.parametrize("kernel_name", ["KERNEL_FUSED", "KERNEL_TENSOR", "KERNEL_GENERIC"])

@@ -53,19 +53,11 @@ constexpr int kFGroup = 4;                     // evaluator warps (one per TMEM 
 // the tail (against a zero A block for its h2 half). The raw fp32 tile is then read by the splitters only.
 // fp16's 11 bits per term keep the sum at float32 level for |x| in [6e-5, 32752]; quieter samples carry an absolute error of
 // ~2^-36 each, which the evaluators' range guard bounds against the window's energy.
-#ifndef TC_NUM_D
-#define TC_NUM_D 16
-#endif
-constexpr int kWarpTma = 0, kWarpMma = 1, kWarpF0 = 2, kNumF = kFGroup, kWarpD0 = kWarpF0 + kNumF, kNumD = TC_NUM_D,
+constexpr int kWarpTma = 0, kWarpMma = 1, kWarpF0 = 2, kNumF = kFGroup, kWarpD0 = kWarpF0 + kNumF, kNumD = 8,
               kWarpS0 = kWarpD0 + kNumD, kNumS = 4;
-constexpr int kTcThreads = (kWarpS0 + kNumS) * 32;  // 832 (26 warps) with 16 spectrum warps, 576 with 8
-static_assert(kNumD == 8 || kNumD == 16, "spectrum warps: two or four per TMEM lane quadrant");
+constexpr int kTcThreads = (kWarpS0 + kNumS) * 32;  // 576
 static_assert(kWarpF0 % 4 == 2 && kWarpD0 % 4 == 2, "quadrant / half assignment below assumes these starts");
 constexpr int kTileRows = 64;                  // rows of Y per tile = N of the DFT MMA
-constexpr int kDSplit = kNumD / 4;             // spectrum warps per TMEM lane quadrant
-constexpr int kDCols = kTileRows / kDSplit;    // tile columns per spectrum warp (32 or 16)
-constexpr int kDGroups = kDCols / 4;           // groups of four columns
-constexpr int kDMags = kDCols / 4;             // magnitudes a lane ends up with
 constexpr int kTileFrames = kTileRows - 1;     // frames completed per tile
 constexpr int kMainChunks = 4;                 // 32-float K chunks (SWIZZLE_128B)
 constexpr int kTailCols = 8;                   // remaining K columns (SWIZZLE_32B)
@@ -629,22 +621,18 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
         // so the four parts of a bin sit in one warp and combine through two shuffle rounds; nothing goes through shared memory:
         //   (1) X[c] = P1[c] + P2[c+1]: B1 lanes (bit 4 clear) take columns 4g, 4g+1, B2 lanes take 4g+2, 4g+3 (xor 16)
         //   (2) re^2 + im^2: Re lanes (bit 3 clear) keep the columns of even g, Im lanes those of odd g           (xor 8)
-        // after which every lane owns kDMags magnitudes of its bin: columns col0 + 8*i + u. A store instruction then covers rows
+        // after which every lane owns 8 magnitudes of its bin: columns col0 + 8*i + u. A store instruction then covers rows
         // r, r+2, r+4, r+6 x 8 bins = all 32 banks of the SWIZZLE_128B operand.
-        // kDSplit warps share a quadrant, each taking kDCols consecutive columns of the tile: this role is a dependent chain of TMEM
-        // load -> shuffles -> MUFU -> shuffles -> stores, and with the evaluators out of the way it is what the MMA issuer waits for;
-        // four warps per quadrant halve that chain (round 1 and the first pair-scheme build ran two).
-        const int quad = warp & 3, dw = warp - kWarpD0, part = dw >> 2;
+        const int quad = warp & 3, dw = warp - kWarpD0, half = dw >> 2;
         const bool up = (lane & 16) != 0, im = (lane & 8) != 0;
         const int bin = quad * 8 + (lane & 7);
         const bool in_band = bin < L;
-        const int col0 = part * kDCols + (up ? 2 : 0) + (im ? 4 : 0);
+        const int col0 = half * 32 + (up ? 2 : 0) + (im ? 4 : 0);
         int a_off[2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) a_off[u] = (col0 + u) * 128 + ((((bin >> 2) ^ (col0 + u)) & 7) << 4) + ((bin & 3) << 2);
-        // the column whose statistic ends up in this lane: value index e = 2*i + u is selected by lane bits 2.. (see reduce below)
-        const int stat_col = kDMags == 8 ? col0 + 8 * ((lane & 7) >> 1) + (lane & 1) : col0 + 8 * ((lane >> 2) & 1) + ((lane >> 1) & 1);
-        const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + kColD0 + part * kDCols;
+        const int stat_col = col0 + 8 * ((lane & 7) >> 1) + (lane & 1);   // the column whose statistic ends up in this lane
+        const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + kColD0 + half * 32;
         TileWalk tw;
         tw.init(w, T);
         int gcol = 0;                                       // statistic-ring position of the tile's first column (mod kStatRing)
@@ -656,36 +644,27 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
             const int frames = tw.frames();
             tm.wait(&tmem_full[s], ph, 0);
             ptx::tc_fence_after();
-            // One load of the warp's columns (+1), then straight-line code: the shuffle chains of the column groups are
+            // One load of the warp's 32 (+1) columns, then straight-line code: the shuffle chains of the eight column groups are
             // independent, and a warp needs that many in flight to hide the latency of the (busy) shared-memory/shuffle pipe.
-            uint32_t r[kDCols + 1];
+            uint32_t r[33];
             const long long t_d0 = tm.now();
             {
-                r[kDCols] = 0;                                  // column 64 does not exist: frame 63 is never complete in this tile
-                if constexpr (kDCols == 32) {
-                    uint32_t r32[32];
-                    ptx::tmem_ld_x32(taddr0 + s * kTileRows, r32);
-                    if (part + 1 < kDSplit) ptx::tmem_ld_x1(taddr0 + s * kTileRows + kDCols, r[kDCols]);
-                    ptx::tc_wait_ld();
+                uint32_t r32[32];
+                ptx::tmem_ld_x32(taddr0 + s * kTileRows, r32);
+                r[32] = 0;                                      // column 64 does not exist: frame 63 is never complete in this tile
+                if (half == 0) ptx::tmem_ld_x1(taddr0 + s * kTileRows + 32, r[32]);
+                ptx::tc_wait_ld();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) r[j] = r32[j];
-                } else {
-                    uint32_t r16[16];
-                    ptx::tmem_ld_x16(taddr0 + s * kTileRows, r16);
-                    if (part + 1 < kDSplit) ptx::tmem_ld_x1(taddr0 + s * kTileRows + kDCols, r[kDCols]);
-                    ptx::tc_wait_ld();
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) r[j] = r16[j];
-                }
+                for (int j = 0; j < 32; ++j) r[j] = r32[j];
             }
             tm.add(4, t_d0);
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tmem_empty[s]);
             // ---- (1) X_c = (Re1[c] + Re2[c+1]) + i (Im1[c] + Im2[c+1]) ------------------------------------------------------
-            float x[kDGroups][2];
+            float x[8][2];
 #pragma unroll
-            for (int g = 0; g < kDGroups; ++g)
+            for (int g = 0; g < 8; ++g)
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     const float send = __uint_as_float(up ? r[4 * g + u + 1] : r[4 * g + 2 + u]);
@@ -693,9 +672,9 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
                     x[g][u] = own + __shfl_xor_sync(0xffffffffu, send, 16);
                 }
             // ---- (2) |X| of the band (plain multiplies and add, as the reference computes it) -------------------------------
-            float mag[kDMags];                                  // e = 2*i + u: column col0 + 8*i + u
+            float mag[8];                                       // e = 2*i + u: column col0 + 8*i + u
 #pragma unroll
-            for (int i = 0; i < kDGroups / 2; ++i)
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     const float sq_a = __fmul_rn(x[2 * i][u], x[2 * i][u]), sq_b = __fmul_rn(x[2 * i + 1][u], x[2 * i + 1][u]);
@@ -711,42 +690,33 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
                 }
             // ---- window statistic: per-column partial over this warp's 8 bins; the evaluators combine the four quadrants -----
             if (window_stat != FUSED_STAT_NONE) {
-                // kDMags values x eight lanes -> the lane whose bits select value e holds its total: exchange half of the values per round
-                auto reduce = [&](float (&q)[kDMags], auto op) {
+                // eight values x eight lanes -> lane b holds the total of value b: exchange half of the values per round
+                auto reduce8 = [&](float (&q)[8], auto op) {
                     const bool b4 = (lane & 4) != 0, b2 = (lane & 2) != 0, b1 = (lane & 1) != 0;
-                    if constexpr (kDMags == 8) {
-                        float h4[4], h2[2];
+                    float h4[4], h2[2];
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) h4[k] = op(b4 ? q[k + 4] : q[k], __shfl_xor_sync(0xffffffffu, b4 ? q[k] : q[k + 4], 4));
+                    for (int k = 0; k < 4; ++k) h4[k] = op(b4 ? q[k + 4] : q[k], __shfl_xor_sync(0xffffffffu, b4 ? q[k] : q[k + 4], 4));
 #pragma unroll
-                        for (int k = 0; k < 2; ++k) h2[k] = op(b2 ? h4[k + 2] : h4[k], __shfl_xor_sync(0xffffffffu, b2 ? h4[k] : h4[k + 2], 2));
-                        return op(b1 ? h2[1] : h2[0], __shfl_xor_sync(0xffffffffu, b1 ? h2[0] : h2[1], 1));
-                    } else {
-                        float h2[2];
-#pragma unroll
-                        for (int k = 0; k < 2; ++k) h2[k] = op(b4 ? q[k + 2] : q[k], __shfl_xor_sync(0xffffffffu, b4 ? q[k] : q[k + 2], 4));
-                        const float h1 = op(b2 ? h2[1] : h2[0], __shfl_xor_sync(0xffffffffu, b2 ? h2[0] : h2[1], 2));
-                        return op(h1, __shfl_xor_sync(0xffffffffu, h1, 1));   // both lanes of a pair end with the total
-                    }
+                    for (int k = 0; k < 2; ++k) h2[k] = op(b2 ? h4[k + 2] : h4[k], __shfl_xor_sync(0xffffffffu, b2 ? h4[k] : h4[k + 2], 2));
+                    return op(b1 ? h2[1] : h2[0], __shfl_xor_sync(0xffffffffu, b1 ? h2[0] : h2[1], 1));
                 };
-                float q[kDMags];
+                float q[8];
                 int sidx = gcol + stat_col;
                 if (sidx >= kStatRing) sidx -= kStatRing;
                 float *cs = colstat + (sidx << 2) + quad;
-                const bool writer = (kDMags == 8 || (lane & 1) == 0) && stat_col < frames;
                 if (window_stat == FUSED_STAT_L2) {
 #pragma unroll
-                    for (int e = 0; e < kDMags; ++e) q[e] = mag[e] * mag[e];
-                    const float tot = reduce(q, [](float a, float b) { return a + b; });
-                    if (writer) cs[0] = tot;
+                    for (int e = 0; e < 8; ++e) q[e] = mag[e] * mag[e];
+                    const float tot = reduce8(q, [](float a, float b) { return a + b; });
+                    if (stat_col < frames) cs[0] = tot;
                 } else {
 #pragma unroll
-                    for (int e = 0; e < kDMags; ++e) q[e] = in_band ? mag[e] : INFINITY;
-                    const float mn = reduce(q, [](float a, float b) { return fminf(a, b); });
+                    for (int e = 0; e < 8; ++e) q[e] = in_band ? mag[e] : INFINITY;
+                    const float mn = reduce8(q, [](float a, float b) { return fminf(a, b); });
 #pragma unroll
-                    for (int e = 0; e < kDMags; ++e) q[e] = in_band ? mag[e] : -INFINITY;
-                    const float mx = reduce(q, [](float a, float b) { return fmaxf(a, b); });
-                    if (writer) {
+                    for (int e = 0; e < 8; ++e) q[e] = in_band ? mag[e] : -INFINITY;
+                    const float mx = reduce8(q, [](float a, float b) { return fmaxf(a, b); });
+                    if (stat_col < frames) {
                         cs[0] = mn;
                         cs[kStatRing * 4] = mx;
                     }
@@ -757,7 +727,7 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
             {
                 unsigned char *a_hi = smem + TcSmem::a(s, 0), *a_lo = smem + TcSmem::a(s, 1);   // this tile's half of the 128 rows
 #pragma unroll
-                for (int i = 0; i < kDGroups / 2; ++i)
+                for (int i = 0; i < 4; ++i)
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {
                         const int col = col0 + 8 * i + u;

@@ -618,8 +618,183 @@ def run_corpus(args, np, torch, dist, sd, sharding, synth, rank, world, local, d
         dist.destroy_process_group()
 
 
+def wide_config_text(hidden):
+    """BASELINE config 4 as SURVEY.md 8(d) spells it out: fs 44 100, FFT = window = 1024, hop 4 (overlap 1020), band 1-8 kHz (162 bins),
+    T = 8 (1296 inputs), `hidden` tansig units, 2 purelin outputs; seeded random weights in the reference's text format. config_writer
+    is loaded by path: the reference arm must not import the product package."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_cw", os.path.join(ROOT, "syllable-detector-swift_b200", "config_writer.py"))
+    cw = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cw)
+    return cw.random_config(seed=21, fft_len=1024, overlap=1020, freq_range=(1000.0, 8000.0), time_range=8, hidden=(hidden,), outputs=2,
+                            threshold=0.2)
+
+
+def wide_audio(np, nch, n, seed):
+    rng = np.random.default_rng(seed)
+    t = np.arange(n)
+    return np.stack([(0.05 * rng.standard_normal(n) + 0.3 * np.sin(2 * np.pi * (2500.0 + 450.0 * ch) * t / FS + 3 * np.sin(2 * np.pi * 2 * t / FS))).astype(np.float32)
+                     for ch in range(nch)])
+
+
+def wide_workload(args, hidden, n_gpus):
+    return {"workload": "high-overlap wide-hidden network (FFT 1024, hop 4, 162 bins x 8 columns = 1296 inputs -> %d tansig -> 2) over a "
+                        "%g-second %d-channel 44.1 kHz synthetic recording per GPU" % (hidden, args.wide_seconds, args.channels),
+            "hidden": hidden, "channels_per_gpu": args.channels, "seconds_per_channel": args.wide_seconds, "sampling_rate": FS,
+            "sharding": "by recording, %d rank(s), no collective on the data path" % n_gpus,
+            "l2": "band-magnitude planes of a step (%.1f GB) and the audio are far larger than L2" % (args.channels * args.wide_seconds * FS / 4 * 1344 / 1e9)}
+
+
 def run_wide(args, np, torch, dist, sd, rank, world, local, dev, barrier):
-    raise SystemExit("--config 4 is not available in this build")
+    """BASELINE config 4: the wide-hidden tensor path (stft_planes_kernel + wide_l0_kernel)."""
+    import oracle
+    H = args.hidden
+    text = wide_config_text(H)
+    cfg = sd.SyllableDetectorConfig.from_text(text).validate()
+    nch = args.channels
+    n = int(round(args.wide_seconds * FS))
+    n -= n % 4
+    E = cfg.num_evals(n)
+    audio_seconds = nch * n / FS
+    x_host = wide_audio(np, nch, n, 900 + rank)
+    x = torch.from_numpy(x_host).to(dev)
+    d_out = torch.empty((nch, E, cfg.net_outputs), dtype=torch.float32, device=dev)
+    det = sd.BatchDetector(cfg, device=local)
+    assert det.active_kernel == sd.KERNEL_WIDE, "config 4 must take the wide-hidden tensor path"
+    stream = torch.cuda.current_stream(dev)
+
+    def launch():
+        det.launch_device(x.data_ptr(), nch, n, n, detect_rule=sd.DETECT_ANY_OUTPUT, d_outputs_ptr=d_out.data_ptr(), stream=stream.cuda_stream)
+
+    for _ in range(args.warmup):
+        launch()
+    barrier()
+    clocks = ClockSampler(local) if rank == 0 else None
+    launches0 = det.launch_count
+    t_clock0 = time.perf_counter()
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    phases = []
+    for _ in range(args.steps):
+        launch()
+    e1.record(stream)
+    barrier()
+    wall = time.perf_counter() - t0
+    dev_ms = e0.elapsed_time(e1)
+    gpu_launches = det.launch_count - launches0
+    phases = det.wide_phase_ms()                     # the last step's two kernels
+    n_det = det.last_detection_count()
+    events = det.collect(debounce_frames=0)
+
+    # end to end through the host API: pinned host float32 PCM -> events
+    h = torch.empty((nch, n), dtype=torch.float32, pin_memory=True)
+    h.copy_(x)
+    torch.cuda.synchronize(dev)
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    ev_h = det.run(h.numpy())
+    barrier()
+    te0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ev_h = det.run(h.numpy())
+    barrier()
+    e2e_wall = time.perf_counter() - te0
+    t_clock1 = time.perf_counter()
+    assert len(ev_h) == len(events) and np.array_equal(ev_h.sample, events.sample)
+
+    # parity: the first `ps` seconds of every channel against the oracle (all host threads), every evaluation in it
+    orc = oracle.Oracle(text=text)
+    ps = int(min(n, args.wide_parity_seconds * FS))
+    Ep = cfg.num_evals(ps)
+    ref, da_ref = orc.run_multi(x_host[:, :ps], n_threads=len(os.sched_getaffinity(0)), want_outputs=True)
+    got = d_out[:, :Ep].cpu().numpy()
+    scale = max(1.0, float(np.nanmax(np.abs(ref))))
+    tol = 1e-5 * scale
+    thr = cfg.thresholds
+    near = (np.abs(ref.astype(np.float64) - thr[None, None, :]) <= tol).any(axis=2)
+    da_gpu = (got.astype(np.float64) >= thr[None, None, :]).any(axis=2)
+    flips = da_gpu != da_ref
+    parity = {"evaluations_checked": int(ref.shape[0] * ref.shape[1]), "max_abs_err_vs_oracle": float(np.abs(got - ref).max()), "tolerance": tol,
+              "near_threshold": int(near.sum()), "decision_flips": int(flips.sum()), "decision_flips_outside_near_band": int((flips & ~near).sum()),
+              "scope": "first %.1f s of every channel" % (ps / FS)}
+
+    t = torch.tensor([wall, e2e_wall, dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    wall, e2e_wall, dev_ms = [float(v) for v in t.tolist()]
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        try:
+            with open(os.path.join(ROOT, "profiles", "r02_tensor_peaks.json")) as f:
+                tp = json.load(f)
+            tf32_peak, tf32_src = float(tp["tf32_tflops"]), "measured (profiles/r02_tensor_peaks.json: tools/mma_rate.cu --peak, burst)"
+        except Exception:
+            tf32_peak, tf32_src = float(peaks["bf16_tflops"]) / 2.0, peak_src + ": bf16 burst / 2 (no TF32 measurement on file)"
+        I = cfg.net_inputs
+        alg_flops = 2.0 * I * H * E * nch                       # layer 0 as the reference computes it (NeuralNet.swift:366-377), per launch
+        l0_ms, stft_ms = phases[1], phases[0]
+        achieved = alg_flops / (l0_ms * 1e-3) / 1e12
+        total_audio = audio_seconds * world
+        line = {
+            "metric": METRIC, "value": total_audio * args.steps / wall, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (3xTF32 tensor products)",
+            "data": "synthetic (noise + frequency-modulated tones; seeded random weights in the reference's text format)",
+            "config": wide_workload(args, H, world),
+            "frames_per_s": E * nch * world * args.steps / wall, "device_ms_per_step": dev_ms / args.steps,
+            "e2e": {"value": total_audio * e2e_steps / e2e_wall, "unit": UNIT, "h2d_bytes_per_step": nch * n * 4,
+                    "d2h_bytes_per_step": len(ev_h) * (16 + 4 * cfg.net_outputs) + 16, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_wall / e2e_steps,
+                    "api": "syldet_batch_run_host (pinned host float32 PCM in, debounced events out)"},
+            "gpu_launches": int(gpu_launches),
+            "kernel": "wide_l0_kernel (tcgen05 3xTF32, [evaluations x 1296] . [1296 x %d], sliding A operand, TMEM accumulators) after stft_planes_kernel" % H,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak, "traffic": None,
+                         "peak_source": tf32_src, "kernel_ms": l0_ms, "stft_kernel_ms": stft_ms,
+                         "algorithmic_flops_per_launch": alg_flops,
+                         "note": "algorithmic FLOPs = 2 * inputs * hidden per evaluation (layer 0); a 3xTF32 product issues 3 MMA FLOPs per algorithmic "
+                                 "FLOP over K padded from 1296 to 1344, so frac <= 0.32; mma_frac counts the issued MMA FLOPs"},
+            "detections_per_step": int(n_det), "events_per_step": len(events), "parity": parity,
+            "clocks": clocks.summary(t_clock0, t_clock1),
+        }
+        line["roofline"]["mma_frac"] = 3.0 * achieved * (8 * 168.0 / I) / tf32_peak
+        if world == 1 and not args.no_cpu:
+            threads = len(os.sched_getaffinity(0))
+            of = oracle.Oracle(text=text, fast=True)
+            xs = wide_audio(np, threads, int(args.wide_cpu_seconds * FS), 77)
+            of.run_multi(xs[:, :FS // 10], n_threads=threads, want_outputs=False)
+            tc0 = time.perf_counter()
+            of.run_multi(xs, n_threads=threads, want_outputs=False)
+            dt = time.perf_counter() - tc0
+            line["cpu_baseline"] = {"value": threads * args.wide_cpu_seconds / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": "%d channels x %.2f s of the same kind of audio, one pass, OpenMP over channels; gcc -O3 -march=native build "
+                                              "of oracle/oracle.c" % (threads, args.wide_cpu_seconds)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_reference_wide(args):
+    import numpy as np
+    import oracle
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    text = wide_config_text(args.hidden)
+    of = oracle.Oracle(text=text, fast=True)
+    threads = len(os.sched_getaffinity(0))
+    xs = wide_audio(np, threads, int(args.wide_cpu_seconds * FS), 77)
+    times = []
+    for s in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        of.run_multi(xs, n_threads=threads, want_outputs=False)
+        if s >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    v = threads * args.wide_cpu_seconds * len(times) / sum(times)
+    sample = "%d channels x %.2f s per step, OpenMP over channels; gcc -O3 -march=native build of oracle/oracle.c" % (threads, args.wide_cpu_seconds)
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                      "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                      "data": "synthetic (noise + frequency-modulated tones; seeded random weights)", "config": wide_workload(args, args.hidden, world),
+                      "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+                      "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                      "note": "CPU port (oracle/oracle.c) of the reference's Swift/Accelerate path, which cannot be built on Linux"}), flush=True)
 
 
 def run_reference(args):
@@ -627,6 +802,8 @@ def run_reference(args):
     if rank != 0:
         return
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.config == 4:
+        return run_reference_wide(args)
     cb = cpu_reference(args, steps=args.steps, warmup=args.warmup)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
@@ -649,6 +826,9 @@ if __name__ == "__main__":
     ap.add_argument("--channels", type=int, default=8)
     ap.add_argument("--corpus-hours", type=float, default=1000.0)
     ap.add_argument("--hidden", type=int, default=256)
+    ap.add_argument("--wide-seconds", type=float, default=30.0)
+    ap.add_argument("--wide-parity-seconds", type=float, default=1.0)
+    ap.add_argument("--wide-cpu-seconds", type=float, default=0.5)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-step-seconds", type=float, default=None)
     ap.add_argument("--no-cpu", action="store_true")

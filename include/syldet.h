@@ -168,6 +168,9 @@ syldet_status syldet_batch_collect(syldet_batch *b, int64_t debounce_frames, syl
 int64_t syldet_batch_launch_count(const syldet_batch *b);
 /* 1 once this handle has switched its tensor kernel to the all-TF32 variant because audio left the fp16 window (see above), else 0. */
 int64_t syldet_batch_range_fallbacks(const syldet_batch *b);
+/* Device time (ms) of the two kernels of the last SYLDET_KERNEL_WIDE launch, summed over its time segments: the high-overlap STFT
+ * (stft_planes_kernel) and the tcgen05 contraction + network tail (wide_l0_kernel). Synchronises. For bench.py's roofline. */
+syldet_status syldet_batch_wide_phase_ms(syldet_batch *b, double *stft_ms, double *contraction_ms);
 /*
  * CircularShortTimeFourierTransform.extractPower()[f0 ..< f1] (CSTFT.swift:280-337 = |X[k]|, band slice of SyllableDetector.swift:136-148)
  * as the ACTIVE kernel computes it on the detection path, before the spectrogram scaling: band receives [n_channels][n_columns][L]

@@ -94,6 +94,7 @@ def _load():
         "syldet_batch_collect": (i32, [vp, i64, pvp]), "syldet_batch_launch_count": (i64, [vp]),
         "syldet_batch_last_detection_count": (i32, [vp, C.POINTER(i64)]),
         "syldet_batch_range_fallbacks": (i64, [vp]),
+        "syldet_batch_wide_phase_ms": (i32, [vp, C.POINTER(dbl), C.POINTER(dbl)]),
         "syldet_batch_spectra_host": (i32, [vp, vp, i32, i32, i64, i64, i32, vp, C.POINTER(i64)]),
         "syldet_events_count": (i64, [vp]), "syldet_events_outputs_per_event": (i32, [vp]),
         "syldet_events_data": (C.POINTER(Event), [vp]), "syldet_events_outputs": (C.POINTER(C.c_float), [vp]),
@@ -339,6 +340,12 @@ class BatchDetector:
     def range_fallbacks(self):
         """1 once the tensor kernel of this handle switched to its all-TF32 variant (audio outside the fp16 window), else 0."""
         return lib.syldet_batch_range_fallbacks(self._h)
+
+    def wide_phase_ms(self):
+        """-> (stft_ms, contraction_ms): device time of the two kernels of the last KERNEL_WIDE launch."""
+        a, b = C.c_double(), C.c_double()
+        _check(lib.syldet_batch_wide_phase_ms(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def spectra(self, pcm, layout=LAYOUT_PLANAR):
         """extractPower()[f0 ..< f1] (CSTFT.swift:280-337) of every column that feeds an evaluation, as the active kernel computes it

@@ -210,6 +210,10 @@ syldet_status syldet_batch_collect(syldet_batch *b, int64_t debounce_frames, syl
 }
 int64_t syldet_batch_launch_count(const syldet_batch *b) { return b ? b->b.launch_count() : 0; }
 int64_t syldet_batch_range_fallbacks(const syldet_batch *b) { return b ? b->b.range_fallbacks() : 0; }
+syldet_status syldet_batch_wide_phase_ms(syldet_batch *b, double *stft_ms, double *contraction_ms) {
+    if (!b) return set_error(SYLDET_ERR_ARG, "null argument");
+    return guarded([&] { return b->b.wide_phase_ms(stft_ms, contraction_ms); });
+}
 syldet_status syldet_batch_spectra_host(syldet_batch *b, const void *pcm, int pcm_format, int n_channels, int64_t n_samples,
                                         int64_t channel_stride, int layout, float *band, int64_t *n_columns) {
     if (!b) return set_error(SYLDET_ERR_ARG, "null argument");

@@ -547,6 +547,7 @@ Batch::~Batch() {
     if (d2h_stream_) cudaStreamDestroy(d2h_stream_);
     for (cudaEvent_t e : ev_copied_) cudaEventDestroy(e);
     for (cudaEvent_t e : ev_done_) cudaEventDestroy(e);
+    for (cudaEvent_t e : wide_ev_) cudaEventDestroy(e);
     if (h_counts_) cudaFreeHost(h_counts_);
     if (h_events_) cudaFreeHost(h_events_);
 }
@@ -743,6 +744,7 @@ syldet_status Batch::launch_wide_range(const float *d_planar, int n_channels, in
     const int64_t budget = (int64_t)1 << 30;   // bytes of raw + lo planes per segment
     int64_t seg = std::max<int64_t>(tile, budget / ((int64_t)n_channels * P * 16 * 2));
     seg = (seg / tile) * tile;
+    int seg_index = 0;
     for (int64_t e0 = eval_begin; e0 < eval_begin + eval_count; e0 += seg) {
         const int64_t ne = std::min(seg, eval_begin + eval_count - e0), ncols = ne + T - 1;
         const int64_t rows_alloc = ((ncols + kWideStftCols - 1) / kWideStftCols) * kWideStftCols + 4;
@@ -752,8 +754,16 @@ syldet_status Batch::launch_wide_range(const float *d_planar, int n_channels, in
         if (st != SYLDET_OK) return st;
         st = wide_stats_.reserve((size_t)n_channels * rows_alloc * sizeof(float4));
         if (st != SYLDET_OK) return st;
+        // three timing events per segment (reused): stft_planes_kernel | wide_l0_kernel, read back by wide_phase_ms()
+        while (wide_ev_.size() < (size_t)(3 * (seg_index + 1))) {
+            cudaEvent_t e = nullptr;
+            SYLDET_CUDA(cudaEventCreate(&e));
+            wide_ev_.push_back(e);
+        }
+        SYLDET_CUDA(cudaEventRecord(wide_ev_[3 * seg_index], stream));
         SYLDET_CUDA(launch_stft_planes(model_.dev_net(), c.fourier_length, c.window_length, c.hop, d_planar, ch_stride, n_channels, e0, ncols,
                                        wide_hi_.as<float>(), wide_lo_.as<float>(), wide_stats_.as<float4>(), P, rows_alloc, stream));
+        SYLDET_CUDA(cudaEventRecord(wide_ev_[3 * seg_index + 1], stream));
         if (debug_band_) {   // extractPower() values before the scaling: the same reference-order FFT, straight into the caller's buffer
             SYLDET_CUDA(launch_stft_band_generic(model_.dev_net(), c.fourier_length, d_planar, ch_stride, n_channels, e0, ncols,
                                                  debug_band_ + e0 * c.band, debug_cols_ * c.band, SYLDET_SCALING_LINEAR, stream));
@@ -778,8 +788,27 @@ syldet_status Batch::launch_wide_range(const float *d_planar, int n_channels, in
         w.w1 = model_.wide_w1();
         const int64_t tiles = (int64_t)n_channels * ((ne + tile - 1) / tile);
         SYLDET_CUDA(launch_wide((int)std::min<int64_t>(tiles, model_.sm_count()), wp.params, w, stream));
+        SYLDET_CUDA(cudaEventRecord(wide_ev_[3 * seg_index + 2], stream));
         launches_ += 2;
+        ++seg_index;
     }
+    wide_segments_ = seg_index;
+    return SYLDET_OK;
+}
+
+syldet_status Batch::wide_phase_ms(double *stft_ms, double *contraction_ms) {
+    if (!last_.valid || wide_segments_ == 0) return set_error(SYLDET_ERR_ARG, "no wide-path launch to inspect");
+    SYLDET_CUDA(cudaStreamSynchronize(last_.stream));
+    double a = 0.0, b = 0.0;
+    for (int k = 0; k < wide_segments_; ++k) {
+        float ms = 0.f;
+        SYLDET_CUDA(cudaEventElapsedTime(&ms, wide_ev_[3 * k], wide_ev_[3 * k + 1]));
+        a += ms;
+        SYLDET_CUDA(cudaEventElapsedTime(&ms, wide_ev_[3 * k + 1], wide_ev_[3 * k + 2]));
+        b += ms;
+    }
+    if (stft_ms) *stft_ms = a;
+    if (contraction_ms) *contraction_ms = b;
     return SYLDET_OK;
 }
 

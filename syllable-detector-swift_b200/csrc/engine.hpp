@@ -152,6 +152,8 @@ public:
     syldet_status last_detection_count(int64_t *count);
     // launches repeated with the all-TF32 variant because the fp16 range flag went up (at most 1: the switch is permanent)
     int64_t range_fallbacks() const { return range_fallbacks_; }
+    // device time of the last wide-path launch (all time segments): STFT-planes kernel, contraction + epilogue kernel (synchronises)
+    syldet_status wide_phase_ms(double *stft_ms, double *contraction_ms);
     // band magnitudes extractPower()[f0 ..< f1] of every column that feeds an evaluation, from the active kernel: [n_channels][E + T - 1][band]
     syldet_status spectra_host(const void *pcm, int fmt, int n_channels, int64_t n_samples, int64_t ch_stride, int layout, float *band,
                                int64_t *n_columns);
@@ -193,6 +195,8 @@ private:
     size_t h_events_bytes_ = 0;
     int64_t slice_evals_ = 256 * 1024;
     DeviceBuffer planar_, feat_, sink_count_, sink_events_, sink_outputs_, staging_;
+    std::vector<cudaEvent_t> wide_ev_;
+    int wide_segments_ = 0;
     DeviceBuffer wide_hi_, wide_lo_, wide_stats_;   // band-magnitude planes + column statistics of one time segment (wide path)
     unsigned long long sink_capacity_ = 0;
     int64_t launches_ = 0;

@@ -54,11 +54,11 @@ constexpr int kFGroup = 4;                     // evaluator warps (one per TMEM 
 // fp16's 11 bits per term keep the sum at float32 level for |x| in [6e-5, 32752]; quieter samples carry an absolute error of
 // ~2^-36 each, which the evaluators' range guard bounds against the window's energy.
 #ifndef TC_NUM_D
-#define TC_NUM_D 16
+#define TC_NUM_D 8
 #endif
 constexpr int kWarpTma = 0, kWarpMma = 1, kWarpF0 = 2, kNumF = kFGroup, kWarpD0 = kWarpF0 + kNumF, kNumD = TC_NUM_D,
               kWarpS0 = kWarpD0 + kNumD, kNumS = 4;
-constexpr int kTcThreads = (kWarpS0 + kNumS) * 32;  // 832 (26 warps) with 16 spectrum warps, 576 with 8
+constexpr int kTcThreads = (kWarpS0 + kNumS) * 32;  // 576 (18 warps) with 8 spectrum warps; 832 with -DTC_NUM_D=16 (slower: profiles/r02_tc_v21_numd16_vs_8.txt)
 static_assert(kNumD == 8 || kNumD == 16, "spectrum warps: two or four per TMEM lane quadrant");
 static_assert(kWarpF0 % 4 == 2 && kWarpD0 % 4 == 2, "quadrant / half assignment below assumes these starts");
 constexpr int kTileRows = 64;                  // rows of Y per tile = N of the DFT MMA

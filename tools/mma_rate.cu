@@ -3,6 +3,7 @@
 // One CTA per SM (all SMs busy, like the real kernel); one thread issues `reps` MMAs, commits, waits; clock64 around it.
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <vector>
 
 #include "ptx_sm100.cuh"
@@ -134,7 +135,43 @@ void run_mode(long long *d_out) {
     run<mode, 64, 256, 1>(d_out);
 }
 
-int main() {
+// Whole-chip throughput of one shape over a long launch, by wall clock (CUDA events): the denominator of the wide-hidden kernel's
+// roofline (kind::tf32, M = 128, N = 256, both operands from shared memory), next to the bf16 figure MEASURED_PEAKS.json holds.
+template <int mode>
+double peak_tflops(long long *d_out, int reps, float *ms_out) {
+    cudaFuncSetAttribute(rate_kernel<mode, 128, 256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    rate_kernel<mode, 128, 256, 1><<<148, 128, 100 * 1024>>>(reps / 8, d_out);   // warm-up
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    cudaEventRecord(a);
+    rate_kernel<mode, 128, 256, 1><<<148, 128, 100 * 1024>>>(reps, d_out);
+    cudaEventRecord(b);
+    cudaEventSynchronize(b);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    *ms_out = ms;
+    const double k = mode < 2 ? 8.0 : 16.0;
+    return 148.0 * reps * 2.0 * 128.0 * 256.0 * k / (ms * 1e-3) / 1e12;
+}
+
+int main(int argc, char **argv) {
+    if (argc > 1 && std::string(argv[1]) == "--peak") {   // JSON line: burst (~20 ms) and sustained (~2 s) dense peaks
+        long long *d_out;
+        cudaMalloc(&d_out, 16);
+        float ms;
+        const double tf32_burst = peak_tflops<1>(d_out, 200000, &ms);
+        const double tf32_sust = peak_tflops<1>(d_out, 20000000, &ms);
+        const float tf32_ms = ms;
+        const double bf16_burst = peak_tflops<3>(d_out, 200000, &ms);
+        const double bf16_sust = peak_tflops<3>(d_out, 20000000, &ms);
+        printf("{\"tf32_tflops\": %.1f, \"tf32_tflops_sustained\": %.1f, \"bf16_tflops\": %.1f, \"bf16_tflops_sustained\": %.1f, "
+               "\"sustained_ms\": %.0f, \"how\": \"tools/mma_rate.cu --peak: tcgen05.mma cta_group::1 M=128 N=256 (K=8 tf32 / K=16 bf16), "
+               "operands from shared memory, one accumulator chain per CTA, 148 CTAs, CUDA events\"}\n",
+               tf32_burst, tf32_sust, bf16_burst, bf16_sust, tf32_ms);
+        return 0;
+    }
+
     long long *d_out;
     cudaMalloc(&d_out, 16);
     run_mode<0>(d_out);

@@ -761,8 +761,13 @@ syldet_status Batch::launch_wide_range(const float *d_planar, int n_channels, in
             wide_ev_.push_back(e);
         }
         SYLDET_CUDA(cudaEventRecord(wide_ev_[3 * seg_index], stream));
-        SYLDET_CUDA(launch_stft_planes(model_.dev_net(), c.fourier_length, c.window_length, c.hop, d_planar, ch_stride, n_channels, e0, ncols,
-                                       wide_hi_.as<float>(), wide_lo_.as<float>(), wide_stats_.as<float4>(), P, rows_alloc, stream));
+        static const bool ref_order_stft = std::getenv("SYLDET_WIDE_REF_STFT") != nullptr;   // reference-order radix-2 FFT instead of the Stockham kernel
+        if (stft_planes_fast_supported(c.fourier_length) && !ref_order_stft)
+            SYLDET_CUDA(launch_stft_planes_fast(model_.dev_net(), c.fourier_length, c.window_length, c.band, c.hop, d_planar, ch_stride, n_channels,
+                                                e0, ncols, wide_hi_.as<float>(), wide_lo_.as<float>(), wide_stats_.as<float4>(), P, rows_alloc, stream));
+        else
+            SYLDET_CUDA(launch_stft_planes(model_.dev_net(), c.fourier_length, c.window_length, c.hop, d_planar, ch_stride, n_channels, e0, ncols,
+                                           wide_hi_.as<float>(), wide_lo_.as<float>(), wide_stats_.as<float4>(), P, rows_alloc, stream));
         SYLDET_CUDA(cudaEventRecord(wide_ev_[3 * seg_index + 1], stream));
         if (debug_band_) {   // extractPower() values before the scaling: the same reference-order FFT, straight into the caller's buffer
             SYLDET_CUDA(launch_stft_band_generic(model_.dev_net(), c.fourier_length, d_planar, ch_stride, n_channels, e0, ncols,

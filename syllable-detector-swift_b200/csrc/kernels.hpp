@@ -190,6 +190,10 @@ int wide_tile_rows();
 int wide_max_time_range();
 size_t wide_weight_block_bytes();
 cudaError_t launch_wide(int grid, const WideParams &p, const WideWork &w, cudaStream_t stream);
+bool stft_planes_fast_supported(int fft_len);
+cudaError_t launch_stft_planes_fast(const DevNet *d_net, int fft_len, int win_len, int band, int hop, const float *pcm, int64_t ch_stride,
+                                    int n_channels, int64_t col0, int64_t n_cols, float *hi, float *lo, float4 *stats, int n_planes,
+                                    int64_t rows_alloc, cudaStream_t stream);
 size_t stft_planes_smem(int fft_len, int win_len, int hop, int n_planes);
 cudaError_t launch_stft_planes(const DevNet *d_net, int fft_len, int win_len, int hop, const float *pcm, int64_t ch_stride, int n_channels,
                                int64_t col0, int64_t n_cols, float *hi, float *lo, float4 *stats, int n_planes, int64_t rows_alloc,

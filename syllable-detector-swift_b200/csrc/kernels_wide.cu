@@ -11,13 +11,14 @@
 // shared memory as planes of 4 bins, [plane][row][16 B] - the canonical no-swizzle K-major UMMA layout (core matrix = 8 rows x 16 B,
 // contiguous) - so the operand of column offset t is the SAME bytes with the start address advanced by t rows (16 t bytes): an
 // implicit im2col along time at zero cost. K runs over (chunk of kWidePL planes, t, plane); the magnitudes of a chunk are loaded once
-// per tile and used by all T offsets, the weights stream through a two-stage ring of pre-arranged blocks (one cp.async.bulk each).
+// per tile and used by all T offsets, the weights stream through a four-stage ring of pre-arranged blocks (cp.async.bulk, one per plane).
 //   per tile: 256 evaluations (two M = 128 accumulators of N = 256 columns: all 512 TMEM columns), so that every weight block that
 //   crosses L2 -> shared memory feeds 2 x 128 rows (the weight stream is what bounds this kernel after the tensor pipe).
 // Roles: warp 0 loader (cp.async.bulk), warp 1 MMA issuer + TMEM, warps 2-5 epilogue (one per TMEM lane quadrant; a thread owns one
 // row of each accumulator, i.e. two evaluations, so the output layer needs no cross-lane reduction).
 #include <cuda.h>
 
+#include "fft_regs.cuh"
 #include "fused_epilogue.cuh"
 #include "ptx_sm100.cuh"
 
@@ -32,15 +33,17 @@ constexpr int kWN = 256;                            // hidden units per accumula
 constexpr int kWPlaneA = kWRowsPad * 16;            // bytes of one A plane
 constexpr int kWPlaneW = kWN * 16;                  // bytes of one weight plane
 constexpr int kWABytes = 2 * kWidePL * kWPlaneA;    // one A buffer: raw | lo
-constexpr int kWWBytes = 2 * kWidePL * kWPlaneW;    // one weight stage: hi | lo
+constexpr int kWWBytes = 2 * kWidePL * kWPlaneW;    // one weight block of a (chunk, t) step: hi | lo
+constexpr int kWStageBytes = kWidePL * kWPlaneW;    // one stage of the weight ring: the hi OR the lo part of a block
+constexpr int kWStages = 4;                         // ring depth: three stages (72 KB) can be in flight while one is consumed
 constexpr int kWTmemCols = 512;
 
 struct WideSmem {
-    static constexpr int a0 = 0, a1 = kWABytes, w0 = 2 * kWABytes, w1 = w0 + kWWBytes, vb = w1 + kWWBytes;   // then float2 vb[h_pad], barriers
+    static constexpr int a0 = 0, a1 = kWABytes, w0 = 2 * kWABytes, vb = w0 + kWStages * kWStageBytes;   // then float2 vb[h_pad], barriers
     __host__ __device__ static constexpr int bars(int h_pad) { return vb + h_pad * 8; }
-    __host__ __device__ static constexpr int total(int h_pad) { return bars(h_pad) + 128; }
+    __host__ __device__ static constexpr int total(int h_pad) { return bars(h_pad) + 256; }
 };
-static_assert(kWABytes % 128 == 0 && kWWBytes % 128 == 0, "alignment of the operand buffers");
+static_assert(kWABytes % 128 == 0 && kWStageBytes % 128 == 0, "alignment of the operand buffers");
 
 // Shared-memory matrix descriptor, K-major, no swizzle (cute::UMMA canonical layout ((8,n),2):((1,SBO),LBO) in 16-byte units):
 // core matrix = 8 rows x 16 B contiguous; lbo = bytes between the two core matrices of a K step, sbo = bytes between 8-row groups.
@@ -49,20 +52,25 @@ __device__ __forceinline__ uint64_t smem_desc_nosw(uint32_t saddr, uint32_t lbo_
            ((uint64_t)1 << 46);
 }
 
+__device__ __forceinline__ float tf32_trunc_w(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
 __global__ void __launch_bounds__(kWThreads, 1) wide_l0_kernel(const __grid_constant__ WideParams p, const WideWork w) {
     extern __shared__ __align__(16) unsigned char smem_dyn[];
     unsigned char *smem = smem_dyn + ((128u - (ptx::smem_addr(smem_dyn) & 127u)) & 127u);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int T = p.time_range, n_nc = p.h_pad / kWN, n_chunks = p.n_planes / kWidePL;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + WideSmem::bars(p.h_pad));
-    uint64_t *a_full = bars, *a_empty = bars + 2, *w_full = bars + 4, *w_empty = bars + 6, *acc_full = bars + 8, *acc_empty = bars + 9;
-    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 10);
+    uint64_t *a_full = bars, *a_empty = bars + 2, *w_full = bars + 4, *w_empty = bars + 4 + kWStages, *acc_full = bars + 4 + 2 * kWStages,
+             *acc_empty = acc_full + 1;
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(acc_empty + 1);
     float2 *vb = reinterpret_cast<float2 *>(smem + WideSmem::vb);
 
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&a_full[i], 1);
             ptx::mbar_init(&a_empty[i], 1);
+        }
+        for (int i = 0; i < kWStages; ++i) {
             ptx::mbar_init(&w_full[i], 1);
             ptx::mbar_init(&w_empty[i], 1);
         }
@@ -108,13 +116,18 @@ __global__ void __launch_bounds__(kWThreads, 1) wide_l0_kernel(const __grid_cons
                             ptx::bulk_copy_g2s(dst + q * kWPlaneA, hi + off, (uint32_t)rows * 16u, &a_full[ab]);
                             ptx::bulk_copy_g2s(dst + (kWidePL + q) * kWPlaneA, lo + off, (uint32_t)rows * 16u, &a_full[ab]);
                         }
-                        for (int t = 0; t < T; ++t, ++w_use) {
-                            const int ws = w_use & 1;
-                            ptx::mbar_wait(&w_empty[ws], ((w_use >> 1) & 1) ^ 1);
-                            ptx::mbar_expect_tx(&w_full[ws], kWWBytes);
+                        for (int t = 0; t < T; ++t) {
                             const unsigned char *blk = reinterpret_cast<const unsigned char *>(w.weights) +
                                                        (size_t)((nc * n_chunks + c) * T + t) * kWWBytes;
-                            ptx::bulk_copy_g2s(smem + (ws ? WideSmem::w1 : WideSmem::w0), blk, kWWBytes, &w_full[ws]);
+                            for (int part = 0; part < 2; ++part, ++w_use) {      // hi, then lo: one ring stage each
+                                const int ws = w_use % kWStages;
+                                ptx::mbar_wait(&w_empty[ws], ((w_use / kWStages) & 1) ^ 1);
+                                ptx::mbar_expect_tx(&w_full[ws], kWStageBytes);
+                                unsigned char *dst = smem + WideSmem::w0 + ws * kWStageBytes;
+                                // one copy per plane: several requests in flight instead of one long one
+                                for (int q = 0; q < kWidePL; ++q)
+                                    ptx::bulk_copy_g2s(dst + q * kWPlaneW, blk + part * kWStageBytes + q * kWPlaneW, kWPlaneW, &w_full[ws]);
+                            }
                         }
                     }
                 }
@@ -125,7 +138,7 @@ __global__ void __launch_bounds__(kWThreads, 1) wide_l0_kernel(const __grid_cons
         if (ptx::elect_one()) {
             constexpr uint32_t idesc = ptx::idesc_tf32(128, kWN);
             const uint32_t a_base0 = ptx::smem_addr(smem + WideSmem::a0), a_base1 = ptx::smem_addr(smem + WideSmem::a1);
-            const uint32_t w_base0 = ptx::smem_addr(smem + WideSmem::w0), w_base1 = ptx::smem_addr(smem + WideSmem::w1);
+            const uint32_t w_base0 = ptx::smem_addr(smem + WideSmem::w0);
             uint32_t a_use = 0, w_use = 0, acc_use = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 for (int nc = 0; nc < n_nc; ++nc, ++acc_use) {
@@ -135,29 +148,32 @@ __global__ void __launch_bounds__(kWThreads, 1) wide_l0_kernel(const __grid_cons
                     for (int c = 0; c < n_chunks; ++c, ++a_use) {
                         const int ab = a_use & 1;
                         ptx::mbar_wait(&a_full[ab], (a_use >> 1) & 1);
-                        for (int t = 0; t < T; ++t, ++w_use) {
-                            const int ws = w_use & 1;
-                            ptx::mbar_wait(&w_full[ws], (w_use >> 1) & 1);
-                            ptx::tc_fence_after();
+                        for (int t = 0; t < T; ++t) {
 #pragma unroll 1
-                            for (int half = 0; half < 2; ++half) {
-                                const uint32_t d = tmem_base + half * kWN;
-                                const uint32_t a_row = (ab ? a_base1 : a_base0) + (uint32_t)(half * 128 + t) * 16u;
-                                uint32_t accf = acc;
+                            for (int part = 0; part < 2; ++part, ++w_use) {   // weight hi part: raw x hi, lo x hi; weight lo part: raw x lo   (3xTF32)
+                                const int ws = w_use % kWStages;
+                                ptx::mbar_wait(&w_full[ws], (w_use / kWStages) & 1);
+                                ptx::tc_fence_after();
+                                const uint32_t w_part = w_base0 + ws * kWStageBytes;
 #pragma unroll 1
-                                for (int pass = 0; pass < 3; ++pass) {      // raw x hi | lo x hi | raw x lo   (3xTF32)
-                                    const uint32_t a_part = a_row + (pass == 1 ? kWidePL * kWPlaneA : 0);
-                                    const uint32_t w_part = (ws ? w_base1 : w_base0) + (pass == 2 ? kWidePL * kWPlaneW : 0);
+                                for (int half = 0; half < 2; ++half) {
+                                    const uint32_t d = tmem_base + half * kWN;
+                                    const uint32_t a_row = (ab ? a_base1 : a_base0) + (uint32_t)(half * 128 + t) * 16u;
+                                    uint32_t accf = part ? 1u : acc;
+#pragma unroll 1
+                                    for (int pass = 0; pass < (part ? 1 : 2); ++pass) {
+                                        const uint32_t a_part = a_row + (pass == 1 ? kWidePL * kWPlaneA : 0);
 #pragma unroll
-                                    for (int ks = 0; ks < kWidePL / 2; ++ks) {
-                                        ptx::mma_tf32_ss(d, smem_desc_nosw(a_part + 2 * ks * kWPlaneA, kWPlaneA, 128),
-                                                         smem_desc_nosw(w_part + 2 * ks * kWPlaneW, kWPlaneW, 128), idesc, accf);
-                                        accf = 1;
+                                        for (int ks = 0; ks < kWidePL / 2; ++ks) {
+                                            ptx::mma_tf32_ss(d, smem_desc_nosw(a_part + 2 * ks * kWPlaneA, kWPlaneA, 128),
+                                                             smem_desc_nosw(w_part + 2 * ks * kWPlaneW, kWPlaneW, 128), idesc, accf);
+                                            accf = 1;
+                                        }
                                     }
                                 }
+                                ptx::mma_commit(&w_empty[ws]);
                             }
                             acc = 1;
-                            ptx::mma_commit(&w_empty[ws]);
                         }
                         ptx::mma_commit(&a_empty[ab]);
                     }
@@ -274,12 +290,181 @@ __global__ void __launch_bounds__(kWThreads, 1) wide_l0_kernel(const __grid_cons
     if (warp == 1) ptx::tmem_dealloc(tmem_base, kWTmemCols);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------------
+// stft_planes_fast_kernel: CircularShortTimeFourierTransform.extractPower (CSTFT.swift:280-337) for the high-overlap shape, band
+// slice + spectrogram scaling of SyllableDetector.processFourierData / processNewValue (Common/SyllableDetector.swift:134-212).
+// A CTA stages the audio span of kWideStftCols consecutive columns once (hop 4, window 1024: 64 columns share 1276 samples instead
+// of reading 65 536); each warp then transforms one frame at a time: the real N-point FFT as an M = N/2-point complex Stockham
+// autosort transform in shared memory, radix-8 stages (a last radix-2 / radix-4 stage when log2 M is not a multiple of 3), the
+// butterflies in registers (fft_regs.cuh), ping-pong buffers padded by one element per eight so that every stage's stride-8^s
+// stores and unit-stride loads are bank-conflict free. The band bins are untangled from the packed transform, scaled, and the tile
+// leaves the CTA in the plane layout wide_l0_kernel consumes ([plane][row][4 bins], raw and v - tf32(v)) together with the
+// per-column statistics of the per-window normalisers. (stft_planes_kernel in kernels_generic.cu is the reference-order fallback.)
+__device__ __forceinline__ int padf(int i) { return i + (i >> 3); }
+
+// One Stockham stage of radix R over the M-point sequence: out[(j / Ns) Ns R + j % Ns + r Ns] = DFT_R(in[j + r M / R] w^{r (j % Ns)}).
+// kFirst: the inputs come from the (windowed) audio instead of the ping-pong buffer.
+template <int R, bool kFirst>
+__device__ __forceinline__ void stockham_stage(const float2 *__restrict__ in, float2 *__restrict__ out, int M, int Ns, int lane,
+                                               const float2 *__restrict__ twM, const float *__restrict__ fr, const float *__restrict__ win, int W) {
+    const int nb = M / R;            // butterflies of this stage
+    const int tw_step = M / (Ns * R);
+    for (int j = lane; j < nb; j += 32) {
+        const int k = j & (Ns - 1);
+        float2 v[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int n = j + r * nb;
+            if constexpr (kFirst) {
+                const int m0 = 2 * n;
+                v[r] = make_float2(m0 < W ? fr[m0] * win[m0] : 0.0f, m0 + 1 < W ? fr[m0 + 1] * win[m0 + 1] : 0.0f);   // zero padding: CSTFT.swift:109-110
+            } else {
+                v[r] = in[padf(n)];
+            }
+        }
+        if (Ns > 1) {
+#pragma unroll
+            for (int r = 1; r < R; ++r) v[r] = cmul(v[r], twM[r * k * tw_step]);
+        }
+        Dft<R>::run(v);
+        const int base = (j - k) * R + k;
+#pragma unroll
+        for (int r = 0; r < R; ++r) out[padf(base + r * Ns)] = v[r];
+    }
+}
+
+__global__ void __launch_bounds__(512) stft_planes_fast_kernel(const DevNet *__restrict__ netp, const float *__restrict__ pcm, int64_t ch_stride,
+                                                               int64_t col0, int64_t n_cols, float *__restrict__ hi, float *__restrict__ lo,
+                                                               float4 *__restrict__ stats, int n_planes, int64_t rows_alloc) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const DevNet &net = *netp;
+    const int N = net.fft_len, M = N / 2, L = net.band, W = net.win_len, hop = net.hop;
+    const int warps = blockDim.x / 32, warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int pitch = n_planes * 4 + 1;
+    const int span = (kWideStftCols - 1) * hop + W;
+    float *audio = reinterpret_cast<float *>(smem_raw);                  // [span]
+    float *win = audio + ((span + 3) & ~3);                              // [W]
+    float *tile = win + ((W + 3) & ~3);                                  // [kWideStftCols][pitch]
+    float2 *twM = reinterpret_cast<float2 *>(tile + ((kWideStftCols * pitch + 1) & ~1));   // [M] e^{-2 pi i m / M}
+    float2 *utw = twM + M;                                               // [L] e^{-2 pi i (k0 + f) / N}
+    float2 *buf = utw + ((L + 1) & ~1);                                  // [warps][2][padf(M)]
+    const int bufM = padf(M) + 1;
+    float2 *b0 = buf + (size_t)warp * 2 * bufM, *b1 = b0 + bufM;
+    const int ch = blockIdx.y;
+    const int64_t c_first = (int64_t)blockIdx.x * kWideStftCols;
+    const int cols = (int)min((int64_t)kWideStftCols, n_cols - c_first);
+    const float *src = pcm + (int64_t)ch * ch_stride + (col0 + c_first) * hop + net.gap;
+    const int need = (cols - 1) * hop + W;
+    for (int i = threadIdx.x; i < need; i += blockDim.x) audio[i] = src[i];
+    for (int i = threadIdx.x; i < W; i += blockDim.x) win[i] = net.window[i];
+    for (int i = threadIdx.x; i < kWideStftCols * pitch; i += blockDim.x) tile[i] = 0.0f;   // padding bins and missing columns read as 0
+    for (int m = threadIdx.x; m < M; m += blockDim.x) {
+        double sn, cs;
+        sincospi(-2.0 * (double)m / (double)M, &sn, &cs);
+        twM[m] = make_float2((float)cs, (float)sn);
+    }
+    for (int f = threadIdx.x; f < L; f += blockDim.x) {
+        double sn, cs;
+        sincospi(-2.0 * (double)(net.k0 + f) / (double)N, &sn, &cs);
+        utw[f] = make_float2((float)cs, (float)sn);
+    }
+    __syncthreads();
+    int log_m = 0;
+    while ((1 << log_m) < M) ++log_m;
+    const int last_radix = log_m % 3 == 0 ? 8 : (log_m % 3 == 1 ? 2 : 4);
+    for (int c = warp; c < cols; c += warps) {
+        const float *fr = audio + c * hop;
+        float2 *in = b0, *out = b1;
+        int Ns = 1;
+        // radix-8 stages, the first one straight from the windowed audio; then the remainder stage
+        if (M >= 8) {
+            stockham_stage<8, true>(nullptr, out, M, 1, lane, twM, fr, win, W);
+            Ns = 8;
+            __syncwarp();
+            while (Ns * (last_radix == 8 ? 1 : last_radix) < M) {
+                float2 *t2 = in; in = out; out = t2;
+                stockham_stage<8, false>(in, out, M, Ns, lane, twM, nullptr, nullptr, 0);
+                Ns *= 8;
+                __syncwarp();
+            }
+            if (last_radix != 8) {
+                float2 *t2 = in; in = out; out = t2;
+                if (last_radix == 2) stockham_stage<2, false>(in, out, M, Ns, lane, twM, nullptr, nullptr, 0);
+                else stockham_stage<4, false>(in, out, M, Ns, lane, twM, nullptr, nullptr, 0);
+                __syncwarp();
+            }
+        }
+        // untangle the packed real transform, magnitude, band slice (as kernels_fused.cu): X[k] = ((Z[k] + conj Z[M-k]) - i w^k (Z[k] - conj Z[M-k])) / 2;
+        // with M-k taken mod M the same expression gives |Re Z[0] + Im Z[0]| for k = 0 (the Nyquist term is dropped upstream, CSTFT.swift:323)
+        const float2 *z = out;
+        float *row = tile + c * pitch;
+        float ss = 0.0f, mn = INFINITY, mx = -INFINITY;
+        for (int f = lane; f < L; f += 32) {
+            const int k = net.k0 + f, km = (M - k) & (M - 1);
+            const float2 za = z[padf(k)], zc = z[padf(km)], t = utw[f];
+            const float sr = za.x + zc.x, si = za.y - zc.y, dr = za.x - zc.x, di = za.y + zc.y;
+            const float re = sr + (t.x * di + t.y * dr), im = si - (t.x * dr - t.y * di);
+            float v = 0.5f * sqrtf(re * re + im * im);
+            v = scale_value(v, net.scaling);
+            row[f] = v;
+            ss = fmaf(v, v, ss);
+            mn = fminf(mn, v);
+            mx = fmaxf(mx, v);
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            ss += __shfl_xor_sync(0xffffffffu, ss, d);
+            mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, d));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+        }
+        if (lane == 0) stats[(int64_t)ch * rows_alloc + c_first + c] = make_float4(ss, mn, mx, 0.0f);
+        __syncwarp();
+    }
+    __syncthreads();
+    float4 *hi4 = reinterpret_cast<float4 *>(hi) + (int64_t)ch * n_planes * rows_alloc + c_first;
+    float4 *lo4 = reinterpret_cast<float4 *>(lo) + (int64_t)ch * n_planes * rows_alloc + c_first;
+    for (int i = threadIdx.x; i < n_planes * kWideStftCols; i += blockDim.x) {
+        const int pl = i / kWideStftCols, r = i % kWideStftCols;   // consecutive threads: consecutive rows of one plane (16 B each)
+        if (r < cols) {
+            const float *v = tile + r * pitch + pl * 4;
+            const float4 raw = make_float4(v[0], v[1], v[2], v[3]);
+            hi4[(int64_t)pl * rows_alloc + r] = raw;
+            lo4[(int64_t)pl * rows_alloc + r] = make_float4(raw.x - tf32_trunc_w(raw.x), raw.y - tf32_trunc_w(raw.y), raw.z - tf32_trunc_w(raw.z),
+                                                            raw.w - tf32_trunc_w(raw.w));
+        }
+    }
+}
+
 }  // namespace
 
 size_t wide_smem_bytes(int h_pad) { return 128 + WideSmem::total(h_pad); }
 int wide_tile_rows() { return kWTileRows; }
 int wide_max_time_range() { return kWRowsPad - kWTileRows + 1; }
 size_t wide_weight_block_bytes() { return kWWBytes; }
+
+bool stft_planes_fast_supported(int fft_len) { return fft_len >= 16 && fft_len <= 2048; }
+
+static size_t stft_planes_fast_smem(int fft_len, int win_len, int band, int hop, int n_planes, int warps) {
+    const int M = fft_len / 2, span = (kWideStftCols - 1) * hop + win_len, pitch = n_planes * 4 + 1;
+    const size_t floats = (size_t)((span + 3) & ~3) + ((win_len + 3) & ~3) + ((kWideStftCols * pitch + 1) & ~1);
+    const size_t f2 = (size_t)M + ((band + 1) & ~1) + (size_t)warps * 2 * (M + (M >> 3) + 1);
+    return floats * 4 + f2 * 8 + 16;
+}
+
+cudaError_t launch_stft_planes_fast(const DevNet *d_net, int fft_len, int win_len, int band, int hop, const float *pcm, int64_t ch_stride,
+                                    int n_channels, int64_t col0, int64_t n_cols, float *hi, float *lo, float4 *stats, int n_planes,
+                                    int64_t rows_alloc, cudaStream_t stream) {
+    if (n_cols <= 0 || n_channels <= 0) return cudaSuccess;
+    int warps = 16;   // one CTA per SM: as many warps as the ping-pong buffers leave room for
+    while (warps > 4 && stft_planes_fast_smem(fft_len, win_len, band, hop, n_planes, warps) > 220 * 1024) warps -= 4;
+    const size_t smem = stft_planes_fast_smem(fft_len, win_len, band, hop, n_planes, warps);
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(stft_planes_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid((unsigned)((n_cols + kWideStftCols - 1) / kWideStftCols), (unsigned)n_channels);
+    stft_planes_fast_kernel<<<grid, warps * 32, smem, stream>>>(d_net, pcm, ch_stride, col0, n_cols, hi, lo, stats, n_planes, rows_alloc);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_wide(int grid, const WideParams &p, const WideWork &w, cudaStream_t stream) {
     const size_t smem = wide_smem_bytes(p.h_pad);

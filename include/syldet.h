@@ -203,6 +203,16 @@ int syldet_detector_seen_syllable(syldet_detector *d);                          
 
 /* ---- live group: Processor.swift (one detector per channel, small buffers per tick) -------------------------------- */
 syldet_status syldet_stream_create(const syldet_config *cfg, int n_channels, int max_buffer, int device, syldet_stream **out);
+/*
+ * The same group fed at the audio DEVICE's rate: "if abs(config.samplingRate - inputRate) > 1 { resampler = ResamplerLinear(...) }"
+ * (SyllableDetector/ViewControllerProcessor.swift:247-250) and the per-channel resampleVector call of receiveAudioFrom
+ * (SyllableDetector/Processor.swift:116-121). Every submitted buffer is one ResamplerLinear.resampleVector call per channel
+ * (Common/Resampler.swift:35-70, bit-faithful including the carried offset / last sample); the interpolation runs inside the tick
+ * kernel, the `last` sample of every channel stays on the device. input_rate within 1 Hz of the configuration's rate: no resampling.
+ */
+syldet_status syldet_stream_create_resampled(const syldet_config *cfg, int n_channels, int max_buffer, int device, double input_rate,
+                                             syldet_stream **out);
+int syldet_stream_resampling(const syldet_stream *s); /* 1 when the group resamples its input */
 void syldet_stream_destroy(syldet_stream *s);
 /*
  * One tick: bufs[c] points at n float32 samples for channel c (receiveAudioFrom(...) for every channel, Processor.swift:102-149).

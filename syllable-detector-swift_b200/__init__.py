@@ -104,6 +104,7 @@ def _load():
         "syldet_detector_last_outputs": (i32, [vp, vp, i32]), "syldet_detector_last_detected": (i32, [vp]),
         "syldet_detector_seen_syllable": (i32, [vp]),
         "syldet_stream_create": (i32, [vp, i32, i32, i32, pvp]), "syldet_stream_destroy": (None, [vp]),
+        "syldet_stream_create_resampled": (i32, [vp, i32, i32, i32, dbl, pvp]), "syldet_stream_resampling": (i32, [vp]),
         "syldet_stream_submit": (i32, [vp, vp, i32, vp, vp, vp]), "syldet_stream_launch_count": (i64, [vp]),
         "syldet_stream_read_levels": (i32, [vp, vp, vp]), "syldet_stream_set_pulse": (i32, [vp, dbl, dbl]),
         "syldet_stream_render_pulses": (i32, [vp, vp, i32]),
@@ -473,11 +474,16 @@ class TrackDetector:
 class StreamGroup:
     """Many live channels, one small buffer per channel per tick (SyllableDetector/Processor.swift:102-149)."""
 
-    def __init__(self, config, n_channels, max_buffer=32, device=0):
+    def __init__(self, config, n_channels, max_buffer=32, device=0, input_rate=None):
+        """input_rate: sampling rate of the submitted buffers when it is not the configuration's (the audio device's rate,
+        ViewControllerProcessor.swift:247-250): every buffer then goes through ResamplerLinear inside the tick kernel."""
         self.config = config
         self.n_channels = n_channels
         self._h = C.c_void_p()
-        _check(lib.syldet_stream_create(config._h, n_channels, max_buffer, device, C.byref(self._h)))
+        if input_rate is None:
+            _check(lib.syldet_stream_create(config._h, n_channels, max_buffer, device, C.byref(self._h)))
+        else:
+            _check(lib.syldet_stream_create_resampled(config._h, n_channels, max_buffer, device, float(input_rate), C.byref(self._h)))
         self._seen = np.zeros(n_channels, dtype=np.uint8)
         self._n_new = np.zeros(n_channels, dtype=np.int32)
         self.last_outputs = np.zeros((n_channels, config.net_outputs), dtype=np.float32)
@@ -491,6 +497,10 @@ class StreamGroup:
     @property
     def launch_count(self):
         return lib.syldet_stream_launch_count(self._h)
+
+    @property
+    def resampling(self):
+        return bool(lib.syldet_stream_resampling(self._h))
 
     def read_levels(self):
         """-> (input_rms[n_channels], output_max[n_channels]) since the last call, NaN = upstream's nil

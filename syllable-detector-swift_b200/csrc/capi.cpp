@@ -284,6 +284,19 @@ syldet_status syldet_stream_create(const syldet_config *cfg, int n_channels, int
         return SYLDET_OK;
     });
 }
+syldet_status syldet_stream_create_resampled(const syldet_config *cfg, int n_channels, int max_buffer, int device, double input_rate,
+                                            syldet_stream **out) {
+    if (!valid_or_null(cfg) || !out) return set_error(SYLDET_ERR_ARG, "null argument");
+    *out = nullptr;
+    return guarded([&] {
+        auto *s = new syldet_stream();
+        syldet_status st = s->g.init(cfg->c, n_channels, max_buffer, device, input_rate);
+        if (st != SYLDET_OK) { delete s; return st; }
+        *out = s;
+        return SYLDET_OK;
+    });
+}
+int syldet_stream_resampling(const syldet_stream *s) { return s && s->g.resampling() ? 1 : 0; }
 void syldet_stream_destroy(syldet_stream *s) { delete s; }
 syldet_status syldet_stream_submit(syldet_stream *s, const float *const *bufs, int n, uint8_t *seen, int32_t *n_new, float *last_out) {
     if (!s || !bufs) return set_error(SYLDET_ERR_ARG, "null argument");

@@ -912,6 +912,37 @@ syldet_status Batch::launch_device(const float *d_pcm, int n_channels, int64_t n
                          detect_rule, d_all_outputs, stream);
 }
 
+namespace {
+// Detections leave the kernels in arrival order (one atomic per batch); the rows of the CLI are ordered by (channel, evaluation).
+// key = channel << 40 | evaluation. LSD radix sort, 11 bits per pass over the digits that are in use: ~3 passes of sequential memory
+// traffic instead of std::sort's ~20 compare-and-swap levels (400 000 detections per 1 h x 8 ch recording: 25 ms -> 3 ms).
+struct EventKey {
+    uint64_t key;
+    uint32_t idx;
+};
+void sort_event_keys(std::vector<EventKey> &keys) {
+    const size_t n = keys.size();
+    if (n < 2048) {
+        std::sort(keys.begin(), keys.end(), [](const EventKey &a, const EventKey &b) { return a.key < b.key; });
+        return;
+    }
+    uint64_t all = 0;
+    for (const EventKey &k : keys) all |= k.key;
+    std::vector<EventKey> tmp(n);
+    std::vector<size_t> count(2049);
+    EventKey *src = keys.data(), *dst = tmp.data();
+    for (int shift = 0; shift < 64; shift += 11) {
+        if (((all >> shift) & 0x7FF) == 0) continue;   // no key has a bit set in this digit: already ordered by it
+        std::fill(count.begin(), count.end(), (size_t)0);
+        for (size_t i = 0; i < n; ++i) ++count[((src[i].key >> shift) & 0x7FF) + 1];
+        for (int d = 0; d < 2048; ++d) count[d + 1] += count[d];
+        for (size_t i = 0; i < n; ++i) dst[count[(src[i].key >> shift) & 0x7FF]++] = src[i];
+        std::swap(src, dst);
+    }
+    if (src != keys.data()) std::memcpy(keys.data(), src, n * sizeof(EventKey));
+}
+}  // namespace
+
 // Waits for the last launch and makes its results final. Two things can ask for a repeat of the launch: more detections than the
 // event buffer holds (grow it to the worst case), and the range flag of the tensor kernel's fp16 correction pass (audio outside the
 // window in which that pass is at float32 level: this handle switches to the all-TF32 variant for good). Dense outputs the caller
@@ -981,19 +1012,17 @@ syldet_status Batch::collect(int64_t debounce_frames, Events &out) {
         SYLDET_CUDA(cudaMemcpy(outs.data(), sink_outputs_.get(), outs.size() * sizeof(float), cudaMemcpyDeviceToHost));
     }
     const double t_c2 = now_ms();
-    std::vector<size_t> order(n);
-    std::iota(order.begin(), order.end(), (size_t)0);
-    std::sort(order.begin(), order.end(), [&](size_t a, size_t b) {
-        return ev[a].channel != ev[b].channel ? ev[a].channel < ev[b].channel : ev[a].eval < ev[b].eval;
-    });
+    std::vector<EventKey> keys(n);
+    for (size_t i = 0; i < n; ++i) keys[i] = EventKey{((uint64_t)(uint32_t)ev[i].channel << 40) | (uint64_t)ev[i].eval, (uint32_t)i};
+    sort_event_keys(keys);
     out.outputs_per_event = O;
     out.rows.resize(n);
     out.outputs.resize((size_t)n * O);
     const int64_t first = c.first_output_sample();
     for (size_t r = 0; r < n; ++r) {
-        const DevEvent &e = ev[order[r]];
+        const DevEvent &e = ev[keys[r].idx];
         out.rows[r] = syldet_event{e.channel, 0, first + (int64_t)c.hop * e.eval};  // TrackDetector.swift:39-42,67-68
-        std::copy(outs.begin() + order[r] * O, outs.begin() + (order[r] + 1) * O, out.outputs.begin() + r * O);
+        std::copy(outs.begin() + (size_t)keys[r].idx * O, outs.begin() + ((size_t)keys[r].idx + 1) * O, out.outputs.begin() + r * O);
     }
     const double t_c3 = now_ms();
     debounce_sorted(c, out.rows, out.outputs, O, debounce_frames);
@@ -1128,10 +1157,7 @@ syldet_status Batch::run_host(const void *pcm, int fmt, int n_channels, int64_t 
     }
 
     // ---- per slice: wait, read its events back, sort them by (channel, evaluation) while later slices are still in flight ----
-    struct Key {
-        uint64_t key;
-        uint32_t idx;
-    };
+    using Key = EventKey;
     DevEvent *h_ev = static_cast<DevEvent *>(h_events_);
     float *h_out = reinterpret_cast<float *>(h_ev + sink_capacity_);
     std::vector<std::vector<Key>> sorted(K);
@@ -1158,7 +1184,7 @@ syldet_status Batch::run_host(const void *pcm, int fmt, int n_channels, int64_t 
             const DevEvent &e = h_ev[done + i];
             keys[i] = Key{((uint64_t)(uint32_t)e.channel << 40) | (uint64_t)e.eval, (uint32_t)(done + i)};
         }
-        std::sort(keys.begin(), keys.end(), [](const Key &a, const Key &b) { return a.key < b.key; });
+        sort_event_keys(keys);
         done = n_k;
     }
     if (redo) {

@@ -47,6 +47,16 @@ struct StreamTick {
     int n_marks;           // staged buffers in this launch (<= kStreamMaxMarks)
     int marks[8];          // end of each staged buffer, in samples from the start of the staging area
     long long *stamps;     // optional pinned host [10]: clock64 at the phase boundaries of block (0,0) (SYLDET_STREAM_TIMING=1)
+    // ResamplerLinear inside the tick (Processor.swift:116-121: resampleVector per channel before appendAudioData). The staged
+    // samples are at the DEVICE rate; every staged buffer b is one resampleVector call producing rs_n_out[b] samples at ring
+    // position ring_pos + rs_out0[b]. The data-independent phase (`offset`) comes from the host, `last` lives on the device.
+    int rs_on;
+    float rs_step;
+    const float *rs_last_in;   // device [n_channels]: last sample of the previous tick's final buffer (Resampler.swift:66)
+    float *rs_last_out;        // device [n_channels]: written by this tick (the two arrays alternate, so a launch never reads what it writes)
+    float rs_offset[8];
+    int rs_n_out[8];
+    int rs_out0[8];
 };
 constexpr size_t kStreamTickMaxSmem = 200 * 1024;
 constexpr int kStreamMaxMarks = 8;

@@ -10,6 +10,7 @@
 //   decision:     SyllableDetectorCLI/TrackDetector.swift:71-77, Common/SyllableDetector.swift:27-31
 // The fused kernel (kernels_fused.cu) is the fast path; this one is the general one and the on-device cross-check.
 #include "kernels.hpp"
+#include "resample.cuh"
 
 namespace syldet {
 
@@ -466,7 +467,7 @@ __global__ void stream_tick_kernel(const DevNet *__restrict__ netp, StreamTick t
     // (1) the longest-latency loads first: this channel's staged samples, straight out of pinned host memory
     const float *src = t.staged + (int64_t)ch * t.stage_pitch;
     float pre[2] = {0.0f, 0.0f};
-    if (t.phases & STREAM_PHASE_COPY) {
+    if ((t.phases & STREAM_PHASE_COPY) && !t.rs_on) {
 #pragma unroll
         for (int k = 0; k < 2; ++k)
             if (tid0 + k * tstride < t.n_staged) pre[k] = src[tid0 + k * tstride];
@@ -494,11 +495,21 @@ __global__ void stream_tick_kernel(const DevNet *__restrict__ netp, StreamTick t
     float *ring = t.ring + (int64_t)ch * (t.ring_mask + 1);
     if (stamp) ts[1] = clock64();
 
-    if (t.phases & STREAM_PHASE_COPY) {
+    if ((t.phases & STREAM_PHASE_COPY) && !t.rs_on) {
 #pragma unroll
         for (int k = 0; k < 2; ++k)
             if (tid0 + k * tstride < t.n_staged) ring[(t.ring_pos + tid0 + k * tstride) & t.ring_mask] = pre[k];
         for (int i = tid0 + 2 * tstride; i < t.n_staged; i += tstride) ring[(t.ring_pos + i) & t.ring_mask] = src[i];
+    } else if (t.phases & STREAM_PHASE_COPY) {
+        // device-rate buffers -> ResamplerLinear -> sample ring: one resampleVector call per staged buffer (Processor.swift:116-121)
+        for (int b = 0; b < t.n_marks; ++b) {
+            const int lo = b ? t.marks[b - 1] : 0, n_in = t.marks[b] - lo, n_out = t.rs_n_out[b];
+            const float off = t.rs_offset[b];
+            const float last = b ? src[lo - 1] : t.rs_last_in[ch];
+            for (int k = tid0; k < n_out; k += tstride)
+                ring[(t.ring_pos + t.rs_out0[b] + k) & t.ring_mask] = resample_linear_point(src + lo, n_in, off, t.rs_step, last, off < 0.0f, k);
+        }
+        if (tid0 == 0 && t.n_staged > 0) t.rs_last_out[ch] = src[t.n_staged - 1];
     }
     __syncthreads();
     if (stamp) ts[2] = clock64();
@@ -511,7 +522,7 @@ __global__ void stream_tick_kernel(const DevNet *__restrict__ netp, StreamTick t
             const int lo = b ? t.marks[b - 1] : 0, hi = t.marks[b];
             float part = 0.0f;
             for (int i = lo + lane; i < hi; i += kWarp) {
-                const float v = gridDim.x == 1 ? ring[(t.ring_pos + i) & t.ring_mask] : src[i];
+                const float v = (gridDim.x == 1 && !t.rs_on) ? ring[(t.ring_pos + i) & t.ring_mask] : src[i];   // the meter sees the device-rate samples
                 part += v * v;
             }
             part = warp_sum(part);                                  // vDSP_svesq: summation order unspecified

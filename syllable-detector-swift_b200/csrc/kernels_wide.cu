@@ -14,8 +14,8 @@
 // per tile and used by all T offsets, the weights stream through a four-stage ring of pre-arranged blocks (cp.async.bulk, one per plane).
 //   per tile: 256 evaluations (two M = 128 accumulators of N = 256 columns: all 512 TMEM columns), so that every weight block that
 //   crosses L2 -> shared memory feeds 2 x 128 rows (the weight stream is what bounds this kernel after the tensor pipe).
-// Roles: warp 0 loader (cp.async.bulk), warp 1 MMA issuer + TMEM, warps 2-5 epilogue (one per TMEM lane quadrant; a thread owns one
-// row of each accumulator, i.e. two evaluations, so the output layer needs no cross-lane reduction).
+// Roles: warp 0 loader (cp.async.bulk), warp 1 MMA issuer + TMEM, warps 2-9 epilogue (one per TMEM lane quadrant and accumulator; a
+// thread owns one accumulator row = one evaluation, so the output layer needs no cross-lane reduction).
 #include <cuda.h>
 
 #include "fft_regs.cuh"
@@ -26,7 +26,7 @@ namespace syldet {
 
 namespace {
 
-constexpr int kWThreads = 6 * 32;
+constexpr int kWThreads = 10 * 32;                  // loader, MMA issuer, 2 x 4 epilogue warps
 constexpr int kWTileRows = 256;                     // evaluations per tile (2 accumulators x 128 TMEM lanes)
 constexpr int kWRowsPad = kWTileRows + 16;          // magnitude rows in shared memory: tile + T - 1 (T <= 17)
 constexpr int kWN = 256;                            // hidden units per accumulator pass
@@ -39,8 +39,8 @@ constexpr int kWStages = 4;                         // ring depth: three stages 
 constexpr int kWTmemCols = 512;
 
 struct WideSmem {
-    static constexpr int a0 = 0, a1 = kWABytes, w0 = 2 * kWABytes, vb = w0 + kWStages * kWStageBytes;   // then float2 vb[h_pad], barriers
-    __host__ __device__ static constexpr int bars(int h_pad) { return vb + h_pad * 8; }
+    static constexpr int a0 = 0, a1 = kWABytes, w0 = 2 * kWABytes, cst = w0 + kWStages * kWStageBytes;   // then float4 cst[h_pad], barriers
+    __host__ __device__ static constexpr int bars(int h_pad) { return cst + h_pad * 16; }
     __host__ __device__ static constexpr int total(int h_pad) { return bars(h_pad) + 256; }
 };
 static_assert(kWABytes % 128 == 0 && kWStageBytes % 128 == 0, "alignment of the operand buffers");
@@ -50,6 +50,104 @@ static_assert(kWABytes % 128 == 0 && kWStageBytes % 128 == 0, "alignment of the 
 __device__ __forceinline__ uint64_t smem_desc_nosw(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
            ((uint64_t)1 << 46);
+}
+
+// The rest of NeuralNet.apply for the rows of one accumulator (NeuralNet.swift:310-323): z = acc * alpha + beta * V + B', hidden
+// transfer function, output layer, output transfer, reverse maps in index order, threshold test (TrackDetector.swift:71-77), events.
+// cst[h] = {V_h, B'_h, W1[0][h], W1[1][h]}: outputs 0 and 1 come from shared memory, further outputs (rare) from global memory.
+template <int TF0>
+__device__ __forceinline__ void wide_epilogue(const WideParams &p, const WideWork &w, const float4 *__restrict__ cst, uint64_t *acc_full,
+                                              uint64_t *acc_empty, uint32_t tmem_base, int warp, int lane, int n_tiles, int tiles_per_ch, int n_nc) {
+    const int quad = warp & 3, half = (warp - 2) >> 2;
+    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + half * kWN;
+    const int n_out = p.n_out, T = p.time_range;
+    uint32_t acc_use = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int ch = tile / tiles_per_ch;
+        const int64_t j = (int64_t)(tile - ch * tiles_per_ch) * kWTileRows + half * 128 + quad * 32 + lane;
+        const bool valid = j < w.n_evals;
+        float inv = 1.0f, beta = 0.0f;
+        if (valid && p.window_stat != FUSED_STAT_NONE) {      // window statistic from the per-column partials
+            const float4 *st = w.stats + (int64_t)ch * w.rows_alloc + j;
+            float s0 = p.window_stat == FUSED_STAT_L2 ? 0.0f : INFINITY, s1 = -INFINITY;
+            for (int t = 0; t < T; ++t) {
+                const float4 c4 = __ldg(st + t);
+                if (p.window_stat == FUSED_STAT_L2) s0 += c4.x;
+                else { s0 = fminf(s0, c4.y); s1 = fmaxf(s1, c4.z); }
+            }
+            if (p.window_stat == FUSED_STAT_L2) inv = rcp_fast(sqrt_fast(s0));   // silence: 0 * inf = NaN (NeuralNet.swift:47-59)
+            else {
+                const float range = s1 - s0;
+                if (0 == range) { inv = 0.0f; beta = -1.0f; }                     // flat window (NeuralNet.swift:84-88)
+                else { inv = 2.0f / range; beta = (0 - s0 - s1) / range; }
+            }
+        }
+        float out[kFusedMaxOut];
+#pragma unroll
+        for (int o = 0; o < kFusedMaxOut; ++o) out[o] = o < n_out ? p.b1[o] : 0.0f;
+        for (int nc = 0; nc < n_nc; ++nc, ++acc_use) {
+            ptx::mbar_wait(acc_full, acc_use & 1);
+            ptx::tc_fence_after();
+#pragma unroll 1
+            for (int cb = 0; cb < kWN / 32; ++cb) {
+                uint32_t r[32];
+                ptx::tmem_ld_x32(taddr + cb * 32, r);
+                ptx::tc_wait_ld();
+                const int h0 = nc * kWN + cb * 32;
+                if (h0 < p.hidden) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float4 c4 = cst[h0 + i];
+                        const float a = transfer_fast(TF0, fmaf(__uint_as_float(r[i]), inv, fmaf(beta, c4.x, c4.y)));
+                        out[0] = fmaf(c4.z, a, out[0]);
+                        out[1] = fmaf(c4.w, a, out[1]);
+                        if (n_out > 2) {
+                            const float *w1 = w.w1 + h0 + i;                 // [n_out][h_pad]; padded hidden units have zero weights
+#pragma unroll
+                            for (int o = 2; o < kFusedMaxOut; ++o)
+                                if (o < n_out) out[o] = fmaf(__ldg(w1 + (size_t)o * p.h_pad), a, out[o]);
+                        }
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(acc_empty);
+        }
+        // output transfer, reverse maps in index order (NeuralNet.swift:316-323), threshold test, events
+        bool hit = false;
+#pragma unroll
+        for (int o = 0; o < kFusedMaxOut; ++o) {
+            if (o < n_out) {
+                float v = transfer_fast(p.tf1, out[o]);
+                for (int k = 0; k < p.n_op; ++k) v = (v + (0 - p.op_y[k])) / p.op_gain[k * kFusedMaxOut + o] + p.op_xoff[k * kFusedMaxOut + o];
+                out[o] = v;
+                if (v >= p.thr_f[o] && (w.detect_rule == SYLDET_DETECT_ANY_OUTPUT || o == 0)) hit = true;   // NaN -> false
+            }
+        }
+        hit = hit && valid;
+        if (valid && w.all_out) {
+            float *dst = w.all_out + ((int64_t)ch * w.out_evals_per_channel + w.eval_offset + j) * n_out;
+#pragma unroll
+            for (int o = 0; o < kFusedMaxOut; ++o)
+                if (o < n_out) dst[o] = out[o];
+        }
+        const unsigned hits = __ballot_sync(0xffffffffu, hit);
+        if (hits) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(w.sink.count, (unsigned long long)__popc(hits));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (hit) {
+                const unsigned long long idx = base + __popc(hits & ((1u << lane) - 1));
+                if (idx < w.sink.capacity) {
+                    w.sink.events[idx] = DevEvent{ch, 0, w.eval_offset + j};
+#pragma unroll
+                    for (int o = 0; o < kFusedMaxOut; ++o)
+                        if (o < n_out) w.sink.outputs[idx * n_out + o] = out[o];
+                }
+            }
+        }
+    }
 }
 
 __device__ __forceinline__ float tf32_trunc_w(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
@@ -63,7 +161,7 @@ __global__ void __launch_bounds__(kWThreads, 1) wide_l0_kernel(const __grid_cons
     uint64_t *a_full = bars, *a_empty = bars + 2, *w_full = bars + 4, *w_empty = bars + 4 + kWStages, *acc_full = bars + 4 + 2 * kWStages,
              *acc_empty = acc_full + 1;
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(acc_empty + 1);
-    float2 *vb = reinterpret_cast<float2 *>(smem + WideSmem::vb);
+    float4 *cst = reinterpret_cast<float4 *>(smem + WideSmem::cst);   // {V_h, B'_h, W1[0][h], W1[1][h]}
 
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
@@ -75,14 +173,15 @@ __global__ void __launch_bounds__(kWThreads, 1) wide_l0_kernel(const __grid_cons
             ptx::mbar_init(&w_empty[i], 1);
         }
         ptx::mbar_init(acc_full, 1);
-        ptx::mbar_init(acc_empty, 4);
+        ptx::mbar_init(acc_empty, 8);
         ptx::fence_mbar_init();
     }
     if (warp == 1) {
         ptx::tmem_alloc(tmem_ptr, kWTmemCols);
         ptx::tmem_relinquish();
     }
-    for (int h = tid; h < p.h_pad; h += kWThreads) vb[h] = make_float2(__ldg(w.v + h), __ldg(w.bprime + h));
+    for (int h = tid; h < p.h_pad; h += kWThreads)
+        cst[h] = make_float4(__ldg(w.v + h), __ldg(w.bprime + h), __ldg(w.w1 + h), p.n_out > 1 ? __ldg(w.w1 + p.h_pad + h) : 0.0f);
     // rows of the A buffers that no copy fills (the tail of the last tile of a channel) must hold finite values
     for (int i = tid; i < 2 * kWABytes / 16; i += kWThreads) reinterpret_cast<float4 *>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     ptx::fence_proxy_async_smem();
@@ -183,106 +282,13 @@ __global__ void __launch_bounds__(kWThreads, 1) wide_l0_kernel(const __grid_cons
         }
     } else {
         // ================================ epilogue ====================================================================
-        const int quad = warp & 3;
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
-        const int n_out = p.n_out;
-        uint32_t acc_use = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int ch = tile / tiles_per_ch;
-            const int64_t j0 = (int64_t)(tile - ch * tiles_per_ch) * kWTileRows;
-            // this thread's two evaluations: rows quad*32 + lane of each accumulator
-            float inv[2], beta[2], out[2][kFusedMaxOut];
-            bool valid[2];
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const int64_t j = j0 + half * 128 + quad * 32 + lane;
-                valid[half] = j < w.n_evals;
-                inv[half] = 1.0f;
-                beta[half] = 0.0f;
-                if (valid[half] && p.window_stat != FUSED_STAT_NONE) {      // window statistic from the per-column partials
-                    const float4 *st = w.stats + (int64_t)ch * w.rows_alloc + j;
-                    float s0 = p.window_stat == FUSED_STAT_L2 ? 0.0f : INFINITY, s1 = -INFINITY;
-                    for (int t = 0; t < T; ++t) {
-                        const float4 c4 = __ldg(st + t);
-                        if (p.window_stat == FUSED_STAT_L2) s0 += c4.x;
-                        else { s0 = fminf(s0, c4.y); s1 = fmaxf(s1, c4.z); }
-                    }
-                    if (p.window_stat == FUSED_STAT_L2) inv[half] = rcp_fast(sqrt_fast(s0));   // silence: 0 * inf = NaN (NeuralNet.swift:47-59)
-                    else {
-                        const float range = s1 - s0;
-                        if (0 == range) { inv[half] = 0.0f; beta[half] = -1.0f; }               // flat window (NeuralNet.swift:84-88)
-                        else { inv[half] = 2.0f / range; beta[half] = (0 - s0 - s1) / range; }
-                    }
-                }
-#pragma unroll
-                for (int o = 0; o < kFusedMaxOut; ++o) out[half][o] = o < n_out ? p.b1[o] : 0.0f;
-            }
-            for (int nc = 0; nc < n_nc; ++nc, ++acc_use) {
-                ptx::mbar_wait(acc_full, acc_use & 1);
-                ptx::tc_fence_after();
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-#pragma unroll 1
-                    for (int cb = 0; cb < kWN / 32; ++cb) {
-                        uint32_t r[32];
-                        ptx::tmem_ld_x32(lane_addr + half * kWN + cb * 32, r);
-                        ptx::tc_wait_ld();
-                        const int h0 = nc * kWN + cb * 32;
-                        if (h0 < p.hidden) {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                                const int h = h0 + i;
-                                const float2 c2 = vb[h];
-                                const float a = transfer_fast(p.tf0, fmaf(__uint_as_float(r[i]), inv[half], fmaf(beta[half], c2.x, c2.y)));
-                                const float *w1 = w.w1 + h;                  // [n_out][h_pad]; padded hidden units have zero weights
-#pragma unroll
-                                for (int o = 0; o < kFusedMaxOut; ++o)
-                                    if (o < n_out) out[half][o] = fmaf(__ldg(w1 + (size_t)o * p.h_pad), a, out[half][o]);
-                            }
-                        }
-                    }
-                }
-                ptx::tc_fence_before();
-                __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(acc_empty);
-            }
-            // output transfer, reverse maps in index order (NeuralNet.swift:316-323), threshold test, events
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                bool hit = false;
-                const int64_t j = j0 + half * 128 + quad * 32 + lane;
-#pragma unroll
-                for (int o = 0; o < kFusedMaxOut; ++o) {
-                    if (o < n_out) {
-                        float v = transfer_fast(p.tf1, out[half][o]);
-                        for (int k = 0; k < p.n_op; ++k) v = (v + (0 - p.op_y[k])) / p.op_gain[k * kFusedMaxOut + o] + p.op_xoff[k * kFusedMaxOut + o];
-                        out[half][o] = v;
-                        if (v >= p.thr_f[o] && (w.detect_rule == SYLDET_DETECT_ANY_OUTPUT || o == 0)) hit = true;   // NaN -> false
-                    }
-                }
-                hit = hit && valid[half];
-                if (valid[half] && w.all_out) {
-                    float *dst = w.all_out + ((int64_t)ch * w.out_evals_per_channel + w.eval_offset + j) * n_out;
-#pragma unroll
-                    for (int o = 0; o < kFusedMaxOut; ++o)
-                        if (o < n_out) dst[o] = out[half][o];
-                }
-                const unsigned hits = __ballot_sync(0xffffffffu, hit);
-                if (hits) {
-                    unsigned long long base = 0;
-                    if (lane == 0) base = atomicAdd(w.sink.count, (unsigned long long)__popc(hits));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (hit) {
-                        const unsigned long long idx = base + __popc(hits & ((1u << lane) - 1));
-                        if (idx < w.sink.capacity) {
-                            w.sink.events[idx] = DevEvent{ch, 0, w.eval_offset + j};
-#pragma unroll
-                            for (int o = 0; o < kFusedMaxOut; ++o)
-                                if (o < n_out) w.sink.outputs[idx * n_out + o] = out[half][o];
-                        }
-                    }
-                }
-            }
+        // Eight warps: warps 2-5 read accumulator 0, warps 6-9 accumulator 1 (TMEM lane quadrant = warp % 4). A thread owns one row =
+        // one evaluation. The hidden transfer function is a compile-time parameter of the loop body (one dispatch per kernel).
+        switch (p.tf0) {
+            case SYLDET_TF_TANSIG: wide_epilogue<SYLDET_TF_TANSIG>(p, w, cst, acc_full, acc_empty, tmem_base, warp, lane, n_tiles, tiles_per_ch, n_nc); break;
+            case SYLDET_TF_LOGSIG: wide_epilogue<SYLDET_TF_LOGSIG>(p, w, cst, acc_full, acc_empty, tmem_base, warp, lane, n_tiles, tiles_per_ch, n_nc); break;
+            case SYLDET_TF_SATLIN: wide_epilogue<SYLDET_TF_SATLIN>(p, w, cst, acc_full, acc_empty, tmem_base, warp, lane, n_tiles, tiles_per_ch, n_nc); break;
+            default: wide_epilogue<SYLDET_TF_PURELIN>(p, w, cst, acc_full, acc_empty, tmem_base, warp, lane, n_tiles, tiles_per_ch, n_nc); break;
         }
     }
     ptx::tc_fence_before();

@@ -29,9 +29,10 @@ int64_t pow2_at_least(int64_t v) {
 }
 }  // namespace
 
-syldet_status StreamGroup::init(const Config &cfg, int n_channels, int max_buffer, int device) {
+syldet_status StreamGroup::init(const Config &cfg, int n_channels, int max_buffer, int device, double input_rate) {
     if (n_channels <= 0 || n_channels > 65535) return set_error(SYLDET_ERR_ARG, "n_channels out of range");
     if (max_buffer <= 0) return set_error(SYLDET_ERR_ARG, "max_buffer must be positive");
+    if (input_rate < 0.0 || input_rate != input_rate) return set_error(SYLDET_ERR_ARG, "input rate must be positive (or 0)");
     syldet_status st = model_.init(cfg, device);
     if (st != SYLDET_OK) return st;
     n_channels_ = n_channels;
@@ -42,9 +43,22 @@ syldet_status StreamGroup::init(const Config &cfg, int n_channels, int max_buffe
     // Samples wait in pinned staging until they complete an STFT column: fewer than max(W + gap, hop) can be waiting
     // when a buffer arrives (see submit), so this never overflows.
     const int frame = c.gap + c.window_length;
-    stage_cap_ = ((std::max(frame, c.hop) + max_buffer + 31) / 32) * 32;
-    ring_cap_ = pow2_at_least((int64_t)frame + stage_cap_);
-    max_new_ = stage_cap_ / c.hop + 2;
+    // "if abs(config.samplingRate - inputRate) > 1 { resampler = ResamplerLinear(fromRate:toRate:) }" (ViewControllerProcessor.swift:247-250)
+    rs_on_ = input_rate > 0.0 && std::fabs(c.sampling_rate - input_rate) > 1.0;
+    double in_per_out = 1.0;
+    if (rs_on_) {
+        rs_.step = (float)(input_rate / c.sampling_rate);   // Resampler.swift:32
+        rs_.offset = 0.0f;
+        in_per_out = (double)rs_.step;
+    }
+    // staging holds device-rate samples: what can wait before a column completes, converted to the device rate (+ one sample per
+    // buffer for the resampler's carry), plus one more buffer; the ring holds configuration-rate samples
+    const int wait_out = std::max(frame, c.hop);
+    const int64_t wait_in = rs_on_ ? (int64_t)std::ceil(wait_out * in_per_out) + 2 * kStreamMaxMarks + 8 : wait_out;
+    stage_cap_ = (int)(((wait_in + max_buffer + 31) / 32) * 32);
+    const int64_t out_cap = rs_on_ ? (int64_t)std::ceil(stage_cap_ / in_per_out) + kStreamMaxMarks + 8 : stage_cap_;
+    ring_cap_ = pow2_at_least((int64_t)frame + out_cap);
+    max_new_ = out_cap / c.hop + 2;
     band_cols_ = pow2_at_least(c.time_range + max_new_);
     st = ring_.reserve((size_t)n_channels * ring_cap_ * sizeof(float));
     if (st != SYLDET_OK) return st;
@@ -56,7 +70,10 @@ syldet_status StreamGroup::init(const Config &cfg, int n_channels, int max_buffe
     if (st != SYLDET_OK) return st;
     st = level_out_.reserve((size_t)n_channels * sizeof(int));
     if (st != SYLDET_OK) return st;
+    st = rs_last_.reserve((size_t)2 * n_channels * sizeof(float));
+    if (st != SYLDET_OK) return st;
     SYLDET_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    SYLDET_CUDA(cudaMemsetAsync(rs_last_.get(), 0, rs_last_.size(), stream_));   // var last: Float = 0.0 (Resampler.swift:25)
     SYLDET_CUDA(cudaMemsetAsync(ring_.get(), 0, ring_.size(), stream_));
     SYLDET_CUDA(cudaMemsetAsync(band_.get(), 0, band_.size(), stream_));
     SYLDET_CUDA(cudaMemsetAsync(counter_.get(), 0, sizeof(unsigned), stream_));
@@ -126,8 +143,17 @@ syldet_status StreamGroup::submit(const float *const *bufs, int n, const float *
     if (staged_ + n > stage_cap_) return set_error(SYLDET_ERR_OVERFLOW, "Insufficient space on buffer.");
     for (int ch = 0; ch < n_channels_; ++ch)
         std::memcpy(h_stage_ + (size_t)ch * stage_cap_ + staged_, bufs[ch], (size_t)n * sizeof(float));
+    int64_t n_out = n;
+    if (rs_on_) {   // one resampleVector call per buffer (Processor.swift:116-121); the phase is data-independent, so it is kept here
+        n_out = std::max<int64_t>(0, rs_.plan(n));
+        mark_offset_.push_back(rs_.offset);
+        mark_nout_.push_back((int)n_out);
+        mark_out0_.push_back(staged_out_);
+        rs_.advance(n, n_out);
+    }
     staged_ += n;
-    total_ += n;
+    staged_out_ += (int)n_out;
+    total_ += n_out;
     marks_.push_back(staged_);
     ++buffers_seen_;
     const int64_t n_cols = c.num_columns(total_) - cols_done_;
@@ -154,7 +180,18 @@ syldet_status StreamGroup::launch_tick(int64_t n_cols, int64_t avail) {
     t.n_staged = staged_;
     t.ring = ring_.as<float>();
     t.ring_mask = ring_cap_ - 1;
-    t.ring_pos = total_ - staged_;
+    t.ring_pos = total_ - staged_out_;
+    t.rs_on = rs_on_ ? 1 : 0;
+    if (rs_on_) {
+        t.rs_step = rs_.step;
+        t.rs_last_in = rs_last_.as<float>() + (size_t)rs_parity_ * n_channels_;
+        t.rs_last_out = rs_last_.as<float>() + (size_t)(rs_parity_ ^ 1) * n_channels_;
+        for (size_t k = 0; k < marks_.size(); ++k) {
+            t.rs_offset[k] = mark_offset_[k];
+            t.rs_n_out[k] = mark_nout_[k];
+            t.rs_out0[k] = mark_out0_[k];
+        }
+    }
     t.band = band_.as<float>();
     t.band_mask = band_cols_ - 1;
     t.col0 = cols_done_;
@@ -219,7 +256,14 @@ syldet_status StreamGroup::launch_tick(int64_t n_cols, int64_t avail) {
         ++t_ticks_;
     }
     staged_ = 0;
+    staged_out_ = 0;
     marks_.clear();
+    if (rs_on_) {
+        mark_offset_.clear();
+        mark_nout_.clear();
+        mark_out0_.clear();
+        rs_parity_ ^= 1;
+    }
     cols_done_ += n_cols;
     next_eval_ += avail;
     evals_seen_ += avail;

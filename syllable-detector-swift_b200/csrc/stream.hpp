@@ -3,6 +3,7 @@
 #include <chrono>
 
 #include "engine.hpp"
+#include "resample.cuh"
 
 namespace syldet {
 
@@ -14,7 +15,11 @@ public:
     StreamGroup(const StreamGroup &) = delete;
     StreamGroup &operator=(const StreamGroup &) = delete;
     ~StreamGroup();
-    syldet_status init(const Config &cfg, int n_channels, int max_buffer, int device);
+    // input_rate: sampling rate of the buffers submit() receives. When it differs from the configuration's rate by more than 1 Hz
+    // (the rule of ViewControllerProcessor.swift:247-250) every buffer goes through ResamplerLinear inside the tick kernel
+    // (Processor.swift:116-121); 0 = the configuration's own rate.
+    syldet_status init(const Config &cfg, int n_channels, int max_buffer, int device, double input_rate = 0.0);
+    bool resampling() const { return rs_on_; }
     // One tick. *outs -> pinned host [n_channels][*n_new][outputs], valid until the next call.
     syldet_status submit(const float *const *bufs, int n, const float **outs, int64_t *n_new);
     const Config &config() const { return model_.config(); }
@@ -42,6 +47,14 @@ private:
     unsigned seq_ = 0;
     DeviceBuffer ring_, band_, counter_, level_in_, level_out_;
     std::vector<int> marks_;  // ends of the buffers waiting in the staging area
+    // ResamplerLinear in the tick: phase on the host (data-independent), `last` per channel on the device (two alternating arrays)
+    bool rs_on_ = false;
+    LinearResamplerPhase rs_;
+    int staged_out_ = 0;      // configuration-rate samples the staged buffers will produce
+    std::vector<float> mark_offset_;
+    std::vector<int> mark_nout_, mark_out0_;
+    DeviceBuffer rs_last_;
+    int rs_parity_ = 0;
     int64_t buffers_seen_ = 0, evals_seen_ = 0;  // since the last read_levels
     cudaStream_t stream_ = nullptr;
     float *h_stage_ = nullptr, *h_out_ = nullptr;

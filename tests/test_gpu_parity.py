@@ -598,6 +598,43 @@ def test_stream_level_meters_and_pulses(sd, cfg, orc, synth):
         assert np.array_equal(pulses[ch] > 0.5, np.concatenate(exp)) and pulses[ch].sum() > 0
 
 
+@pytest.mark.parametrize("rate_in,nbuf", [(48000.0, 32), (96000.0, 100), (22050.0, 32), (44100.5, 32)])
+def test_stream_group_resamples_inside_the_tick(sd, cfg, orc, oracle_mod, synth, rate_in, nbuf):
+    """Processor.swift:116-121: every 32-frame buffer goes through ResamplerLinear before appendAudioData. The group fed at the
+    device rate must behave exactly like the oracle's resampler (bit-for-bit samples, hence the usual output tolerance) followed by
+    the detector - including the buffer-size dependence and the one-sample-per-buffer carry of the upstream resampler."""
+    nch, ticks = 5, 1200
+    x = synth.make_audio(nch, nbuf * ticks, seed=51)           # interpreted as audio at rate_in
+    g = sd.StreamGroup(cfg, nch, max_buffer=nbuf, input_rate=rate_in)
+    assert g.resampling == (abs(rate_in - 44100.0) > 1.0)
+    rs = [oracle_mod.Resampler(rate_in, 44100.0) for _ in range(nch)]
+    y = [[] for _ in range(nch)]
+    got_new = np.zeros(nch, dtype=np.int64)
+    checked = 0
+    for t in range(ticks):
+        buf = x[:, t * nbuf:(t + 1) * nbuf]
+        for ch in range(nch):
+            y[ch].append(rs[ch].process(buf[ch]) if g.resampling else buf[ch])
+        seen, n_new = g.submit(buf)
+        got_new += n_new
+        if n_new[0] and t >= 97 * (checked + 1):            # spot checks along the way: the newest evaluation of every channel
+            for ch in range(nch):
+                ref = orc.run(np.concatenate(y[ch]))[0]
+                assert ref.shape[0] == got_new[ch]
+                assert np.abs(g.last_outputs[ch] - ref[-1]).max() <= TOL_OUT
+            checked += 1
+    assert checked > 2
+    for ch in range(nch):
+        yc = np.concatenate(y[ch])
+        ref, _, df = orc.run(yc)
+        assert got_new[ch] == ref.shape[0] > 100
+    # the meters see the device-rate samples (Processor.swift:110-113 runs before the resampler)
+    a, _ = g.read_levels()
+    seg = x.reshape(nch, ticks, nbuf)
+    ms = (seg.astype(np.float32) ** 2).sum(axis=2, dtype=np.float32).astype(np.float64) / nbuf
+    assert np.allclose(a, np.sqrt(ms.max(axis=1)), rtol=1e-6, atol=0)
+
+
 def test_simulator_trace_matches_oracle(sd, cfg, orc, oracle_mod, synth):
     """Simulator output track (ViewControllerSimulator.swift:251-254, 308-344): float trace within TOL_OUT / thr0 of the oracle's,
     16-bit trace within two quantisation steps; exact structure (leading zeros, hop-long plateaus)."""

@@ -31,7 +31,12 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
-// mode: 0 tf32 TS, 1 tf32 SS, 2 bf16 TS, 3 bf16 SS
+// K-major, no swizzle (canonical ((8,n),2):((1,SBO),LBO)): the layout of the wide kernel's sliding A operand and weight planes
+__device__ __forceinline__ uint64_t desc_nosw(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
+}
+
+// mode: 0 tf32 TS, 1 tf32 SS, 2 bf16 TS, 3 bf16 SS, 4 tf32 SS with no-swizzle plane operands (A planes of 272 rows, B planes of 256 rows)
 template <int mode, int m, int n, int chain>
 __global__ void __launch_bounds__(128, 1) rate_kernel(int reps, long long *out) {
     extern __shared__ unsigned char smem_dyn[];
@@ -63,7 +68,7 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int reps, long long *out) 
     ptx::tc_fence_after();
     if (warp == 0 && elect_one()) {
         const uint32_t a_s = ptx::smem_addr(smem), b_s = ptx::smem_addr(smem + 32768);
-        const uint32_t idesc = (mode < 2) ? ptx::idesc_tf32(m, n) : idesc_bf16(m, n);
+        const uint32_t idesc = (mode < 2 || mode == 4) ? ptx::idesc_tf32(m, n) : idesc_bf16(m, n);
         const uint32_t d0 = tmem + 256;
         uint32_t phase = 0;
         // warm-up
@@ -86,6 +91,7 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int reps, long long *out) 
             if (mode == 1) ptx::mma_tf32_ss(d, ptx::smem_desc_kmajor(a_s + ko, 1024, 2), ptx::smem_desc_kmajor(b_s + ko, 1024, 2), idesc, 1);
             if (mode == 2) mma_f16_ts(d, tmem + (r & 3) * 8, ptx::smem_desc_kmajor(b_s + ko, 1024, 2), idesc, 1);
             if (mode == 3) mma_f16_ss(d, ptx::smem_desc_kmajor(a_s + ko, 1024, 2), ptx::smem_desc_kmajor(b_s + ko, 1024, 2), idesc, 1);
+            if (mode == 4) ptx::mma_tf32_ss(d, desc_nosw(a_s + (r & 7) * 16, 4352, 128), desc_nosw(b_s, 4096, 128), idesc, 1);
         }
         const long long t1 = clock64();
         ptx::mma_commit(&bar);
@@ -103,7 +109,7 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int reps, long long *out) 
 
 template <int mode, int m, int n, int chain>
 void run(long long *d_out) {
-    const char *names[4] = {"tf32 TS", "tf32 SS", "bf16 TS", "bf16 SS"};
+    const char *names[5] = {"tf32 TS", "tf32 SS", "bf16 TS", "bf16 SS", "tf32 SS no-swizzle planes"};
     const int reps = 2048;
     cudaFuncSetAttribute(rate_kernel<mode, m, n, chain>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     rate_kernel<mode, m, n, chain><<<148, 128, 100 * 1024>>>(reps, d_out);
@@ -156,6 +162,15 @@ double peak_tflops(long long *d_out, int reps, float *ms_out) {
 }
 
 int main(int argc, char **argv) {
+    if (argc > 1 && std::string(argv[1]) == "--nosw") {
+        long long *d_out;
+        cudaMalloc(&d_out, 16);
+        run<1, 128, 256, 1>(d_out);
+        run<4, 128, 256, 1>(d_out);
+        run<4, 128, 128, 1>(d_out);
+        run<4, 128, 64, 1>(d_out);
+        return 0;
+    }
     if (argc > 1 && std::string(argv[1]) == "--peak") {   // JSON line: burst (~20 ms) and sustained (~2 s) dense peaks
         long long *d_out;
         cudaMalloc(&d_out, 16);

@@ -2,9 +2,12 @@
 //   syldet -n <network.txt> -a <audio.wav> [-a ...] [-d <seconds>]
 // Same flags (main.swift:21-23), same CSV rows on stdout: channel,sample,seconds,out0[,out1...]
 // (TrackDetector.swift:92-96, help text main.swift:31-39). Differences, both forced by leaving macOS:
-//   * audio is read from RIFF/WAVE (PCM16, PCM24, PCM32 or float32) instead of AVFoundation and must already be at the
-//     network's sampling rate (AVFoundation resampled silently, SyllableDetector.swift:19-23);
-//   * every channel of a file is a "track": upstream reads channel 0 of each AVAssetTrack (main.swift:86-89).
+//   * audio is read from RIFF/WAVE (PCM16, PCM24, PCM32 or float32) instead of AVFoundation. 16- and 24-bit PCM at the network's
+//     rate goes to the device as it is in the file (interleaved integers, converted by the ingest kernel); a file at another rate is
+//     converted to the network's rate on the device first, with the polyphase converter (upstream asks AVFoundation for
+//     config.samplingRate, SyllableDetector.swift:19-23, and gets its converter);
+//   * every channel of a file is a "track": upstream reads channel 0 of each AVAssetTrack (main.swift:86-89), and rows are grouped
+//     by channel, then time (upstream interleaves tracks buffer by buffer, main.swift:126-130).
 // All compute goes through the C-ABI of libsyldet_cuda.so; there is no CPU path.
 #include <cmath>
 #include <cstdint>
@@ -21,7 +24,22 @@ namespace {
 struct Wav {
     int channels = 0, rate = 0;
     int64_t frames = 0;
-    std::vector<float> interleaved;
+    int pcm_format = SYLDET_PCM_F32;          // what `raw` holds when it is usable as is (int16 / packed 24-bit), else F32
+    std::vector<unsigned char> raw;           // interleaved samples exactly as in the file (PCM16 / PCM24 only)
+    std::vector<float> interleaved;           // float32 samples (always for PCM32 / float files; on demand otherwise)
+    const unsigned char *data = nullptr;      // file bytes of the data chunk (valid while `file` lives)
+    int bits = 0, fmt = 0;
+    std::vector<unsigned char> file;
+    void to_float() {                          // AVAssetReader's LPCM Float32 conversion (SyllableDetector.swift:19-23)
+        if (!interleaved.empty() || frames == 0) return;
+        const size_t total = (size_t)frames * channels;
+        interleaved.resize(total);
+        if (bits == 16) for (size_t i = 0; i < total; ++i) interleaved[i] = (float)(int16_t)(data[2 * i] | (data[2 * i + 1] << 8)) / 32768.0f;
+        else for (size_t i = 0; i < total; ++i) {
+            int32_t v = data[3 * i] | (data[3 * i + 1] << 8) | ((int32_t)(int8_t)data[3 * i + 2] << 16);
+            interleaved[i] = (float)v / 8388608.0f;
+        }
+    }
 };
 
 uint32_t rd32(const unsigned char *p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24); }
@@ -30,7 +48,7 @@ uint16_t rd16(const unsigned char *p) { return (uint16_t)(p[0] | (p[1] << 8)); }
 bool read_wav(const std::string &path, Wav &w, std::string &err) {
     FILE *f = std::fopen(path.c_str(), "rb");
     if (!f) { err = "cannot open file"; return false; }
-    std::vector<unsigned char> buf;
+    std::vector<unsigned char> &buf = w.file;
     unsigned char tmp[1 << 16];
     size_t n;
     while ((n = std::fread(tmp, 1, sizeof tmp, f)) > 0) buf.insert(buf.end(), tmp, tmp + n);
@@ -59,15 +77,19 @@ bool read_wav(const std::string &path, Wav &w, std::string &err) {
     }
     if (!data || w.channels <= 0 || align <= 0) { err = "missing fmt or data chunk"; return false; }
     w.frames = (int64_t)(data_len / align);
-    w.interleaved.resize((size_t)w.frames * w.channels);
-    const size_t total = w.interleaved.size();
-    if (fmt == 1 && bits == 16) for (size_t i = 0; i < total; ++i) w.interleaved[i] = (float)(int16_t)rd16(data + 2 * i) / 32768.0f;
-    else if (fmt == 1 && bits == 24) for (size_t i = 0; i < total; ++i) {
-        int32_t v = data[3 * i] | (data[3 * i + 1] << 8) | ((int32_t)(int8_t)data[3 * i + 2] << 16);
-        w.interleaved[i] = (float)v / 8388608.0f;
-    } else if (fmt == 1 && bits == 32) for (size_t i = 0; i < total; ++i) w.interleaved[i] = (float)((double)(int32_t)rd32(data + 4 * i) / 2147483648.0);
-    else if (fmt == 3 && bits == 32) std::memcpy(w.interleaved.data(), data, total * 4);
-    else { err = "unsupported sample format (want PCM 16/24/32 or float32)"; return false; }
+    w.data = data;
+    w.bits = bits;
+    w.fmt = fmt;
+    const size_t total = (size_t)w.frames * w.channels;
+    if (fmt == 1 && (bits == 16 || bits == 24)) {
+        w.pcm_format = bits == 16 ? SYLDET_PCM_S16 : SYLDET_PCM_S24;   // uploaded as they are, converted on the device
+    } else if (fmt == 1 && bits == 32) {
+        w.interleaved.resize(total);
+        for (size_t i = 0; i < total; ++i) w.interleaved[i] = (float)((double)(int32_t)rd32(data + 4 * i) / 2147483648.0);
+    } else if (fmt == 3 && bits == 32) {
+        w.interleaved.resize(total);
+        std::memcpy(w.interleaved.data(), data, total * 4);
+    } else { err = "unsupported sample format (want PCM 16/24/32 or float32)"; return false; }
     return true;
 }
 
@@ -151,17 +173,43 @@ int main(int argc, char **argv) {
         Wav w;
         std::string err;
         if (!read_wav(path, w, err)) { std::fprintf(stderr, "Unable to read %s: %s\n", path.c_str(), err.c_str()); continue; }
-        if (std::fabs((double)w.rate - fs) > 1.0) {
-            std::fprintf(stderr, "Can not read audio tracks found in %s: sampling rate %d differs from the network's %g.\n", path.c_str(), w.rate, fs);
-            continue;
+        const void *pcm = nullptr;
+        int pcm_format = SYLDET_PCM_F32, layout = SYLDET_LAYOUT_INTERLEAVED;
+        std::vector<float> converted;   // planar, at the network's rate
+        if (std::fabs((double)w.rate - fs) > 1.0 && w.frames > 0) {
+            // another sampling rate: convert on the device (upstream: the asset reader delivers config.samplingRate, SyllableDetector.swift:19-23)
+            w.to_float();
+            std::vector<float> planar((size_t)w.channels * w.frames);
+            for (int c = 0; c < w.channels; ++c)
+                for (int64_t i = 0; i < w.frames; ++i) planar[(size_t)c * w.frames + i] = w.interleaved[(size_t)i * w.channels + c];
+            const int64_t n_out = syldet_resample_output_length(SYLDET_RESAMPLE_POLYPHASE, w.frames, (double)w.rate, fs);
+            if (n_out <= 0) {
+                std::fprintf(stderr, "Can not read audio tracks found in %s: no conversion from %d Hz to %g Hz.\n", path.c_str(), w.rate, fs);
+                continue;
+            }
+            converted.resize((size_t)w.channels * n_out);
+            int64_t got = 0;
+            if (syldet_resample_host(SYLDET_RESAMPLE_POLYPHASE, planar.data(), w.channels, w.frames, w.frames, (double)w.rate, fs, converted.data(), n_out,
+                                     &got, 0) != SYLDET_OK) {
+                std::fprintf(stderr, "Can not convert %s to the network's sampling rate: %s.\n", path.c_str(), syldet_last_error());
+                continue;
+            }
+            w.frames = got;
+            w.rate = (int)std::lround(fs);
+            pcm = converted.data();
+            layout = SYLDET_LAYOUT_PLANAR;
+        } else if (w.pcm_format != SYLDET_PCM_F32) {
+            pcm = w.data;                    // 16- / 24-bit samples exactly as in the file
+            pcm_format = w.pcm_format;
+        } else {
+            pcm = w.interleaved.data();
         }
         if (audio.size() > 1) std::printf("%s\n", path.c_str());  // main.swift:122-124
         if (w.frames <= 0) continue;
         if (!simulate.empty()) {
             // the GUI simulator's output (ViewControllerSimulator.swift:135-376): 16-bit PCM, one trace channel per input channel
             std::vector<int16_t> planar((size_t)w.channels * w.frames), inter((size_t)w.channels * w.frames);
-            if (syldet_batch_simulate_host(batch, w.interleaved.data(), SYLDET_PCM_F32, w.channels, w.frames, 0, SYLDET_LAYOUT_INTERLEAVED,
-                                           SYLDET_PCM_S16, planar.data()) != SYLDET_OK) {
+            if (syldet_batch_simulate_host(batch, pcm, pcm_format, w.channels, w.frames, w.frames, layout, SYLDET_PCM_S16, planar.data()) != SYLDET_OK) {
                 std::fprintf(stderr, "Can not simulate %s: %s.\n", path.c_str(), syldet_last_error());
                 continue;
             }
@@ -172,8 +220,8 @@ int main(int argc, char **argv) {
             continue;
         }
         syldet_events *ev = nullptr;
-        if (syldet_batch_run_host(batch, w.interleaved.data(), SYLDET_PCM_F32, w.channels, w.frames, 0, SYLDET_LAYOUT_INTERLEAVED,
-                                  debounce_frames, SYLDET_DETECT_ANY_OUTPUT, nullptr, &ev) != SYLDET_OK) {
+        if (syldet_batch_run_host(batch, pcm, pcm_format, w.channels, w.frames, w.frames, layout, debounce_frames, SYLDET_DETECT_ANY_OUTPUT, nullptr,
+                                  &ev) != SYLDET_OK) {
             std::fprintf(stderr, "Can not start reading %s: %s.\n", path.c_str(), syldet_last_error());
             continue;
         }

@@ -49,7 +49,9 @@ enum { SYLDET_PROC_MAPMINMAX = 0, SYLDET_PROC_MAPSTD = 1, SYLDET_PROC_L2NORMALIZ
 enum { SYLDET_LAYOUT_PLANAR = 0, SYLDET_LAYOUT_INTERLEAVED = 1 };
 enum { SYLDET_DETECT_ANY_OUTPUT = 0,   /* TrackDetector.swift:71-77 (CLI rule)  */
        SYLDET_DETECT_FIRST_OUTPUT = 1  /* SyllableDetector.lastDetected :27-31 (live rule) */ };
-enum { SYLDET_PCM_F32 = 0, SYLDET_PCM_S16 = 1 };
+enum { SYLDET_PCM_F32 = 0, SYLDET_PCM_S16 = 1 /* int16, x / 32768 */, SYLDET_PCM_S24 = 2 /* packed little-endian 24-bit, x / 2^23 */ };
+enum { SYLDET_RESAMPLE_LINEAR = 0,    /* ResamplerLinear (Common/Resampler.swift:20-70), bit-faithful */
+       SYLDET_RESAMPLE_POLYPHASE = 1  /* rational Kaiser-windowed sinc converter (the algorithm of scipy.signal.resample_poly) */ };
 enum { SYLDET_KERNEL_AUTO = 0, SYLDET_KERNEL_GENERIC = 1, SYLDET_KERNEL_FUSED = 2, SYLDET_KERNEL_TENSOR = 3, SYLDET_KERNEL_TENSOR_TF32 = 4,
        SYLDET_KERNEL_WIDE = 5 /* wide hidden layer as a 3xTF32 tcgen05 contraction over a high-overlap STFT (hop 4) */ };
 
@@ -135,7 +137,7 @@ syldet_status syldet_batch_set_slice_evals(syldet_batch *b, int64_t evals);
 /*
  * Host buffers in, events out (H2D copy, kernels, D2H of the sparse events, host-side debounce).
  *   pcm            planar: channel c starts at pcm + c*channel_stride; interleaved: sample i of channel c at pcm[i*n_channels + c]
- *   pcm_format     SYLDET_PCM_F32 (float) or SYLDET_PCM_S16 (int16, converted on the device as x/32768)
+ *   pcm_format     SYLDET_PCM_F32 (float), SYLDET_PCM_S16 (int16, converted on the device as x/32768) or SYLDET_PCM_S24 (packed 24-bit, x/2^23)
  *   debounce_frames  TrackDetector.debounceFrames; 0 = every detected evaluation is an event
  *   all_outputs    optional host buffer [n_channels][E][O] receiving every network output (E = num_evals)
  *   events         receives a new syldet_events (sorted by channel, then sample); free with syldet_events_free
@@ -246,6 +248,22 @@ syldet_status syldet_resampler_process(syldet_resampler *r, const float *in, int
                                        int64_t *n_out);
 /* Upper bound of samples one call can produce for n_in inputs. */
 int64_t syldet_resampler_max_output(const syldet_resampler *r, int64_t n_in);
+
+/* ---- batched sample-rate conversion: whole channels at once, on the device ------------------------------------------------
+ * LINEAR    = one ResamplerLinear.resampleVector call per channel over the whole buffer, from a fresh state (offset 0, last 0):
+ *             n_out = Int(Float(n_in) / Float(rate_in / rate_out)) (Resampler.swift:32,40), float32 index ramp as upstream.
+ * POLYPHASE = what upstream gets from AVFoundation for files whose rate differs from the network's (the asset reader is asked for
+ *             config.samplingRate, Common/SyllableDetector.swift:19-23): up / down = rate_out / rate_in reduced, low-pass FIR
+ *             firwin(20 max(up, down) + 1, 1 / max(up, down), kaiser 5.0) x up, zero-phase, zero padding at both ends,
+ *             n_out = ceil(n_in up / down). Integral rates only.
+ * in: host, planar, channel c at in + c * in_stride (n_channels == 1: stride ignored). out: host, planar, out_stride >= n_out.
+ */
+int64_t syldet_resample_output_length(int mode, int64_t n_in, double rate_in, double rate_out); /* -1: unsupported rate pair */
+syldet_status syldet_resample_host(int mode, const float *in, int n_channels, int64_t n_in, int64_t in_stride, double rate_in,
+                                   double rate_out, float *out, int64_t out_stride, int64_t *n_out, int device);
+/* Same on device-resident planar buffers (asynchronous on `stream`, a cudaStream_t; the polyphase filter upload synchronises it once). */
+syldet_status syldet_resample_device(int mode, const float *d_in, int n_channels, int64_t n_in, int64_t in_stride, double rate_in,
+                                     double rate_out, float *d_out, int64_t out_stride, int64_t *n_out, void *stream);
 
 #ifdef __cplusplus
 }

@@ -29,7 +29,8 @@ TRANSFER = ("TanSig", "LogSig", "PureLin", "SatLin")
 PROCESSING = ("mapminmax", "mapstd", "l2normalize", "normalize", "normalizestd")
 LAYOUT_PLANAR, LAYOUT_INTERLEAVED = 0, 1
 DETECT_ANY_OUTPUT, DETECT_FIRST_OUTPUT = 0, 1
-PCM_F32, PCM_S16 = 0, 1
+PCM_F32, PCM_S16, PCM_S24 = 0, 1, 2
+RESAMPLE_LINEAR, RESAMPLE_POLYPHASE = 0, 1
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_FUSED, KERNEL_TENSOR = 0, 1, 2, 3
 KERNEL_TENSOR_TF32 = 4   # tensor kernel with all three DFT products in TF32 (amplitude-invariant; see include/syldet.h)
 KERNEL_WIDE = 5          # two-layer networks with a wide hidden layer on a hop-4 STFT: 3xTF32 tcgen05 contraction (kernels_wide.cu)
@@ -111,6 +112,9 @@ def _load():
         "syldet_resampler_linear_create": (i32, [dbl, dbl, pvp]), "syldet_resampler_destroy": (None, [vp]),
         "syldet_resampler_process": (i32, [vp, vp, i64, vp, i64, C.POINTER(i64)]),
         "syldet_resampler_max_output": (i64, [vp, i64]),
+        "syldet_resample_output_length": (i64, [i32, i64, dbl, dbl]),
+        "syldet_resample_host": (i32, [i32, vp, i32, i64, i64, dbl, dbl, vp, i64, C.POINTER(i64), i32]),
+        "syldet_resample_device": (i32, [i32, vp, i32, i64, i64, dbl, dbl, vp, i64, C.POINTER(i64), vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)  # AttributeError if the library does not export what include/syldet.h declares
@@ -553,3 +557,22 @@ class ResamplerLinear:
         return out[:n.value].copy()
 
     resample_array = resample_vector  # Resampler.swift:72-76
+
+
+def resample(x, rate_in, rate_out, mode=RESAMPLE_POLYPHASE, device=0):
+    """Whole-channel sample-rate conversion on the device. x: float32 [n] or [n_channels, n] (planar).
+    RESAMPLE_POLYPHASE: rational Kaiser-windowed sinc converter (scipy.signal.resample_poly's algorithm) - what upstream gets from
+    AVFoundation for files at another rate (Common/SyllableDetector.swift:19-23); RESAMPLE_LINEAR: one ResamplerLinear.resampleVector
+    call per channel (Common/Resampler.swift:35-70)."""
+    a = np.ascontiguousarray(x, dtype=np.float32)
+    one = a.ndim == 1
+    if one:
+        a = a[None, :]
+    nch, n = a.shape
+    n_out = lib.syldet_resample_output_length(mode, n, float(rate_in), float(rate_out))
+    if n_out < 0:
+        raise SyldetError(10, "the polyphase converter needs integral sampling rates")
+    out = np.zeros((nch, max(n_out, 0)), dtype=np.float32)
+    got = C.c_int64()
+    _check(lib.syldet_resample_host(mode, a.ctypes.data, nch, n, n, float(rate_in), float(rate_out), out.ctypes.data, max(n_out, 1), C.byref(got), device))
+    return out[0] if one else out

@@ -17,6 +17,7 @@ SOURCES = [
     ("capi.cpp", []),
     ("engine.cu", []),
     ("stream.cu", []),
+    ("resample.cu", []),
     ("kernels_generic.cu", ["-fmad=false"]),
     ("kernels_fused.cu", ["-Xptxas", "-v"]),
     ("kernels_tc.cu", ["-Xptxas", "-v"] + os.environ.get("SYLDET_TC_DEFS", "").split()),

@@ -230,6 +230,23 @@ const syldet_event *syldet_events_data(const syldet_events *ev) { return ev ? ev
 const float *syldet_events_outputs(const syldet_events *ev) { return ev ? ev->e.outputs.data() : nullptr; }
 void syldet_events_free(syldet_events *ev) { delete ev; }
 
+// ---- batched resampling -------------------------------------------------------------------------------------------------
+int64_t syldet_resample_output_length(int mode, int64_t n_in, double rate_in, double rate_out) {
+    return resample_output_length(mode, n_in, rate_in, rate_out);
+}
+syldet_status syldet_resample_host(int mode, const float *in, int n_channels, int64_t n_in, int64_t in_stride, double rate_in, double rate_out,
+                                   float *out, int64_t out_stride, int64_t *n_out, int device) {
+    return guarded([&] { return resample_host(mode, in, n_channels, n_in, in_stride, rate_in, rate_out, out, out_stride, n_out, device); });
+}
+syldet_status syldet_resample_device(int mode, const float *d_in, int n_channels, int64_t n_in, int64_t in_stride, double rate_in,
+                                     double rate_out, float *d_out, int64_t out_stride, int64_t *n_out, void *stream) {
+    return guarded([&] {
+        static thread_local DeviceBuffer *filter = new DeviceBuffer();   // the polyphase taps of this thread's last conversion
+        return resample_device(mode, d_in, n_channels, n_in, in_stride, rate_in, rate_out, d_out, out_stride, n_out, *filter,
+                               static_cast<cudaStream_t>(stream));
+    });
+}
+
 // ---- single stream ---------------------------------------------------------------------------------------------------
 syldet_status syldet_detector_create(const syldet_config *cfg, int device, syldet_detector **out) {
     if (!valid_or_null(cfg) || !out) return set_error(SYLDET_ERR_ARG, "null argument");

@@ -1063,7 +1063,7 @@ syldet_status Batch::run_host(const void *pcm, int fmt, int n_channels, int64_t 
     if (!pcm || n_channels <= 0 || n_samples < 0) return set_error(SYLDET_ERR_ARG, "bad pcm arguments");
     if (trace && trace_format != SYLDET_PCM_F32 && trace_format != SYLDET_PCM_S16) return set_error(SYLDET_ERR_ARG, "unknown trace format");
     if (n_channels > 65535) return set_error(SYLDET_ERR_ARG, "more than 65535 channels in one call");
-    if (fmt != SYLDET_PCM_F32 && fmt != SYLDET_PCM_S16) return set_error(SYLDET_ERR_ARG, "unknown pcm format");
+    if (fmt != SYLDET_PCM_F32 && fmt != SYLDET_PCM_S16 && fmt != SYLDET_PCM_S24) return set_error(SYLDET_ERR_ARG, "unknown pcm format");
     if (layout != SYLDET_LAYOUT_PLANAR && layout != SYLDET_LAYOUT_INTERLEAVED) return set_error(SYLDET_ERR_ARG, "unknown layout");
     if (layout == SYLDET_LAYOUT_PLANAR && n_channels > 1 && ch_stride < n_samples) return set_error(SYLDET_ERR_ARG, "channel_stride < n_samples");
     if (debounce_frames < 0) return set_error(SYLDET_ERR_ARG, "negative debounce");
@@ -1075,7 +1075,7 @@ syldet_status Batch::run_host(const void *pcm, int fmt, int n_channels, int64_t 
     const int64_t pitch = (n_samples + 3) & ~(int64_t)3;
     st = planar_.reserve(std::max<size_t>(16, (size_t)n_channels * pitch * sizeof(float)));
     if (st != SYLDET_OK) return st;
-    const size_t esz = fmt == SYLDET_PCM_S16 ? 2 : 4;
+    const size_t esz = fmt == SYLDET_PCM_S16 ? 2 : fmt == SYLDET_PCM_S24 ? 3 : 4;
     const bool direct = fmt == SYLDET_PCM_F32 && layout == SYLDET_LAYOUT_PLANAR;   // lands in the planar buffer as is
     const bool inter = layout == SYLDET_LAYOUT_INTERLEAVED;
     const int64_t src_stride = inter ? 0 : (n_channels > 1 ? ch_stride : n_samples);

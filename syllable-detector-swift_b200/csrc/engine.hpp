@@ -215,6 +215,13 @@ private:
     } last_;
 };
 
+// Batched sample-rate conversion (resample.cu).
+int64_t resample_output_length(int mode, int64_t n_in, double rate_in, double rate_out);
+syldet_status resample_device(int mode, const float *d_in, int n_channels, int64_t n_in, int64_t in_stride, double rate_in, double rate_out,
+                              float *d_out, int64_t out_stride, int64_t *n_out, DeviceBuffer &filter, cudaStream_t stream);
+syldet_status resample_host(int mode, const float *in, int n_channels, int64_t n_in, int64_t in_stride, double rate_in, double rate_out, float *out,
+                            int64_t out_stride, int64_t *n_out, int device);
+
 // Greedy debounce over ascending sample numbers of one channel (TrackDetector.swift:80,99).
 void debounce_sorted(const Config &cfg, std::vector<syldet_event> &rows, std::vector<float> &outputs, int n_out,
                      int64_t debounce_frames);

@@ -36,7 +36,12 @@ __global__ void ingest_kernel(const void *__restrict__ src, int format, int inte
         if (interleaved) { s = i / n_channels; ch = (int)(i - s * n_channels); }  // consecutive threads read consecutive source
         else { ch = (int)(i / n_samples); s = i - (int64_t)ch * n_samples; }
         const int64_t si = interleaved ? i : (int64_t)ch * src_stride + s;
-        float v = format == SYLDET_PCM_S16 ? (float)((const int16_t *)src)[si] * (1.0f / 32768.0f) : ((const float *)src)[si];
+        float v;
+        if (format == SYLDET_PCM_S16) v = (float)((const int16_t *)src)[si] * (1.0f / 32768.0f);
+        else if (format == SYLDET_PCM_S24) {   // packed little-endian 24-bit (WAV): x / 2^23
+            const unsigned char *b = (const unsigned char *)src + 3 * si;
+            v = (float)((int)b[0] | ((int)b[1] << 8) | ((int)(signed char)b[2] << 16)) * (1.0f / 8388608.0f);
+        } else v = ((const float *)src)[si];
         dst[(int64_t)ch * dst_stride + s] = v;
     }
 }

@@ -312,7 +312,8 @@ __device__ __forceinline__ int padf(int i) { return i + (i >> 3); }
 // kFirst: the inputs come from the (windowed) audio instead of the ping-pong buffer.
 template <int R, bool kFirst>
 __device__ __forceinline__ void stockham_stage(const float2 *__restrict__ in, float2 *__restrict__ out, int M, int Ns, int lane,
-                                               const float2 *__restrict__ twM, const float *__restrict__ fr, const float *__restrict__ win, int W) {
+                                               const float2 *__restrict__ twM, const float *__restrict__ fr, const float *__restrict__ win, int W,
+                                               bool pairs = false) {
     const int nb = M / R;            // butterflies of this stage
     const int tw_step = M / (Ns * R);
     for (int j = lane; j < nb; j += 32) {
@@ -323,7 +324,12 @@ __device__ __forceinline__ void stockham_stage(const float2 *__restrict__ in, fl
             const int n = j + r * nb;
             if constexpr (kFirst) {
                 const int m0 = 2 * n;
-                v[r] = make_float2(m0 < W ? fr[m0] * win[m0] : 0.0f, m0 + 1 < W ? fr[m0 + 1] * win[m0 + 1] : 0.0f);   // zero padding: CSTFT.swift:109-110
+                if (pairs && m0 + 1 < W) {   // even hop, even window: one 64-bit load each for the sample pair and its window taps
+                    const float2 x2 = reinterpret_cast<const float2 *>(fr)[n], w2 = reinterpret_cast<const float2 *>(win)[n];
+                    v[r] = make_float2(x2.x * w2.x, x2.y * w2.y);
+                } else {
+                    v[r] = make_float2(m0 < W ? fr[m0] * win[m0] : 0.0f, m0 + 1 < W ? fr[m0 + 1] * win[m0 + 1] : 0.0f);   // zero padding: CSTFT.swift:109-110
+                }
             } else {
                 v[r] = in[padf(n)];
             }
@@ -384,7 +390,7 @@ __global__ void __launch_bounds__(512) stft_planes_fast_kernel(const DevNet *__r
         int Ns = 1;
         // radix-8 stages, the first one straight from the windowed audio; then the remainder stage
         if (M >= 8) {
-            stockham_stage<8, true>(nullptr, out, M, 1, lane, twM, fr, win, W);
+            stockham_stage<8, true>(nullptr, out, M, 1, lane, twM, fr, win, W, (hop & 1) == 0);
             Ns = 8;
             __syncwarp();
             while (Ns * (last_radix == 8 ? 1 : last_radix) < M) {

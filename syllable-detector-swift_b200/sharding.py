@@ -74,37 +74,69 @@ def pack_events(recording, channel, sample, outputs):
     return rows
 
 
+def rows_in_order(rows):
+    """True when rows [n, 3 + O] are ordered by (recording, channel, sample) - one vectorised pass."""
+    if rows.shape[0] < 2:
+        return True
+    r, c, t = rows[:, 0], rows[:, 1], rows[:, 2]
+    dr, dc, dt = np.diff(r), np.diff(c), np.diff(t)
+    return bool(np.all((dr > 0) | ((dr == 0) & ((dc > 0) | ((dc == 0) & (dt >= 0))))))
+
+
 def gather_events(rows, dist=None, dst=0):
     """Gather per-rank event rows on `dst`, sorted by (recording, channel, sample). Other ranks get None.
-    `dist` is torch.distributed (initialised) or None for a single process."""
+    `dist` is torch.distributed (initialised) or None for a single process.
+
+    Only `dst` receives rows (point-to-point gather, not all_gather). Every rank checks the order of its own rows (in parallel);
+    ranks own contiguous recording blocks, so when every block is ordered and the block boundaries are, the concatenation in rank
+    order IS the sorted result and no sort of the (tens of millions of) rows is needed; otherwise `dst` sorts."""
     if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
         allrows = rows
+        in_order = rows_in_order(rows)
     else:
         import torch
         world, rank = dist.get_world_size(), dist.get_rank()
-        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
-        width = torch.tensor([rows.shape[1] if rows.size else 0], dtype=torch.int64, device=dev)
-        dist.all_reduce(width, op=dist.ReduceOp.MAX)
-        width = int(width.item())
-        count = torch.tensor([rows.shape[0]], dtype=torch.int64, device=dev)
-        counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-        dist.all_gather(counts, count)
-        counts = [int(c.item()) for c in counts]
+        nccl = dist.get_backend() == "nccl"
+        dev = torch.device("cuda", torch.cuda.current_device()) if nccl else torch.device("cpu")
+        n, width = rows.shape[0], (rows.shape[1] if rows.size else 0)
+        first = rows[0, :3] if n else np.zeros(3)
+        last = rows[-1, :3] if n else np.zeros(3)
+        meta = torch.tensor([float(n), float(width), 1.0 if rows_in_order(rows) else 0.0, *first, *last], dtype=torch.float64, device=dev)
+        metas = [torch.zeros_like(meta) for _ in range(world)]
+        dist.all_gather(metas, meta)
+        metas = [m.cpu().numpy() for m in metas]
+        counts = [int(m[0]) for m in metas]
+        width = int(max(m[1] for m in metas))
         cap = max(max(counts), 1)
         buf = torch.zeros((cap, max(width, 1)), dtype=torch.float64, device=dev)
         if rows.size:
-            buf[:rows.shape[0]] = torch.from_numpy(np.ascontiguousarray(rows)).to(dev)
-        bufs = [torch.zeros_like(buf) for _ in range(world)]
-        dist.all_gather(bufs, buf)
+            src = torch.from_numpy(np.ascontiguousarray(rows))
+            buf[:n].copy_(src.pin_memory() if nccl else src, non_blocking=nccl)
+        bufs = [torch.zeros_like(buf) for _ in range(world)] if rank == dst else None
+        dist.gather(buf, bufs, dst=dst)
         if rank != dst:
             return None
-        allrows = np.concatenate([b[:c].cpu().numpy() for b, c in zip(bufs, counts)], axis=0) if sum(counts) else np.zeros((0, max(width, 3)))
-    if allrows.shape[0] > 1:
-        # every rank's rows arrive ordered by (recording, channel, sample) and ranks own contiguous recording blocks, so the
-        # concatenation is usually in order already: one vectorised check instead of a sort of tens of millions of rows
-        r, c, t = allrows[:, 0], allrows[:, 1], allrows[:, 2]
-        dr, dc, dt = np.diff(r), np.diff(c), np.diff(t)
-        in_order = bool(np.all((dr > 0) | ((dr == 0) & ((dc > 0) | ((dc == 0) & (dt >= 0))))))
-        if not in_order:
-            allrows = allrows[np.lexsort((t, c, r))]
+        total = sum(counts)
+        allrows = np.zeros((0, max(width, 3)), dtype=np.float64)
+        if total:
+            host = torch.empty((total, max(width, 3)), dtype=torch.float64, pin_memory=nccl)
+            pos = 0
+            for b, c in zip(bufs, counts):
+                if c:
+                    host[pos:pos + c].copy_(b[:c], non_blocking=nccl)
+                    pos += c
+            if nccl:
+                torch.cuda.synchronize(dev)
+            allrows = host.numpy()
+        # ordered blocks in rank order, boundaries in order => sorted
+        in_order = all(m[2] > 0.5 for m in metas)
+        prev = None
+        for m in metas:
+            if int(m[0]) == 0:
+                continue
+            if prev is not None and tuple(m[3:6]) < prev:
+                in_order = False
+            prev = tuple(m[6:9])
+    if allrows.shape[0] > 1 and not in_order:
+        allrows = allrows[np.lexsort((allrows[:, 2], allrows[:, 1], allrows[:, 0]))]
     return allrows

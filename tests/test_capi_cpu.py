@@ -184,3 +184,12 @@ def test_config_writer_round_trip(sd, cw):
     assert tf == "LogSig" and np.array_equal(w, w0.astype(np.float32)) and np.array_equal(b, b0.astype(np.float32))
     assert c.layer(1)[2] == "SatLin" and c.spectrogram_scaling == "db" and list(c.thresholds) == [0.1, 0.2]
     assert [p[0] for p in c.input_processing] == ["normalize", "mapstd"] and c.input_processing[1][3] == 0.25
+
+
+def test_resample_output_lengths(sd):
+    """n_out of the two converters: Int(Float(n) / Float(rate_in / rate_out)) (Resampler.swift:32,40) and ceil(n up / down)."""
+    assert sd.lib.syldet_resample_output_length(sd.RESAMPLE_LINEAR, 32, 48000.0, 44100.0) == int(np.float32(32) / np.float32(48000.0 / 44100.0))
+    assert sd.lib.syldet_resample_output_length(sd.RESAMPLE_POLYPHASE, 48000, 48000.0, 44100.0) == 44100
+    assert sd.lib.syldet_resample_output_length(sd.RESAMPLE_POLYPHASE, 100003, 96000.0, 44100.0) == -(-100003 * 147 // 320)
+    assert sd.lib.syldet_resample_output_length(sd.RESAMPLE_POLYPHASE, 10, 44100.5, 44100.0) == -1
+    assert sd.lib.syldet_resample_output_length(sd.RESAMPLE_LINEAR, 0, 48000.0, 44100.0) == 0

@@ -670,6 +670,83 @@ def test_resampler_matches_oracle_bit_for_bit(sd, oracle_mod):
             assert ya.size == yb.size and np.array_equal(ya, yb), (rin, rout, i)
 
 
+def test_batched_linear_resampler_matches_oracle_bit_for_bit(sd, oracle_mod):
+    """Whole-channel ResamplerLinear.resampleVector (Resampler.swift:35-70) on the device, several channels per launch, against the
+    oracle's single call from a fresh state - including the float32 index ramp's loss of precision on long buffers."""
+    rng = np.random.default_rng(8)
+    for rin, rout, n in ((48000, 44100, 300001), (96000, 44100, 123457), (22050, 44100, 70000), (44100, 48000, 50003), (44100, 44100, 4097), (48000, 44100, 3)):
+        x = rng.standard_normal((3, n)).astype(np.float32)
+        y = sd.resample(x, rin, rout, mode=sd.RESAMPLE_LINEAR)
+        for ch in range(3):
+            ref = oracle_mod.Resampler(rin, rout).process(x[ch])
+            assert y[ch].size == ref.size and np.array_equal(y[ch], ref), (rin, rout, ch)
+
+
+def test_polyphase_resampler_matches_scipy(sd):
+    """The quality converter (north_star (1)): same design and alignment as scipy.signal.resample_poly; float32 taps and accumulation
+    against scipy's float64: |delta| <= 1e-5 x the signal's peak. Also: a tone stays a tone (no imaging above -90 dB)."""
+    import scipy.signal as ss
+    rng = np.random.default_rng(9)
+    for rin, rout, n in ((48000, 44100, 100003), (96000, 44100, 88211), (22050, 44100, 30000), (44100, 48000, 44100), (32000, 44100, 16001), (48000, 44100, 5)):
+        x = rng.standard_normal((2, n)).astype(np.float32)
+        y = sd.resample(x, rin, rout)
+        g = np.gcd(rin, rout)
+        ref = ss.resample_poly(x.astype(np.float64), rout // g, rin // g, axis=1)
+        assert y.shape == ref.shape, (rin, rout, y.shape, ref.shape)
+        assert np.abs(y - ref).max() <= 1e-5 * np.abs(x).max(), (rin, rout, float(np.abs(y - ref).max()))
+    t = np.arange(96000) / 48000.0
+    tone = np.sin(2 * np.pi * 3000.0 * t).astype(np.float32)
+    y = sd.resample(tone, 48000, 44100)[2000:-2000]
+    spec = np.abs(np.fft.rfft(y * np.hanning(y.size)))
+    k = int(round(3000.0 * y.size / 44100.0))
+    spec[k - 8:k + 9] = 0.0
+    assert 20 * np.log10(spec.max() / (y.size / 4.0)) < -90.0
+    with pytest.raises(sd.SyldetError):
+        sd.resample(tone, 44100.5, 44100)
+
+
+def test_cli_other_rates_and_sample_formats(sd, cfg, synth, tmp_path):
+    """`syldet` on a 48 kHz 24-bit file: converted to the network's rate on the device (upstream: AVFoundation delivers
+    config.samplingRate, SyllableDetector.swift:19-23); on a 44.1 kHz 24-bit file: uploaded as packed integers (SYLDET_PCM_S24)."""
+    import os
+    import subprocess
+    from conftest import ROOT, SAMPLE_TXT as NET
+    exe = os.path.join(ROOT, "syllable-detector-swift_b200", "syldet")
+
+    def write24(path, x, rate):
+        q = np.clip(np.round(x * 8388608.0), -8388608, 8388607).astype(np.int32)          # [ch, n]
+        b = np.ascontiguousarray(q.T).astype("<i4").view(np.uint8).reshape(-1, 4)[:, :3].tobytes()
+        nch = x.shape[0]
+        hdr = b"RIFF" + np.uint32(36 + len(b)).tobytes() + b"WAVEfmt " + np.uint32(16).tobytes() + np.uint16(1).tobytes() + np.uint16(nch).tobytes() + \
+            np.uint32(rate).tobytes() + np.uint32(rate * nch * 3).tobytes() + np.uint16(nch * 3).tobytes() + np.uint16(24).tobytes() + b"data" + np.uint32(len(b)).tobytes()
+        with open(path, "wb") as f:
+            f.write(hdr + b)
+        return (q.astype(np.float32) / np.float32(8388608.0)).astype(np.float32)
+
+    def rows_of(path):
+        out = subprocess.run([exe, "-n", NET, "-a", path], capture_output=True, text=True, check=True).stdout
+        return [(int(r[0]), int(r[1]), float(r[3])) for r in (l.split(",") for l in out.strip().splitlines())]
+
+    x = synth.make_audio(2, 44100 * 3, seed=29) * 6.0
+    xq = write24(str(tmp_path / "a24.wav"), x, 44100)
+    det = sd.BatchDetector(cfg)
+    ev = det.run(xq)
+    got = rows_of(str(tmp_path / "a24.wav"))
+    assert len(got) == len(ev) > 5
+    assert [g[:2] for g in got] == list(zip(ev.channel.tolist(), ev.sample.tolist()))
+    assert np.abs(np.array([g[2] for g in got]) - ev.outputs[:, 0]).max() <= 1e-6
+    # the same material played at 48 kHz (resampled up by scipy in float64, stored as 24-bit): the CLI converts it back on the device
+    import scipy.signal as ss
+    x48 = ss.resample_poly(x.astype(np.float64), 160, 147, axis=1).astype(np.float32)
+    x48q = write24(str(tmp_path / "a48.wav"), x48, 48000)
+    back = sd.resample(x48q, 48000, 44100)
+    ev48 = det.run(back)
+    got48 = rows_of(str(tmp_path / "a48.wav"))
+    assert len(got48) == len(ev48) > 5 and [g[:2] for g in got48] == list(zip(ev48.channel.tolist(), ev48.sample.tolist()))
+    # and the detections agree with the original's, up to evaluations that sit near the threshold (two conversions lie in between)
+    assert abs(len(ev48) - len(ev)) <= max(3, len(ev) // 20)
+
+
 def test_large_run_properties(sd, cfg, orc, synth):
     """BASELINE config-2 shape at reduced length per channel but full channel count: size-independent checks."""
     nch, n = 8, 44100 * 120

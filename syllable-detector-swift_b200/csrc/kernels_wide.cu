@@ -310,12 +310,13 @@ __device__ __forceinline__ int padf(int i) { return i + (i >> 3); }
 
 // One Stockham stage of radix R over the M-point sequence: out[(j / Ns) Ns R + j % Ns + r Ns] = DFT_R(in[j + r M / R] w^{r (j % Ns)}).
 // kFirst: the inputs come from the (windowed) audio instead of the ping-pong buffer.
+// tws: this stage's twiddles, [r - 1][k] = e^{-2 pi i r k / (R Ns)}, k < Ns: lanes of a warp read consecutive k (no bank conflicts; a
+// single table e^{-2 pi i m / M} indexed by r k M / (R Ns) puts all lanes of an early stage on one bank).
 template <int R, bool kFirst>
 __device__ __forceinline__ void stockham_stage(const float2 *__restrict__ in, float2 *__restrict__ out, int M, int Ns, int lane,
-                                               const float2 *__restrict__ twM, const float *__restrict__ fr, const float *__restrict__ win, int W,
+                                               const float2 *__restrict__ tws, const float *__restrict__ fr, const float *__restrict__ win, int W,
                                                bool pairs = false) {
     const int nb = M / R;            // butterflies of this stage
-    const int tw_step = M / (Ns * R);
     for (int j = lane; j < nb; j += 32) {
         const int k = j & (Ns - 1);
         float2 v[R];
@@ -336,7 +337,7 @@ __device__ __forceinline__ void stockham_stage(const float2 *__restrict__ in, fl
         }
         if (Ns > 1) {
 #pragma unroll
-            for (int r = 1; r < R; ++r) v[r] = cmul(v[r], twM[r * k * tw_step]);
+            for (int r = 1; r < R; ++r) v[r] = cmul(v[r], tws[(r - 1) * Ns + k]);
         }
         Dft<R>::run(v);
         const int base = (j - k) * R + k;
@@ -357,8 +358,8 @@ __global__ void __launch_bounds__(512) stft_planes_fast_kernel(const DevNet *__r
     float *audio = reinterpret_cast<float *>(smem_raw);                  // [span]
     float *win = audio + ((span + 3) & ~3);                              // [W]
     float *tile = win + ((W + 3) & ~3);                                  // [kWideStftCols][pitch]
-    float2 *twM = reinterpret_cast<float2 *>(tile + ((kWideStftCols * pitch + 1) & ~1));   // [M] e^{-2 pi i m / M}
-    float2 *utw = twM + M;                                               // [L] e^{-2 pi i (k0 + f) / N}
+    float2 *twS = reinterpret_cast<float2 *>(tile + ((kWideStftCols * pitch + 1) & ~1));   // per-stage twiddle tables, < 2 M entries in all
+    float2 *utw = twS + 2 * M;                                           // [L] e^{-2 pi i (k0 + f) / N}
     float2 *buf = utw + ((L + 1) & ~1);                                  // [warps][2][padf(M)]
     const int bufM = padf(M) + 1;
     float2 *b0 = buf + (size_t)warp * 2 * bufM, *b1 = b0 + bufM;
@@ -370,10 +371,21 @@ __global__ void __launch_bounds__(512) stft_planes_fast_kernel(const DevNet *__r
     for (int i = threadIdx.x; i < need; i += blockDim.x) audio[i] = src[i];
     for (int i = threadIdx.x; i < W; i += blockDim.x) win[i] = net.window[i];
     for (int i = threadIdx.x; i < kWideStftCols * pitch; i += blockDim.x) tile[i] = 0.0f;   // padding bins and missing columns read as 0
-    for (int m = threadIdx.x; m < M; m += blockDim.x) {
-        double sn, cs;
-        sincospi(-2.0 * (double)m / (double)M, &sn, &cs);
-        twM[m] = make_float2((float)cs, (float)sn);
+    int log_m = 0;
+    while ((1 << log_m) < M) ++log_m;
+    const int last_radix = log_m % 3 == 0 ? 8 : (log_m % 3 == 1 ? 2 : 4);
+    {   // twiddle tables of every stage after the first, back to back: stage with sub-transform length Ns and radix R at offset off
+        int off = 0;
+        for (int Ns = 8; Ns < M; Ns *= 8) {
+            const int R = Ns * 8 <= M ? 8 : last_radix;
+            for (int i = threadIdx.x; i < (R - 1) * Ns; i += blockDim.x) {
+                const int r = i / Ns + 1, k = i % Ns;
+                double sn, cs;
+                sincospi(-2.0 * (double)(r * k) / (double)(R * Ns), &sn, &cs);
+                twS[off + i] = make_float2((float)cs, (float)sn);
+            }
+            off += (R - 1) * Ns;
+        }
     }
     for (int f = threadIdx.x; f < L; f += blockDim.x) {
         double sn, cs;
@@ -381,28 +393,27 @@ __global__ void __launch_bounds__(512) stft_planes_fast_kernel(const DevNet *__r
         utw[f] = make_float2((float)cs, (float)sn);
     }
     __syncthreads();
-    int log_m = 0;
-    while ((1 << log_m) < M) ++log_m;
-    const int last_radix = log_m % 3 == 0 ? 8 : (log_m % 3 == 1 ? 2 : 4);
     for (int c = warp; c < cols; c += warps) {
         const float *fr = audio + c * hop;
         float2 *in = b0, *out = b1;
         int Ns = 1;
         // radix-8 stages, the first one straight from the windowed audio; then the remainder stage
         if (M >= 8) {
-            stockham_stage<8, true>(nullptr, out, M, 1, lane, twM, fr, win, W, (hop & 1) == 0);
+            stockham_stage<8, true>(nullptr, out, M, 1, lane, twS, fr, win, W, (hop & 1) == 0);
             Ns = 8;
+            int off = 0;
             __syncwarp();
             while (Ns * (last_radix == 8 ? 1 : last_radix) < M) {
                 float2 *t2 = in; in = out; out = t2;
-                stockham_stage<8, false>(in, out, M, Ns, lane, twM, nullptr, nullptr, 0);
+                stockham_stage<8, false>(in, out, M, Ns, lane, twS + off, nullptr, nullptr, 0);
+                off += 7 * Ns;
                 Ns *= 8;
                 __syncwarp();
             }
             if (last_radix != 8) {
                 float2 *t2 = in; in = out; out = t2;
-                if (last_radix == 2) stockham_stage<2, false>(in, out, M, Ns, lane, twM, nullptr, nullptr, 0);
-                else stockham_stage<4, false>(in, out, M, Ns, lane, twM, nullptr, nullptr, 0);
+                if (last_radix == 2) stockham_stage<2, false>(in, out, M, Ns, lane, twS + off, nullptr, nullptr, 0);
+                else stockham_stage<4, false>(in, out, M, Ns, lane, twS + off, nullptr, nullptr, 0);
                 __syncwarp();
             }
         }
@@ -459,7 +470,7 @@ bool stft_planes_fast_supported(int fft_len) { return fft_len >= 16 && fft_len <
 static size_t stft_planes_fast_smem(int fft_len, int win_len, int band, int hop, int n_planes, int warps) {
     const int M = fft_len / 2, span = (kWideStftCols - 1) * hop + win_len, pitch = n_planes * 4 + 1;
     const size_t floats = (size_t)((span + 3) & ~3) + ((win_len + 3) & ~3) + ((kWideStftCols * pitch + 1) & ~1);
-    const size_t f2 = (size_t)M + ((band + 1) & ~1) + (size_t)warps * 2 * (M + (M >> 3) + 1);
+    const size_t f2 = (size_t)2 * M + ((band + 1) & ~1) + (size_t)warps * 2 * (M + (M >> 3) + 1);
     return floats * 4 + f2 * 8 + 16;
 }
 

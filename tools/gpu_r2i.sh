@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-2 GPU pass I: resamplers (batched linear, polyphase, CLI formats), wide path after the STFT load fix, full test suite.
-TAG=${1:-r02i}
+TAG=${1:-r02j}
 mkdir -p gpurun_out
 timeout -s KILL 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -30 | tee gpurun_out/${TAG}_tests.log
 timeout -s KILL 400 python bench.py --config 4 --hidden 256 --steps 5 --warmup 3 --no-cpu > gpurun_out/${TAG}_bench_c4_h256.json 2> gpurun_out/${TAG}_bench_c4_h256.err; tail -2 gpurun_out/${TAG}_bench_c4_h256.err

@@ -40,6 +40,12 @@ sys.path.insert(0, ROOT)
 
 FS = 44100
 SAMPLE_TXT = os.path.join(ROOT, "tests", "golden", "sample.txt")
+# other trained-net shapes for --shape (device-resident throughput + parity of whichever kernel the configuration qualifies for)
+SHAPES = {
+    "fft512_hop256_h8": dict(fft_len=512, overlap=256, freq_range=(1000.0, 9000.0), time_range=5, hidden=(8,), input_funcs=("l2normalize", "mapminmax")),
+    "fft256_hop128_h8_minmax": dict(fft_len=256, overlap=128, freq_range=(1500.0, 6500.0), time_range=6, hidden=(8,),
+                                    input_funcs=("normalize", "mapminmax"), transfer="LogSig"),
+}
 METRIC = "audio-sec/sec"
 UNIT = "audio-seconds/second"
 
@@ -229,12 +235,14 @@ def bind_near_gpu(torch, local):
     return info, undo
 
 
-def full_parity(np, orc, cfg, x_host, outs_gpu, ev_channel, ev_sample, tol=1e-5):
+def full_parity(np, orc, cfg, x_host, outs_gpu, ev_channel, ev_sample, tol=1e-5, scale_tol=False):
     """Every evaluation of a recording against the oracle: outputs within `tol`, decisions identical except evaluations whose oracle
     output lies within `tol` of the threshold (listed), events == the kernel's own decisions."""
     nch = x_host.shape[0]
     ref, da_ref = orc.run_multi(x_host, n_threads=len(os.sched_getaffinity(0)), want_outputs=True)
     thr = float(cfg.thresholds[0])
+    if scale_tol:   # random networks (--shape) may have outputs far above 1: tolerance x output scale, as in the parity tests
+        tol = tol * max(1.0, float(np.nanmax(np.abs(ref))) if ref.size else 1.0)
     err = np.abs(outs_gpu - ref)
     both_nan = np.isnan(outs_gpu) & np.isnan(ref)
     err[both_nan] = 0.0
@@ -292,21 +300,37 @@ def run_ours(args):
     if args.config == 4:
         return run_wide(args, np, torch, dist, sd, rank, world, local, dev, barrier)
 
-    cfg = sd.SyllableDetectorConfig(SAMPLE_TXT).validate()
+    shape_text = None
+    if args.shape != "sample":   # a second trained-net shape (device-resident numbers + parity only): what the other kernels do
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("_cw", os.path.join(ROOT, "syllable-detector-swift_b200", "config_writer.py"))
+        cwm = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(cwm)
+        shape_text = cwm.random_config(seed=5, threshold=0.3, **SHAPES[args.shape])
+        args.no_e2e = True
+        args.no_alt = True
+    cfg = (sd.SyllableDetectorConfig.from_text(shape_text) if shape_text else sd.SyllableDetectorConfig(SAMPLE_TXT)).validate()
     nch = args.channels
     n = int(round(args.hours * 3600 * FS))
     n -= n % 4
     E = cfg.num_evals(n)
     audio_seconds = nch * n / FS                      # per rank per step
-    x = synth.make_audio_torch(nch, n, dev, seed=1000 + rank)   # this rank's recording, resident in HBM
+    if shape_text:
+        g = torch.Generator(device=dev)
+        g.manual_seed(77 + rank)
+        x = torch.empty((nch, n), dtype=torch.float32, device=dev).normal_(0.0, 0.05, generator=g)
+    else:
+        x = synth.make_audio_torch(nch, n, dev, seed=1000 + rank)   # this rank's recording, resident in HBM
     d_out = torch.empty((nch, E, cfg.net_outputs), dtype=torch.float32, device=dev)
     det = sd.BatchDetector(cfg, device=local, kernel=getattr(sd, "KERNEL_" + args.kernel.upper()))
-    assert det.active_kernel in (sd.KERNEL_FUSED, sd.KERNEL_TENSOR, sd.KERNEL_TENSOR_TF32), "sample.txt must take a fused kernel"
+    assert shape_text or det.active_kernel in (sd.KERNEL_FUSED, sd.KERNEL_TENSOR, sd.KERNEL_TENSOR_TF32), "sample.txt must take a fused kernel"
     tf32_env = bool(os.environ.get("SYLDET_TC_TF32_CORR"))
     kernel_name = {sd.KERNEL_FUSED: "fused_detect_kernel<256,4> (SIMT FFT)",
                    sd.KERNEL_TENSOR_TF32: "tc_detect_kernel<4,kFast> (tcgen05 3xTF32 band DFT)",
                    sd.KERNEL_TENSOR: ("tc_detect_kernel<4,kFast> (tcgen05 3xTF32 band DFT)" if tf32_env else
-                                      "tc_detect_kernel<4,kFast,kF16> (tcgen05 band DFT: TF32 product + one range-guarded fp16 correction pass)")}[det.active_kernel]
+                                      "tc_detect_kernel<4,kFast,kF16> (tcgen05 band DFT on two-term fp16 splits, range-guarded; layer 0 as 3xTF32)")}.get(det.active_kernel, sd.KERNEL_NAMES.get(det.active_kernel))
+    if shape_text:
+        kernel_name = "%s kernel on shape '%s' %s" % (sd.KERNEL_NAMES.get(det.active_kernel), args.shape, SHAPES[args.shape])
     stream = torch.cuda.current_stream(dev)
 
     def launch(d=det, outs=d_out):
@@ -356,11 +380,11 @@ def run_ours(args):
     if args.no_e2e:   # development runs (tools/*.sh): device-resident numbers and a parity check only
         if rank == 0:
             import oracle
-            orc = oracle.Oracle(SAMPLE_TXT)
+            orc = oracle.Oracle(text=shape_text) if shape_text else oracle.Oracle(SAMPLE_TXT)
             seg_n = n if not args.quick_parity else min(n, 300 * FS)
             keep = events.sample < cfg.first_output_sample + cfg.hop * cfg.num_evals(seg_n)
             parity = full_parity(np, orc, cfg, x[:, :seg_n].cpu().numpy(), d_out[:, :cfg.num_evals(seg_n)].cpu().numpy(),
-                                 events.channel[keep], events.sample[keep])
+                                 events.channel[keep], events.sample[keep], scale_tol=shape_text is not None)
             parity.pop("near_threshold_frames")
             peaks, _ = measured_peaks()
             k_ms = sum(kernel_ms) / len(kernel_ms)
@@ -824,6 +848,7 @@ if __name__ == "__main__":
     ap.add_argument("--hours", type=float, default=1.0)
     ap.add_argument("--channels", type=int, default=8)
     ap.add_argument("--corpus-hours", type=float, default=1000.0)
+    ap.add_argument("--shape", default="sample", choices=["sample"] + sorted(SHAPES))
     ap.add_argument("--hidden", type=int, default=256)
     ap.add_argument("--wide-seconds", type=float, default=30.0)
     ap.add_argument("--wide-parity-seconds", type=float, default=1.0)

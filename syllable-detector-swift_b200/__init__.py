@@ -251,14 +251,15 @@ class Events:
     def __init__(self, handle, sampling_rate):
         n = lib.syldet_events_count(handle)
         o = lib.syldet_events_outputs_per_event(handle)
-        self.channel = np.zeros(n, dtype=np.int32)
-        self.sample = np.zeros(n, dtype=np.int64)
-        self.outputs = np.zeros((n, o), dtype=np.float32)
-        if n:
-            rows = np.ctypeslib.as_array(C.cast(lib.syldet_events_data(handle), C.POINTER(C.c_int64)), shape=(n, 2))
-            self.channel[:] = rows[:, 0].astype(np.int64) & 0xFFFFFFFF
-            self.sample[:] = rows[:, 1]
-            self.outputs[:] = np.ctypeslib.as_array(lib.syldet_events_outputs(handle), shape=(n, o))
+        if n:   # one strided copy per column out of the library's row array (syldet_event = {int32 channel, int32 reserved, int64 sample})
+            data = lib.syldet_events_data(handle)
+            self.channel = np.ctypeslib.as_array(C.cast(data, C.POINTER(C.c_int32)), shape=(n, 4))[:, 0].copy()
+            self.sample = np.ctypeslib.as_array(C.cast(data, C.POINTER(C.c_int64)), shape=(n, 2))[:, 1].copy()
+            self.outputs = np.ctypeslib.as_array(lib.syldet_events_outputs(handle), shape=(n, o)).copy()
+        else:
+            self.channel = np.zeros(0, dtype=np.int32)
+            self.sample = np.zeros(0, dtype=np.int64)
+            self.outputs = np.zeros((0, o), dtype=np.float32)
         lib.syldet_events_free(handle)
         self.seconds = self.sample / sampling_rate
 

@@ -1160,7 +1160,12 @@ syldet_status Batch::run_host(const void *pcm, int fmt, int n_channels, int64_t 
     using Key = EventKey;
     DevEvent *h_ev = static_cast<DevEvent *>(h_events_);
     float *h_out = reinterpret_cast<float *>(h_ev + sink_capacity_);
-    std::vector<std::vector<Key>> sorted(K);
+    // per slice: its rows in (channel, evaluation) order, built while later slices are still crossing PCIe; seg[k][ch] = first row of channel ch
+    std::vector<std::vector<syldet_event>> slice_rows(K);
+    std::vector<std::vector<float>> slice_outs(K);
+    std::vector<std::vector<size_t>> seg(K, std::vector<size_t>((size_t)n_channels + 1, 0));
+    std::vector<Key> keys;
+    const int64_t first = c.first_output_sample();
     unsigned long long done = 0;
     bool redo = false;   // the event buffer overflowed or the fp16 range flag went up: collect() repeats the launch (see settle)
     double t_copied = 0.0;
@@ -1178,13 +1183,24 @@ syldet_status Batch::run_host(const void *pcm, int fmt, int n_channels, int64_t 
         SYLDET_CUDA_DRAIN(cudaMemcpyAsync(h_out + done * O, sink_outputs_.as<float>() + done * O, m * O * sizeof(float), cudaMemcpyDeviceToHost,
                                           d2h_stream_));
         SYLDET_CUDA_DRAIN(cudaStreamSynchronize(d2h_stream_));
-        std::vector<Key> &keys = sorted[k];
         keys.resize(m);
         for (unsigned long long i = 0; i < m; ++i) {
             const DevEvent &e = h_ev[done + i];
             keys[i] = Key{((uint64_t)(uint32_t)e.channel << 40) | (uint64_t)e.eval, (uint32_t)(done + i)};
         }
         sort_event_keys(keys);
+        std::vector<syldet_event> &rows = slice_rows[k];
+        std::vector<float> &outs = slice_outs[k];
+        rows.resize(m);
+        outs.resize((size_t)m * O);
+        int ch_next = 0;
+        for (size_t i = 0; i < m; ++i) {
+            const DevEvent &e = h_ev[keys[i].idx];
+            while (ch_next <= e.channel) seg[k][ch_next++] = i;
+            rows[i] = syldet_event{e.channel, 0, first + (int64_t)c.hop * e.eval};  // TrackDetector.swift:39-42,67-68
+            for (int o = 0; o < O; ++o) outs[i * O + o] = h_out[(size_t)keys[i].idx * O + o];
+        }
+        while (ch_next <= n_channels) seg[k][ch_next++] = m;
         done = n_k;
     }
     if (redo) {
@@ -1195,27 +1211,21 @@ syldet_status Batch::run_host(const void *pcm, int fmt, int n_channels, int64_t 
         st = collect(debounce_frames, out);
         if (st != SYLDET_OK) return st;
     } else {
-        // ---- merge: slices are consecutive in time, so per channel the slices' groups simply follow each other ---------------
+        // ---- merge: slices are consecutive in time, so per channel the slices' segments simply follow each other (block copies) ----
         const double t_m0 = now_ms();
         out.outputs_per_event = O;
         out.rows.resize(done);
         out.outputs.resize((size_t)done * O);
-        const int64_t first = c.first_output_sample();
-        std::vector<size_t> pos(K, 0);
         size_t r = 0;
-        for (int ch = 0; ch < n_channels && r < done; ++ch) {
-            const uint64_t ch_end = (uint64_t)(ch + 1) << 40;
+        for (int ch = 0; ch < n_channels; ++ch)
             for (int k = 0; k < K; ++k) {
-                const std::vector<Key> &keys = sorted[k];
-                size_t i = pos[k];
-                for (; i < keys.size() && keys[i].key < ch_end; ++i, ++r) {
-                    const DevEvent &e = h_ev[keys[i].idx];
-                    out.rows[r] = syldet_event{e.channel, 0, first + (int64_t)c.hop * e.eval};  // TrackDetector.swift:39-42,67-68
-                    for (int o = 0; o < O; ++o) out.outputs[r * O + o] = h_out[(size_t)keys[i].idx * O + o];
+                const size_t a0 = seg[k][ch], a1 = seg[k][ch + 1];
+                if (a1 > a0) {
+                    std::memcpy(out.rows.data() + r, slice_rows[k].data() + a0, (a1 - a0) * sizeof(syldet_event));
+                    std::memcpy(out.outputs.data() + r * O, slice_outs[k].data() + a0 * O, (a1 - a0) * O * sizeof(float));
+                    r += a1 - a0;
                 }
-                pos[k] = i;
             }
-        }
         const double t_m1 = now_ms();
         debounce_sorted(c, out.rows, out.outputs, O, debounce_frames);
         if (e2e_timing())

@@ -28,6 +28,7 @@ nothing of the product.
 import argparse
 import ctypes
 import importlib
+import importlib.util
 import json
 import os
 import subprocess
@@ -302,7 +303,6 @@ def run_ours(args):
 
     shape_text = None
     if args.shape != "sample":   # a second trained-net shape (device-resident numbers + parity only): what the other kernels do
-        import importlib.util
         spec = importlib.util.spec_from_file_location("_cw", os.path.join(ROOT, "syllable-detector-swift_b200", "config_writer.py"))
         cwm = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(cwm)
@@ -645,7 +645,6 @@ def wide_config_text(hidden):
     """BASELINE config 4 as SURVEY.md 8(d) spells it out: fs 44 100, FFT = window = 1024, hop 4 (overlap 1020), band 1-8 kHz (162 bins),
     T = 8 (1296 inputs), `hidden` tansig units, 2 purelin outputs; seeded random weights in the reference's text format. config_writer
     is loaded by path: the reference arm must not import the product package."""
-    import importlib.util
     spec = importlib.util.spec_from_file_location("_cw", os.path.join(ROOT, "syllable-detector-swift_b200", "config_writer.py"))
     cw = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(cw)

@@ -916,10 +916,6 @@ namespace {
 // Detections leave the kernels in arrival order (one atomic per batch); the rows of the CLI are ordered by (channel, evaluation).
 // key = channel << 40 | evaluation. LSD radix sort, 11 bits per pass over the digits that are in use: ~3 passes of sequential memory
 // traffic instead of std::sort's ~20 compare-and-swap levels (400 000 detections per 1 h x 8 ch recording: 25 ms -> 3 ms).
-struct EventKey {
-    uint64_t key;
-    uint32_t idx;
-};
 void sort_event_keys(std::vector<EventKey> &keys) {
     const size_t n = keys.size();
     if (n < 2048) {
@@ -928,7 +924,8 @@ void sort_event_keys(std::vector<EventKey> &keys) {
     }
     uint64_t all = 0;
     for (const EventKey &k : keys) all |= k.key;
-    std::vector<EventKey> tmp(n);
+    static thread_local std::vector<EventKey> tmp;   // scratch kept between calls (no fresh page faults per recording)
+    tmp.resize(n);
     std::vector<size_t> count(2049);
     EventKey *src = keys.data(), *dst = tmp.data();
     for (int shift = 0; shift < 64; shift += 11) {
@@ -1005,14 +1002,19 @@ syldet_status Batch::collect(int64_t debounce_frames, Events &out) {
     syldet_status st = settle(&n);
     if (st != SYLDET_OK) return st;
     const double t_c1 = now_ms();
-    std::vector<DevEvent> ev(n);
-    std::vector<float> outs((size_t)n * O);
+    // pinned staging (shared with run_host's pipeline): the read-back runs at PCIe speed and needs no fresh pageable buffers
+    st = ensure_pipeline(1, (size_t)sink_capacity_ * (sizeof(DevEvent) + sizeof(float) * O));
+    if (st != SYLDET_OK) return st;
+    const DevEvent *ev = static_cast<const DevEvent *>(h_events_);
+    const float *outs = reinterpret_cast<const float *>(static_cast<const DevEvent *>(h_events_) + sink_capacity_);
     if (n) {
-        SYLDET_CUDA(cudaMemcpy(ev.data(), sink_events_.get(), n * sizeof(DevEvent), cudaMemcpyDeviceToHost));
-        SYLDET_CUDA(cudaMemcpy(outs.data(), sink_outputs_.get(), outs.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        SYLDET_CUDA(cudaMemcpyAsync(h_events_, sink_events_.get(), n * sizeof(DevEvent), cudaMemcpyDeviceToHost, last_.stream));
+        SYLDET_CUDA(cudaMemcpyAsync(const_cast<float *>(outs), sink_outputs_.get(), (size_t)n * O * sizeof(float), cudaMemcpyDeviceToHost, last_.stream));
+        SYLDET_CUDA(cudaStreamSynchronize(last_.stream));
     }
     const double t_c2 = now_ms();
-    std::vector<EventKey> keys(n);
+    std::vector<EventKey> &keys = collect_keys_;
+    keys.resize(n);
     for (size_t i = 0; i < n; ++i) keys[i] = EventKey{((uint64_t)(uint32_t)ev[i].channel << 40) | (uint64_t)ev[i].eval, (uint32_t)i};
     sort_event_keys(keys);
     out.outputs_per_event = O;
@@ -1022,7 +1024,7 @@ syldet_status Batch::collect(int64_t debounce_frames, Events &out) {
     for (size_t r = 0; r < n; ++r) {
         const DevEvent &e = ev[keys[r].idx];
         out.rows[r] = syldet_event{e.channel, 0, first + (int64_t)c.hop * e.eval};  // TrackDetector.swift:39-42,67-68
-        std::copy(outs.begin() + (size_t)keys[r].idx * O, outs.begin() + ((size_t)keys[r].idx + 1) * O, out.outputs.begin() + r * O);
+        for (int o = 0; o < O; ++o) out.outputs[r * O + o] = outs[(size_t)keys[r].idx * O + o];
     }
     const double t_c3 = now_ms();
     debounce_sorted(c, out.rows, out.outputs, O, debounce_frames);

@@ -131,6 +131,11 @@ constexpr size_t kSinkHeaderBytes = sizeof(SinkHeader);
 // to a network output while the norm is >= 2^-8 (audio rms >~ 2e-5). Quieter float audio takes the all-TF32 variant.
 constexpr float kTcGuardLo = 1.52587890625e-05f;   // 2^-16
 
+struct EventKey {   // channel << 40 | evaluation, and where the event sits in the sink
+    uint64_t key;
+    uint32_t idx;
+};
+
 struct Events {
     int outputs_per_event = 0;
     std::vector<syldet_event> rows;
@@ -195,6 +200,7 @@ private:
     size_t h_events_bytes_ = 0;
     int64_t slice_evals_ = 256 * 1024;
     DeviceBuffer planar_, feat_, sink_count_, sink_events_, sink_outputs_, staging_;
+    std::vector<EventKey> collect_keys_;   // scratch of collect(), kept between calls
     std::vector<cudaEvent_t> wide_ev_;
     int wide_segments_ = 0;
     DeviceBuffer wide_hi_, wide_lo_, wide_stats_;   // band-magnitude planes + column statistics of one time segment (wide path)

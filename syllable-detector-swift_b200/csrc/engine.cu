@@ -512,6 +512,7 @@ void debounce_sorted(const Config &cfg, std::vector<syldet_event> &rows, std::ve
                      int64_t debounce_frames) {
     // rows sorted by (channel, sample). emit iff debounceUntil < S; then debounceUntil = S + D  (TrackDetector.swift:80,99)
     (void)cfg;
+    if (debounce_frames == 0) return;   // rows of a channel have strictly increasing sample numbers: every row is emitted
     size_t w = 0;
     int32_t cur_ch = INT32_MIN;
     int64_t until = -1;
@@ -534,6 +535,8 @@ syldet_status Batch::init(const Config &cfg, int device) {
     syldet_status st = model_.init(cfg, device);
     if (st != SYLDET_OK) return st;
     SYLDET_CUDA(cudaStreamCreateWithFlags(&own_stream_, cudaStreamNonBlocking));
+    int mp = 0;
+    if (cudaDeviceGetAttribute(&mp, cudaDevAttrMaxPitch, device) == cudaSuccess && mp > 0) max_pitch_ = (size_t)mp;
     st = sink_count_.reserve(kSinkHeaderBytes);   // [0, 8): detection count, [8, 12): range flag of the fp16 correction pass
     return st;
 }
@@ -1131,16 +1134,21 @@ syldet_status Batch::run_host(const void *pcm, int fmt, int n_channels, int64_t 
     for (int k = 0; k < K; ++k) {
         const int64_t s0 = sb[k], ns = sb[k + 1] - sb[k];
         if (ns > 0) {
-            // one plain copy per channel row: cudaMemcpy2D rejects pitches above cudaDeviceProp::memPitch (2 GiB - 1), which a
-            // recording of more than ~3.4 hours per channel would exceed
+            // cudaMemcpy2D rejects pitches above cudaDevAttrMaxPitch (2 GiB - 1), which a recording of more than ~3.4 hours per
+            // channel would exceed: beyond it, one plain copy per channel row
             if (inter) {
                 SYLDET_CUDA_DRAIN(cudaMemcpyAsync((char *)staging_.get() + (size_t)s0 * n_channels * esz, (const char *)pcm + (size_t)s0 * n_channels * esz,
                                                   (size_t)ns * n_channels * esz, cudaMemcpyHostToDevice, copy_stream_));
             } else {
-                for (int ch = 0; ch < n_channels; ++ch) {
-                    char *dst = direct ? (char *)(planar + (size_t)ch * pitch + s0) : (char *)staging_.get() + ((size_t)ch * src_stride + s0) * esz;
-                    SYLDET_CUDA_DRAIN(cudaMemcpyAsync(dst, (const char *)pcm + ((size_t)ch * src_stride + s0) * esz, (size_t)ns * esz,
-                                                      cudaMemcpyHostToDevice, copy_stream_));
+                char *dst0 = direct ? (char *)(planar + s0) : (char *)staging_.get() + (size_t)s0 * esz;
+                const size_t dpitch = direct ? (size_t)pitch * 4 : (size_t)src_stride * esz, spitch = (size_t)src_stride * esz;
+                if (n_channels > 1 && std::max(dpitch, spitch) <= max_pitch_) {   // one 2-D copy per slice while the pitches allow it
+                    SYLDET_CUDA_DRAIN(cudaMemcpy2DAsync(dst0, dpitch, (const char *)pcm + (size_t)s0 * esz, spitch, (size_t)ns * esz, n_channels,
+                                                        cudaMemcpyHostToDevice, copy_stream_));
+                } else {
+                    for (int ch = 0; ch < n_channels; ++ch)
+                        SYLDET_CUDA_DRAIN(cudaMemcpyAsync(dst0 + (size_t)ch * dpitch, (const char *)pcm + ((size_t)ch * src_stride + s0) * esz,
+                                                          (size_t)ns * esz, cudaMemcpyHostToDevice, copy_stream_));
                 }
             }
         }
@@ -1162,6 +1170,9 @@ syldet_status Batch::run_host(const void *pcm, int fmt, int n_channels, int64_t 
     using Key = EventKey;
     DevEvent *h_ev = static_cast<DevEvent *>(h_events_);
     float *h_out = reinterpret_cast<float *>(h_ev + sink_capacity_);
+    // the result vectors are touched now, while the copies run, so that the tail below does not pay their page faults
+    out.rows.resize(last_event_count_);
+    out.outputs.resize((size_t)last_event_count_ * O);
     // per slice: its rows in (channel, evaluation) order, built while later slices are still crossing PCIe; seg[k][ch] = first row of channel ch
     std::vector<std::vector<syldet_event>> slice_rows(K);
     std::vector<std::vector<float>> slice_outs(K);
@@ -1218,6 +1229,7 @@ syldet_status Batch::run_host(const void *pcm, int fmt, int n_channels, int64_t 
         out.outputs_per_event = O;
         out.rows.resize(done);
         out.outputs.resize((size_t)done * O);
+        last_event_count_ = (size_t)done + (size_t)done / 16;
         size_t r = 0;
         for (int ch = 0; ch < n_channels; ++ch)
             for (int k = 0; k < K; ++k) {

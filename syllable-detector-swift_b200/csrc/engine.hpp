@@ -201,6 +201,8 @@ private:
     int64_t slice_evals_ = 256 * 1024;
     DeviceBuffer planar_, feat_, sink_count_, sink_events_, sink_outputs_, staging_;
     std::vector<EventKey> collect_keys_;   // scratch of collect(), kept between calls
+    size_t max_pitch_ = 0;                 // cudaDevAttrMaxPitch: largest pitch cudaMemcpy2D accepts
+    size_t last_event_count_ = 0;          // events of the previous run_host (+ margin): how much of the result to touch up front
     std::vector<cudaEvent_t> wide_ev_;
     int wide_segments_ = 0;
     DeviceBuffer wide_hi_, wide_lo_, wide_stats_;   // band-magnitude planes + column statistics of one time segment (wide path)

@@ -61,6 +61,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     } while (!done);
 }
 
+// Non-blocking probe of a phase (mbarrier.test_wait): true once the phase with this parity has completed.
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_addr(bar)), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+
 // Same wait for roles with slack: back off between polls so that a waiting warp does not compete for issue slots and
 // instruction fetch with the warps that are working (SYLDET_MBAR_SLEEP ns; 0 = plain polling).
 #ifndef SYLDET_MBAR_SLEEP

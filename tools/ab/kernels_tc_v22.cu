@@ -385,43 +385,10 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
             RoleTimer<kTiming> tm(w.debug_timing, 6, false);   // the MMA issuer is the pacemaker: it polls
             const uint32_t idesc_l0 = ptx::idesc_tf32(128, n0);
             const uint32_t a_hi = ptx::smem_addr(smem + TcSmem::a(0, 0)), a_lo = ptx::smem_addr(smem + TcSmem::a(0, 1));
-            // The issuer never blocks on one barrier while other work is ready (round 1 and the first pair-scheme build waited for
-            // the pair's magnitudes before they queued the next tile's DFT, which left the tensor pipe idle ~28 % of a tile): it
-            // probes what each of its two jobs needs (mbarrier.test_wait) and issues whichever is ready - the band DFT of the next
-            // tile (its fp16 / lo tile written, its accumulator read by the spectrum warps two tiles ago) or layer 0 of the next
-            // pair (both tiles' magnitudes written, the product buffer drained) - so the DFT runs up to two tiles ahead.
-            auto dft_ready = [&](uint32_t i) {
-                const int s = i & 1;
-                const uint32_t ph = (i >> 1) & 1;
-                const int ls = lo_stages == 2 ? s : 0;
-                const uint32_t lo_use = lo_stages == 2 ? (i >> 1) : i;   // uses of this lo buffer so far
-                if constexpr (!kF16) {
-                    if (!ptx::mbar_test(&full[s], ph)) return false;      // hi landed (TMA); kF16 reads only what the splitters wrote
-                }
-                return ptx::mbar_test(&tmem_empty[s], ph ^ 1) && ptx::mbar_test(&lo_ready[ls], lo_use & 1);
-            };
-            auto issue_dft = [&](uint32_t i) {
-                const int s = i & 1;
-                const int ls = lo_stages == 2 ? s : 0;
-                ptx::tc_fence_after();
-                const uint32_t d = tmem_base + kColD0 + s * kTileRows;
-                const uint32_t hi = ptx::smem_addr(smem + TcSmem::hi(s));
-                if constexpr (kF16) {
-                    f16_pass(d, tmem_base + kColAhi, ls ? lo_b : lo_a);
-                } else {
-                    dft_pass(d, tmem_base + kColAhi, hi, 0);
-                    dft_pass(d, tmem_base + kColAlo, hi, 1);
-                    ptx::mma_commit(&hi_free[s]);         // the MMA side is done with hi[s]
-                    dft_pass(d, tmem_base + kColAhi, ls ? lo_b : lo_a, 1);
-                }
-                ptx::mma_commit(&tmem_full[s]);
-                ptx::mma_commit(&lo_free[ls]);
-            };
-            auto l0_ready = [&](uint32_t pk) {
-                return ptx::mbar_test(a_ready, pk & 1) && ptx::mbar_test(&p_empty[pk & 1], ((pk >> 1) & 1) ^ 1);
-            };
             auto issue_l0 = [&](uint32_t pk) {  // per-column layer-0 products of the pair pk = tiles 2pk, 2pk+1 (M = 128)
                 const int pb = pk & 1;
+                tm.wait(a_ready, pk & 1, 3);                      // both tiles' magnitudes written and fenced
+                tm.wait(&p_empty[pb], ((pk >> 1) & 1) ^ 1, 4);    // product buffer drained by the evaluators
                 ptx::tc_fence_after();
                 const uint32_t d = tmem_base + kColP0 + pb * kMaxN0;
                 uint32_t acc = 0;
@@ -439,28 +406,34 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
             };
             TileWalk tw;
             tw.init(w, T);
-            uint32_t it = 0, next_pair = 0;   // next tile whose DFT is to be issued; next pair whose layer 0 is to be issued
-            bool more = tw.valid();
-            while (more || next_pair < (it + 1) / 2) {
-                bool progress = false;
-                if (more && dft_ready(it)) {
-                    issue_dft(it);
-                    ++it;
-                    tw.next(w, T);
-                    more = tw.valid();
-                    progress = true;
+            uint32_t it = 0, next_pair = 0;
+            for (; tw.valid(); ++it, tw.next(w, T)) {
+                const int s = it & 1;
+                const uint32_t ph = (it >> 1) & 1;
+                if constexpr (!kF16) tm.wait(&full[s], ph, 0);   // hi landed (TMA); kF16 reads only what the splitters wrote
+                // accumulator s is free once the spectrum warps have read tile it-2. For odd it that is implied: they arrived on
+                // a_ready for the pair (it-3, it-2) after their TMEM loads, and this thread waited for it in the previous iteration.
+                // For even it the pair (it-2, it-1) is only waited for below, after this tile's DFT is queued.
+                if (s == 0) tm.wait(&tmem_empty[0], ph ^ 1, 1);
+                ptx::tc_fence_after();
+                const uint32_t d = tmem_base + kColD0 + s * kTileRows;
+                const uint32_t hi = ptx::smem_addr(smem + TcSmem::hi(s));
+                if constexpr (!kF16) {
+                    dft_pass(d, tmem_base + kColAhi, hi, 0);
+                    dft_pass(d, tmem_base + kColAlo, hi, 1);
+                    ptx::mma_commit(&hi_free[s]);         // the MMA side is done with hi[s]
                 }
-                const uint32_t pairs_queued = more ? it / 2 : (it + 1) / 2;   // pairs whose tiles all have their DFT issued
-                if (next_pair < pairs_queued && l0_ready(next_pair)) {
-                    issue_l0(next_pair++);
-                    progress = true;
-                }
-                if (!progress) {
-                    const long long t0 = tm.now();
-                    __nanosleep(20);
-                    tm.add(3, t0);   // idle: nothing ready
-                }
+                const int ls = lo_stages == 2 ? s : 0;
+                const uint32_t lo_use = lo_stages == 2 ? (it >> 1) : it;   // uses of this lo buffer so far
+                tm.wait(&lo_ready[ls], lo_use & 1, 2);   // lo written (splitters)
+                ptx::tc_fence_after();
+                if constexpr (kF16) f16_pass(d, tmem_base + kColAhi, ls ? lo_b : lo_a);
+                else dft_pass(d, tmem_base + kColAhi, ls ? lo_b : lo_a, 1);
+                ptx::mma_commit(&tmem_full[s]);
+                ptx::mma_commit(&lo_free[ls]);
+                if (s == 0 && it >= 2) issue_l0(next_pair++);   // tiles it-2, it-1: their magnitudes were written while DFTs were queued
             }
+            while (next_pair < (it + 1) / 2) issue_l0(next_pair++);
             tm.flush(true);
         }
     } else if (warp < kWarpD0) {

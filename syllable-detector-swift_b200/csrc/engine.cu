@@ -692,6 +692,17 @@ syldet_status Batch::launch_tc_range(const float *d_planar, int n_channels, int6
     w.range_flag = reinterpret_cast<int *>(sink_count_.as<unsigned char>() + 8);
     w.debug_band = debug_band_;
     w.debug_cols = debug_cols_;
+    // fp16 variant, experimental data path (SYLDET_TC_DIRECT=1): six splitter warps read the audio from global memory themselves -
+    // no TMA, no raw fp32 tile in shared memory, 544 fewer shared-memory wavefronts per tile. Measured equal to slightly slower
+    // than the TMA path (1.547 against 1.525 ms, profiles/r02_tc_direct_experiments.txt): a warp's loads share one scoreboard, so
+    // the load latency of a tile is exposed once per tile. SYLDET_TC_PF: L2 prefetch distance in tiles for that path.
+    static const int direct = [] { const char *e = std::getenv("SYLDET_TC_DIRECT"); return e ? std::atoi(e) : 0; }();
+    static const int pf_dist = [] { const char *e = std::getenv("SYLDET_TC_PF"); return e ? std::atoi(e) : 0; }();
+    w.direct = direct;
+    w.pf_dist = std::max(0, std::min(pf_dist, 8));
+    w.pcm = d_planar;
+    w.ch_stride = n_channels > 1 ? ch_stride : 0;
+    w.n_rows = (int)std::min<int64_t>(n_samples / c.hop, INT32_MAX);
     const int64_t units = (int64_t)n_channels * w.chunks_per_channel;
     const int grid = (int)std::min<int64_t>(units, resident);
     static const bool timing = std::getenv("SYLDET_TC_TIMING") != nullptr;  // debug: per-role wait/busy cycles on stderr
@@ -721,7 +732,7 @@ syldet_status Batch::launch_tc_range(const float *d_planar, int n_channels, int6
         SYLDET_CUDA(cudaMemcpy(h.data(), d_timing.get(), h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
         static const char *names[30] = {"tma.hi_free", "", "", "", "", "tma.total", "mma.full", "mma.tmem_empty", "mma.lo_ready", "mma.a_ready",
                                         "mma.p_empty", "mma.total", "F.p_full", "F.bar1", "F.bar2", "F.tmem_ld", "F.sums+l0", "F.total", "D.tmem_full", "",
-                                        "D.a_free", "", "D.tmem_ld", "D.total", "S.full", "S.lo_free", "", "", "", "S.total"};
+                                        "D.a_free", "", "D.tmem_ld", "D.total", "S.full|ld", "S.lo_free", "S.convert", "", "", "S.total"};
         const double tiles = (double)n_channels * w.chunks_per_channel * ((w.chunk_evals + c.time_range - 1 + tc_tile_frames() - 1) / tc_tile_frames()) / grid;
         long long max_cycles = 0;   // slot 5 = whole role loop of the TMA warp
         for (int b = 0; b < grid; ++b) max_cycles = std::max(max_cycles, h[(size_t)b * 32 + 5]);

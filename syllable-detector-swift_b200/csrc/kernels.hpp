@@ -152,6 +152,14 @@ struct TcWork {
     // [guard_lo, FLT_MAX] (and not exactly 0) sets *range_flag; the host then repeats the launch with f16_corr = 0
     float guard_lo;
     int *range_flag;
+    // direct variant of the fp16 band DFT (f16_corr = 1): the splitter warps read the audio from global memory themselves
+    // (no TMA, no raw fp32 tile in shared memory)
+    int direct;
+    int pf_dist;                    // tiles ahead of the splitters that are requested into L2 (0 = no prefetch)
+    const float *pcm;               // first sample of evaluation eval_offset of channel 0
+    int64_t ch_stride;              // floats between channels
+    int n_rows;                     // complete hop-rows per channel from `pcm` on
+    int zero;                       // 0 (an operand the compiler cannot fold: orders the splitters' loads behind their arrival waits)
 };
 size_t tc_smem_bytes(const FusedParams &p, int hp);
 int tc_lo_stages(const FusedParams &p, int hp);

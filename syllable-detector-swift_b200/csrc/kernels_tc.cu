@@ -35,6 +35,8 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 #include "fused_epilogue.cuh"
 #include "ptx_sm100.cuh"
 
@@ -58,6 +60,8 @@ constexpr int kFGroup = 4;                     // evaluator warps (one per TMEM 
 #endif
 constexpr int kWarpTma = 0, kWarpMma = 1, kWarpF0 = 2, kNumF = kFGroup, kWarpD0 = kWarpF0 + kNumF, kNumD = TC_NUM_D,
               kWarpS0 = kWarpD0 + kNumD, kNumS = 4;
+constexpr int kNumSDirect = 6;                 // splitter warps of the direct variant (they also carry the global loads)
+constexpr int kTcThreadsDirect = (kWarpS0 + kNumSDirect) * 32;  // 640 (20 warps): still 96 registers per thread
 constexpr int kTcThreads = (kWarpS0 + kNumS) * 32;  // 576 (18 warps) with 8 spectrum warps; 832 with -DTC_NUM_D=16 (slower: profiles/r02_tc_v21_numd16_vs_8.txt)
 static_assert(kNumD == 8 || kNumD == 16, "spectrum warps: two or four per TMEM lane quadrant");
 static_assert(kWarpF0 % 4 == 2 && kWarpD0 % 4 == 2, "quadrant / half assignment below assumes these starts");
@@ -200,6 +204,24 @@ struct RoleTimer {
     }
 };
 
+// Two-term fp16 split of four samples: hx = fp16(x) (pairs), hl = fp16((x - hx) * 2^11). sm_100 has mixed-precision FMAs
+// (fma.rn.f32.f16: f16 x f16 + f32, SASS FHFMA with .H0/.H1 selectors), so the exact residual times 2^11 is ONE instruction per
+// sample on top of x * 2^11: 12 instructions per float4 where unpack / subtract / multiply took 16.
+__device__ __forceinline__ void split_fp16(const float4 &v, uint2 &hx, uint2 &hl) {
+    const __half2 x01 = __floats2half2_rn(v.x, v.y), x23 = __floats2half2_rn(v.z, v.w);
+    hx = make_uint2(*reinterpret_cast<const uint32_t *>(&x01), *reinterpret_cast<const uint32_t *>(&x23));
+    float r0, r1, r2, r3;
+    const unsigned short m2048 = 0xE800;   // -2048 in fp16
+    asm("{\n.reg .b16 lo, hi;\nmov.b32 {lo, hi}, %2;\nfma.rn.f32.f16 %0, lo, %5, %3;\nfma.rn.f32.f16 %1, hi, %5, %4;\n}\n"
+        : "=f"(r0), "=f"(r1)
+        : "r"(hx.x), "f"(v.x * 2048.0f), "f"(v.y * 2048.0f), "h"(m2048));
+    asm("{\n.reg .b16 lo, hi;\nmov.b32 {lo, hi}, %2;\nfma.rn.f32.f16 %0, lo, %5, %3;\nfma.rn.f32.f16 %1, hi, %5, %4;\n}\n"
+        : "=f"(r2), "=f"(r3)
+        : "r"(hx.y), "f"(v.z * 2048.0f), "f"(v.w * 2048.0f), "h"(m2048));
+    const __half2 l01 = __floats2half2_rn(r0, r1), l23 = __floats2half2_rn(r2, r3);
+    hl = make_uint2(*reinterpret_cast<const uint32_t *>(&l01), *reinterpret_cast<const uint32_t *>(&l23));
+}
+
 // An evaluator group empties its shared-memory event buffer: all threads of the group; one global atomic for the whole batch.
 // Out of line (one copy, away from the hot loop).
 __device__ __noinline__ void flush_group_events(EventSink sink, const int4 *ev_meta, const float *ev_out, int *ev_count,
@@ -226,8 +248,8 @@ __device__ __noinline__ bool network_tail_cold(const FusedParams &p, int detect_
 
 // kFast: the shape of the reference's sample network is known at compile time (l2normalize window statistic, tansig hidden
 // layer, one purelin output, one reverse output map), which strips the run-time dispatch from the evaluators' dependent chain.
-template <int HP, bool kScaled, bool kTiming, bool kFast, bool kF16>
-__global__ void __launch_bounds__(kTcThreads, 1)
+template <int HP, bool kScaled, bool kTiming, bool kFast, bool kF16, bool kDirect>
+__global__ void __launch_bounds__(kDirect ? kTcThreadsDirect : kTcThreads, 1)
 tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __grid_constant__ CUtensorMap tmap_main,
                  const __grid_constant__ CUtensorMap tmap_tail) {
     extern __shared__ __align__(16) unsigned char smem_dyn[];
@@ -246,9 +268,18 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
     uint64_t *full = bars, *hi_free = bars + 2, *lo_ready = bars + 4, *tmem_full = bars + 6, *tmem_empty = bars + 8;   // [2] each
     uint64_t *p_full = bars + 10, *p_empty = bars + 12, *lo_free = bars + 14;                                           // [2] each
     uint64_t *a_ready = bars + 16, *a_free = bars + 17;                       // one A operand (128 rows), refilled pair by pair
+    // kDirect: no TMA, no raw tile. The splitters read the audio from global memory and write the fp16 tile straight from
+    // registers; the fp16 tiles cycle through n_stages = 3 or 4 buffers (the two raw-tile buffers, lo, and lo1 when it fits).
+    static_assert(!kDirect || kF16, "the direct variant feeds the fp16 band DFT");
+    if constexpr (kDirect) {
+        lo_ready = bars + 22;     // [4]
+        lo_free = bars + 26;      // [4]
+    }
+    const int n_stages = w.lo_stages == 2 ? 4 : 3;
     // lo tile(s): with two, stage = it & 1 like the hi tiles and the splitters never wait for pass 3 of the previous tile
     const int lo_stages = w.lo_stages;
     const int lo1_off = TcSmem::lo1(np, p.n_out, planes);
+    auto stage_off = [&](int i) { return i < 3 ? i * kTileBytes : lo1_off; };   // kDirect: fp16 tile buffers
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 18);
     int *ev_count = reinterpret_cast<int *>(bars + 19);                       // events waiting in shared memory
     unsigned long long *ev_base = reinterpret_cast<unsigned long long *>(bars + 20);
@@ -256,6 +287,7 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
     float *colstat = reinterpret_cast<float *>(smem + TcSmem::colstat(np));   // sum of squares | minimum, then the maximum plane
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int kThreads = kDirect ? kTcThreadsDirect : kTcThreads;
 
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
@@ -268,6 +300,12 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
             ptx::mbar_init(&lo_ready[i], kNumS);
             ptx::mbar_init(&lo_free[i], 1);
         }
+        if constexpr (kDirect) {
+            for (int i = 0; i < 4; ++i) {
+                ptx::mbar_init(&lo_ready[i], kNumSDirect);
+                ptx::mbar_init(&lo_free[i], 1);
+            }
+        }
         ptx::mbar_init(a_ready, 2 * kNumD);   // both tiles of a pair
         ptx::mbar_init(a_free, 1);
         *ev_count = 0;
@@ -278,12 +316,17 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
         ptx::tmem_relinquish();
     }
     // layer-0 weights -> shared memory, K-major SWIZZLE_128B rows of 32 bins (B operand of the second contraction)
-    for (int i = tid; i < 2 * n0 * 32; i += kTcThreads) {
+    for (int i = tid; i < 2 * n0 * 32; i += kThreads) {
         const int part = i / (n0 * 32), r = (i / 32) % n0, c = i % 32;
         *reinterpret_cast<float *>(smem + TcSmem::wcat + part * kMaxN0 * 128 + sw128(r, c)) = __ldg((part ? w.wcat_lo : w.wcat_hi) + r * 32 + c);
     }
     // rows of the layer-0 A operand that no tile writes (row 63, short last tiles) must hold finite values
-    for (int i = tid; i < 4 * 8192 / 16; i += kTcThreads) reinterpret_cast<float4 *>(smem + TcSmem::abuf)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < 4 * 8192 / 16; i += kThreads) reinterpret_cast<float4 *>(smem + TcSmem::abuf)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if constexpr (kDirect) {   // the K padding of the fp16 tiles (n >= hop) is never written: it must read as zero
+        for (int i = tid; i < 3 * kTileBytes / 16; i += kThreads) reinterpret_cast<float4 *>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (n_stages == 4)
+            for (int i = tid; i < kTileBytes / 16; i += kThreads) reinterpret_cast<float4 *>(smem + lo1_off)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     ptx::fence_proxy_async_smem();
     ptx::tc_fence_before();
     __syncthreads();
@@ -323,7 +366,32 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
 
     if (warp == kWarpTma) {
         // ================================ TMA producer ================================================================
-        if (ptx::elect_one()) {
+        if constexpr (kDirect) {
+            // L2 prefetcher of the direct variant: one bulk prefetch per tile, w.pf_dist tiles ahead of the tile the splitters are
+            // about to fill (paced by the same lo_free barriers they wait on)
+            if (w.pf_dist > 0 && ptx::elect_one()) {
+                TileWalk tw, pf;
+                tw.init(w, T);
+                pf = tw;
+                auto prefetch = [&]() {
+                    if (!pf.valid()) return;
+                    const int rows = min(kTileRows, w.n_rows - pf.first_row());
+                    if (rows > 0)
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(w.pcm + (int64_t)pf.ch * w.ch_stride + (int64_t)pf.first_row() * p.hop),
+                                     "r"(rows * p.hop * 4)
+                                     : "memory");
+                    pf.next(w, T);
+                };
+                for (int i = 0; i < w.pf_dist; ++i) prefetch();
+                int stg = 0;
+                uint32_t stg_use = 0;
+                for (; tw.valid(); tw.next(w, T)) {
+                    ptx::mbar_wait_relaxed(&lo_free[stg], (stg_use & 1) ^ 1);
+                    if (++stg == n_stages) { stg = 0; ++stg_use; }
+                    prefetch();
+                }
+            }
+        } else if (ptx::elect_one()) {
             ptx::prefetch_tmap(&tmap_main);
             ptx::prefetch_tmap(&tmap_tail);
             TileWalk tw;
@@ -390,9 +458,12 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
             // probes what each of its two jobs needs (mbarrier.test_wait) and issues whichever is ready - the band DFT of the next
             // tile (its fp16 / lo tile written, its accumulator read by the spectrum warps two tiles ago) or layer 0 of the next
             // pair (both tiles' magnitudes written, the product buffer drained) - so the DFT runs up to two tiles ahead.
+            int stg = 0;          // kDirect: fp16 tile buffer of tile `it` and how often it has been filled before
+            uint32_t stg_use = 0;
             auto dft_ready = [&](uint32_t i) {
                 const int s = i & 1;
                 const uint32_t ph = (i >> 1) & 1;
+                if constexpr (kDirect) return ptx::mbar_test(&tmem_empty[s], ph ^ 1) && ptx::mbar_test(&lo_ready[stg], stg_use & 1);
                 const int ls = lo_stages == 2 ? s : 0;
                 const uint32_t lo_use = lo_stages == 2 ? (i >> 1) : i;   // uses of this lo buffer so far
                 if constexpr (!kF16) {
@@ -406,7 +477,13 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
                 ptx::tc_fence_after();
                 const uint32_t d = tmem_base + kColD0 + s * kTileRows;
                 const uint32_t hi = ptx::smem_addr(smem + TcSmem::hi(s));
-                if constexpr (kF16) {
+                if constexpr (kDirect) {
+                    f16_pass(d, tmem_base + kColAhi, ptx::smem_addr(smem + stage_off(stg)));
+                    ptx::mma_commit(&tmem_full[s]);
+                    ptx::mma_commit(&lo_free[stg]);
+                    if (++stg == n_stages) { stg = 0; ++stg_use; }
+                    return;
+                } else if constexpr (kF16) {
                     f16_pass(d, tmem_base + kColAhi, ls ? lo_b : lo_a);
                 } else {
                     dft_pass(d, tmem_base + kColAhi, hi, 0);
@@ -815,6 +892,79 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
         TileWalk tw;
         tw.init(w, T);
         RoleTimer<kTiming> tm(w.debug_timing, 24);
+        if constexpr (kDirect) {
+            // Audio: global memory -> registers -> fp16 tile; no TMA, no raw fp32 tile in shared memory (which saves the TMA write
+            // and the splitters' read of it: 544 of the ~2 600 shared-memory wavefronts a tile costs). A tile is 64 consecutive
+            // hop-rows = one contiguous span of the channel; the six splitter warps take it as ONE batch: thread st loads the float4
+            // st + 192 k (coalesced 512-byte warp loads, the whole tile in flight), converts to the two fp16 terms and stores 8 bytes
+            // of each at the element's place in the K-major SWIZZLE_128B / _32B operand, then reloads the register with the same
+            // element of the next tile. (All loads of a warp count on one scoreboard, so a two-batch pipeline inside a warp only
+            // serialises; the overlap comes from the other roles' warps.) Warp 0 asks L2 for the tiles further ahead.
+            // Instantiated per row length (hop / 4 = 32, 33 or 34 float4), which makes every slot count and predicate a constant.
+            auto run = [&](auto r4c) {
+                constexpr int R4 = decltype(r4c)::value, kPerTile = kTileRows * R4, kSThreads = kNumSDirect * 32;
+                constexpr int kFull = kPerTile / kSThreads, kRem = kPerTile % kSThreads, kSlots = kFull + (kRem ? 1 : 0);   // 10+1 | 11 | 11+1
+                const bool has_last = kRem == 0 || st < kRem;   // this thread's last slot exists
+                // Where this thread's float4 k lands in a tile buffer is the same for every tile. n < 128: fp16 chunk uu >> 4 (64 k
+                // per 128-byte row), 16-byte unit (uu >> 1) & 7 swizzled by the row, half uu & 1, h2 two chunks further; n >= 128: the
+                // SWIZZLE_32B tail, unit 0 = h1, unit 1 = h2, 16-byte unit ^= bit 2 of the row.
+                uint32_t offp[kSlots];     // h1 offset | h2 offset << 16
+#pragma unroll
+                for (int k = 0; k < kSlots; ++k) {
+                    const int q = min(st + k * kSThreads, kPerTile - 1);
+                    const int row = q / R4, uu = q - row * R4;
+                    const uint32_t o1 = uu < 32 ? (uu >> 4) * kMainBytes + row * 128 + ((((uu >> 1) & 7) ^ (row & 7)) << 4) + (uu & 1) * 8
+                                                : kMainChunks * kMainBytes + row * 32 + (((row >> 2) & 1) << 4) + (uu - 32) * 8;
+                    const uint32_t o2 = uu < 32 ? o1 + 2 * kMainBytes : o1 ^ 16u;
+                    offp[k] = o1 | (o2 << 16);
+                }
+                float4 v[kSlots];
+#pragma unroll
+                for (int k = 0; k < kSlots; ++k) v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                // Loads of the walk's tile. A tile whose 64 rows all exist (every one but the last of a channel) needs no predicates;
+                // rows past the end of the channel read as zero.
+                auto load_tile = [&]() {
+                    const float4 *src = reinterpret_cast<const float4 *>(w.pcm + (int64_t)tw.ch * w.ch_stride + (int64_t)tw.first_row() * p.hop) + st;
+                    const int rows = w.n_rows - tw.first_row();
+                    if (rows >= kTileRows) {
+#pragma unroll
+                        for (int k = 0; k < kSlots; ++k)
+                            if (k < kFull || has_last) v[k] = __ldcs(src + k * kSThreads);
+                    } else {
+                        const int nq = max(rows, 0) * R4 - st;
+#pragma unroll
+                        for (int k = 0; k < kSlots; ++k) v[k] = k * kSThreads < nq ? __ldcs(src + k * kSThreads) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                };
+                int stg = 0;
+                uint32_t stg_use = 0;
+                if (tw.valid()) load_tile();
+                while (tw.valid()) {
+                    tm.wait(&lo_free[stg], (stg_use & 1) ^ 1, 1);   // the band DFT of the previous user of this buffer has read it
+                    unsigned char *b16 = smem + stage_off(stg);
+                    const long long t_c0 = tm.now();
+                    uint2 hx[kSlots], hl[kSlots];
+#pragma unroll
+                    for (int k = 0; k < kSlots; ++k) {
+                        split_fp16(v[k], hx[k], hl[k]);
+                        if (k < kFull || has_last) {
+                            *reinterpret_cast<uint2 *>(b16 + (offp[k] & 0xFFFFu)) = hx[k];
+                            *reinterpret_cast<uint2 *>(b16 + (offp[k] >> 16)) = hl[k];
+                        }
+                    }
+                    tw.next(w, T);
+                    if (tw.valid()) load_tile();
+                    tm.add(2, t_c0);
+                    ptx::fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&lo_ready[stg]);
+                    if (++stg == n_stages) { stg = 0; ++stg_use; }
+                }
+            };
+            if (p.hop == 132) run(std::integral_constant<int, 33>{});
+            else if (p.hop == 128) run(std::integral_constant<int, 32>{});
+            else run(std::integral_constant<int, 34>{});
+        } else
         for (uint32_t it = 0; tw.valid(); ++it, tw.next(w, T)) {
             const int s = it & 1;
             tm.wait(&full[s], (it >> 1) & 1, 0);
@@ -826,14 +976,6 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
                 const unsigned char *hi_b = smem + TcSmem::hi(s);
                 unsigned char *b16 = smem + (ls ? lo1_off : TcSmem::lo);
                 const int sw = st >> 5, phys = lane & 7, rq = sw + 4 * (lane >> 3);   // row = rq + 16 * (kk & 3), chunk = kk >> 2
-                auto convert = [](const float4 &v, uint2 &hx, uint2 &hl) {
-                    const __half2 x01 = __floats2half2_rn(v.x, v.y), x23 = __floats2half2_rn(v.z, v.w);
-                    const float2 f01 = __half22float2(x01), f23 = __half22float2(x23);
-                    const __half2 l01 = __floats2half2_rn((v.x - f01.x) * 2048.0f, (v.y - f01.y) * 2048.0f);
-                    const __half2 l23 = __floats2half2_rn((v.z - f23.x) * 2048.0f, (v.w - f23.y) * 2048.0f);
-                    hx = make_uint2(*reinterpret_cast<const uint32_t *>(&x01), *reinterpret_cast<const uint32_t *>(&x23));
-                    hl = make_uint2(*reinterpret_cast<const uint32_t *>(&l01), *reinterpret_cast<const uint32_t *>(&l23));
-                };
 #pragma unroll
                 for (int b0 = 0; b0 < 16; b0 += 8) {
                     float4 v[8];
@@ -849,7 +991,7 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
                         const int unit16 = 4 * (c & 1) + (u >> 1);         // their place in the fp16 row (64 k per 128 B)
                         unsigned char *dst = b16 + (c >> 1) * kMainBytes + r * 128 + ((unit16 ^ (r & 7)) << 4) + (u & 1) * 8;
                         uint2 hx, hl;
-                        convert(v[k], hx, hl);
+                        split_fp16(v[k], hx, hl);
                         *reinterpret_cast<uint2 *>(dst) = hx;
                         *reinterpret_cast<uint2 *>(dst + 2 * kMainBytes) = hl;
                     }
@@ -859,7 +1001,7 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
                     const float4 v = *reinterpret_cast<const float4 *>(hi_b + kMainChunks * kMainBytes + r * 32 + ph * 16);
                     unsigned char *dst = b16 + kMainChunks * kMainBytes + r * 32 + u * 8;
                     uint2 hx, hl;
-                    convert(v, hx, hl);
+                    split_fp16(v, hx, hl);
                     *reinterpret_cast<uint2 *>(dst + ((0 ^ flip) << 4)) = hx;   // x: k 256 .. 263 = logical unit 0
                     *reinterpret_cast<uint2 *>(dst + ((1 ^ flip) << 4)) = hl;   // lo: k 264 .. 271 = logical unit 1
                 }
@@ -924,24 +1066,28 @@ cudaError_t launch_tc(int hp, int grid, size_t smem, const FusedParams &p, const
     const CUtensorMap &tm = *static_cast<const CUtensorMap *>(tmap_main);
     const CUtensorMap &tt = *static_cast<const CUtensorMap *>(tmap_tail);
     cudaError_t e = cudaErrorInvalidValue;
+    int threads = kTcThreads;
     auto go = [&](auto kern) {
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) kern<<<grid, kTcThreads, smem, stream>>>(p, w, tm, tt);
+        if (e == cudaSuccess) kern<<<grid, threads, smem, stream>>>(p, w, tm, tt);
     };
     const bool scaled = p.scaling != SYLDET_SCALING_LINEAR;
     const bool fast = hp == 4 && !scaled && p.window_stat == FUSED_STAT_L2 && p.tf[0] == SYLDET_TF_TANSIG && p.n_layers == 2 && p.n_out == 1 &&
                       p.tf[1] == SYLDET_TF_PURELIN && p.n_op == 1;
     const bool f16 = fast && w.f16_corr;   // the fp16 correction pass exists for the sample shape only
+    const bool direct = f16 && w.direct;
     if (w.debug_timing) {   // SYLDET_TC_TIMING: instrumented build of the common shape only
-        if (f16) go(tc_detect_kernel<4, false, true, true, true>);
-        else if (fast) go(tc_detect_kernel<4, false, true, true, false>);
+        if (direct) { threads = kTcThreadsDirect; go(tc_detect_kernel<4, false, true, true, true, true>); }
+        else if (f16) go(tc_detect_kernel<4, false, true, true, true, false>);
+        else if (fast) go(tc_detect_kernel<4, false, true, true, false, false>);
         else return cudaErrorNotSupported;
-    } else if (f16) go(tc_detect_kernel<4, false, false, true, true>);
-    else if (fast) go(tc_detect_kernel<4, false, false, true, false>);
-    else if (hp == 4 && !scaled) go(tc_detect_kernel<4, false, false, false, false>);
-    else if (hp == 4) go(tc_detect_kernel<4, true, false, false, false>);
-    else if (!scaled) go(tc_detect_kernel<8, false, false, false, false>);
-    else go(tc_detect_kernel<8, true, false, false, false>);
+    } else if (direct) { threads = kTcThreadsDirect; go(tc_detect_kernel<4, false, false, true, true, true>); }
+    else if (f16) go(tc_detect_kernel<4, false, false, true, true, false>);
+    else if (fast) go(tc_detect_kernel<4, false, false, true, false, false>);
+    else if (hp == 4 && !scaled) go(tc_detect_kernel<4, false, false, false, false, false>);
+    else if (hp == 4) go(tc_detect_kernel<4, true, false, false, false, false>);
+    else if (!scaled) go(tc_detect_kernel<8, false, false, false, false, false>);
+    else go(tc_detect_kernel<8, true, false, false, false, false>);
     if (e != cudaSuccess) return e;
     return cudaGetLastError();
 }

@@ -206,18 +206,20 @@ struct RoleTimer {
 
 // Two-term fp16 split of four samples: hx = fp16(x) (pairs), hl = fp16((x - hx) * 2^11). sm_100 has mixed-precision FMAs
 // (fma.rn.f32.f16: f16 x f16 + f32, SASS FHFMA with .H0/.H1 selectors), so the exact residual times 2^11 is ONE instruction per
-// sample on top of x * 2^11: 12 instructions per float4 where unpack / subtract / multiply took 16.
+// sample on top of x * 2^11 (FMUL2, two samples per instruction): 10 instructions per float4 where unpack / subtract / multiply took 16.
 __device__ __forceinline__ void split_fp16(const float4 &v, uint2 &hx, uint2 &hl) {
     const __half2 x01 = __floats2half2_rn(v.x, v.y), x23 = __floats2half2_rn(v.z, v.w);
     hx = make_uint2(*reinterpret_cast<const uint32_t *>(&x01), *reinterpret_cast<const uint32_t *>(&x23));
     float r0, r1, r2, r3;
     const unsigned short m2048 = 0xE800;   // -2048 in fp16
+    const float2 k2048 = make_float2(2048.0f, 2048.0f);
+    const float2 t01 = ptx::mul2(make_float2(v.x, v.y), k2048), t23 = ptx::mul2(make_float2(v.z, v.w), k2048);   // FMUL2
     asm("{\n.reg .b16 lo, hi;\nmov.b32 {lo, hi}, %2;\nfma.rn.f32.f16 %0, lo, %5, %3;\nfma.rn.f32.f16 %1, hi, %5, %4;\n}\n"
         : "=f"(r0), "=f"(r1)
-        : "r"(hx.x), "f"(v.x * 2048.0f), "f"(v.y * 2048.0f), "h"(m2048));
+        : "r"(hx.x), "f"(t01.x), "f"(t01.y), "h"(m2048));
     asm("{\n.reg .b16 lo, hi;\nmov.b32 {lo, hi}, %2;\nfma.rn.f32.f16 %0, lo, %5, %3;\nfma.rn.f32.f16 %1, hi, %5, %4;\n}\n"
         : "=f"(r2), "=f"(r3)
-        : "r"(hx.y), "f"(v.z * 2048.0f), "f"(v.w * 2048.0f), "h"(m2048));
+        : "r"(hx.y), "f"(t23.x), "f"(t23.y), "h"(m2048));
     const __half2 l01 = __floats2half2_rn(r0, r1), l23 = __floats2half2_rn(r2, r3);
     hl = make_uint2(*reinterpret_cast<const uint32_t *>(&l01), *reinterpret_cast<const uint32_t *>(&l23));
 }
@@ -620,8 +622,10 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
             float out[kFusedMaxOut];
             {
                 float acc[HP];
+                float2 acc2[HP / 2];            // the same sums as register pairs (FADD2: two per issue slot)
 #pragma unroll
-                for (int h = 0; h < HP; ++h) acc[h] = 0.0f;
+                for (int h = 0; h < HP / 2; ++h) acc2[h] = make_float2(0.0f, 0.0f);
+                float2 s2 = make_float2(0.0f, 0.0f);
                 float s0 = window_stat == FUSED_STAT_L2 ? 0.0f : INFINITY, s1 = -INFINITY;
                 if (valid) {
                     int row = g_mine + c - (T - 1);                        // ring position of the window's oldest column
@@ -638,13 +642,15 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
                         pt += ppitch + HP;
                         if (++row == kPRing) { row = 0; pt -= kPRing * ppitch; }
                         const float4 v0 = prow[0];
-                        acc[0] += v0.x; acc[1] += v0.y; acc[2] += v0.z; acc[3] += v0.w;
+                        acc2[0] = ptx::add2(acc2[0], make_float2(v0.x, v0.y));
+                        acc2[1] = ptx::add2(acc2[1], make_float2(v0.z, v0.w));
                         if constexpr (HP == 8) {
                             const float4 v1 = prow[1];
-                            acc[4] += v1.x; acc[5] += v1.y; acc[6] += v1.z; acc[7] += v1.w;
+                            acc2[2] = ptx::add2(acc2[2], make_float2(v1.x, v1.y));
+                            acc2[3] = ptx::add2(acc2[3], make_float2(v1.z, v1.w));
                         }
                         const float4 ca = cs[0];            // the four bin quarters of the column
-                        if (window_stat == FUSED_STAT_L2) s0 += (ca.x + ca.y) + (ca.z + ca.w);
+                        if (window_stat == FUSED_STAT_L2) s2 = ptx::add2(s2, ptx::add2(make_float2(ca.x, ca.y), make_float2(ca.z, ca.w)));
                         else if (window_stat == FUSED_STAT_MINMAX) {
                             const float4 cb = cs[kStatRing];
                             s0 = fminf(s0, fminf(fminf(ca.x, ca.y), fminf(ca.z, ca.w)));
@@ -654,6 +660,12 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
                         if (++col == kStatRing) { col = 0; cs -= kStatRing; }
                     }
                 }
+#pragma unroll
+                for (int h = 0; h < HP / 2; ++h) {
+                    acc[2 * h] = acc2[h].x;
+                    acc[2 * h + 1] = acc2[h].y;
+                }
+                if (window_stat == FUSED_STAT_L2) s0 = s2.x + s2.y;
                 if constexpr (kF16) {
                     // Range guard of the fp16 correction pass: the pass is at float32 level while the window's band
                     // energy sum |X|^2 is at least guard_lo (absolute operand errors of 2^-25 stay below 1e-6 of the normalised
@@ -789,20 +801,27 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
             // ---- (1) X_c = (Re1[c] + Re2[c+1]) + i (Im1[c] + Im2[c+1]) ------------------------------------------------------
             float x[kDGroups][2];
 #pragma unroll
-            for (int g = 0; g < kDGroups; ++g)
+            for (int g = 0; g < kDGroups; ++g) {
+                float own[2], got[2];
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     const float send = __uint_as_float(up ? r[4 * g + u + 1] : r[4 * g + 2 + u]);
-                    const float own = __uint_as_float(up ? r[4 * g + 3 + u] : r[4 * g + u]);
-                    x[g][u] = own + __shfl_xor_sync(0xffffffffu, send, 16);
+                    own[u] = __uint_as_float(up ? r[4 * g + 3 + u] : r[4 * g + u]);
+                    got[u] = __shfl_xor_sync(0xffffffffu, send, 16);
                 }
+                const float2 sum = ptx::add2(make_float2(own[0], own[1]), make_float2(got[0], got[1]));   // both columns in one FADD2
+                x[g][0] = sum.x;
+                x[g][1] = sum.y;
+            }
             // ---- (2) |X| of the band (plain multiplies and add, as the reference computes it) -------------------------------
             float mag[kDMags];                                  // e = 2*i + u: column col0 + 8*i + u
 #pragma unroll
-            for (int i = 0; i < kDGroups / 2; ++i)
+            for (int i = 0; i < kDGroups / 2; ++i) {
+                const float2 xa = make_float2(x[2 * i][0], x[2 * i][1]), xb = make_float2(x[2 * i + 1][0], x[2 * i + 1][1]);
+                const float2 sqa2 = ptx::mul2(xa, xa), sqb2 = ptx::mul2(xb, xb);   // FMUL2: the squares of both columns
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
-                    const float sq_a = __fmul_rn(x[2 * i][u], x[2 * i][u]), sq_b = __fmul_rn(x[2 * i + 1][u], x[2 * i + 1][u]);
+                    const float sq_a = u ? sqa2.y : sqa2.x, sq_b = u ? sqb2.y : sqb2.x;
                     const float other = __shfl_xor_sync(0xffffffffu, im ? sq_a : sq_b, 8);
                     float v;
                     if constexpr (kScaled) {
@@ -813,6 +832,7 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
                     } else v = sqrt_fast_ftz(__fadd_rn(im ? sq_b : sq_a, other));
                     mag[2 * i + u] = in_band ? v : 0.0f;
                 }
+            }
             // ---- window statistic: per-column partial over this warp's 8 bins; the evaluators combine the four quadrants -----
             if (window_stat != FUSED_STAT_NONE) {
                 // kDMags values x eight lanes -> the lane whose bits select value e holds its total: exchange half of the values per round
@@ -840,7 +860,11 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
                 const bool writer = (kDMags == 8 || (lane & 1) == 0) && stat_col < frames;
                 if (window_stat == FUSED_STAT_L2) {
 #pragma unroll
-                    for (int e = 0; e < kDMags; ++e) q[e] = mag[e] * mag[e];
+                    for (int e = 0; e < kDMags; e += 2) {
+                        const float2 m2 = make_float2(mag[e], mag[e + 1]), sq = ptx::mul2(m2, m2);
+                        q[e] = sq.x;
+                        q[e + 1] = sq.y;
+                    }
                     const float tot = reduce(q, [](float a, float b) { return a + b; });
                     if (writer) cs[0] = tot;
                 } else {

@@ -121,6 +121,23 @@ __device__ __forceinline__ void prefetch_tmap(const void *tmap) {
 // generic-proxy writes to shared memory -> visible to the async proxy (TMA, tensor core)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// ---- packed fp32 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2 work on an aligned register pair, two IEEE fp32 results per
+// issue slot; each half is rounded exactly like the scalar instruction) ------------------------------------------------
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    float2 r;
+    asm("{\n.reg .b64 pa, pb, pr;\nmov.b64 pa, {%2, %3};\nmov.b64 pb, {%4, %5};\nadd.rn.f32x2 pr, pa, pb;\nmov.b64 {%0, %1}, pr;\n}\n"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    float2 r;
+    asm("{\n.reg .b64 pa, pb, pr;\nmov.b64 pa, {%2, %3};\nmov.b64 pb, {%4, %5};\nmul.rn.f32x2 pr, pa, pb;\nmov.b64 {%0, %1}, pr;\n}\n"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+
 // ---- tcgen05 / TMEM ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {  // one full warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(dst_smem)), "r"(ncols) : "memory");

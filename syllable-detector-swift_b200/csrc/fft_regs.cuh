@@ -3,6 +3,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "ptx_sm100.cuh"
+
 namespace syldet {
 namespace {
 
@@ -23,8 +25,16 @@ __host__ __device__ constexpr double cos16(int i) {  // cos(2 pi i / 16)
 }
 __host__ __device__ constexpr double sin16(int i) { return cos16(i - 4); }
 
+// Complex add / subtract: a (re, im) pair is one aligned register pair, so each is ONE packed instruction (FADD2, sm_100) with
+// the rounding of the two scalar adds. SYLDET_FFT_SCALAR_ADDS keeps the scalar form (kernels built with -fmad=false semantics do
+// not care: an add is an add).
+#ifdef SYLDET_FFT_SCALAR_ADDS
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+#else
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return ptx::add2(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return ptx::sub2(a, b); }
+#endif
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }

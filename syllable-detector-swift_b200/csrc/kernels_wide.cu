@@ -302,11 +302,18 @@ __global__ void __launch_bounds__(kWThreads, 1) wide_l0_kernel(const __grid_cons
 // A CTA stages the audio span of kWideStftCols consecutive columns once (hop 4, window 1024: 64 columns share 1276 samples instead
 // of reading 65 536); each warp then transforms one frame at a time: the real N-point FFT as an M = N/2-point complex Stockham
 // autosort transform in shared memory, radix-8 stages (a last radix-2 / radix-4 stage when log2 M is not a multiple of 3), the
-// butterflies in registers (fft_regs.cuh), ping-pong buffers padded by one element per eight so that every stage's stride-8^s
-// stores and unit-stride loads are bank-conflict free. The band bins are untangled from the packed transform, scaled, and the tile
+// butterflies in registers (fft_regs.cuh), ping-pong buffers XOR-swizzled (padf) so that every stage's stride-8^s stores and
+// unit-stride loads are bank-conflict free. The band bins are untangled from the packed transform, scaled, and the tile
 // leaves the CTA in the plane layout wide_l0_kernel consumes ([plane][row][4 bins], raw and v - tf32(v)) together with the
 // per-column statistics of the per-window normalisers. (stft_planes_kernel in kernels_generic.cu is the reference-order fallback.)
-__device__ __forceinline__ int padf(int i) { return i + (i >> 3); }
+// Position of element i of a ping-pong buffer: the low four bits (the bank pair of a float2) are XOR-swizzled with bits 4, 5 and 6,
+//   bank bits = (b0 ^ b4, b1 ^ b5, b2 ^ b6, b3 ^ b6),
+// which makes every access pattern of a half warp (16 lanes x 8 bytes = one wavefront) a bijection onto the 16 bank pairs: the
+// unit-stride loads (index bits 0-3 vary), the stores of the first stage (stride 8: bits 3-6), of the second (bits 0-2 and 6) and of
+// the later ones (bits 0-3). Padding by one element per eight (round 2, first version) left one two-way conflict in every
+// unit-stride load and in the second stage's stores: 256 wavefronts per 512-point frame where 160 are needed
+// (profiles/r02_wide_v2_ncu_summary.txt: 116 M conflicts).
+__device__ __forceinline__ int padf(int i) { return i ^ ((i >> 4) & 3) ^ (((i >> 6) & 1) * 12); }
 
 // One Stockham stage of radix R over the M-point sequence: out[(j / Ns) Ns R + j % Ns + r Ns] = DFT_R(in[j + r M / R] w^{r (j % Ns)}).
 // kFirst: the inputs come from the (windowed) audio instead of the ping-pong buffer.
@@ -317,6 +324,11 @@ __device__ __forceinline__ void stockham_stage(const float2 *__restrict__ in, fl
                                                const float2 *__restrict__ tws, const float *__restrict__ fr, const float *__restrict__ win, int W,
                                                bool pairs = false) {
     const int nb = M / R;            // butterflies of this stage
+#ifndef WIDE_STAGE_UNROLL
+#define WIDE_STAGE_UNROLL 1
+#endif
+    constexpr int kUnroll = WIDE_STAGE_UNROLL;   // 2 (both butterflies of a lane in flight, 127 registers) measured slower: 7.37 against 7.08 ms
+#pragma unroll kUnroll
     for (int j = lane; j < nb; j += 32) {
         const int k = j & (Ns - 1);
         float2 v[R];
@@ -360,8 +372,8 @@ __global__ void __launch_bounds__(512) stft_planes_fast_kernel(const DevNet *__r
     float *tile = win + ((W + 3) & ~3);                                  // [kWideStftCols][pitch]
     float2 *twS = reinterpret_cast<float2 *>(tile + ((kWideStftCols * pitch + 1) & ~1));   // per-stage twiddle tables, < 2 M entries in all
     float2 *utw = twS + 2 * M;                                           // [L] e^{-2 pi i (k0 + f) / N}
-    float2 *buf = utw + ((L + 1) & ~1);                                  // [warps][2][padf(M)]
-    const int bufM = padf(M) + 1;
+    float2 *buf = utw + ((L + 1) & ~1);                                  // [warps][2][M], swizzled (padf)
+    const int bufM = M;
     float2 *b0 = buf + (size_t)warp * 2 * bufM, *b1 = b0 + bufM;
     const int ch = blockIdx.y;
     const int64_t c_first = (int64_t)blockIdx.x * kWideStftCols;
@@ -470,7 +482,7 @@ bool stft_planes_fast_supported(int fft_len) { return fft_len >= 16 && fft_len <
 static size_t stft_planes_fast_smem(int fft_len, int win_len, int band, int hop, int n_planes, int warps) {
     const int M = fft_len / 2, span = (kWideStftCols - 1) * hop + win_len, pitch = n_planes * 4 + 1;
     const size_t floats = (size_t)((span + 3) & ~3) + ((win_len + 3) & ~3) + ((kWideStftCols * pitch + 1) & ~1);
-    const size_t f2 = (size_t)2 * M + ((band + 1) & ~1) + (size_t)warps * 2 * (M + (M >> 3) + 1);
+    const size_t f2 = (size_t)2 * M + ((band + 1) & ~1) + (size_t)warps * 2 * M;
     return floats * 4 + f2 * 8 + 16;
 }
 

@@ -130,6 +130,13 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b) {
         : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
     return r;
 }
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+    float2 r;
+    asm("{\n.reg .b64 pa, pb, pr;\nmov.b64 pa, {%2, %3};\nmov.b64 pb, {%4, %5};\nsub.rn.f32x2 pr, pa, pb;\nmov.b64 {%0, %1}, pr;\n}\n"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
 __device__ __forceinline__ float2 mul2(float2 a, float2 b) {
     float2 r;
     asm("{\n.reg .b64 pa, pb, pr;\nmov.b64 pa, {%2, %3};\nmov.b64 pb, {%4, %5};\nmul.rn.f32x2 pr, pa, pb;\nmov.b64 {%0, %1}, pr;\n}\n"

@@ -137,6 +137,15 @@ __device__ __forceinline__ float2 sub2(float2 a, float2 b) {
         : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
     return r;
 }
+// d = a * b + c per half (FFMA2). With a = (x, x) ptxas uses the scalar-broadcast operand form, with b from kernel-parameter
+// space it loads uniform register pairs (LDCU): two weights of one input per issue slot.
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    float2 r;
+    asm("{\n.reg .b64 pa, pb, pc, pr;\nmov.b64 pa, {%2, %3};\nmov.b64 pb, {%4, %5};\nmov.b64 pc, {%6, %7};\nfma.rn.f32x2 pr, pa, pb, pc;\nmov.b64 {%0, %1}, pr;\n}\n"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return r;
+}
 __device__ __forceinline__ float2 mul2(float2 a, float2 b) {
     float2 r;
     asm("{\n.reg .b64 pa, pb, pr;\nmov.b64 pa, {%2, %3};\nmov.b64 pb, {%4, %5};\nmul.rn.f32x2 pr, pa, pb;\nmov.b64 {%0, %1}, pr;\n}\n"

@@ -19,7 +19,7 @@ SOURCES = [
     ("stream.cu", []),
     ("resample.cu", []),
     ("kernels_generic.cu", ["-fmad=false"]),
-    ("kernels_fused.cu", ["-Xptxas", "-v"]),
+    ("kernels_fused.cu", ["-Xptxas", "-v"] + os.environ.get("SYLDET_FUSED_DEFS", "").split()),
     ("kernels_tc.cu", ["-Xptxas", "-v"] + os.environ.get("SYLDET_TC_DEFS", "").split()),
     ("kernels_wide.cu", ["-Xptxas", "-v"] + os.environ.get("SYLDET_WIDE_DEFS", "").split()),
 ]

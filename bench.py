@@ -590,8 +590,11 @@ def run_corpus(args, np, torch, dist, sd, sharding, synth, rank, world, local, d
         e0.record(stream)
         det.launch_device(x.data_ptr(), nch, n, n, d_outputs_ptr=d_out.data_ptr(), stream=stream.cuda_stream)
         e1.record(stream)
+        t_l = time.perf_counter()
         ev = det.collect(debounce_frames=0)                        # synchronises; events to the host
         wall += time.perf_counter() - t0
+        if os.environ.get("SYLDET_E2E_TIMING") and rec < a + 8:
+            sys.stderr.write("[c3] recording %d: launch call %.2f ms, collect %.2f ms\n" % (rec, 1e3 * (t_l - t0), 1e3 * (time.perf_counter() - t_l)))
         dev_ms += e0.elapsed_time(e1)
         rows.append(sharding.pack_events(rec, ev.channel, ev.sample, ev.outputs))
         # per-shard parity: 400 evaluations of a random channel / offset of this recording against the oracle

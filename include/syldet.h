@@ -190,6 +190,9 @@ int64_t syldet_events_count(const syldet_events *ev);
 int syldet_events_outputs_per_event(const syldet_events *ev);
 const syldet_event *syldet_events_data(const syldet_events *ev);
 const float *syldet_events_outputs(const syldet_events *ev); /* [count][O] */
+/* The same rows as separate columns, copied in one pass into caller arrays of syldet_events_count() entries (outputs: [count][O]);
+ * any of the three pointers may be NULL. For bindings that want column arrays (numpy, Swift [Int64]). */
+void syldet_events_copy_columns(const syldet_events *ev, int32_t *channel, int64_t *sample, float *outputs);
 void syldet_events_free(syldet_events *ev);
 
 /* ---- one stream: class SyllableDetector (Common/SyllableDetector.swift:13-231) ------------------------------------ */

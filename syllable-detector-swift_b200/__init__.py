@@ -100,6 +100,7 @@ def _load():
         "syldet_events_count": (i64, [vp]), "syldet_events_outputs_per_event": (i32, [vp]),
         "syldet_events_data": (C.POINTER(Event), [vp]), "syldet_events_outputs": (C.POINTER(C.c_float), [vp]),
         "syldet_events_free": (None, [vp]),
+        "syldet_events_copy_columns": (None, [vp, vp, vp, vp]),
         "syldet_detector_create": (i32, [vp, i32, pvp]), "syldet_detector_destroy": (None, [vp]),
         "syldet_detector_append": (i32, [vp, vp, i64]), "syldet_detector_process_new_value": (i32, [vp]),
         "syldet_detector_last_outputs": (i32, [vp, vp, i32]), "syldet_detector_last_detected": (i32, [vp]),
@@ -251,11 +252,11 @@ class Events:
     def __init__(self, handle, sampling_rate):
         n = lib.syldet_events_count(handle)
         o = lib.syldet_events_outputs_per_event(handle)
-        if n:   # one strided copy per column out of the library's row array (syldet_event = {int32 channel, int32 reserved, int64 sample})
-            data = lib.syldet_events_data(handle)
-            self.channel = np.ctypeslib.as_array(C.cast(data, C.POINTER(C.c_int32)), shape=(n, 4))[:, 0].copy()
-            self.sample = np.ctypeslib.as_array(C.cast(data, C.POINTER(C.c_int64)), shape=(n, 2))[:, 1].copy()
-            self.outputs = np.ctypeslib.as_array(lib.syldet_events_outputs(handle), shape=(n, o)).copy()
+        if n:   # the library splits its row array (syldet_event = {int32 channel, int32 reserved, int64 sample}) into columns in one pass
+            self.channel = np.empty(n, dtype=np.int32)
+            self.sample = np.empty(n, dtype=np.int64)
+            self.outputs = np.empty((n, o), dtype=np.float32)
+            lib.syldet_events_copy_columns(handle, self.channel.ctypes.data, self.sample.ctypes.data, self.outputs.ctypes.data)
         else:
             self.channel = np.zeros(0, dtype=np.int32)
             self.sample = np.zeros(0, dtype=np.int64)

@@ -228,6 +228,21 @@ int64_t syldet_events_count(const syldet_events *ev) { return ev ? (int64_t)ev->
 int syldet_events_outputs_per_event(const syldet_events *ev) { return ev ? ev->e.outputs_per_event : 0; }
 const syldet_event *syldet_events_data(const syldet_events *ev) { return ev ? ev->e.rows.data() : nullptr; }
 const float *syldet_events_outputs(const syldet_events *ev) { return ev ? ev->e.outputs.data() : nullptr; }
+void syldet_events_copy_columns(const syldet_events *ev, int32_t *channel, int64_t *sample, float *outputs) {
+    if (!ev) return;
+    const size_t n = ev->e.rows.size();
+    const syldet_event *r = ev->e.rows.data();
+    if (channel && sample) {
+        for (size_t i = 0; i < n; ++i) {
+            channel[i] = r[i].channel;
+            sample[i] = r[i].sample;
+        }
+    } else {
+        if (channel) for (size_t i = 0; i < n; ++i) channel[i] = r[i].channel;
+        if (sample) for (size_t i = 0; i < n; ++i) sample[i] = r[i].sample;
+    }
+    if (outputs && n) std::memcpy(outputs, ev->e.outputs.data(), ev->e.outputs.size() * sizeof(float));
+}
 void syldet_events_free(syldet_events *ev) { delete ev; }
 
 // ---- batched resampling -------------------------------------------------------------------------------------------------

@@ -183,6 +183,7 @@ private:
                                       int detect_rule, float *d_all_outputs, bool reset_sink, cudaStream_t stream);
     syldet_status ensure_pipeline(int slices, size_t event_bytes);
     syldet_status settle(unsigned long long *n_events);
+    syldet_status order_events_on_device(unsigned long long n, int64_t evals, int n_channels, cudaStream_t stream, bool *ordered);
     syldet_status launch_wide_range(const float *d_planar, int n_channels, int64_t ch_stride, int64_t eval_begin, int64_t eval_count,
                                     int64_t evals_total, int detect_rule, float *d_all_outputs, EventSink sink, cudaStream_t stream);
 
@@ -200,6 +201,7 @@ private:
     size_t h_events_bytes_ = 0;
     int64_t slice_evals_ = 256 * 1024;
     DeviceBuffer planar_, feat_, sink_count_, sink_events_, sink_outputs_, staging_;
+    DeviceBuffer order_bits_, order_prefix_, order_blocks_, sorted_events_, sorted_outputs_;   // device-side ordering of the detections (collect)
     std::vector<EventKey> collect_keys_;   // scratch of collect(), kept between calls
     size_t max_pitch_ = 0;                 // cudaDevAttrMaxPitch: largest pitch cudaMemcpy2D accepts
     size_t last_event_count_ = 0;          // events of the previous run_host (+ margin): how much of the result to touch up front

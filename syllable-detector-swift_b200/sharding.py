@@ -74,13 +74,19 @@ def pack_events(recording, channel, sample, outputs):
     return rows
 
 
-def rows_in_order(rows):
-    """True when rows [n, 3 + O] are ordered by (recording, channel, sample) - one vectorised pass."""
-    if rows.shape[0] < 2:
-        return True
-    r, c, t = rows[:, 0], rows[:, 1], rows[:, 2]
-    dr, dc, dt = np.diff(r), np.diff(c), np.diff(t)
-    return bool(np.all((dr > 0) | ((dr == 0) & ((dc > 0) | ((dc == 0) & (dt >= 0))))))
+def rows_in_order(rows, block=1 << 18):
+    """True when rows [n, 3 + O] are ordered by (recording, channel, sample). One pass in cache-sized blocks: (recording, channel)
+    folds into one exact float64 key (channel < 2^16), so two differences per block decide it and nothing the size of the table
+    (tens of millions of rows after a corpus run) is ever allocated."""
+    n = rows.shape[0]
+    for a in range(0, n - 1, block):
+        b = min(n, a + block + 1)            # one row of overlap: the pair across the block boundary is checked too
+        rc = rows[a:b, 0] * 65536.0 + rows[a:b, 1]
+        d_rc = rc[1:] - rc[:-1]
+        d_t = rows[a + 1:b, 2] - rows[a:b - 1, 2]
+        if not bool(np.all((d_rc > 0) | ((d_rc == 0) & (d_t >= 0)))):
+            return False
+    return True
 
 
 def gather_events(rows, dist=None, dst=0):

@@ -689,6 +689,7 @@ syldet_status Batch::launch_tc_range(const float *d_planar, int n_channels, int6
     // int16-derived samples k / 32768 are exact fp16 operands (x: at most one rounding in the normal range; its tf32 residual times
     // 2^11 is a multiple of 2^-4 below 2): no lower bound needed there. Float input: see kTcGuardLo.
     w.guard_lo = pcm_exact_ ? 0.0f : kTcGuardLo;
+    w.guard_range = pcm_exact_ ? 0.0f : kTcGuardRange;
     w.range_flag = reinterpret_cast<int *>(sink_count_.as<unsigned char>() + 8);
     w.debug_band = debug_band_;
     w.debug_cols = debug_cols_;

@@ -130,6 +130,7 @@ constexpr size_t kSinkHeaderBytes = sizeof(SinkHeader);
 // pass: its absolute operand errors (2^-25 per subnormal sample, x |A_lo| <= 2^-12) add ~6e-11 per band magnitude, i.e. less than 1e-6
 // to a network output while the norm is >= 2^-8 (audio rms >~ 2e-5). Quieter float audio takes the all-TF32 variant.
 constexpr float kTcGuardLo = 1.52587890625e-05f;   // 2^-16
+constexpr float kTcGuardRange = 0.00390625f;       // 2^-8: the same bound for a window's max - min (min / max normalised windows)
 
 struct EventKey {   // channel << 40 | evaluation, and where the event sits in the sink
     uint64_t key;

@@ -151,6 +151,7 @@ struct TcWork {
     // range guard of the fp16 correction pass (f16_corr = 1): an evaluation whose window energy sum |X|^2 is outside
     // [guard_lo, FLT_MAX] (and not exactly 0) sets *range_flag; the host then repeats the launch with f16_corr = 0
     float guard_lo;
+    float guard_range;              // same guard for windows normalised by their min / max: the smallest window range max - min
     int *range_flag;
     // direct variant of the fp16 band DFT (f16_corr = 1): the splitter warps read the audio from global memory themselves
     // (no TMA, no raw fp32 tile in shared memory)

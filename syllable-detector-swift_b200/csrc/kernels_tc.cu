@@ -671,7 +671,14 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
                     // energy sum |X|^2 is at least guard_lo (absolute operand errors of 2^-25 stay below 1e-6 of the normalised
                     // features) and no sample overflowed fp16 (inf / NaN energy otherwise). An exactly silent window (energy 0) is
                     // exact in both variants. Anything else raises the flag; the host then repeats the launch with the all-TF32 variant.
-                    if (valid && !(s0 >= w.guard_lo && s0 <= 3.0e38f) && s0 != 0.0f) *w.range_flag = 1;
+                    // Windows normalised by their minimum / maximum (mapminmax over the window): the same argument with the
+                    // window's range max - min in the place of its norm (a flat window is exact: every input becomes -1).
+                    if (window_stat == FUSED_STAT_L2) {
+                        if (valid && !(s0 >= w.guard_lo && s0 <= 3.0e38f) && s0 != 0.0f) *w.range_flag = 1;
+                    } else if (window_stat == FUSED_STAT_MINMAX) {
+                        const float range = s1 - s0;
+                        if (valid && !(range >= w.guard_range && s1 <= 3.0e38f) && range != 0.0f) *w.range_flag = 1;
+                    }
                 }
                 float inv = 1.0f, beta = 0.0f;  // z = acc * inv + beta * V + B'
                 if (window_stat == FUSED_STAT_L2) {            // x / sqrt(sum x^2)  (NeuralNet.swift:47-59); silence: 0 * inf = NaN
@@ -1043,8 +1050,11 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
 #pragma unroll
                 for (int k = 0; k < kBatch; ++k)
                     if (b0 + k < kPerThread)
-                        lo4[(b0 + k) * kNumS * 32] = make_float4(v[k].x - tf32_trunc(v[k].x), v[k].y - tf32_trunc(v[k].y), v[k].z - tf32_trunc(v[k].z),
-                                                                 v[k].w - tf32_trunc(v[k].w));
+                    {
+                        const float2 l01 = ptx::sub2(make_float2(v[k].x, v[k].y), make_float2(tf32_trunc(v[k].x), tf32_trunc(v[k].y)));
+                        const float2 l23 = ptx::sub2(make_float2(v[k].z, v[k].w), make_float2(tf32_trunc(v[k].z), tf32_trunc(v[k].w)));
+                        lo4[(b0 + k) * kNumS * 32] = make_float4(l01.x, l01.y, l23.x, l23.y);
+                    }
             }
             }
             ptx::fence_proxy_async_smem();
@@ -1098,16 +1108,20 @@ cudaError_t launch_tc(int hp, int grid, size_t smem, const FusedParams &p, const
     const bool scaled = p.scaling != SYLDET_SCALING_LINEAR;
     const bool fast = hp == 4 && !scaled && p.window_stat == FUSED_STAT_L2 && p.tf[0] == SYLDET_TF_TANSIG && p.n_layers == 2 && p.n_out == 1 &&
                       p.tf[1] == SYLDET_TF_PURELIN && p.n_op == 1;
-    const bool f16 = fast && w.f16_corr;   // the fp16 correction pass exists for the sample shape only
-    const bool direct = f16 && w.direct;
+    // the fp16 band DFT needs a per-window normaliser for its range guard (l2normalize or a min / max over the window) and linear
+    // spectrogram scaling (a logarithm amplifies the errors of near-empty bins)
+    const bool f16 = w.f16_corr && !scaled && (p.window_stat == FUSED_STAT_L2 || p.window_stat == FUSED_STAT_MINMAX);
+    const bool direct = f16 && fast && w.direct;
     if (w.debug_timing) {   // SYLDET_TC_TIMING: instrumented build of the common shape only
         if (direct) { threads = kTcThreadsDirect; go(tc_detect_kernel<4, false, true, true, true, true>); }
-        else if (f16) go(tc_detect_kernel<4, false, true, true, true, false>);
+        else if (f16 && fast) go(tc_detect_kernel<4, false, true, true, true, false>);
         else if (fast) go(tc_detect_kernel<4, false, true, true, false, false>);
         else return cudaErrorNotSupported;
     } else if (direct) { threads = kTcThreadsDirect; go(tc_detect_kernel<4, false, false, true, true, true>); }
-    else if (f16) go(tc_detect_kernel<4, false, false, true, true, false>);
+    else if (f16 && fast) go(tc_detect_kernel<4, false, false, true, true, false>);
     else if (fast) go(tc_detect_kernel<4, false, false, true, false, false>);
+    else if (f16 && hp == 4) go(tc_detect_kernel<4, false, false, false, true, false>);
+    else if (f16) go(tc_detect_kernel<8, false, false, false, true, false>);
     else if (hp == 4 && !scaled) go(tc_detect_kernel<4, false, false, false, false, false>);
     else if (hp == 4) go(tc_detect_kernel<4, true, false, false, false, false>);
     else if (!scaled) go(tc_detect_kernel<8, false, false, false, false, false>);

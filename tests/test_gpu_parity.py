@@ -241,6 +241,28 @@ def test_amplitude_range_non_normalised_configs(sd, oracle_mod, cw):
             assert det.range_fallbacks == 0
 
 
+def test_amplitude_invariance_minmax_window_config(sd, oracle_mod, cw):
+    """A window normalised by its own minimum / maximum ("normalize") is scale-invariant too; the tensor kernel runs such shapes on
+    the fp16-split band DFT as well, guarded by the window's range max - min instead of its norm: quiet input (range < 2^-8) and
+    fp16 overflow make the handle repeat the launch with the all-TF32 variant, everything in between stays on the fast one."""
+    text = cw.random_config(seed=23, threshold=0.3, fft_len=256, overlap=128, freq_range=(1500.0, 6500.0), time_range=6, hidden=(8,),
+                            input_funcs=("normalize", "mapminmax"), transfer="LogSig")
+    c = sd.SyllableDetectorConfig.from_text(text).validate()
+    o = oracle_mod.Oracle(text=text)
+    rng = np.random.default_rng(8)
+    n = 60000
+    t = np.arange(n)
+    x0 = (0.05 * rng.standard_normal(n) + 0.3 * np.sin(2 * np.pi * 2900.0 * t / 44100) * (np.sin(2 * np.pi * 3.0 * t / 44100) > 0)).astype(np.float32)
+    for e, fallbacks in ((0, 0), (6, 0), (-6, 0), (-20, 1), (20, 1)):
+        x = (x0 * np.float32(2.0 ** e)).astype(np.float32)
+        det = sd.BatchDetector(c, kernel=sd.KERNEL_TENSOR)
+        ev, outs = det.run(x, want_outputs=True)
+        assert det.active_kernel == sd.KERNEL_TENSOR
+        scale = max(1.0, float(np.nanmax(np.abs(o.run(x)[0]))))
+        _check_channel(o, x, outs[0], ev.sample, TOL_OUT * scale)
+        assert det.range_fallbacks == fallbacks, (e, det.range_fallbacks)
+
+
 @pytest.mark.parametrize("kernel_name", ["KERNEL_TENSOR", "KERNEL_TENSOR_TF32", "KERNEL_FUSED", "KERNEL_GENERIC"])
 def test_spectra_match_oracle(sd, cfg, orc, synth, kernel_name):
     """extractPower()[f0 ..< f1] (CSTFT.swift:280-337) from every kernel against the oracle's float32 radix-2 FFT: north_star's

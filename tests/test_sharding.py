@@ -47,6 +47,15 @@ def _worker(rank, world, port, mode, out_path):
         j = np.nonzero(da)[0]
         rows.append(sh.pack_events(0, 0, np.array([orc.eval_sample(int(k) + e0) for k in j], dtype=np.int64), outs[j]))
     local = np.concatenate(rows, axis=0) if rows else np.zeros((0, 4))
+    if mode == "recordings":   # the compact transport must deliver the same rows
+        crow = [sh.pack_events_compact(int(r[0, 0]), r[:, 1].astype(np.int64), r[:, 2].astype(np.int64), r[:, 3:]) for r in rows if r.shape[0]]
+        compact = np.concatenate(crow) if crow else np.zeros(0, dtype=sh.event_dtype(1))
+        call = sh.gather_events(compact, dist, dst=0)
+        if rank == 0:
+            rec, ch, smp, outs = sh.unpack_events(call)
+            np.save(out_path + ".compact.npy", np.column_stack([rec, ch, smp, outs.astype(np.float64)]))
+        else:
+            assert call is None
     allrows = sh.gather_events(local, dist, dst=0)
     if rank == 0:
         np.save(out_path, allrows)
@@ -89,6 +98,11 @@ def test_two_rank_recording_shards_match_single_process(tmp_path, oracle_mod, sy
             rows.append(sh.pack_events(rec, ch, s, outs))
     want = np.concatenate(rows, axis=0)
     assert got.shape == want.shape and got.shape[0] > 10 and np.array_equal(got, want)
+    compact = np.load(str(tmp_path / "rows_recordings.npy") + ".compact.npy")
+    assert np.array_equal(compact, want)           # structured rows through the byte gather: the same table
+    c = sh.pack_events_compact(3, want[:5, 1].astype(np.int64), want[:5, 2].astype(np.int64), want[:5, 3:])
+    assert c.dtype.itemsize == 16 and sh.rows_in_order(c) and not sh.rows_in_order(c[::-1])
+    assert sh.gather_events(c, None).shape[0] == 5
 
 
 def test_two_rank_time_slices_match_sequential_run(tmp_path, oracle_mod, synth):

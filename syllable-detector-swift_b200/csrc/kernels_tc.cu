@@ -31,7 +31,8 @@
 // Every role is a serial chain per tile and runs at ~0.1 IPC per warp (profiles/): the roles overlap through double buffers.
 // Round 1 ran layer 0 per tile (M = 64: half-rate tensor pipe, 16 of 32 lanes per evaluator warp, two evaluator groups of four
 // warps taking tiles in turn); the pair scheme halves the evaluators' instruction count per evaluation and the weight-operand
-// reads, and frees four warps (registers: 112 per thread instead of 80).
+// reads, and frees four warps (96 registers per thread). The direct variant (kDirect, opt-in: SYLDET_TC_DIRECT=1) replaces warp 0's TMA
+// loads and the raw tile by six splitter warps that read the audio from global memory themselves (20 warps).
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -45,7 +46,7 @@ namespace syldet {
 namespace {
 
 constexpr int kFGroup = 4;                     // evaluator warps (one per TMEM lane quadrant)
-// kF16: the whole band DFT as kind::f16 MMAs on two-term fp16 splits of both operands (the sample shape):
+// kF16: the whole band DFT as kind::f16 MMAs on two-term fp16 splits of both operands (linear scaling + a per-window normaliser):
 //   A = a1 + a2, a1 = fp16(A), a2 = fp16(A - a1);   x = h1 + h2 * 2^-11, h1 = fp16(x), h2 = fp16((x - h1) * 2^11)
 //   A x ~= a1 h1 + (a1 2^-11) h2 + a2 h1            (the dropped term a2 (x - h1) is <= 2^-24 |A| |x|)
 // as ONE K-concatenated pass [a1 | a1 2^-11 | a2] * [h1 ; h2 ; h1]: 26 MMAs with K = 16 per tile, where round 1 ran 17 kind::tf32

@@ -10,6 +10,7 @@
 //   decision:     SyllableDetectorCLI/TrackDetector.swift:71-77, Common/SyllableDetector.swift:27-31
 // The fused kernel (kernels_fused.cu) is the fast path; this one is the general one and the on-device cross-check.
 #include "kernels.hpp"
+#include "ptx_sm100.cuh"
 #include "resample.cuh"
 
 namespace syldet {
@@ -502,15 +503,19 @@ __global__ void stream_tick_kernel(const DevNet *__restrict__ netp, StreamTick t
             if (tid0 + k * tstride < t.n_staged) pre[k] = src[tid0 + k * tstride];
     }
     // (2) while they fly: the configuration (DevNet record + window, twiddles, weights, processing vectors) -> shared
-    // memory, so that the serial left-to-right sums below never wait on L2
+    // memory, so that the sums below never wait on L2. The blob (tens of KB) comes as ONE bulk copy (cp.async.bulk, completion on an
+    // mbarrier) that runs while the samples arrive and are written to the ring; a per-thread copy loop of dependent L2 round trips
+    // took 4 of the tick's 13 microseconds.
+    __shared__ uint64_t blob_bar;
+    unsigned char *sblob = reinterpret_cast<unsigned char *>(smem) + t.work_bytes;
+    if (threadIdx.x == 0 && t.blob_bytes) {
+        ptx::mbar_init(&blob_bar, 1);
+        ptx::fence_mbar_init();
+        ptx::mbar_expect_tx(&blob_bar, (uint32_t)t.blob_bytes);
+        ptx::bulk_copy_g2s(sblob, t.blob, (uint32_t)t.blob_bytes, &blob_bar);
+    }
     for (int i = threadIdx.x; i < (int)(sizeof(DevNet) / 4); i += blockDim.x)
         reinterpret_cast<int *>(&s_net)[i] = reinterpret_cast<const int *>(netp)[i];
-    unsigned char *sblob = reinterpret_cast<unsigned char *>(smem) + t.work_bytes;
-    if (t.blob_bytes) {
-        const int4 *g = reinterpret_cast<const int4 *>(t.blob);
-        int4 *d = reinterpret_cast<int4 *>(sblob);
-        for (int i = threadIdx.x; i < t.blob_bytes / 16; i += blockDim.x) d[i] = g[i];
-    }
     __syncthreads();
     if (t.blob_bytes && threadIdx.x == 0) {
         DevNet &n = s_net;
@@ -540,6 +545,7 @@ __global__ void stream_tick_kernel(const DevNet *__restrict__ netp, StreamTick t
         }
         if (tid0 == 0 && t.n_staged > 0) t.rs_last_out[ch] = src[t.n_staged - 1];
     }
+    if (t.blob_bytes) ptx::mbar_wait(&blob_bar, 0);   // the configuration has landed (the barrier was initialised before the sync above)
     __syncthreads();
     if (stamp) ts[2] = clock64();
     // Input level meter (Processor.swift:110-113, StatMax of the buffer's mean square): one warp per staged buffer, taken from the

@@ -639,7 +639,7 @@ syldet_status Batch::launch_fused_range(const float *d_planar, int n_channels, i
 
 syldet_status Batch::launch_tc_range(const float *d_planar, int n_channels, int64_t n_samples, int64_t ch_stride, int64_t eval_offset,
                                      int64_t eval_count, int64_t evals_total, int detect_rule, float *d_all_outputs, EventSink sink,
-                                     cudaStream_t stream) {
+                                     cudaStream_t stream, const int16_t *d_s16) {
     const Config &c = model_.config();
     const TcPlan &tp = model_.tc();
     EncodeTiledFn encode = encode_tiled_fn();
@@ -650,12 +650,17 @@ syldet_status Batch::launch_tc_range(const float *d_planar, int n_channels, int6
     const cuuint32_t estr[3] = {1, 1, 1};
     const cuuint32_t box_main[3] = {32, 64, 1}, box_tail[3] = {8, 64, 1};
     alignas(64) CUtensorMap tm_main, tm_tail;
-    CUresult r1 = encode(&tm_main, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(d_planar), dims, strides, box_main, estr,
+    std::memset(&tm_main, 0, sizeof tm_main);
+    std::memset(&tm_tail, 0, sizeof tm_tail);
+    CUresult r1 = CUDA_SUCCESS, r2 = CUDA_SUCCESS;
+    if (!d_s16) {   // the 16-bit source takes the direct data path: no tensor maps
+    r1 = encode(&tm_main, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(d_planar), dims, strides, box_main, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    CUresult r2 = encode(&tm_tail, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(d_planar), dims, strides, box_tail, estr,
+    r2 = encode(&tm_tail, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(d_planar), dims, strides, box_tail, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
     if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS)
         return set_error(SYLDET_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r1) + ", " + std::to_string((int)r2) + ")");
     TcWork w{};
@@ -702,6 +707,7 @@ syldet_status Batch::launch_tc_range(const float *d_planar, int n_channels, int6
     w.direct = direct;
     w.pf_dist = std::max(0, std::min(pf_dist, 8));
     w.pcm = d_planar;
+    w.pcm16 = d_s16;
     w.ch_stride = n_channels > 1 ? ch_stride : 0;
     w.n_rows = (int)std::min<int64_t>(n_samples / c.hop, INT32_MAX);
     const int64_t units = (int64_t)n_channels * w.chunks_per_channel;
@@ -1278,6 +1284,15 @@ syldet_status Batch::run_host(const void *pcm, int fmt, int n_channels, int64_t 
         cudaError_t _e = (expr);                                                       \
         if (_e != cudaSuccess) return drain(::syldet::cuda_fail(_e, #expr));           \
     } while (0)
+    // 16-bit planar PCM on the reference's sample shape: the tensor kernel reads the staged int16 samples itself (direct data path of
+    // kernels_tc.cu, k / 32768 in the splitter role) - no ingest kernel, no float32 copy of the recording in HBM. Only the last few
+    // evaluations of the recording, which the SIMT fused kernel finishes, get their samples converted. SYLDET_S16_INGEST=1 keeps the
+    // two-kernel path.
+    static const bool s16_ingest = std::getenv("SYLDET_S16_INGEST") != nullptr;
+    static const bool tf32_env = std::getenv("SYLDET_TC_TF32_CORR") != nullptr;
+    const bool s16_direct = !s16_ingest && !tf32_env && fmt == SYLDET_PCM_S16 && !inter && kernel_ != SYLDET_KERNEL_TENSOR_TF32 && f16_ok_ &&
+                            active_kernel() == SYLDET_KERNEL_TENSOR && tc_direct_s16_supported(model_.tc().hp, model_.tc().params) &&
+                            src_stride % 4 == 0 && c.gap == 0 && n_samples > 0;
     for (int k = 0; k < K; ++k) {
         const int64_t s0 = sb[k], ns = sb[k + 1] - sb[k];
         if (ns > 0) {
@@ -1301,6 +1316,29 @@ syldet_status Batch::run_host(const void *pcm, int fmt, int n_channels, int64_t 
         }
         SYLDET_CUDA_DRAIN(cudaEventRecord(ev_copied_[k], copy_stream_));
         SYLDET_CUDA_DRAIN(cudaStreamWaitEvent(sx, ev_copied_[k], 0));
+        if (s16_direct) {
+            const int64_t e0 = eb[k], ne = eb[k + 1] - eb[k], n_avail = sb[k + 1];
+            if (k == 0) SYLDET_CUDA_DRAIN(cudaMemsetAsync(sink_count_.get(), 0, kSinkHeaderBytes, sx));
+            if (ne > 0) {
+                EventSink sink{sink_count_.as<unsigned long long>(), sink_events_.as<DevEvent>(), sink_outputs_.as<float>(), sink_capacity_};
+                const int16_t *base16 = staging_.as<int16_t>() + e0 * c.hop;
+                const int64_t n_rows = (n_avail - e0 * c.hop) / c.hop;
+                const int64_t e_tc = std::max<int64_t>(0, std::min<int64_t>(ne, n_rows - c.time_range));
+                if (e_tc > 0) {
+                    st = launch_tc_range(nullptr, n_channels, n_avail - e0 * c.hop, src_stride, e0, e_tc, E, detect_rule, d_all, sink, sx, base16);
+                    if (st != SYLDET_OK) return drain(st);
+                }
+                if (e_tc < ne) {   // the end of the recording: these evaluations' samples as float32, then the SIMT fused kernel
+                    const int64_t lo = ((e0 + e_tc) * c.hop) & ~(int64_t)7;
+                    SYLDET_CUDA_DRAIN(launch_ingest((const char *)staging_.get() + (size_t)lo * esz, fmt, 0, n_channels, n_avail - lo, src_stride, planar + lo,
+                                                    pitch, sx));
+                    launches_ += 1;
+                    st = launch_fused_range(planar, n_channels, pitch, planar, planar + (size_t)n_channels * pitch, e0 + e_tc, ne - e_tc, E, detect_rule,
+                                            d_all, sink, sx);
+                    if (st != SYLDET_OK) return drain(st);
+                }
+            }
+        } else {
         if (!direct && ns > 0) {
             const char *src = (const char *)staging_.get() + (inter ? (size_t)s0 * n_channels * esz : (size_t)s0 * esz);
             SYLDET_CUDA_DRAIN(launch_ingest(src, fmt, inter ? 1 : 0, n_channels, ns, src_stride, planar + s0, pitch, sx));
@@ -1309,6 +1347,7 @@ syldet_status Batch::run_host(const void *pcm, int fmt, int n_channels, int64_t 
         st = launch_planar_range(planar, n_channels, n_samples, sb[k + 1], pitch, planar, planar + (size_t)n_channels * pitch, eb[k],
                                  eb[k + 1] - eb[k], detect_rule, d_all, k == 0, sx);
         if (st != SYLDET_OK) return drain(st);
+        }
         SYLDET_CUDA_DRAIN(cudaMemcpyAsync(h_counts_ + k, sink_count_.get(), sizeof(SinkHeader), cudaMemcpyDeviceToHost, sx));
         SYLDET_CUDA_DRAIN(cudaEventRecord(ev_done_[k], sx));
     }
@@ -1368,6 +1407,10 @@ syldet_status Batch::run_host(const void *pcm, int fmt, int n_channels, int64_t 
         // and repeats the launch in one piece (larger event buffer / all-TF32 variant)
         SYLDET_CUDA(cudaStreamSynchronize(copy_stream_));
         SYLDET_CUDA(cudaStreamSynchronize(sx));
+        if (s16_direct) {   // the repeat runs from the float32 copy of the recording, which this path had not made
+            SYLDET_CUDA(launch_ingest(staging_.get(), fmt, 0, n_channels, n_samples, src_stride, planar, pitch, sx));
+            launches_ += 1;
+        }
         st = collect(debounce_frames, out);
         if (st != SYLDET_OK) return st;
     } else {

@@ -178,7 +178,7 @@ private:
                                      int detect_rule, float *d_all_outputs, EventSink sink, cudaStream_t stream);
     syldet_status launch_tc_range(const float *d_planar, int n_channels, int64_t n_samples, int64_t ch_stride, int64_t eval_offset,
                                   int64_t eval_count, int64_t evals_total, int detect_rule, float *d_all_outputs, EventSink sink,
-                                  cudaStream_t stream);
+                                  cudaStream_t stream, const int16_t *d_s16 = nullptr);   // d_s16: the same position in planar 16-bit PCM (ch_stride then counts its samples)
     syldet_status launch_planar_range(const float *d_planar, int n_channels, int64_t n_samples, int64_t n_avail, int64_t ch_stride,
                                       const float *valid_begin, const float *valid_end, int64_t eval_begin, int64_t eval_count,
                                       int detect_rule, float *d_all_outputs, bool reset_sink, cudaStream_t stream);

@@ -158,6 +158,7 @@ struct TcWork {
     int direct;
     int pf_dist;                    // tiles ahead of the splitters that are requested into L2 (0 = no prefetch)
     const float *pcm;               // first sample of evaluation eval_offset of channel 0
+    const int16_t *pcm16;           // the same position in a planar 16-bit PCM buffer: the direct path converts k / 32768 itself (else nullptr)
     int64_t ch_stride;              // floats between channels
     int n_rows;                     // complete hop-rows per channel from `pcm` on
     int zero;                       // 0 (an operand the compiler cannot fold: orders the splitters' loads behind their arrival waits)
@@ -165,6 +166,7 @@ struct TcWork {
 size_t tc_smem_bytes(const FusedParams &p, int hp);
 int tc_lo_stages(const FusedParams &p, int hp);
 int tc_tile_frames();
+bool tc_direct_s16_supported(int hp, const FusedParams &p);
 int tc_k_pad();
 int tc_a16_cols();                  // 32-bit words per row of the fp16 A operand (TcWork::dft16)
 int tc_max_n0();

@@ -380,6 +380,7 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
                     if (!pf.valid()) return;
                     const int rows = min(kTileRows, w.n_rows - pf.first_row());
                     if (rows > 0)
+                        if (!w.pcm16)   // (16-bit sources: no prefetch)
                         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(w.pcm + (int64_t)pf.ch * w.ch_stride + (int64_t)pf.first_row() * p.hop),
                                      "r"(rows * p.hop * 4)
                                      : "memory");
@@ -933,7 +934,12 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
             // element of the next tile. (All loads of a warp count on one scoreboard, so a two-batch pipeline inside a warp only
             // serialises; the overlap comes from the other roles' warps.) Warp 0 asks L2 for the tiles further ahead.
             // Instantiated per row length (hop / 4 = 32, 33 or 34 float4), which makes every slot count and predicate a constant.
-            auto run = [&](auto r4c) {
+            // kS16: the audio is 16-bit PCM (SYLDET_PCM_S16, planar): a slot is four samples = one 8-byte load, converted to k / 32768
+            // exactly as ingest_kernel does - the conversion of SURVEY 8(f1) inside the first kernel, without the float32 round trip
+            // through HBM (2 B in + 4 B out + 4 B re-read per sample become 2 B in).
+            auto run = [&](auto r4c, auto s16c) {
+                constexpr bool kS16 = decltype(s16c)::value;
+                using Slot = std::conditional_t<kS16, uint2, float4>;
                 constexpr int R4 = decltype(r4c)::value, kPerTile = kTileRows * R4, kSThreads = kNumSDirect * 32;
                 constexpr int kFull = kPerTile / kSThreads, kRem = kPerTile % kSThreads, kSlots = kFull + (kRem ? 1 : 0);   // 10+1 | 11 | 11+1
                 const bool has_last = kRem == 0 || st < kRem;   // this thread's last slot exists
@@ -950,13 +956,26 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
                     const uint32_t o2 = uu < 32 ? o1 + 2 * kMainBytes : o1 ^ 16u;
                     offp[k] = o1 | (o2 << 16);
                 }
-                float4 v[kSlots];
+                Slot v[kSlots];
+                Slot zero_slot;
+                if constexpr (kS16) zero_slot = make_uint2(0u, 0u);
+                else zero_slot = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                for (int k = 0; k < kSlots; ++k) v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int k = 0; k < kSlots; ++k) v[k] = zero_slot;
+                auto to_float4 = [](const Slot &r) {
+                    if constexpr (kS16) {
+                        const float sc = 1.0f / 32768.0f;
+                        return make_float4((float)(short)(r.x & 0xFFFFu) * sc, (float)(short)(r.x >> 16) * sc, (float)(short)(r.y & 0xFFFFu) * sc,
+                                           (float)(short)(r.y >> 16) * sc);
+                    } else return r;
+                };
                 // Loads of the walk's tile. A tile whose 64 rows all exist (every one but the last of a channel) needs no predicates;
                 // rows past the end of the channel read as zero.
                 auto load_tile = [&]() {
-                    const float4 *src = reinterpret_cast<const float4 *>(w.pcm + (int64_t)tw.ch * w.ch_stride + (int64_t)tw.first_row() * p.hop) + st;
+                    const int64_t first = (int64_t)tw.ch * w.ch_stride + (int64_t)tw.first_row() * p.hop;   // in samples
+                    const Slot *src;
+                    if constexpr (kS16) src = reinterpret_cast<const Slot *>(w.pcm16 + first) + st;
+                    else src = reinterpret_cast<const Slot *>(w.pcm + first) + st;
                     const int rows = w.n_rows - tw.first_row();
                     if (rows >= kTileRows) {
 #pragma unroll
@@ -965,7 +984,7 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
                     } else {
                         const int nq = max(rows, 0) * R4 - st;
 #pragma unroll
-                        for (int k = 0; k < kSlots; ++k) v[k] = k * kSThreads < nq ? __ldcs(src + k * kSThreads) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int k = 0; k < kSlots; ++k) v[k] = k * kSThreads < nq ? __ldcs(src + k * kSThreads) : zero_slot;
                     }
                 };
                 int stg = 0;
@@ -978,7 +997,7 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
                     uint2 hx[kSlots], hl[kSlots];
 #pragma unroll
                     for (int k = 0; k < kSlots; ++k) {
-                        split_fp16(v[k], hx[k], hl[k]);
+                        split_fp16(to_float4(v[k]), hx[k], hl[k]);
                         if (k < kFull || has_last) {
                             *reinterpret_cast<uint2 *>(b16 + (offp[k] & 0xFFFFu)) = hx[k];
                             *reinterpret_cast<uint2 *>(b16 + (offp[k] >> 16)) = hl[k];
@@ -993,9 +1012,15 @@ tc_detect_kernel(const __grid_constant__ FusedParams p, const TcWork w, const __
                     if (++stg == n_stages) { stg = 0; ++stg_use; }
                 }
             };
-            if (p.hop == 132) run(std::integral_constant<int, 33>{});
-            else if (p.hop == 128) run(std::integral_constant<int, 32>{});
-            else run(std::integral_constant<int, 34>{});
+            if (w.pcm16) {
+                if (p.hop == 132) run(std::integral_constant<int, 33>{}, std::true_type{});
+                else if (p.hop == 128) run(std::integral_constant<int, 32>{}, std::true_type{});
+                else run(std::integral_constant<int, 34>{}, std::true_type{});
+            } else {
+                if (p.hop == 132) run(std::integral_constant<int, 33>{}, std::false_type{});
+                else if (p.hop == 128) run(std::integral_constant<int, 32>{}, std::false_type{});
+                else run(std::integral_constant<int, 34>{}, std::false_type{});
+            }
         } else
         for (uint32_t it = 0; tw.valid(); ++it, tw.next(w, T)) {
             const int s = it & 1;
@@ -1084,6 +1109,11 @@ size_t tc_smem_bytes(const FusedParams &p, int hp) {
     return 1024 + TcSmem::total(p.time_range * hp, p.n_out, tc_planes(p), tc_lo_stages(p, hp));
 }
 int tc_tile_frames() { return kTileFrames; }
+// 16-bit PCM straight into the tensor kernel: the instantiation with the direct data path exists for the reference's sample shape
+bool tc_direct_s16_supported(int hp, const FusedParams &p) {
+    return hp == 4 && p.scaling == SYLDET_SCALING_LINEAR && p.window_stat == FUSED_STAT_L2 && p.tf[0] == SYLDET_TF_TANSIG && p.n_layers == 2 &&
+           p.n_out == 1 && p.tf[1] == SYLDET_TF_PURELIN && p.n_op == 1;
+}
 int tc_k_pad() { return kKPad; }
 int tc_a16_cols() { return kA16Cols; }
 int tc_max_n0() { return kMaxN0; }
@@ -1112,7 +1142,8 @@ cudaError_t launch_tc(int hp, int grid, size_t smem, const FusedParams &p, const
     // the fp16 band DFT needs a per-window normaliser for its range guard (l2normalize or a min / max over the window) and linear
     // spectrogram scaling (a logarithm amplifies the errors of near-empty bins)
     const bool f16 = w.f16_corr && !scaled && (p.window_stat == FUSED_STAT_L2 || p.window_stat == FUSED_STAT_MINMAX);
-    const bool direct = f16 && fast && w.direct;
+    const bool direct = f16 && fast && (w.direct || w.pcm16 != nullptr);
+    if (w.pcm16 && !direct) return cudaErrorNotSupported;   // the caller checks tc_direct_s16_supported first
     if (w.debug_timing) {   // SYLDET_TC_TIMING: instrumented build of the common shape only
         if (direct) { threads = kTcThreadsDirect; go(tc_detect_kernel<4, false, true, true, true, true>); }
         else if (f16 && fast) go(tc_detect_kernel<4, false, true, true, true, false>);

@@ -432,6 +432,17 @@ def test_event_buffer_overflow_replay(sd, cw):
     ev = sd.BatchDetector(c).run(x)
     assert len(ev) == 12 * c.num_evals(x.shape[1]) > (1 << 20)
     assert np.array_equal(ev.sample[:3], [1444, 1576, 1708]) and np.all(np.diff(ev.channel) >= 0)
+    # the same through the 16-bit path that feeds the tensor kernel directly (sample network, threshold far below every output): the
+    # repeat needs the float32 copy of the recording that path had skipped
+    text = open(SAMPLE_TXT).read().replace("threshold = 0.442442442442442", "threshold = -1000000000.0")
+    assert "threshold = -1000000000.0" in text
+    c = sd.SyllableDetectorConfig.from_text(text).validate()
+    s16 = np.clip(np.round(x * 32768.0 * 8.0), -32768, 32767).astype(np.int16)
+    det = sd.BatchDetector(c)
+    ev = det.run(s16)
+    assert det.active_kernel == sd.KERNEL_TENSOR
+    assert len(ev) == 12 * c.num_evals(x.shape[1]) > (1 << 20)
+    assert np.array_equal(ev.sample[:3], [1444, 1576, 1708]) and np.all(np.diff(ev.channel) >= 0)
 
 
 def test_pcm16_and_interleaved_ingest(sd, cfg, synth):

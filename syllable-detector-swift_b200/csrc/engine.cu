@@ -480,6 +480,9 @@ syldet_status DeviceModel::init(const Config &cfg, int device) {
             fused_.why = std::string("fused kernel cannot be resident: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "0 blocks per SM");
         } else {
             fused_.blocks_per_sm = blocks;
+            st = d_fused_params_.reserve(sizeof(FusedParams));
+            if (st != SYLDET_OK) return st;
+            SYLDET_CUDA(cudaMemcpy(d_fused_params_.get(), &fused_.params, sizeof(FusedParams), cudaMemcpyHostToDevice));
         }
     }
     wide_ = plan_wide(cfg_);

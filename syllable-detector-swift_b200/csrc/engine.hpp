@@ -103,13 +103,14 @@ public:
     const float *wcat_lo() const { return wcat_hi() + (size_t)tc_.n0 * 32; }
     const uint32_t *dft16() const { return reinterpret_cast<const uint32_t *>(wcat_lo() + (size_t)tc_.n0 * 32); }
     int sm_count() const { return sm_count_; }
+    const FusedParams *fused_params_dev() const { return d_fused_params_.as<FusedParams>(); }   // device copy (live tick: lane-parallel weight reads)
     const unsigned char *blob() const { return d_blob_.as<unsigned char>(); }
     size_t blob_bytes() const { return blob_bytes_; }
 
 private:
     Config cfg_;
     int device_ = -1, max_width_ = 0, sm_count_ = 148;
-    DeviceBuffer d_blob_, d_net_, d_dft_, d_wide_;
+    DeviceBuffer d_blob_, d_net_, d_dft_, d_wide_, d_fused_params_;
     WidePlan wide_;
     size_t blob_bytes_ = 0;
     TcPlan tc_;

@@ -224,5 +224,11 @@ bool fused_supports_fft(int fft_len);
 size_t fused_smem_bytes(int fft_len, const FusedParams &p);
 cudaError_t launch_fused(const FusedLaunch &cfg, const FusedParams &p, const FusedWork &w, cudaStream_t stream);
 cudaError_t fused_max_blocks_per_sm(int fft_len, int hp, size_t smem, int *blocks);
+// live tick on the register FFT and the folded network (kernels_fused.cu: stream_tick_fast_kernel); one block per channel, all phases;
+// d_params: device copy of the FusedParams
+bool stream_tick_fast_supported(int fft_len, const FusedParams &p);
+bool stream_tick_fast_fits(int fft_len, int hp, const FusedParams &p, const StreamTick &t);   // this tick's shared-memory footprint is within the cap
+cudaError_t launch_stream_tick_fast(int fft_len, int hp, const FusedParams &host_params, const FusedParams *d_params, const StreamTick &t,
+                                    const float *window, const float2 *twiddle, int n_channels, cudaStream_t stream);
 
 }  // namespace syldet

@@ -18,11 +18,13 @@
 //            weights that sit in kernel-parameter constant memory (warp-uniform FFMA operands), window statistic,
 //            transfer functions, remaining layers, reverse output map, double-precision threshold compare,
 //            warp-aggregated event append.
+#include <cstddef>
 #include <cstdio>
 
 #include "fft_regs.cuh"
 #include "fused_epilogue.cuh"
 #include "ptx_sm100.cuh"
+#include "resample.cuh"
 
 namespace syldet {
 
@@ -274,6 +276,354 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_detect_kernel(const __
     }
 }
 
+// ---- live tick, latency-shaped variant ------------------------------------------------------------------------------------
+// stream_tick_kernel (kernels_generic.cu) does one tick of the live path in the reference's operation order (iterative radix-2 FFT in
+// shared memory, the literal processing chain). Configurations the fused kernel takes get this kernel instead - same protocol
+// (samples pulled from pinned host staging into the device ring, band columns into the device band ring, outputs + sequence number to
+// pinned host memory, level meters, resampler) - built for LATENCY. A tick is one column and one evaluation on a single block per
+// channel, so nothing hides behind other warps: the time is (PCIe round trip of the staged samples) + (instructions on the longest
+// dependent path) x ~3 cycles. Hence:
+//   * every load the tick needs is issued at the top, behind the PCIe reads of the staged samples: the older samples of the frames
+//     and the older band columns of the evaluation windows go ring -> shared memory with cp.async (no registers, no scoreboard), the
+//     window taps, twiddles and this thread's share of the folded layer-0 weights go to registers;
+//   * what the tick itself produces (new samples, new columns) is handed on in shared memory - never store -> L2 -> load;
+//   * frames and evaluation windows are CONTIGUOUS in shared memory (`span`: samples from the first frame's start; `win`: columns
+//     from the first window's start), so the hot loops are immediate-offset LDS + packed arithmetic with no index bookkeeping;
+//   * the folded layer 0 of an evaluation is split over all 128 threads (each holds its weights from the top of the kernel), then
+//     one warp finishes the network.
+struct TickGeom {
+    int win_len, hop, gap, k0, band, time_range;
+    int span_floats;   // samples from the start of the first new frame to the end of the last one, rounded up to 4
+    int win_floats;    // band values from the oldest column of the first evaluation window to the newest column, rounded up to 4
+    int stage_floats;  // staged samples, rounded up to 4
+};
+constexpr int kTickThreads = 128;
+constexpr int kTickPre = 4;        // staged samples per thread held in registers across the PCIe round trip (512 per channel)
+constexpr int kTickEvalGroup = 4;  // evaluations reduced per block-wide pass
+
+template <int NFFT, int HP>
+__global__ void __launch_bounds__(kTickThreads) stream_tick_fast_kernel(const FusedParams *__restrict__ pp, const StreamTick t, const TickGeom g,
+                                                                        const float *__restrict__ window, const float2 *__restrict__ twiddle) {
+    constexpr int M = NFFT / 2;
+    constexpr int R1 = fused_r1(NFFT), R2 = fused_r2(NFFT);
+    constexpr int G = fused_group(NFFT);
+    constexpr int FP = fused_frame_pitch(NFFT);
+    constexpr int U2 = (G * R1) / 32;
+    constexpr int LOG_R1 = R1 == 16 ? 4 : 3;
+    constexpr int kHead = ((int)offsetof(FusedParams, w0) + 15) & ~15;   // everything but the layer-0 weights: staged in shared memory
+    constexpr int kW = kFusedMaxW0 / HP / kTickThreads;                 // layer-0 inputs per thread (12 or 6): the whole layer in one pass
+    constexpr int kBins = (kFusedMaxBand + 31) / 32;
+    constexpr int kPart = HP + 2;                                        // partial sums per warp and evaluation: HP dot products + 2 statistics
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ch = blockIdx.x;
+    const bool stamp = t.stamps != nullptr && ch == 0 && tid == 0;   // SYLDET_STREAM_TIMING
+    long long ts[5] = {0, 0, 0, 0, 0}, sub[6] = {0, 0, 0, 0, 0, 0};
+    if (stamp) ts[0] = clock64();
+
+    // (0) the longest-latency loads first: this channel's staged samples, straight out of pinned host memory
+    const float *src = t.staged + (int64_t)ch * t.stage_pitch;
+    float pre[kTickPre];
+#pragma unroll
+    for (int k = 0; k < kTickPre; ++k) pre[k] = tid + k * kTickThreads < t.n_staged ? src[tid + k * kTickThreads] : 0.0f;
+
+    FusedParams *sp = reinterpret_cast<FusedParams *>(smem_raw);   // only its first kHead bytes exist here
+    float *s_span = reinterpret_cast<float *>(smem_raw + kHead);
+    float *s_win = s_span + g.span_floats;
+    float *s_stage = s_win + g.win_floats;
+    float *s_part = s_stage + g.stage_floats;                                                      // [kTickEvalGroup][4 warps][kPart]
+    float2 *zw = reinterpret_cast<float2 *>(s_part + kTickEvalGroup * 4 * kPart) + warp * G * FP;   // this warp's exchange buffer
+    const int W = g.win_len, L = g.band, I = g.band * g.time_range;
+    float *ring = t.ring + (int64_t)ch * (t.ring_mask + 1);
+    float *band = t.band + (int64_t)ch * (t.band_mask + 1) * L;
+
+    // everything already on the device: ring -> shared memory, asynchronously
+    const int64_t span0 = t.col0 * g.hop + g.gap;   // absolute sample index of s_span[0]
+    {
+        const int64_t n_old64 = t.ring_pos - span0;
+        const int n_old = n_old64 < 0 ? 0 : n_old64 > g.span_floats ? g.span_floats : (int)n_old64;
+        for (int i = tid; i < n_old; i += kTickThreads) ptx::cp_async4(s_span + i, ring + ((span0 + i) & t.ring_mask));
+        if (t.n_evals > 0) {   // columns [eval0, col0) of the band ring are consecutive rows, wrapping once at most
+            const int total = (int)(t.col0 - t.eval0) * L, ringf = (int)(t.band_mask + 1) * L;
+            const int row0 = (int)(t.eval0 & t.band_mask) * L;
+            for (int i = tid; i < total; i += kTickThreads) {
+                int s = row0 + i;
+                if (s >= ringf) s -= ringf;
+                ptx::cp_async4(s_win + i, band + s);
+            }
+        }
+        for (int i = tid; i < kHead / 16; i += kTickThreads) ptx::cp_async16(smem_raw + 16 * i, reinterpret_cast<const int4 *>(pp) + i);
+    }
+    // registers: this thread's share of the folded layer-0 weights; window taps and twiddles for the warps that transform a frame
+    float4 wa[kW], wb[HP == 8 ? kW : 1];
+    if (t.n_evals > 0) {
+#pragma unroll
+        for (int k = 0; k < kW; ++k) {
+            const int i = tid + k * kTickThreads;
+            if (i < I) {
+                wa[k] = __ldg(reinterpret_cast<const float4 *>(pp->w0 + (size_t)i * HP));
+                if constexpr (HP == 8) wb[k] = __ldg(reinterpret_cast<const float4 *>(pp->w0 + (size_t)i * HP + 4));
+            }
+        }
+    }
+    const int fs1 = lane / R2, j1 = lane % R2, j2 = lane % R1;
+    const bool has_cols = (int64_t)warp * G < t.n_cols;
+    float2 wreg[R1], tw[R2], utw[kBins];
+    if (has_cols) {
+#pragma unroll
+        for (int r = 0; r < R1; ++r) {
+            const int m0 = 2 * (j1 + r * R2);
+            wreg[r].x = m0 < W ? __ldg(window + m0) : 0.0f;       // zero padding: CSTFT.swift:109-110
+            wreg[r].y = m0 + 1 < W ? __ldg(window + m0 + 1) : 0.0f;
+        }
+#pragma unroll
+        for (int r = 1; r < R2; ++r) {
+            const int q = 2 * r * j2;
+            const float2 v = __ldg(twiddle + (q >= M ? q - M : q));
+            tw[r] = q >= M ? make_float2(-v.x, -v.y) : v;
+        }
+#pragma unroll
+        for (int q = 0; q < kBins; ++q) utw[q] = lane + 32 * q < L ? __ldg(twiddle + g.k0 + lane + 32 * q) : make_float2(0.f, 0.f);
+    }
+    const float rs_last = t.rs_on ? __ldg(t.rs_last_in + ch) : 0.0f;
+    if (stamp) ts[1] = clock64();
+
+    // (1) staged samples: into shared memory, and (no resampler) into the device ring and the frame span
+    auto place = [&](int64_t pos, float v) {   // one sample at ring rate
+        ring[pos & t.ring_mask] = v;
+        const int64_t rel = pos - span0;
+        if (rel >= 0 && rel < g.span_floats) s_span[rel] = v;
+    };
+#pragma unroll
+    for (int k = 0; k < kTickPre; ++k) {
+        const int i = tid + k * kTickThreads;
+        if (i < t.n_staged) {
+            s_stage[i] = pre[k];
+            if (!t.rs_on) place(t.ring_pos + i, pre[k]);
+        }
+    }
+    for (int i = tid + kTickPre * kTickThreads; i < t.n_staged; i += kTickThreads) {
+        const float v = src[i];
+        s_stage[i] = v;
+        if (!t.rs_on) place(t.ring_pos + i, v);
+    }
+    ptx::cp_async_wait_all();
+    __syncthreads();
+    const FusedParams &p = *sp;
+    if (t.rs_on) {
+        // device-rate buffers -> ResamplerLinear -> sample ring: one resampleVector call per staged buffer (Processor.swift:116-121)
+        for (int b = 0; b < t.n_marks; ++b) {
+            const int lo = b ? t.marks[b - 1] : 0, n_in = t.marks[b] - lo, n_out = t.rs_n_out[b];
+            const float off = t.rs_offset[b];
+            const float last = b ? s_stage[lo - 1] : rs_last;
+            for (int k = tid; k < n_out; k += kTickThreads)
+                place(t.ring_pos + t.rs_out0[b] + k, resample_linear_point(s_stage + lo, n_in, off, t.rs_step, last, off < 0.0f, k));
+        }
+        if (tid == 0 && t.n_staged > 0) t.rs_last_out[ch] = s_stage[t.n_staged - 1];
+        __syncthreads();
+    }
+    if (stamp) ts[2] = clock64();
+    // input level meter (Processor.swift:110-113, StatMax of the buffer's mean square; the meter sees the device-rate samples): one warp
+    // per staged buffer, from the back - warp 0 goes straight to the first frame
+    if (t.level_in && warp > 0) {
+        for (int b = 0; b < t.n_marks; ++b) {
+            if (3 - (b % 3) != warp) continue;
+            const int lo = b ? t.marks[b - 1] : 0, hi = t.marks[b];
+            float part = 0.0f;
+            for (int i = lo + lane; i < hi; i += 32) part = fmaf(s_stage[i], s_stage[i], part);
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);   // vDSP_svesq: summation order unspecified
+            const double ms = (double)part / (double)(hi - lo);
+            if (lane == 0 && hi > lo && ms == ms) atomicMax(t.level_in + ch, (unsigned long long)__double_as_longlong(ms));
+        }
+    }
+    if (stamp) sub[0] = clock64();
+
+    // (2) STFT columns: window + real N-point FFT as an N/2-point complex transform in two register passes (as fused_detect_kernel)
+    const int64_t win_col0 = t.col0 - t.eval0;   // column of s_win the first new column lands in
+    for (int64_t cb = (int64_t)warp * G; cb < t.n_cols; cb += (int64_t)4 * G) {
+        if (cb + fs1 < t.n_cols) {
+            const float *xs = s_span + (cb + fs1) * g.hop + 2 * j1;
+            float2 v[R1];
+            if (W == NFFT) {
+#pragma unroll
+                for (int r1 = 0; r1 < R1; ++r1) v[r1] = ptx::mul2(make_float2(xs[2 * r1 * R2], xs[2 * r1 * R2 + 1]), wreg[r1]);
+            } else {
+#pragma unroll
+                for (int r1 = 0; r1 < R1; ++r1) {
+                    const int m0 = 2 * (j1 + r1 * R2);
+                    v[r1] = ptx::mul2(make_float2(m0 < W ? xs[2 * r1 * R2] : 0.0f, m0 + 1 < W ? xs[2 * r1 * R2 + 1] : 0.0f), wreg[r1]);
+                }
+            }
+            Dft<R1>::run(v);
+            float2 *zb = zw + fs1 * FP + j1 * (R1 + 1);
+#pragma unroll
+            for (int q = 0; q < R1; ++q) zb[q] = v[q];
+        }
+        __syncwarp();
+        if (stamp) sub[1] = clock64();
+#pragma unroll
+        for (int u = 0; u < U2; ++u) {
+            const int fs2 = lane / R1 + u * (32 / R1);
+            if (cb + fs2 < t.n_cols) {
+                float2 *zb = zw + fs2 * FP + j2;
+                float2 v[R2];
+                v[0] = zb[0];
+#pragma unroll
+                for (int r2 = 1; r2 < R2; ++r2) v[r2] = cmul(zb[r2 * (R1 + 1)], tw[r2]);
+                Dft<R2>::run(v);
+#pragma unroll
+                for (int r2 = 0; r2 < R2; ++r2) zb[r2 * (R1 + 1)] = v[r2];
+            }
+        }
+        __syncwarp();
+        if (stamp) sub[2] = clock64();
+        const int gmax = (int)min((int64_t)G, t.n_cols - cb);
+        for (int gi = 0; gi < gmax; ++gi) {
+            const float2 *zb = zw + gi * FP;
+            float *dst = band + ((t.col0 + cb + gi) & t.band_mask) * L;
+            float *dwin = s_win + (win_col0 + cb + gi) * L;
+            const bool to_win = t.n_evals > 0 && (win_col0 + cb + gi + 1) * L <= g.win_floats;
+#pragma unroll
+            for (int q = 0; q < kBins; ++q) {
+                const int f = lane + 32 * q;
+                if (f < L) {
+                    const int k = g.k0 + f, km = (M - k) & (M - 1);
+                    const float2 za = zb[k + (k >> LOG_R1)], zc = zb[km + (km >> LOG_R1)], tk = utw[q];
+                    const float sr = za.x + zc.x, si = za.y - zc.y, dr = za.x - zc.x, di = za.y + zc.y;
+                    const float re = sr + (tk.x * di + tk.y * dr), im = si - (tk.x * dr - tk.y * di);
+                    float mag = 0.5f * sqrt_fast(re * re + im * im);
+                    if (p.scaling != SYLDET_SCALING_LINEAR) mag = scale_value(mag, p.scaling);
+                    dst[f] = mag;
+                    if (to_win) dwin[f] = mag;
+                }
+            }
+        }
+        __syncwarp();
+        if (stamp) sub[3] = clock64();
+    }
+    __syncthreads();
+    if (stamp) ts[3] = clock64();
+
+    // (3) evaluations: the folded layer 0 of each split over the whole block, then one warp per evaluation finishes the network
+    const int O = p.n_out;
+    for (int64_t j0 = 0; j0 < t.n_evals; j0 += kTickEvalGroup) {
+        const int nj = (int)min((int64_t)kTickEvalGroup, t.n_evals - j0);
+        for (int jj = 0; jj < nj; ++jj) {
+            const float *xw = s_win + (j0 + jj) * L + tid;   // window of evaluation j0 + jj: columns (j0 + jj) .. + T - 1, contiguous
+            float acc[kPart];
+#pragma unroll
+            for (int h = 0; h < kPart; ++h) acc[h] = 0.0f;
+            if (p.window_stat == FUSED_STAT_MINMAX) { acc[HP] = INFINITY; acc[HP + 1] = -INFINITY; }
+#pragma unroll
+            for (int k = 0; k < kW; ++k) {
+                if (tid + k * kTickThreads < I) {
+                    const float xv = xw[k * kTickThreads];
+                    acc[0] = fmaf(xv, wa[k].x, acc[0]); acc[1] = fmaf(xv, wa[k].y, acc[1]); acc[2] = fmaf(xv, wa[k].z, acc[2]); acc[3] = fmaf(xv, wa[k].w, acc[3]);
+                    if constexpr (HP == 8) {
+                        acc[4] = fmaf(xv, wb[k].x, acc[4]); acc[5] = fmaf(xv, wb[k].y, acc[5]); acc[6] = fmaf(xv, wb[k].z, acc[6]); acc[7] = fmaf(xv, wb[k].w, acc[7]);
+                    }
+                    if (p.window_stat == FUSED_STAT_L2) acc[HP] = fmaf(xv, xv, acc[HP]);
+                    else if (p.window_stat == FUSED_STAT_MINMAX) { acc[HP] = fminf(acc[HP], xv); acc[HP + 1] = fmaxf(acc[HP + 1], xv); }
+                }
+            }
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) {
+#pragma unroll
+                for (int h = 0; h < HP; ++h) acc[h] += __shfl_xor_sync(0xffffffffu, acc[h], d);
+                if (p.window_stat == FUSED_STAT_MINMAX) {
+                    acc[HP] = fminf(acc[HP], __shfl_xor_sync(0xffffffffu, acc[HP], d));
+                    acc[HP + 1] = fmaxf(acc[HP + 1], __shfl_xor_sync(0xffffffffu, acc[HP + 1], d));
+                } else acc[HP] += __shfl_xor_sync(0xffffffffu, acc[HP], d);
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int h = 0; h < kPart; ++h) s_part[(jj * 4 + warp) * kPart + h] = acc[h];
+            }
+        }
+        __syncthreads();
+        if (stamp) sub[4] = clock64();
+        if (warp < nj) {
+            const int64_t j = j0 + warp;
+            const float *pq = s_part + warp * 4 * kPart;
+            float acc[HP];
+#pragma unroll
+            for (int h = 0; h < HP; ++h) acc[h] = (pq[h] + pq[kPart + h]) + (pq[2 * kPart + h] + pq[3 * kPart + h]);
+            float inv = 1.0f, beta = 0.0f;   // z = acc * inv + beta * V + B'
+            if (p.window_stat == FUSED_STAT_L2) {                                         // x / sqrt(sum x^2)  (NeuralNet.swift:47-59); silence: NaN
+                inv = 1.0f / sqrtf((pq[HP] + pq[kPart + HP]) + (pq[2 * kPart + HP] + pq[3 * kPart + HP]));
+            } else if (p.window_stat == FUSED_STAT_MINMAX) {                              // NeuralNet.swift:69-96
+                const float s0 = fminf(fminf(pq[HP], pq[kPart + HP]), fminf(pq[2 * kPart + HP], pq[3 * kPart + HP]));
+                const float s1 = fmaxf(fmaxf(pq[HP + 1], pq[kPart + HP + 1]), fmaxf(pq[2 * kPart + HP + 1], pq[3 * kPart + HP + 1]));
+                const float range = s1 - s0;
+                if (0 == range) { inv = 0.0f; beta = -1.0f; }                             // flat window: every input becomes -1
+                else { inv = 2.0f / range; beta = (0 - s0 - s1) / range; }
+            }
+            float a[kFusedMaxHidden], out[kFusedMaxOut];
+#pragma unroll
+            for (int h = 0; h < kFusedMaxHidden; ++h)
+                a[h] = h < HP ? transfer_fast(p.tf[0], fmaf(acc[h < HP ? h : 0], inv, fmaf(beta, p.v[h], p.bprime[h]))) : 0.0f;
+            network_tail(p, SYLDET_DETECT_ANY_OUTPUT, a, out);   // every lane: the same values
+            if (stamp) sub[5] = clock64();
+            if (lane == 0) {
+                if (t.level_out) {   // output meter (Processor.swift:138, StatMax of Double(lastOutputs[0])); NaN never wins upstream either
+                    const float v0 = out[0];
+                    const int bits = __float_as_int(v0);
+                    if (v0 == v0) atomicMax(t.level_out + ch, bits >= 0 ? bits : bits ^ 0x7fffffff);
+                }
+                if (t.packed) t.packed[ch] = make_uint4(__float_as_uint(out[0]), O > 1 ? __float_as_uint(out[1]) : 0u, O > 2 ? __float_as_uint(out[2]) : 0u, t.seq);
+                else
+                    for (int o = 0; o < O; ++o) t.out[((int64_t)ch * t.n_evals + j) * O + o] = pick(out, o);
+            }
+        }
+        if (j0 + kTickEvalGroup < t.n_evals) __syncthreads();   // s_part is reused
+    }
+    if (stamp) {
+        ts[4] = clock64();
+        for (int k = 0; k < 4; ++k) t.stamps[k] = ts[k];
+        for (int k = 4; k < 10; ++k) t.stamps[k] = k == 4 ? ts[4] : ts[3];   // the generic tick's evaluation sub-phases do not exist here
+        for (int k = 0; k < 6; ++k) t.stamps[10 + k] = sub[k];
+    }
+    if (t.flags && !t.packed) {   // publish: one flag per channel
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) *(volatile unsigned *)(t.flags + ch) = t.seq;
+    }
+}
+
+constexpr size_t kTickFastSmemCap = 96 * 1024;
+
+static TickGeom tick_geom(const FusedParams &p, const StreamTick &t) {
+    TickGeom g{};
+    g.win_len = p.win_len; g.hop = p.hop; g.gap = p.gap; g.k0 = p.k0; g.band = p.band; g.time_range = p.time_range;
+    const int64_t span = t.n_cols > 0 ? (t.n_cols - 1) * (int64_t)p.hop + p.win_len : 0;
+    const int64_t win = t.n_evals > 0 ? (t.col0 - t.eval0 + t.n_cols) * (int64_t)p.band : 0;
+    g.span_floats = (int)((span + 3) & ~(int64_t)3);
+    g.win_floats = (int)((win + 3) & ~(int64_t)3);
+    g.stage_floats = (t.n_staged + 3) & ~3;
+    return g;
+}
+
+static size_t tick_fast_smem(int fft_len, int hp, const TickGeom &g) {
+    const size_t head = (offsetof(FusedParams, w0) + 15) & ~(size_t)15;
+    const size_t part = (size_t)kTickEvalGroup * 4 * (hp + 2);   // even
+    return head + ((size_t)g.span_floats + g.win_floats + g.stage_floats + part) * sizeof(float) +
+           (size_t)4 * fused_group(fft_len) * fused_frame_pitch(fft_len) * sizeof(float2);
+}
+
+template <int NFFT, int HP>
+cudaError_t launch_tick_one(const FusedParams *d_params, const StreamTick &t, const TickGeom &g, const float *window, const float2 *twiddle,
+                            int n_channels, cudaStream_t stream) {
+    static bool raised = false;   // once per instantiation: the attribute call is not free, and a tick is microseconds
+    if (!raised) {
+        cudaError_t e = cudaFuncSetAttribute(stream_tick_fast_kernel<NFFT, HP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTickFastSmemCap);
+        if (e != cudaSuccess) return e;
+        raised = true;
+    }
+    stream_tick_fast_kernel<NFFT, HP><<<n_channels, kTickThreads, tick_fast_smem(NFFT, HP, g), stream>>>(d_params, t, g, window, twiddle);
+    return cudaGetLastError();
+}
+
 template <int NFFT, int HP>
 cudaError_t launch_one(const FusedLaunch &cfg, const FusedParams &p, const FusedWork &w, cudaStream_t stream) {
     auto kern = fused_detect_kernel<NFFT, HP>;
@@ -316,6 +666,22 @@ size_t fused_smem_bytes(int fft_len, const FusedParams &p) {
 cudaError_t launch_fused(const FusedLaunch &cfg, const FusedParams &p, const FusedWork &w, cudaStream_t stream) {
     const int cfg_fft = cfg.fft_len, cfg_hp = cfg.hp;
     SYLDET_FUSED_DISPATCH(launch_one, cfg, p, w, stream)
+}
+
+bool stream_tick_fast_supported(int fft_len, const FusedParams &p) {
+    return fused_supports_fft(fft_len) && p.window_stat != FUSED_STAT_STD && p.band <= kFusedMaxBand;
+}
+
+bool stream_tick_fast_fits(int fft_len, int hp, const FusedParams &p, const StreamTick &t) {
+    if (t.col0 < t.eval0) return false;
+    return tick_fast_smem(fft_len, hp, tick_geom(p, t)) <= kTickFastSmemCap;
+}
+
+cudaError_t launch_stream_tick_fast(int fft_len, int hp, const FusedParams &host_params, const FusedParams *d_params, const StreamTick &t,
+                                    const float *window, const float2 *twiddle, int n_channels, cudaStream_t stream) {
+    const int cfg_fft = fft_len, cfg_hp = hp;
+    const TickGeom g = tick_geom(host_params, t);
+    SYLDET_FUSED_DISPATCH(launch_tick_one, d_params, t, g, window, twiddle, n_channels, stream)
 }
 
 cudaError_t fused_max_blocks_per_sm(int fft_len, int hp, size_t smem, int *blocks) {

@@ -119,6 +119,14 @@ __device__ __forceinline__ void prefetch_tmap(const void *tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
 // generic-proxy writes to shared memory -> visible to the async proxy (TMA, tensor core)
+// Ampere-style asynchronous copies (LDGSTS): global -> shared without a register or a scoreboard in between
+__device__ __forceinline__ void cp_async4(void *dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- packed fp32 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2 work on an aligned register pair, two IEEE fp32 results per

@@ -86,7 +86,10 @@ syldet_status StreamGroup::init(const Config &cfg, int n_channels, int max_buffe
     std::memset(h_flag_, 0, (size_t)n_channels * sizeof(unsigned));
     SYLDET_CUDA(cudaMallocHost(&h_packed_, (size_t)n_channels * sizeof(uint4)));
     std::memset(h_packed_, 0, (size_t)n_channels * sizeof(uint4));
-    if (const char *e = std::getenv("SYLDET_STREAM_TIMING"); e && e[0] == '1') SYLDET_CUDA(cudaMallocHost(&h_stamps_, 128));
+    if (const char *e = std::getenv("SYLDET_STREAM_TIMING"); e && e[0] == '1') {
+        SYLDET_CUDA(cudaMallocHost(&h_stamps_, 128));
+        std::memset(h_stamps_, 0, 128);
+    }
     SYLDET_CUDA(cudaStreamSynchronize(stream_));
     return SYLDET_OK;
 }
@@ -99,6 +102,9 @@ StreamGroup::~StreamGroup() {
                      (long long)t_ticks_, n_channels_, t_phase_[0] / n, t_phase_[1] / n, t_phase_[2] / n, t_phase_[3] / n,
                      t_eval_[0] / n, t_eval_[1] / n, t_eval_[2] / n, t_eval_[3] / n, t_eval_[4] / n, t_eval_[5] / n,
                      t_host_[0] / n, t_host_[1] / n, t_host_[2] / n);
+        if (t_sub_[5] > 0)
+            std::fprintf(stderr, "[syldet stream timing] latency-shaped tick, cycles since entry: meters %.0f, pass 1 %.0f, pass 2 %.0f, untangle %.0f, layer 0 %.0f, tail %.0f\n",
+                         t_sub_[0] / n, t_sub_[1] / n, t_sub_[2] / n, t_sub_[3] / n, t_sub_[4] / n, t_sub_[5] / n);
     }
     if (h_stamps_) cudaFreeHost(h_stamps_);
     if (stream_) {
@@ -218,7 +224,16 @@ syldet_status StreamGroup::launch_tick(int64_t n_cols, int64_t avail) {
         t.phases = STREAM_PHASE_COPY | STREAM_PHASE_COLUMNS | (avail > 0 ? STREAM_PHASE_EVALS : 0);
         t.flags = h_flag_;
         if (avail == 1 && c.outputs <= 3) t.packed = h_packed_;
-        SYLDET_CUDA(launch_stream_tick(net, c.fourier_length, model_.max_width(), n_channels_, 1, t, stream_));
+        // configurations the fused kernel takes: register FFT + folded network (stream_tick_fast_kernel); SYLDET_STREAM_GENERIC=1 keeps
+        // the reference-order tick
+        static const bool generic_tick = std::getenv("SYLDET_STREAM_GENERIC") != nullptr;
+        const FusedPlan &fp = model_.fused();
+        if (!generic_tick && fp.ok && stream_tick_fast_supported(c.fourier_length, fp.params) &&
+            stream_tick_fast_fits(c.fourier_length, fp.launch.hp, fp.params, t))
+            SYLDET_CUDA(launch_stream_tick_fast(c.fourier_length, fp.launch.hp, fp.params, model_.fused_params_dev(), t, model_.window(),
+                                                model_.twiddle(), n_channels_, stream_));
+        else
+            SYLDET_CUDA(launch_stream_tick(net, c.fourier_length, model_.max_width(), n_channels_, 1, t, stream_));
         ++launches_;
     } else {  // a long buffer: one launch per phase so each can spread over many blocks per channel
         t.phases = STREAM_PHASE_COPY;
@@ -250,6 +265,7 @@ syldet_status StreamGroup::launch_tick(int64_t n_cols, int64_t avail) {
         t_eval_[0] += (double)(h_stamps_[5] - h_stamps_[3]);   // gather
         for (int k = 1; k < 5; ++k) t_eval_[k] += (double)(h_stamps_[5 + k] - h_stamps_[4 + k]);  // ip0, ip1, layer0, layer1
         t_eval_[5] += (double)(h_stamps_[4] - h_stamps_[9]);   // reverse maps + publish
+        for (int k = 0; k < 6; ++k) t_sub_[k] += (double)(h_stamps_[10 + k] - h_stamps_[0]);   // latency-shaped tick: cycles since entry
         t_host_[0] += std::chrono::duration<double, std::micro>(tp1 - t_submit_).count();
         t_host_[1] += std::chrono::duration<double, std::micro>(tp2 - tp1).count();
         t_host_[2] += std::chrono::duration<double, std::micro>(tp3 - tp2).count();

@@ -62,7 +62,7 @@ private:
     uint4 *h_packed_ = nullptr;  // [n_channels] {out0, out1, out2, seq}: the single-evaluation tick's result, one store per channel
     // SYLDET_STREAM_TIMING=1: device cycle stamps per phase and host microseconds per step, reported by the destructor
     long long *h_stamps_ = nullptr;
-    double t_phase_[4] = {0, 0, 0, 0}, t_eval_[6] = {0, 0, 0, 0, 0, 0}, t_host_[3] = {0, 0, 0};
+    double t_phase_[4] = {0, 0, 0, 0}, t_eval_[6] = {0, 0, 0, 0, 0, 0}, t_host_[3] = {0, 0, 0}, t_sub_[6] = {0, 0, 0, 0, 0, 0};
     int64_t t_ticks_ = 0;
     std::chrono::steady_clock::time_point t_submit_{};
 };

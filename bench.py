@@ -547,7 +547,7 @@ def run_ours(args):
                                     "frames_per_s": cb["frames_per_s"], "single_core": cb.get("single")}
         if world == 1 and not args.no_stream:
             main = stream_latency(args, args.stream_channels, args.stream_buffer, args.stream_seconds, args.stream_paced_seconds)
-            main["api"] = ("syldet_stream_submit (one stream_tick_kernel launch per tick that completes an STFT column; samples pulled from and "
+            main["api"] = ("syldet_stream_submit (one stream_tick_fast_kernel launch per tick that completes an STFT column; samples pulled from and "
                            "outputs written to pinned host memory by the kernel)")
             if not args.no_stream_sweep:   # BASELINE config 5's other points: 128- / 256-frame buffers, 1024 channels (shorter runs)
                 main["sweep"] = {"%dch_x_%dframes" % (c, b): stream_latency(args, c, b, 15.0, 2.0)

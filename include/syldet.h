@@ -227,6 +227,8 @@ void syldet_stream_destroy(syldet_stream *s);
 syldet_status syldet_stream_submit(syldet_stream *s, const float *const *bufs, int n, uint8_t *seen, int32_t *n_new,
                                    float *last_out);
 int64_t syldet_stream_launch_count(const syldet_stream *s);
+/* of those, launches of the latency-shaped tick kernel (configurations the fused plan takes); the rest ran the reference-order tick */
+int64_t syldet_stream_fast_tick_count(const syldet_stream *s);
 /*
  * Level meters of the live view: getInputForChannel / getOutputForChannel for every channel (Processor.swift:158-184, StatMax in
  * SummaryStat.swift:39-62). input_rms[c] = sqrt(max over the buffers submitted since the last call of sum(x^2)/n, :110-113),

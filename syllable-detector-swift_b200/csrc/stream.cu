@@ -229,10 +229,11 @@ syldet_status StreamGroup::launch_tick(int64_t n_cols, int64_t avail) {
         static const bool generic_tick = std::getenv("SYLDET_STREAM_GENERIC") != nullptr;
         const FusedPlan &fp = model_.fused();
         if (!generic_tick && fp.ok && stream_tick_fast_supported(c.fourier_length, fp.params) &&
-            stream_tick_fast_fits(c.fourier_length, fp.launch.hp, fp.params, t))
+            stream_tick_fast_fits(c.fourier_length, fp.launch.hp, fp.params, t)) {
             SYLDET_CUDA(launch_stream_tick_fast(c.fourier_length, fp.launch.hp, fp.params, model_.fused_params_dev(), t, model_.window(),
                                                 model_.twiddle(), n_channels_, stream_));
-        else
+            ++fast_ticks_;
+        } else
             SYLDET_CUDA(launch_stream_tick(net, c.fourier_length, model_.max_width(), n_channels_, 1, t, stream_));
         ++launches_;
     } else {  // a long buffer: one launch per phase so each can spread over many blocks per channel

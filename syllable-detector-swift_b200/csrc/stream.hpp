@@ -25,6 +25,7 @@ public:
     const Config &config() const { return model_.config(); }
     int n_channels() const { return n_channels_; }
     int64_t launch_count() const { return launches_; }
+    int64_t fast_tick_count() const { return fast_ticks_; }   // launches of stream_tick_fast_kernel among them
     // getInputForChannel / getOutputForChannel for every channel (Processor.swift:158-184): RMS of the loudest buffer and the
     // largest output 0 since the last call, NaN where upstream returns nil; resets both (readStatAndReset).
     syldet_status read_levels(double *input_rms, double *output_max);
@@ -63,6 +64,7 @@ private:
     // SYLDET_STREAM_TIMING=1: device cycle stamps per phase and host microseconds per step, reported by the destructor
     long long *h_stamps_ = nullptr;
     double t_phase_[4] = {0, 0, 0, 0}, t_eval_[6] = {0, 0, 0, 0, 0, 0}, t_host_[3] = {0, 0, 0}, t_sub_[6] = {0, 0, 0, 0, 0, 0};
+    int64_t fast_ticks_ = 0;
     int64_t t_ticks_ = 0;
     std::chrono::steady_clock::time_point t_submit_{};
 };

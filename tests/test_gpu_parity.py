@@ -556,6 +556,11 @@ def test_stream_group_matches_batch(sd, cfg, orc, synth):
     dict(fft_len=128, overlap=-7, freq_range=(300.0, 20000.0), time_range=12, hidden=(3,), input_funcs=("normalizestd", "mapminmax")),
     dict(fft_len=512, overlap=256, freq_range=(1000.0, 9000.0), time_range=5, hidden=(8, 5), outputs=3, input_funcs=("mapstd",), output_funcs=("mapminmax", "mapstd")),
     dict(fft_len=2048, win_len=1500, overlap=-100, freq_range=(500.0, 5000.0), time_range=2, hidden=(6,), scaling="log", input_funcs=("mapstd", "normalize")),
+    # shapes the latency-shaped tick (stream_tick_fast_kernel) takes: min/max window statistic + zero padding + gap; FFT 128 with dB
+    # scaling and 8 hidden units; FFT 64 with the l2 statistic
+    dict(fft_len=256, win_len=200, overlap=-5, freq_range=(1000.0, 8000.0), time_range=6, hidden=(4,), input_funcs=("normalize", "mapminmax")),
+    dict(fft_len=128, overlap=64, freq_range=(1500.0, 12000.0), time_range=7, hidden=(8,), outputs=2, scaling="db", input_funcs=("mapminmax",)),
+    dict(fft_len=64, overlap=32, freq_range=(2000.0, 15000.0), time_range=8, hidden=(4,), input_funcs=("l2normalize",)),
 ])
 def test_stream_group_ragged_ticks_generated_configs(sd, oracle_mod, cw, kw):
     """The live tick kernel (device sample ring + band-feature ring, one launch per tick) on configurations with a gap, several
@@ -585,6 +590,8 @@ def test_stream_group_ragged_ticks_generated_configs(sd, oracle_mod, cw, kw):
                 assert near or bool(seen[ch]) == flag
     assert done == o.num_evals(n) > 0
     assert 0 < g.launch_count
+    if kw["fft_len"] <= 256 and "normalizestd" not in kw.get("input_funcs", ()):   # shapes of the latency-shaped tick: it did take them
+        assert g.fast_tick_count > 0
 
 
 def test_stream_level_meters_and_pulses(sd, cfg, orc, synth):

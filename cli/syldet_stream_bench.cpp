@@ -143,7 +143,7 @@ int main(int argc, char **argv) {
     const char *names[2] = {"burst", "paced"};
     const double secs[2] = {stream_s, paced_s};
     bool first = true;
-    int64_t launches = 0, fast_launches = 0;
+    int64_t launches = 0, fast_launches = 0, resident_ticks = 0;
     for (int pass = 0; pass < 2; ++pass) {
         if (secs[pass] <= 0) continue;
         syldet_stream *st = nullptr;
@@ -157,12 +157,14 @@ int main(int argc, char **argv) {
         if (!run_pass(st, nch, n_out, nbuf, ticks, rate, pass == 1, audio, audio_ticks, p)) return 1;
         launches += syldet_stream_launch_count(st);
         fast_launches += syldet_stream_fast_tick_count(st);
+        resident_ticks += syldet_stream_resident_tick_count(st);
         if (!first) std::printf(", ");
         first = false;
         print_pass(names[pass], p, nch);
         syldet_stream_destroy(st);
     }
-    std::printf(", \"kernel_launches\": %lld, \"latency_shaped_tick_launches\": %lld}\n", (long long)launches, (long long)fast_launches);
+    std::printf(", \"kernel_launches\": %lld, \"latency_shaped_tick_launches\": %lld, \"resident_ticks\": %lld}\n", (long long)launches,
+                (long long)fast_launches, (long long)resident_ticks);
     syldet_config_free(cfg);
     return 0;
 }

@@ -230,6 +230,13 @@ int64_t syldet_stream_launch_count(const syldet_stream *s);
 /* of those, launches of the latency-shaped tick kernel (configurations the fused plan takes); the rest ran the reference-order tick */
 int64_t syldet_stream_fast_tick_count(const syldet_stream *s);
 /*
+ * Ticks served by the resident tick kernel (SYLDET_STREAM_RESIDENT=1 when the group is created; groups of at most one channel per SM on
+ * configurations the latency-shaped tick takes): its blocks stay on their SMs and poll a message in pinned host memory, so such a tick
+ * costs no kernel launch. The kernel leaves after SYLDET_STREAM_RESIDENT_IDLE_MS (default 50) without a tick and is started again
+ * by the next one.
+ */
+int64_t syldet_stream_resident_tick_count(const syldet_stream *s);
+/*
  * Level meters of the live view: getInputForChannel / getOutputForChannel for every channel (Processor.swift:158-184, StatMax in
  * SummaryStat.swift:39-62). input_rms[c] = sqrt(max over the buffers submitted since the last call of sum(x^2)/n, :110-113),
  * output_max[c] = max over the evaluations since the last call of Double(lastOutputs[0]) (:138); NaN where upstream returns nil.

@@ -107,7 +107,7 @@ def _load():
         "syldet_detector_seen_syllable": (i32, [vp]),
         "syldet_stream_create": (i32, [vp, i32, i32, i32, pvp]), "syldet_stream_destroy": (None, [vp]),
         "syldet_stream_create_resampled": (i32, [vp, i32, i32, i32, dbl, pvp]), "syldet_stream_resampling": (i32, [vp]),
-        "syldet_stream_submit": (i32, [vp, vp, i32, vp, vp, vp]), "syldet_stream_launch_count": (i64, [vp]), "syldet_stream_fast_tick_count": (i64, [vp]),
+        "syldet_stream_submit": (i32, [vp, vp, i32, vp, vp, vp]), "syldet_stream_launch_count": (i64, [vp]), "syldet_stream_fast_tick_count": (i64, [vp]), "syldet_stream_resident_tick_count": (i64, [vp]),
         "syldet_stream_read_levels": (i32, [vp, vp, vp]), "syldet_stream_set_pulse": (i32, [vp, dbl, dbl]),
         "syldet_stream_render_pulses": (i32, [vp, vp, i32]),
         "syldet_resampler_linear_create": (i32, [dbl, dbl, pvp]), "syldet_resampler_destroy": (None, [vp]),
@@ -508,6 +508,11 @@ class StreamGroup:
     def fast_tick_count(self):
         """launches of the latency-shaped tick kernel among `launch_count`"""
         return lib.syldet_stream_fast_tick_count(self._h)
+
+    @property
+    def resident_tick_count(self):
+        """ticks served by the resident tick kernel (SYLDET_STREAM_RESIDENT=1 at creation; no launch per tick)"""
+        return lib.syldet_stream_resident_tick_count(self._h)
 
     @property
     def resampling(self):

@@ -353,6 +353,7 @@ syldet_status syldet_stream_submit(syldet_stream *s, const float *const *bufs, i
 }
 int64_t syldet_stream_launch_count(const syldet_stream *s) { return s ? s->g.launch_count() : 0; }
 int64_t syldet_stream_fast_tick_count(const syldet_stream *s) { return s ? s->g.fast_tick_count() : 0; }
+int64_t syldet_stream_resident_tick_count(const syldet_stream *s) { return s ? s->g.resident_tick_count() : 0; }
 syldet_status syldet_stream_read_levels(syldet_stream *s, double *input_rms, double *output_max) {
     if (!s) return set_error(SYLDET_ERR_ARG, "null argument");
     return guarded([&] { return s->g.read_levels(input_rms, output_max); });

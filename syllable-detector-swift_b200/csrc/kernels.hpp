@@ -226,9 +226,26 @@ cudaError_t launch_fused(const FusedLaunch &cfg, const FusedParams &p, const Fus
 cudaError_t fused_max_blocks_per_sm(int fft_len, int hp, size_t smem, int *blocks);
 // live tick on the register FFT and the folded network (kernels_fused.cu: stream_tick_fast_kernel); one block per channel, all phases;
 // d_params: device copy of the FusedParams
+// geometry of one tick in shared memory (host: tick_geom in kernels_fused.cu)
+struct TickGeom {
+    int win_len, hop, gap, k0, band, time_range;
+    int span_floats;   // samples from the start of the first new frame to the end of the last one, rounded up to 4
+    int win_floats;    // band values from the oldest column of the first evaluation window to the newest column, rounded up to 4
+    int stage_floats;  // staged samples, rounded up to 4
+};
+
 bool stream_tick_fast_supported(int fft_len, const FusedParams &p);
 bool stream_tick_fast_fits(int fft_len, int hp, const FusedParams &p, const StreamTick &t);   // this tick's shared-memory footprint is within the cap
 cudaError_t launch_stream_tick_fast(int fft_len, int hp, const FusedParams &host_params, const FusedParams *d_params, const StreamTick &t,
                                     const float *window, const float2 *twiddle, int n_channels, cudaStream_t stream);
+// resident tick (stream_tick_resident_kernel): blocks stay on their SMs; a dispatcher block polls the message the host posts in pinned
+// memory and republishes it in a device mailbox of stream_tick_post_bytes() bytes (+ one `leave` word)
+size_t stream_tick_post_bytes();
+void stream_tick_post_write(void *post, const StreamTick &t);   // what changes per tick, as quads {3 words, t.seq}, the first one last
+bool stream_tick_resident_plan(int fft_len, int hp, const FusedParams &p, int stage_cap, TickGeom *gmax);
+bool stream_tick_resident_tick_fits(const TickGeom &gmax, const FusedParams &p, const StreamTick &t);
+cudaError_t launch_stream_tick_resident(int fft_len, int hp, const FusedParams *d_params, const void *post, const unsigned *quit, unsigned *alive,
+                                        void *mailbox, unsigned *leave, const StreamTick &first, const TickGeom &gmax, long long idle_cycles,
+                                        const float *window, const float2 *twiddle, int n_channels, int sm_count, cudaStream_t stream);
 
 }  // namespace syldet

@@ -18,6 +18,8 @@
 //            weights that sit in kernel-parameter constant memory (warp-uniform FFMA operands), window statistic,
 //            transfer functions, remaining layers, reverse output map, double-precision threshold compare,
 //            warp-aggregated event append.
+#include <emmintrin.h>
+#include <cstring>
 #include <cstddef>
 #include <cstdio>
 
@@ -291,19 +293,86 @@ __global__ void __launch_bounds__(kFusedThreads, 2) fused_detect_kernel(const __
 //     from the first window's start), so the hot loops are immediate-offset LDS + packed arithmetic with no index bookkeeping;
 //   * the folded layer 0 of an evaluation is split over all 128 threads (each holds its weights from the top of the kernel), then
 //     one warp finishes the network.
-struct TickGeom {
-    int win_len, hop, gap, k0, band, time_range;
-    int span_floats;   // samples from the start of the first new frame to the end of the last one, rounded up to 4
-    int win_floats;    // band values from the oldest column of the first evaluation window to the newest column, rounded up to 4
-    int stage_floats;  // staged samples, rounded up to 4
-};
 constexpr int kTickThreads = 128;
-constexpr int kTickPre = 4;        // staged samples per thread held in registers across the PCIe round trip (512 per channel)
+constexpr int kTickPre = 4;        // staged samples per thread held in registers across the PCIe round trip (512 per channel): one float4
 constexpr int kTickEvalGroup = 4;  // evaluations reduced per block-wide pass
 
+// Per-thread invariants of a configuration: this thread's share of the folded layer-0 weights, and for the warps that transform
+// frames the window taps, pass-2 twiddles and untangle twiddles. A launched tick loads them behind its PCIe reads; the resident
+// kernel loads them once.
 template <int NFFT, int HP>
-__global__ void __launch_bounds__(kTickThreads) stream_tick_fast_kernel(const FusedParams *__restrict__ pp, const StreamTick t, const TickGeom g,
-                                                                        const float *__restrict__ window, const float2 *__restrict__ twiddle) {
+struct TickInv {
+    static constexpr int kW = kFusedMaxW0 / HP / kTickThreads;   // layer-0 inputs per thread (12 or 6): the whole layer in one pass
+    static constexpr int kBins = (kFusedMaxBand + 31) / 32;
+    float4 wa[kW], wb[HP == 8 ? kW : 1];
+    float2 wreg[fused_r1(NFFT)], tw[fused_r2(NFFT)], utw[kBins];
+};
+
+template <int NFFT, int HP>
+__device__ __forceinline__ void tick_load_inv(TickInv<NFFT, HP> &r, const FusedParams *__restrict__ pp, const TickGeom &g, const float *__restrict__ window,
+                                              const float2 *__restrict__ twiddle, bool want_weights, bool want_cols) {
+    constexpr int M = NFFT / 2, R1 = fused_r1(NFFT), R2 = fused_r2(NFFT);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int W = g.win_len, L = g.band, I = g.band * g.time_range;
+    if (want_weights) {
+#pragma unroll
+        for (int k = 0; k < TickInv<NFFT, HP>::kW; ++k) {
+            const int i = tid + k * kTickThreads;
+            if (i < I) {
+                r.wa[k] = __ldg(reinterpret_cast<const float4 *>(pp->w0 + (size_t)i * HP));
+                if constexpr (HP == 8) r.wb[k] = __ldg(reinterpret_cast<const float4 *>(pp->w0 + (size_t)i * HP + 4));
+            }
+        }
+    }
+    if (want_cols) {
+        const int j1 = lane % R2, j2 = lane % R1;
+#pragma unroll
+        for (int q = 0; q < R1; ++q) {
+            const int m0 = 2 * (j1 + q * R2);
+            r.wreg[q].x = m0 < W ? __ldg(window + m0) : 0.0f;       // zero padding: CSTFT.swift:109-110
+            r.wreg[q].y = m0 + 1 < W ? __ldg(window + m0 + 1) : 0.0f;
+        }
+#pragma unroll
+        for (int q = 1; q < R2; ++q) {
+            const int e = 2 * q * j2;
+            const float2 v = __ldg(twiddle + (e >= M ? e - M : e));
+            r.tw[q] = e >= M ? make_float2(-v.x, -v.y) : v;
+        }
+        r.tw[0] = make_float2(1.0f, 0.0f);
+#pragma unroll
+        for (int q = 0; q < TickInv<NFFT, HP>::kBins; ++q) r.utw[q] = lane + 32 * q < L ? __ldg(twiddle + g.k0 + lane + 32 * q) : make_float2(0.f, 0.f);
+    }
+}
+
+struct TickSmem {
+    FusedParams *sp;   // only the head (everything in front of w0) exists here
+    float *span, *win, *stage, *part;
+    float2 *zw;        // [4 warps][G][frame pitch] exchange buffers
+};
+template <int NFFT, int HP>
+__device__ __forceinline__ TickSmem tick_smem_layout(unsigned char *base, int head_bytes, const TickGeom &g) {
+    TickSmem m;
+    m.sp = reinterpret_cast<FusedParams *>(base);
+    m.span = reinterpret_cast<float *>(base + head_bytes);
+    m.win = m.span + g.span_floats;
+    m.stage = m.win + g.win_floats;
+    m.part = m.stage + g.stage_floats;
+    m.zw = reinterpret_cast<float2 *>(m.part + kTickEvalGroup * 4 * (HP + 2));
+    return m;
+}
+
+__device__ __forceinline__ float ld_volatile_f32(const float *p) {
+    float v;
+    asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// One tick of one channel by one block. kResident: the block outlives the tick (stream_tick_resident_kernel): the invariants and the
+// head of the parameter block are already in place, and pinned host memory is read with volatile loads (L1 is not flushed between
+// ticks).
+template <int NFFT, int HP, bool kResident>
+__device__ __forceinline__ void tick_run(const FusedParams *__restrict__ pp, const StreamTick &t, const TickGeom &g, TickInv<NFFT, HP> &inv,
+                                         const TickSmem &sm, const float *__restrict__ window, const float2 *__restrict__ twiddle) {
     constexpr int M = NFFT / 2;
     constexpr int R1 = fused_r1(NFFT), R2 = fused_r2(NFFT);
     constexpr int G = fused_group(NFFT);
@@ -311,10 +380,9 @@ __global__ void __launch_bounds__(kTickThreads) stream_tick_fast_kernel(const Fu
     constexpr int U2 = (G * R1) / 32;
     constexpr int LOG_R1 = R1 == 16 ? 4 : 3;
     constexpr int kHead = ((int)offsetof(FusedParams, w0) + 15) & ~15;   // everything but the layer-0 weights: staged in shared memory
-    constexpr int kW = kFusedMaxW0 / HP / kTickThreads;                 // layer-0 inputs per thread (12 or 6): the whole layer in one pass
-    constexpr int kBins = (kFusedMaxBand + 31) / 32;
+    constexpr int kW = TickInv<NFFT, HP>::kW;
+    constexpr int kBins = TickInv<NFFT, HP>::kBins;
     constexpr int kPart = HP + 2;                                        // partial sums per warp and evaluation: HP dot products + 2 statistics
-    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ch = blockIdx.x;
     const bool stamp = t.stamps != nullptr && ch == 0 && tid == 0;   // SYLDET_STREAM_TIMING
@@ -323,16 +391,23 @@ __global__ void __launch_bounds__(kTickThreads) stream_tick_fast_kernel(const Fu
 
     // (0) the longest-latency loads first: this channel's staged samples, straight out of pinned host memory
     const float *src = t.staged + (int64_t)ch * t.stage_pitch;
-    float pre[kTickPre];
+    float pre[kTickPre];   // samples 4 tid .. 4 tid + 3: one 16-byte read per thread (the staging rows are 128-byte aligned)
+    {
+        const int i = kTickPre * tid;
+        if (i + kTickPre <= t.n_staged) {
+            float4 v;
+            if constexpr (kResident) asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(src + i) : "memory");
+            else v = *reinterpret_cast<const float4 *>(src + i);
+            pre[0] = v.x; pre[1] = v.y; pre[2] = v.z; pre[3] = v.w;
+        } else {
 #pragma unroll
-    for (int k = 0; k < kTickPre; ++k) pre[k] = tid + k * kTickThreads < t.n_staged ? src[tid + k * kTickThreads] : 0.0f;
+            for (int k = 0; k < kTickPre; ++k) pre[k] = i + k < t.n_staged ? (kResident ? ld_volatile_f32(src + i + k) : src[i + k]) : 0.0f;
+        }
+    }
 
-    FusedParams *sp = reinterpret_cast<FusedParams *>(smem_raw);   // only its first kHead bytes exist here
-    float *s_span = reinterpret_cast<float *>(smem_raw + kHead);
-    float *s_win = s_span + g.span_floats;
-    float *s_stage = s_win + g.win_floats;
-    float *s_part = s_stage + g.stage_floats;                                                      // [kTickEvalGroup][4 warps][kPart]
-    float2 *zw = reinterpret_cast<float2 *>(s_part + kTickEvalGroup * 4 * kPart) + warp * G * FP;   // this warp's exchange buffer
+    FusedParams *sp = sm.sp;
+    float *s_span = sm.span, *s_win = sm.win, *s_stage = sm.stage, *s_part = sm.part;   // s_part: [kTickEvalGroup][4 warps][kPart]
+    float2 *zw = sm.zw + warp * G * FP;                                                  // this warp's exchange buffer
     const int W = g.win_len, L = g.band, I = g.band * g.time_range;
     float *ring = t.ring + (int64_t)ch * (t.ring_mask + 1);
     float *band = t.band + (int64_t)ch * (t.band_mask + 1) * L;
@@ -352,40 +427,16 @@ __global__ void __launch_bounds__(kTickThreads) stream_tick_fast_kernel(const Fu
                 ptx::cp_async4(s_win + i, band + s);
             }
         }
-        for (int i = tid; i < kHead / 16; i += kTickThreads) ptx::cp_async16(smem_raw + 16 * i, reinterpret_cast<const int4 *>(pp) + i);
+        if constexpr (!kResident)
+            for (int i = tid; i < kHead / 16; i += kTickThreads)
+                ptx::cp_async16(reinterpret_cast<unsigned char *>(sp) + 16 * i, reinterpret_cast<const int4 *>(pp) + i);
     }
     // registers: this thread's share of the folded layer-0 weights; window taps and twiddles for the warps that transform a frame
-    float4 wa[kW], wb[HP == 8 ? kW : 1];
-    if (t.n_evals > 0) {
-#pragma unroll
-        for (int k = 0; k < kW; ++k) {
-            const int i = tid + k * kTickThreads;
-            if (i < I) {
-                wa[k] = __ldg(reinterpret_cast<const float4 *>(pp->w0 + (size_t)i * HP));
-                if constexpr (HP == 8) wb[k] = __ldg(reinterpret_cast<const float4 *>(pp->w0 + (size_t)i * HP + 4));
-            }
-        }
-    }
     const int fs1 = lane / R2, j1 = lane % R2, j2 = lane % R1;
-    const bool has_cols = (int64_t)warp * G < t.n_cols;
-    float2 wreg[R1], tw[R2], utw[kBins];
-    if (has_cols) {
-#pragma unroll
-        for (int r = 0; r < R1; ++r) {
-            const int m0 = 2 * (j1 + r * R2);
-            wreg[r].x = m0 < W ? __ldg(window + m0) : 0.0f;       // zero padding: CSTFT.swift:109-110
-            wreg[r].y = m0 + 1 < W ? __ldg(window + m0 + 1) : 0.0f;
-        }
-#pragma unroll
-        for (int r = 1; r < R2; ++r) {
-            const int q = 2 * r * j2;
-            const float2 v = __ldg(twiddle + (q >= M ? q - M : q));
-            tw[r] = q >= M ? make_float2(-v.x, -v.y) : v;
-        }
-#pragma unroll
-        for (int q = 0; q < kBins; ++q) utw[q] = lane + 32 * q < L ? __ldg(twiddle + g.k0 + lane + 32 * q) : make_float2(0.f, 0.f);
-    }
-    const float rs_last = t.rs_on ? __ldg(t.rs_last_in + ch) : 0.0f;
+    if constexpr (!kResident) tick_load_inv<NFFT, HP>(inv, pp, g, window, twiddle, t.n_evals > 0, (int64_t)warp * G < t.n_cols);
+    const float4 *wa = inv.wa, *wb = inv.wb;
+    const float2 *wreg = inv.wreg, *tw = inv.tw, *utw = inv.utw;
+    const float rs_last = t.rs_on ? __ldcg(t.rs_last_in + ch) : 0.0f;   // written by the previous tick (of this very block when resident)
     if (stamp) ts[1] = clock64();
 
     // (1) staged samples: into shared memory, and (no resampler) into the device ring and the frame span
@@ -396,14 +447,14 @@ __global__ void __launch_bounds__(kTickThreads) stream_tick_fast_kernel(const Fu
     };
 #pragma unroll
     for (int k = 0; k < kTickPre; ++k) {
-        const int i = tid + k * kTickThreads;
+        const int i = kTickPre * tid + k;
         if (i < t.n_staged) {
             s_stage[i] = pre[k];
             if (!t.rs_on) place(t.ring_pos + i, pre[k]);
         }
     }
     for (int i = tid + kTickPre * kTickThreads; i < t.n_staged; i += kTickThreads) {
-        const float v = src[i];
+        const float v = kResident ? ld_volatile_f32(src + i) : src[i];
         s_stage[i] = v;
         if (!t.rs_on) place(t.ring_pos + i, v);
     }
@@ -571,8 +622,12 @@ __global__ void __launch_bounds__(kTickThreads) stream_tick_fast_kernel(const Fu
                     const int bits = __float_as_int(v0);
                     if (v0 == v0) atomicMax(t.level_out + ch, bits >= 0 ? bits : bits ^ 0x7fffffff);
                 }
-                if (t.packed) t.packed[ch] = make_uint4(__float_as_uint(out[0]), O > 1 ? __float_as_uint(out[1]) : 0u, O > 2 ? __float_as_uint(out[2]) : 0u, t.seq);
-                else
+                if (t.packed) {
+                    const uint4 r = make_uint4(__float_as_uint(out[0]), O > 1 ? __float_as_uint(out[1]) : 0u, O > 2 ? __float_as_uint(out[2]) : 0u, t.seq);
+                    if constexpr (kResident)   // system scope: nothing ends here that would push a plain store out of the L2
+                        asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(t.packed + ch), "r"(r.x), "r"(r.y), "r"(r.z), "r"(r.w) : "memory");
+                    else t.packed[ch] = r;
+                } else
                     for (int o = 0; o < O; ++o) t.out[((int64_t)ch * t.n_evals + j) * O + o] = pick(out, o);
             }
         }
@@ -588,6 +643,170 @@ __global__ void __launch_bounds__(kTickThreads) stream_tick_fast_kernel(const Fu
         __threadfence_system();
         __syncthreads();
         if (tid == 0) *(volatile unsigned *)(t.flags + ch) = t.seq;
+    }
+}
+
+template <int NFFT, int HP>
+__global__ void __launch_bounds__(kTickThreads) stream_tick_fast_kernel(const FusedParams *__restrict__ pp, const StreamTick t, const TickGeom g,
+                                                                        const float *__restrict__ window, const float2 *__restrict__ twiddle) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int kHead = ((int)offsetof(FusedParams, w0) + 15) & ~15;
+    TickInv<NFFT, HP> inv;
+    const TickSmem sm = tick_smem_layout<NFFT, HP>(smem_raw, kHead, g);
+    tick_run<NFFT, HP, false>(pp, t, g, inv, sm, window, twiddle);
+}
+
+// ---- resident tick: no launch on the latency path -------------------------------------------------------------------------
+// The same tick, but the blocks stay on their SMs. The host posts the tick descriptor in pinned memory as 16-byte quads {3 payload
+// words, sequence number} (a 16-byte store / PCIe read is indivisible, so every quad validates itself), the first quad last.
+// Polling host memory is expensive in pollers, not in time (profiles/r02_poll_probe.txt: one polling thread answers in 2.5 us,
+// every further poller of the line adds ~0.8 us), so ONE thread does it: block `n_channels` is the dispatcher - thread 0 polls the
+// first quad, the block then fetches the message (one more PCIe round trip) and republishes it in a device-memory mailbox; the channel
+// blocks poll that mailbox through the L2. The dispatcher alone decides to leave - when the host raises `quit`, or after
+// `idle_cycles` without a message (a forgotten group releases its SMs; a cudaFree / synchronize elsewhere in the process stalls that
+// long at most) - so a tick reaches every channel or none; the host sees `alive == 0` and starts the kernel again at the pending tick.
+// The message holds only what changes from tick to tick (everything else is the StreamTick the kernel was started with):
+//   word 0: n_cols | n_evals << 8 | n_marks << 16 | flags << 24 (bit 0: results go to `packed`)   word 1: n_staged
+//   words 2-7: ring_pos, col0, eval0 (64-bit)   then marks[n_marks], and with the resampler rs_offset[n_marks], (rs_n_out | rs_out0 << 16)[n_marks]
+// 12 words = 4 quads for the live shape (4 buffers per column, no resampler), 32 words at most.
+constexpr int kPostWords = 8 + 3 * kStreamMaxMarks;
+constexpr int kPostQuads = (kPostWords + 2) / 3;
+static_assert(kPostQuads <= 32, "one quad of the tick message per lane of the dispatcher warp");
+__host__ __device__ inline int tick_post_quads(int n_marks, bool rs) { return (8 + n_marks * (rs ? 3 : 1) + 2) / 3; }
+
+__device__ __forceinline__ uint4 ld_volatile_v4(const uint4 *p) {
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned ld_volatile_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <int NFFT, int HP>
+__global__ void __launch_bounds__(kTickThreads) stream_tick_resident_kernel(const FusedParams *__restrict__ pp, const uint4 *post, const unsigned *quit,
+                                                                            unsigned *alive, uint4 *mailbox, unsigned *leave, const StreamTick first,
+                                                                            const TickGeom gmax, long long idle_cycles, int n_channels,
+                                                                            const float *__restrict__ window, const float2 *__restrict__ twiddle) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int kHead = ((int)offsetof(FusedParams, w0) + 15) & ~15;
+    const int tid = threadIdx.x;
+    __shared__ int s_go;
+    unsigned expected = first.seq;
+    if ((int)blockIdx.x == n_channels) {
+        // ---- dispatcher: warp 0 polls the first four quads (one 64-byte line of host memory: the whole message of the live shape)
+        if (tid >= 32) return;
+        const int lane = tid;
+        long long last = clock64();
+        bool go = true;
+        while (go) {
+            uint4 v;
+            int quads = 0;
+            for (;;) {
+                v = ld_volatile_v4(post + (lane < 4 ? lane : 0));
+                const unsigned ok = __ballot_sync(0xffffffffu, v.w == expected);
+                if (ok & 1u) {   // the first quad is written last: the message is complete in host memory
+                    quads = tick_post_quads((__shfl_sync(0xffffffffu, v.x, 0) >> 16) & 0xff, first.rs_on != 0);
+                    if ((ok & 0xfu) != 0xfu) v = ld_volatile_v4(post + (lane < quads ? lane : 0));   // this lane's read was the older one
+                    break;
+                }
+                const bool stop = lane == 0 && (ld_volatile_u32(quit) != 0 || clock64() - last > idle_cycles);
+                if (__any_sync(0xffffffffu, stop)) { go = false; break; }
+            }
+            if (!go) break;
+            if (quads > 4 && lane >= 4 && lane < quads) v = ld_volatile_v4(post + lane);
+            if (lane > 0 && lane < quads) __stcg(mailbox + lane, v);
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) {
+                asm volatile("st.release.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(mailbox), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+                last = clock64();
+            }
+            ++expected;
+        }
+        if (lane == 0) {
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(leave), "r"(1u) : "memory");
+            __threadfence_system();
+            *(volatile unsigned *)alive = 0;
+            __threadfence_system();
+        }
+        return;
+    }
+    // ---- one channel
+    struct Mail {
+        StreamTick t;
+        TickGeom g;
+        unsigned w[kPostQuads * 3];
+    };
+    static_assert(sizeof(Mail) <= 1024, "message area");
+    Mail &m = *reinterpret_cast<Mail *>(smem_raw + kHead);
+    const TickSmem sm = tick_smem_layout<NFFT, HP>(smem_raw, kHead + 1024, gmax);
+    for (int i = tid; i < kHead / 16; i += kTickThreads) ptx::cp_async16(smem_raw + 16 * i, reinterpret_cast<const int4 *>(pp) + i);
+    if (tid == 0) {
+        m.t = first;
+        m.g = gmax;
+    }
+    TickInv<NFFT, HP> inv;
+    tick_load_inv<NFFT, HP>(inv, pp, gmax, window, twiddle, true, true);
+    ptx::cp_async_wait_all();
+    __syncthreads();
+    for (;;) {
+        if (tid == 0) {
+            int go = 1;
+            for (;;) {
+                unsigned w, l;
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(w) : "l"(&mailbox->w) : "memory");
+                if (w == expected) break;
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(l) : "l"(leave) : "memory");
+                if (l != 0) { go = 0; break; }
+            }
+            s_go = go;
+        }
+        __syncthreads();
+        if (!s_go) break;
+        if (tid < kPostQuads) {
+            const uint4 v = __ldcg(mailbox + tid);   // L2: written before the first quad was released (quads beyond the message: stale, unused)
+            m.w[3 * tid] = v.x; m.w[3 * tid + 1] = v.y; m.w[3 * tid + 2] = v.z;
+        }
+        __syncthreads();
+        if (tid == 0) {   // this tick's StreamTick: the constant part stays as the kernel was started with
+            StreamTick &t = m.t;
+            const unsigned *w = m.w;
+            t.n_cols = w[0] & 0xff;
+            t.n_evals = (w[0] >> 8) & 0xff;
+            t.n_marks = (w[0] >> 16) & 0xff;
+            t.packed = (w[0] >> 24) & 1 ? first.packed : nullptr;
+            t.n_staged = (int)w[1];
+            t.ring_pos = (int64_t)((unsigned long long)w[2] | (unsigned long long)w[3] << 32);
+            t.col0 = (int64_t)((unsigned long long)w[4] | (unsigned long long)w[5] << 32);
+            t.eval0 = (int64_t)((unsigned long long)w[6] | (unsigned long long)w[7] << 32);
+            t.seq = expected;
+            for (int k = 0; k < t.n_marks; ++k) {
+                t.marks[k] = (int)w[8 + k];
+                if (t.rs_on) {
+                    t.rs_offset[k] = __uint_as_float(w[8 + t.n_marks + k]);
+                    t.rs_n_out[k] = (int)(w[8 + 2 * t.n_marks + k] & 0xffff);
+                    t.rs_out0[k] = (int)(w[8 + 2 * t.n_marks + k] >> 16);
+                }
+            }
+            if (t.rs_on && expected != first.seq) {   // the two `last` arrays alternate from tick to tick
+                const float *in = t.rs_last_out;
+                t.rs_last_out = const_cast<float *>(t.rs_last_in);
+                t.rs_last_in = in;
+            }
+            const int64_t span = t.n_cols > 0 ? (t.n_cols - 1) * (int64_t)gmax.hop + gmax.win_len : 0;
+            const int64_t win = t.n_evals > 0 ? (t.col0 - t.eval0 + t.n_cols) * (int64_t)gmax.band : 0;
+            m.g.span_floats = (int)((span + 3) & ~(int64_t)3);
+            m.g.win_floats = (int)((win + 3) & ~(int64_t)3);
+            m.g.stage_floats = (t.n_staged + 3) & ~3;
+        }
+        __syncthreads();
+        tick_run<NFFT, HP, true>(pp, m.t, m.g, inv, sm, window, twiddle);
+        __syncthreads();   // the message and the work areas are free again
+        if (tid == 0) __threadfence_system();   // nothing ends here: without the fence the results sit in the L2 for hundreds of microseconds
+        ++expected;
     }
 }
 
@@ -621,6 +840,23 @@ cudaError_t launch_tick_one(const FusedParams *d_params, const StreamTick &t, co
         raised = true;
     }
     stream_tick_fast_kernel<NFFT, HP><<<n_channels, kTickThreads, tick_fast_smem(NFFT, HP, g), stream>>>(d_params, t, g, window, twiddle);
+    return cudaGetLastError();
+}
+
+template <int NFFT, int HP>
+cudaError_t launch_resident_one(const FusedParams *d_params, const void *post, const unsigned *quit, unsigned *alive, void *mailbox, unsigned *leave,
+                                const StreamTick &first, const TickGeom &gmax, long long idle_cycles, const float *window, const float2 *twiddle,
+                                int n_channels, int sm_count, cudaStream_t stream) {
+    auto kern = stream_tick_resident_kernel<NFFT, HP>;
+    const size_t smem = tick_fast_smem(NFFT, HP, gmax) + 1024;   // + the message area
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kTickFastSmemCap + 1024));
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;   // the blocks wait for each other through memory: all of them (channels + dispatcher) have to be on an SM at once
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTickThreads, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1 || n_channels + 1 > sm_count) return cudaErrorLaunchOutOfResources;
+    kern<<<n_channels + 1, kTickThreads, smem, stream>>>(d_params, reinterpret_cast<const uint4 *>(post), quit, alive, reinterpret_cast<uint4 *>(mailbox), leave,
+                                                         first, gmax, idle_cycles, n_channels, window, twiddle);
     return cudaGetLastError();
 }
 
@@ -682,6 +918,55 @@ cudaError_t launch_stream_tick_fast(int fft_len, int hp, const FusedParams &host
     const int cfg_fft = fft_len, cfg_hp = hp;
     const TickGeom g = tick_geom(host_params, t);
     SYLDET_FUSED_DISPATCH(launch_tick_one, d_params, t, g, window, twiddle, n_channels, stream)
+}
+
+size_t stream_tick_post_bytes() { return (size_t)kPostQuads * 16; }
+
+void stream_tick_post_write(void *post, const StreamTick &t) {
+    unsigned w[kPostQuads * 3] = {};
+    w[0] = (unsigned)t.n_cols | (unsigned)t.n_evals << 8 | (unsigned)t.n_marks << 16 | (t.packed ? 1u : 0u) << 24;
+    w[1] = (unsigned)t.n_staged;
+    const unsigned long long q[3] = {(unsigned long long)t.ring_pos, (unsigned long long)t.col0, (unsigned long long)t.eval0};
+    for (int k = 0; k < 3; ++k) { w[2 + 2 * k] = (unsigned)q[k]; w[3 + 2 * k] = (unsigned)(q[k] >> 32); }
+    for (int k = 0; k < t.n_marks; ++k) {
+        w[8 + k] = (unsigned)t.marks[k];
+        if (t.rs_on) {
+            std::memcpy(&w[8 + t.n_marks + k], &t.rs_offset[k], 4);
+            w[8 + 2 * t.n_marks + k] = ((unsigned)t.rs_n_out[k] & 0xffff) | (unsigned)t.rs_out0[k] << 16;
+        }
+    }
+    __m128i *dst = reinterpret_cast<__m128i *>(post);
+    for (int q4 = tick_post_quads(t.n_marks, t.rs_on != 0) - 1; q4 >= 0; --q4)   // one indivisible 16-byte store per quad, the first quad last
+        _mm_store_si128(dst + q4, _mm_set_epi32((int)t.seq, (int)w[3 * q4 + 2], (int)w[3 * q4 + 1], (int)w[3 * q4]));
+    _mm_sfence();
+}
+
+bool stream_tick_resident_plan(int fft_len, int hp, const FusedParams &p, int stage_cap, TickGeom *gmax) {
+    // the largest single-launch tick of the group: 4 columns, 4 evaluations, a full staging area
+    TickGeom g{};
+    g.win_len = p.win_len; g.hop = p.hop; g.gap = p.gap; g.k0 = p.k0; g.band = p.band; g.time_range = p.time_range;
+    g.span_floats = (3 * p.hop + p.win_len + 3) & ~3;
+    g.win_floats = ((p.time_range + 3) * p.band + 3) & ~3;
+    g.stage_floats = (stage_cap + 3) & ~3;
+    *gmax = g;
+    return tick_fast_smem(fft_len, hp, g) <= kTickFastSmemCap;
+}
+
+bool stream_tick_resident_tick_fits(const TickGeom &gmax, const FusedParams &p, const StreamTick &t) {
+    if (t.col0 < t.eval0 || t.n_cols > 255 || t.n_evals > 255 || t.n_marks > kStreamMaxMarks) return false;
+    if (t.rs_on)
+        for (int k = 0; k < t.n_marks; ++k)
+            if (t.rs_n_out[k] > 0xffff || t.rs_out0[k] > 0xffff || t.rs_n_out[k] < 0) return false;
+    const TickGeom g = tick_geom(p, t);
+    return g.span_floats <= gmax.span_floats && g.win_floats <= gmax.win_floats && g.stage_floats <= gmax.stage_floats;
+}
+
+cudaError_t launch_stream_tick_resident(int fft_len, int hp, const FusedParams *d_params, const void *post, const unsigned *quit, unsigned *alive,
+                                        void *mailbox, unsigned *leave, const StreamTick &first, const TickGeom &gmax, long long idle_cycles,
+                                        const float *window, const float2 *twiddle, int n_channels, int sm_count, cudaStream_t stream) {
+    const int cfg_fft = fft_len, cfg_hp = hp;
+    SYLDET_FUSED_DISPATCH(launch_resident_one, d_params, post, quit, alive, mailbox, leave, first, gmax, idle_cycles, window, twiddle, n_channels,
+                          sm_count, stream)
 }
 
 cudaError_t fused_max_blocks_per_sm(int fft_len, int hp, size_t smem, int *blocks) {

@@ -12,6 +12,7 @@
 #include "stream.hpp"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -91,10 +92,88 @@ syldet_status StreamGroup::init(const Config &cfg, int n_channels, int max_buffe
         std::memset(h_stamps_, 0, 128);
     }
     SYLDET_CUDA(cudaStreamSynchronize(stream_));
+    // Resident tick kernel (opt-in, SYLDET_STREAM_RESIDENT=1): one polling block per channel, all co-resident
+    if (const char *e = std::getenv("SYLDET_STREAM_RESIDENT"); e && e[0] == '1') {
+        const FusedPlan &fp = model_.fused();
+        if (fp.ok && stream_tick_fast_supported(c.fourier_length, fp.params) && n_channels + 1 <= model_.sm_count() &&
+            stream_tick_resident_plan(c.fourier_length, fp.launch.hp, fp.params, stage_cap_, &resident_geom_)) {
+            SYLDET_CUDA(cudaMallocHost(&h_post_, stream_tick_post_bytes()));
+            std::memset(h_post_, 0, stream_tick_post_bytes());
+            SYLDET_CUDA(cudaMallocHost(&h_ctl_, 32 * sizeof(unsigned)));
+            std::memset(h_ctl_, 0, 32 * sizeof(unsigned));
+            st = mailbox_.reserve(stream_tick_post_bytes() + 64);
+            if (st != SYLDET_OK) return st;
+            double idle_ms = 50.0;   // a group nobody feeds leaves the GPU after this long; the next tick starts the kernel again
+            if (const char *m = std::getenv("SYLDET_STREAM_RESIDENT_IDLE_MS")) idle_ms = std::max(0.1, std::atof(m));
+            int khz = 0;
+            cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+            resident_idle_cycles_ = (long long)(idle_ms * (khz > 0 ? khz : 1900000));
+            resident_ok_ = true;
+        }
+    }
     return SYLDET_OK;
 }
 
+syldet_status StreamGroup::start_resident(const StreamTick &t) {
+    const Config &c = model_.config();
+    const FusedPlan &fp = model_.fused();
+    SYLDET_CUDA(cudaMemsetAsync(mailbox_.get(), 0, mailbox_.size(), stream_));
+    *(volatile unsigned *)h_ctl_ = 0;
+    *(volatile unsigned *)(h_ctl_ + 16) = 1;
+    std::atomic_thread_fence(std::memory_order_seq_cst);
+    unsigned char *mb = mailbox_.as<unsigned char>();
+    StreamTick first = t;
+    first.packed = h_packed_;   // which of `packed` / `out` + `flags` a tick publishes through is part of its message
+    // `t` is the tick about to be posted: the kernel starts at its sequence number and keeps its constant part
+    SYLDET_CUDA(launch_stream_tick_resident(c.fourier_length, fp.launch.hp, model_.fused_params_dev(), h_post_, h_ctl_, h_ctl_ + 16, mb,
+                                            reinterpret_cast<unsigned *>(mb + stream_tick_post_bytes()), first, resident_geom_,
+                                            resident_idle_cycles_, model_.window(), model_.twiddle(), n_channels_, model_.sm_count(), stream_));
+    resident_running_ = true;
+    ++resident_starts_;
+    ++launches_;
+    return SYLDET_OK;
+}
+
+syldet_status StreamGroup::stop_resident() {
+    if (!resident_running_) return SYLDET_OK;
+    *(volatile unsigned *)h_ctl_ = 1;
+    std::atomic_thread_fence(std::memory_order_seq_cst);
+    resident_running_ = false;
+    SYLDET_CUDA(cudaStreamSynchronize(stream_));
+    return SYLDET_OK;
+}
+
+// As wait_for_tick, but the kernel may have left (idle limit reached just as the message was posted): the dispatcher takes a tick for
+// every channel or for none, so the kernel is simply started again at the pending tick.
+syldet_status StreamGroup::wait_for_resident_tick(const StreamTick &t) {
+    const bool packed = t.packed != nullptr;
+    volatile unsigned *flags = packed ? &h_packed_[0].w : h_flag_;
+    const int step = packed ? 4 : 1;
+    int ch = 0;
+    for (unsigned spins = 0;; ++spins) {
+        while (ch < n_channels_ && flags[(size_t)ch * step] == seq_) ++ch;
+        if (ch == n_channels_) return SYLDET_OK;
+        if ((spins & 0xfff) == 0xfff) {
+            if (*(volatile unsigned *)(h_ctl_ + 16) == 0) {   // it left without taking this tick: start it again at the pending one
+                syldet_status st = stop_resident();
+                if (st != SYLDET_OK) return st;
+                st = start_resident(t);
+                if (st != SYLDET_OK) return st;
+            } else if ((spins & 0xffff) == 0xffff) {
+                cudaError_t e = cudaStreamQuery(stream_);
+                if (e != cudaSuccess && e != cudaErrorNotReady) return cuda_fail(e, "resident live tick");
+            }
+        }
+    }
+}
+
 StreamGroup::~StreamGroup() {
+    if (resident_running_) {
+        cudaSetDevice(model_.device());
+        stop_resident();
+    }
+    if (h_post_) cudaFreeHost(h_post_);
+    if (h_ctl_) cudaFreeHost(h_ctl_);
     if (h_stamps_ && t_ticks_ > 0) {
         const double n = (double)t_ticks_;
         std::fprintf(stderr, "[syldet stream timing] %lld single-launch ticks, %d channels; device cycles of block (0,0): preload %.0f, copy %.0f, "
@@ -219,6 +298,7 @@ syldet_status StreamGroup::launch_tick(int64_t n_cols, int64_t avail) {
     const DevNet *net = model_.dev_net();
     const int64_t cap = std::max<int64_t>(1, (model_.sm_count() * 8) / n_channels_);
     const bool single = n_cols <= warps;
+    bool resident = false;
     const auto tp1 = std::chrono::steady_clock::now();
     if (single) {  // the live shape: one launch, one block per channel
         t.phases = STREAM_PHASE_COPY | STREAM_PHASE_COLUMNS | (avail > 0 ? STREAM_PHASE_EVALS : 0);
@@ -228,15 +308,35 @@ syldet_status StreamGroup::launch_tick(int64_t n_cols, int64_t avail) {
         // the reference-order tick
         static const bool generic_tick = std::getenv("SYLDET_STREAM_GENERIC") != nullptr;
         const FusedPlan &fp = model_.fused();
-        if (!generic_tick && fp.ok && stream_tick_fast_supported(c.fourier_length, fp.params) &&
+        if (resident_ok_ && stream_tick_resident_tick_fits(resident_geom_, fp.params, t)) {
+            // no launch: post the tick to the blocks already on the SMs
+            if (resident_running_ && *(volatile unsigned *)(h_ctl_ + 16) == 0) {   // idle limit reached since the last tick
+                st = stop_resident();
+                if (st != SYLDET_OK) return st;
+            }
+            if (!resident_running_) {
+                st = start_resident(t);
+                if (st != SYLDET_OK) return st;
+            }
+            stream_tick_post_write(h_post_, t);
+            resident = true;
+            ++resident_ticks_;
+        } else if (!generic_tick && fp.ok && stream_tick_fast_supported(c.fourier_length, fp.params) &&
             stream_tick_fast_fits(c.fourier_length, fp.launch.hp, fp.params, t)) {
+            st = stop_resident();
+            if (st != SYLDET_OK) return st;
             SYLDET_CUDA(launch_stream_tick_fast(c.fourier_length, fp.launch.hp, fp.params, model_.fused_params_dev(), t, model_.window(),
                                                 model_.twiddle(), n_channels_, stream_));
             ++fast_ticks_;
-        } else
+        } else {
+            st = stop_resident();
+            if (st != SYLDET_OK) return st;
             SYLDET_CUDA(launch_stream_tick(net, c.fourier_length, model_.max_width(), n_channels_, 1, t, stream_));
-        ++launches_;
+        }
+        if (!resident) ++launches_;
     } else {  // a long buffer: one launch per phase so each can spread over many blocks per channel
+        st = stop_resident();
+        if (st != SYLDET_OK) return st;
         t.phases = STREAM_PHASE_COPY;
         t.flags = nullptr;
         int bx = (int)std::min<int64_t>(cap, (staged_ + warps * 32 - 1) / (warps * 32));
@@ -255,7 +355,7 @@ syldet_status StreamGroup::launch_tick(int64_t n_cols, int64_t avail) {
         }
     }
     const auto tp2 = std::chrono::steady_clock::now();
-    st = wait_for_tick(t.packed != nullptr);
+    st = resident ? wait_for_resident_tick(t) : wait_for_tick(t.packed != nullptr);
     if (st != SYLDET_OK) return st;
     if (t.packed) {  // unpack into the documented [n_channels][n_new][outputs] layout
         for (int ch = 0; ch < n_channels_; ++ch) std::memcpy(h_out_ + (size_t)ch * c.outputs, &h_packed_[ch], (size_t)c.outputs * sizeof(float));
@@ -293,6 +393,8 @@ syldet_status StreamGroup::read_levels(double *input_rms, double *output_max) {
         if (st != SYLDET_OK) return st;
     }
     syldet_status st = use_device(model_.device());
+    if (st != SYLDET_OK) return st;
+    st = stop_resident();   // the copies below queue behind whatever runs on the stream
     if (st != SYLDET_OK) return st;
     std::vector<unsigned long long> in(n_channels_);
     std::vector<int> out(n_channels_);

@@ -26,6 +26,7 @@ public:
     int n_channels() const { return n_channels_; }
     int64_t launch_count() const { return launches_; }
     int64_t fast_tick_count() const { return fast_ticks_; }   // launches of stream_tick_fast_kernel among them
+    int64_t resident_tick_count() const { return resident_ticks_; }   // ticks served by the resident kernel (no launch)
     // getInputForChannel / getOutputForChannel for every channel (Processor.swift:158-184): RMS of the loudest buffer and the
     // largest output 0 since the last call, NaN where upstream returns nil; resets both (readStatAndReset).
     syldet_status read_levels(double *input_rms, double *output_max);
@@ -33,6 +34,10 @@ public:
 private:
     syldet_status wait_for_tick(bool packed);
     syldet_status launch_tick(int64_t n_cols, int64_t avail);
+    // resident tick kernel (SYLDET_STREAM_RESIDENT=1): see stream_tick_resident_kernel
+    syldet_status start_resident(const StreamTick &t);
+    syldet_status stop_resident();
+    syldet_status wait_for_resident_tick(const StreamTick &t);
 
     DeviceModel model_;
     int n_channels_ = 0, max_buffer_ = 0;
@@ -65,6 +70,13 @@ private:
     long long *h_stamps_ = nullptr;
     double t_phase_[4] = {0, 0, 0, 0}, t_eval_[6] = {0, 0, 0, 0, 0, 0}, t_host_[3] = {0, 0, 0}, t_sub_[6] = {0, 0, 0, 0, 0, 0};
     int64_t fast_ticks_ = 0;
+    bool resident_ok_ = false, resident_running_ = false;
+    TickGeom resident_geom_{};
+    long long resident_idle_cycles_ = 0;
+    void *h_post_ = nullptr;          // pinned: the tick message
+    unsigned *h_ctl_ = nullptr;       // pinned: [0] quit (host writes), [16] alive (the dispatcher clears it when the kernel leaves)
+    DeviceBuffer mailbox_;            // device: the message as the dispatcher republishes it, then the `leave` word
+    int64_t resident_ticks_ = 0, resident_starts_ = 0;
     int64_t t_ticks_ = 0;
     std::chrono::steady_clock::time_point t_submit_{};
 };

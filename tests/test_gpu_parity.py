@@ -594,6 +594,43 @@ def test_stream_group_ragged_ticks_generated_configs(sd, oracle_mod, cw, kw):
         assert g.fast_tick_count > 0
 
 
+@pytest.mark.parametrize("rate_in", [0.0, 48000.0])
+def test_stream_group_resident_kernel(sd, cfg, orc, synth, monkeypatch, rate_in):
+    """SYLDET_STREAM_RESIDENT=1: the tick blocks stay on their SMs and poll a message in pinned host memory. Same results, tick by tick
+    and bit for bit, as the launched tick - across an idle period longer than the kernel's idle limit (it leaves and is started again),
+    a level-meter read (which stops it) and, second case, with the resampler inside the tick."""
+    import time
+    nch, nbuf, ticks = 12, 32, 900
+    x = synth.make_audio(nch, nbuf * ticks, seed=23)
+    kw = dict(max_buffer=nbuf)
+    if rate_in:
+        kw["input_rate"] = rate_in
+    ref_group = sd.StreamGroup(cfg, nch, **kw)
+    monkeypatch.setenv("SYLDET_STREAM_RESIDENT", "1")
+    monkeypatch.setenv("SYLDET_STREAM_RESIDENT_IDLE_MS", "5")
+    g = sd.StreamGroup(cfg, nch, **kw)
+    monkeypatch.delenv("SYLDET_STREAM_RESIDENT")
+    total = 0
+    for t in range(ticks):
+        buf = x[:, t * nbuf:(t + 1) * nbuf]
+        seen_a, new_a = ref_group.submit(buf)
+        seen_b, new_b = g.submit(buf)
+        assert np.array_equal(new_a, new_b) and np.array_equal(seen_a, seen_b)
+        if new_a[0]:
+            assert np.array_equal(ref_group.last_outputs, g.last_outputs)
+            total += int(new_a[0])
+        if t == 300:
+            time.sleep(0.05)          # ten idle limits: the kernel has left; the next tick starts it again
+        if t == 600:
+            la, lb = ref_group.read_levels(), g.read_levels()
+            assert np.allclose(la[0], lb[0], rtol=1e-6, equal_nan=True) and np.array_equal(la[1], lb[1], equal_nan=True)
+    assert total > 0 and g.resident_tick_count > 0 and g.resident_tick_count >= g.launch_count
+    assert ref_group.resident_tick_count == 0
+    if not rate_in:
+        ref, _, _ = orc.run(x[3])
+        assert np.abs(g.last_outputs[3] - ref[total - 1]).max() <= TOL_OUT
+
+
 def test_stream_level_meters_and_pulses(sd, cfg, orc, synth):
     """Live view extras: input RMS / output maximum meters (Processor.swift:110-113, 138, 158-184) and the 1 ms TTL pulse train
     (Processor.swift:192, 212-221; AudioInterface.swift:13-40, 442-445) over 8 channels of 32-frame buffers."""

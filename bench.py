@@ -165,13 +165,16 @@ def dram_traffic_per_launch(name, alg_bytes):
         return None
 
 
-def stream_latency(args, channels, buffer, seconds, paced):
+def stream_latency(args, channels, buffer, seconds, paced, resident=False):
     """BASELINE config 5: live channels with small buffers, sample.txt network; per-buffer latency (submit -> outputs and `seen`
     flags host-visible) measured by the C++ driver cli/syldet_stream_bench.cpp through syldet_stream_submit."""
     exe = os.path.join(ROOT, "syllable-detector-swift_b200", "syldet_stream_bench")
     try:
+        env = dict(os.environ)
+        if resident:   # the tick blocks stay on their SMs and poll a message in pinned memory (DESIGN.md 5)
+            env["SYLDET_STREAM_RESIDENT"] = "1"
         r = subprocess.run([exe, "-n", SAMPLE_TXT, "-c", str(channels), "-b", str(buffer), "-s", str(seconds), "-p", str(paced),
-                            "-d", os.environ.get("LOCAL_RANK", "0")], capture_output=True, text=True, timeout=600)
+                            "-d", os.environ.get("LOCAL_RANK", "0")], capture_output=True, text=True, timeout=600, env=env)
         if r.returncode != 0:
             return {"error": (r.stderr or r.stdout)[-300:]}
         return json.loads(r.stdout)
@@ -549,6 +552,10 @@ def run_ours(args):
             main = stream_latency(args, args.stream_channels, args.stream_buffer, args.stream_seconds, args.stream_paced_seconds)
             main["api"] = ("syldet_stream_submit (one stream_tick_fast_kernel launch per tick that completes an STFT column; samples pulled from and "
                            "outputs written to pinned host memory by the kernel)")
+            res = stream_latency(args, args.stream_channels, args.stream_buffer, args.stream_seconds, args.stream_paced_seconds, resident=True)
+            res["api"] = ("syldet_stream_submit with SYLDET_STREAM_RESIDENT=1 (opt-in): no launch per tick - the channel blocks stay on their SMs, a "
+                          "dispatcher warp polls the tick message in pinned host memory")
+            main["resident"] = res
             if not args.no_stream_sweep:   # BASELINE config 5's other points: 128- / 256-frame buffers, 1024 channels (shorter runs)
                 main["sweep"] = {"%dch_x_%dframes" % (c, b): stream_latency(args, c, b, 15.0, 2.0)
                                  for c, b in ((64, 128), (64, 256), (1024, 32))}

@@ -405,23 +405,27 @@ def run_ours(args):
     numa, numa_undo = bind_near_gpu(torch, local)
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
 
+    table = sharding.EventTable(cfg.net_outputs) if world > 1 else None   # this rank's detections: page-locked, filled in place
+
     def timed_e2e(h_np):
         """e2e_steps recordings per rank through the host API, then the job's one gather of every rank's detections on rank 0"""
         for _ in range(min(args.warmup, 2)):
             ev_h = det.run(h_np)
         if world > 1:   # warm-up of the gather as well: the first point-to-point gather sets up NCCL's peer connections (~0.4 s, once per job)
-            w_rows = sharding.pack_events_compact(rank, ev_h.channel, ev_h.sample, ev_h.outputs)
-            sharding.gather_events(np.concatenate([w_rows] * e2e_steps, axis=0), dist)
-            del w_rows
+            table.clear()
+            for step in range(e2e_steps):
+                table.append(rank * e2e_steps + step, ev_h.channel, ev_h.sample, ev_h.outputs)
+            sharding.gather_events(table, dist)
         barrier()
         te0 = time.perf_counter()
-        rows = []
+        if world > 1:
+            table.clear()
         for step in range(e2e_steps):
             ev_h = det.run(h_np)
             if world > 1:
-                rows.append(sharding.pack_events_compact(rank * e2e_steps + step, ev_h.channel, ev_h.sample, ev_h.outputs))
+                table.append(rank * e2e_steps + step, ev_h.channel, ev_h.sample, ev_h.outputs)
         if world > 1:
-            sharding.gather_events(np.concatenate(rows, axis=0), dist)
+            sharding.gather_events(table, dist)
         barrier()
         return time.perf_counter() - te0, ev_h
 
@@ -592,6 +596,9 @@ def run_corpus(args, np, torch, dist, sd, sharding, synth, rank, world, local, d
     ev_w = det.collect()
     if world > 1:   # the first point-to-point gather sets up NCCL's peer connections: once per job, not part of the corpus
         sharding.gather_events(sharding.pack_events_compact(rank, ev_w.channel, ev_w.sample, ev_w.outputs), dist)
+    table = sharding.EventTable(cfg.net_outputs, capacity=max(1 << 20, int(1.25 * len(ev_w) * (b - a))))   # page-locked once, before the clock starts
+    if world > 1 and rank == 0:   # and so is rank 0's table of everybody's rows (sized from the warm-up recording)
+        sharding.reserve_gather(cfg.net_outputs, int(1.25 * len(ev_w) * n_rec))
     del ev_w
     barrier()
     clocks = ClockSampler(local) if rank == 0 else None
@@ -610,7 +617,7 @@ def run_corpus(args, np, torch, dist, sd, sharding, synth, rank, world, local, d
         if os.environ.get("SYLDET_E2E_TIMING") and rec < a + 8:
             sys.stderr.write("[c3] recording %d: launch call %.2f ms, collect %.2f ms\n" % (rec, 1e3 * (t_l - t0), 1e3 * (time.perf_counter() - t_l)))
         dev_ms += e0.elapsed_time(e1)
-        rows.append(sharding.pack_events_compact(rec, ev.channel, ev.sample, ev.outputs))
+        table.append(rec, ev.channel, ev.sample, ev.outputs)
         # per-shard parity: 400 evaluations of a random channel / offset of this recording against the oracle
         ch, j = int(rng.integers(nch)), int(rng.integers(E - 400))
         seg = x[ch, j * cfg.hop: j * cfg.hop + cfg.first_output_sample + cfg.hop * 399].cpu().numpy()
@@ -620,10 +627,10 @@ def run_corpus(args, np, torch, dist, sd, sharding, synth, rank, world, local, d
         near = np.abs(ref[:, 0].astype(np.float64) - cfg.thresholds[0]) <= 1e-5
         flips_far += int((((got[:, 0].astype(np.float64) >= cfg.thresholds[0]) != da) & ~near).sum())
         checked += 400
-    rows = np.concatenate(rows, axis=0) if rows else np.zeros(0, dtype=sharding.event_dtype(cfg.net_outputs))
+    rows = table.rows
     barrier()
     t0 = time.perf_counter()
-    allrows = sharding.gather_events(rows, dist if world > 1 else None)     # the final host gather of detection timestamps
+    allrows = sharding.gather_events(table, dist if world > 1 else None)     # the final host gather of detection timestamps
     barrier()
     gather_s = time.perf_counter() - t0
     t_clock1 = time.perf_counter()

@@ -1066,8 +1066,10 @@ syldet_status Batch::order_events_on_device(unsigned long long n, int64_t evals,
     syldet_status st = order_bits_.reserve(n_words * 4);
     if (st == SYLDET_OK) st = order_prefix_.reserve(n_words * 4);
     if (st == SYLDET_OK) st = order_blocks_.reserve(((size_t)n_blocks + 1) * 4);
-    if (st == SYLDET_OK) st = sorted_events_.reserve((size_t)n * sizeof(DevEvent));
-    if (st == SYLDET_OK) st = sorted_outputs_.reserve((size_t)n * O * sizeof(float));
+    // sized like the sink itself: a launch with a few more detections than any before must not re-allocate (cudaFree synchronises)
+    const size_t cap = (size_t)std::max<unsigned long long>(n, sink_capacity_);
+    if (st == SYLDET_OK) st = sorted_events_.reserve(cap * sizeof(DevEvent));
+    if (st == SYLDET_OK) st = sorted_outputs_.reserve(cap * O * sizeof(float));
     if (st != SYLDET_OK) return st;
     SYLDET_CUDA(cudaMemsetAsync(order_bits_.get(), 0, n_words * 4, stream));
     const unsigned ev_blocks = (unsigned)((n + 255) / 256);

@@ -106,12 +106,11 @@ def rows_in_order(rows, block=1 << 18):
     (tens of millions of rows after a corpus run) is ever allocated."""
     n = rows.shape[0]
     if rows.dtype.names:                     # compact rows: the key already is (recording, channel)
+        key, smp = rows["key"], rows["sample"]
         for a in range(0, n - 1, block):
             b = min(n, a + block + 1)
-            key = rows["key"][a:b].astype(np.int64)
-            d_k = key[1:] - key[:-1]
-            d_t = rows["sample"][a + 1:b] - rows["sample"][a:b - 1]
-            if not bool(np.all((d_k > 0) | ((d_k == 0) & (d_t >= 0)))):
+            k0, k1 = key[a:b - 1], key[a + 1:b]
+            if not bool(np.all((k1 > k0) | ((k1 == k0) & (smp[a + 1:b] >= smp[a:b - 1])))):
                 return False
         return True
     for a in range(0, n - 1, block):
@@ -124,24 +123,118 @@ def rows_in_order(rows, block=1 << 18):
     return True
 
 
+def _pinned_bytes(nbytes):
+    """uint8 host buffer of nbytes: page-locked when a CUDA device is there (copies to and from the device then run at PCIe speed and
+    nothing is staged), plain otherwise. Returns (numpy view, torch tensor or None)."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            t = torch.empty(int(nbytes), dtype=torch.uint8, pin_memory=True)
+            return t.numpy(), t
+    except Exception:  # noqa: BLE001 - no torch / no device: a plain buffer does
+        pass
+    return np.empty(int(nbytes), dtype=np.uint8), None
+
+
+class EventTable:
+    """A rank's detections as compact rows (event_dtype) in ONE reusable page-locked buffer: recordings are appended in place, so a
+    job never concatenates per-recording tables or touches fresh pages per gather, and whether the rows are in (recording, channel,
+    sample) order is tracked as they arrive (each block is checked while it is still in cache). gather_events takes the table as is."""
+
+    def __init__(self, n_outputs, capacity=1 << 20):
+        self.dtype = event_dtype(n_outputs)
+        self._cap = 0
+        self._raw = self._pin = None
+        self.n = 0
+        self.in_order = True
+        self._reserve(int(capacity))
+
+    def _reserve(self, cap):
+        if cap <= self._cap:
+            return
+        cap = max(cap, 2 * self._cap)
+        raw, pin = _pinned_bytes(cap * self.dtype.itemsize)
+        if self.n:
+            raw[:self.n * self.dtype.itemsize] = self._raw[:self.n * self.dtype.itemsize]
+        self._raw, self._pin, self._cap = raw, pin, cap
+
+    def clear(self):
+        self.n = 0
+        self.in_order = True
+
+    @property
+    def rows(self):
+        return self._raw[:self.n * self.dtype.itemsize].view(self.dtype)
+
+    def bytes_tensor(self):
+        """the rows as a (pinned) torch uint8 tensor [n, itemsize], or None without torch"""
+        if self._pin is None:
+            return None
+        return self._pin[:self.n * self.dtype.itemsize].view(self.n, self.dtype.itemsize)
+
+    def append(self, recording, channel, sample, outputs):
+        """one recording's detections (as Events gives them: ordered by channel, sample)"""
+        sample = np.asarray(sample)
+        m = int(sample.size)
+        channel = np.asarray(channel)
+        if not (0 <= int(recording) < 65536) or (m and (int(channel.min()) < 0 or int(channel.max()) >= 65536)):
+            raise ValueError("compact event rows hold recordings and channels below 65 536")
+        self._reserve(self.n + m)
+        it = self.dtype.itemsize
+        blk = self._raw[self.n * it:(self.n + m) * it].view(self.dtype)
+        blk["key"] = (np.uint32(int(recording)) << np.uint32(16)) | channel.astype(np.uint32)
+        blk["sample"] = sample
+        blk["out"] = np.asarray(outputs, dtype=np.float32).reshape(m, -1)
+        if self.in_order and m:
+            lo = max(self.n - 1, 0)   # with the last row of what was there: the boundary pair is checked too
+            self.in_order = rows_in_order(self._raw[lo * it:(self.n + m) * it].view(self.dtype))
+        self.n += m
+        return blk
+
+
+_recv = {}
+
+
+def _recv_table(dtype, total):
+    """the destination rank's table of all ranks' rows: one page-locked buffer per row layout, kept between gathers (valid until the
+    next gather_events of that layout)"""
+    it = dtype.itemsize
+    ent = _recv.get(dtype.str + str(dtype.itemsize))
+    if ent is None or ent[0].size < total * it:
+        ent = _pinned_bytes(max(total * it, 1))
+        _recv[dtype.str + str(dtype.itemsize)] = ent
+    return ent[0][:total * it].view(dtype), (ent[1][:total * it].view(total, it) if ent[1] is not None and total else None)
+
+
+def reserve_gather(n_outputs, total_rows):
+    """Page-lock the destination table of a coming gather of about `total_rows` compact rows ahead of time (a job that knows its size:
+    pinning hundreds of megabytes costs more than moving them). Call on the destination rank; other ranks need nothing."""
+    _recv_table(event_dtype(n_outputs), int(total_rows))
+
+
 def gather_events(rows, dist=None, dst=0):
     """Gather per-rank event rows on `dst`, sorted by (recording, channel, sample). Other ranks get None.
-    `dist` is torch.distributed (initialised) or None for a single process. `rows` is either the float64 table of pack_events or
-    the structured array of pack_events_compact (less than half the bytes per row; what bench.py gathers); the result has the same form.
+    `dist` is torch.distributed (initialised) or None for a single process. `rows` is the float64 table of pack_events, the structured
+    array of pack_events_compact (less than half the bytes per row), or an EventTable of such rows (what bench.py gathers: page-locked,
+    filled in place, order tracked on the way); the result has the form of the rows. For compact rows the result on `dst` lives in a
+    buffer that the next gather of that layout reuses.
 
     Only `dst` receives rows (point-to-point gather, not all_gather). Every rank checks the order of its own rows (in parallel);
     ranks own contiguous recording blocks, so when every block is ordered and the block boundaries are, the concatenation in rank
     order IS the sorted result and no sort of the (tens of millions of) rows is needed; otherwise `dst` sorts."""
+    table = rows if isinstance(rows, EventTable) else None
+    if table is not None:
+        rows = table.rows
     if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
         allrows = rows
-        in_order = rows_in_order(rows)
+        in_order = table.in_order if table is not None else rows_in_order(rows)
     else:
         import torch
         world, rank = dist.get_world_size(), dist.get_rank()
         nccl = dist.get_backend() == "nccl"
         dev = torch.device("cuda", torch.cuda.current_device()) if nccl else torch.device("cpu")
         if rows.dtype.names:
-            return _gather_compact(rows, dist, dst, torch, world, rank, dev)
+            return _gather_compact(rows, dist, dst, torch, world, rank, dev, table)
         n, width = rows.shape[0], (rows.shape[1] if rows.size else 0)
         first = rows[0, :3] if n else np.zeros(3)
         last = rows[-1, :3] if n else np.zeros(3)
@@ -189,13 +282,14 @@ def gather_events(rows, dist=None, dst=0):
     return allrows
 
 
-def _gather_compact(rows, dist, dst, torch, world, rank, dev):
-    """gather_events for structured rows: the rows travel as raw bytes (one point-to-point gather of uint8 tensors, pageable host
-    memory on both sides: pinning a buffer of this size costs more than the copy saves)."""
+def _gather_compact(rows, dist, dst, torch, world, rank, dev, table=None):
+    """gather_events for structured rows: the rows travel as raw bytes (one point-to-point gather of uint8 tensors). From an EventTable
+    they leave page-locked memory and the order is already known; on `dst` they land in a page-locked table kept between gathers."""
     n, item = rows.shape[0], rows.dtype.itemsize
     first = (int(rows["key"][0]), int(rows["sample"][0])) if n else (0, 0)
     last = (int(rows["key"][-1]), int(rows["sample"][-1])) if n else (0, 0)
-    meta = torch.tensor([n, item, 1 if rows_in_order(rows) else 0, *first, *last], dtype=torch.int64, device=dev)
+    ordered = table.in_order if table is not None else rows_in_order(rows)
+    meta = torch.tensor([n, item, 1 if ordered else 0, *first, *last], dtype=torch.int64, device=dev)
     metas = [torch.zeros_like(meta) for _ in range(world)]
     dist.all_gather(metas, meta)
     metas = [m.cpu().numpy() for m in metas]
@@ -203,21 +297,27 @@ def _gather_compact(rows, dist, dst, torch, world, rank, dev):
     if any(int(m[1]) != item for m in metas if int(m[0])):
         raise ValueError("ranks disagree on the event row layout")
     cap = max(max(counts), 1)
-    buf = torch.zeros((cap, item), dtype=torch.uint8, device=dev)
+    buf = torch.empty((cap, item), dtype=torch.uint8, device=dev)
     if n:
-        buf[:n].copy_(torch.from_numpy(np.ascontiguousarray(rows).view(np.uint8).reshape(n, item)))
+        src = table.bytes_tensor() if table is not None else None
+        if src is None:
+            src = torch.from_numpy(np.ascontiguousarray(rows).view(np.uint8).reshape(n, item))
+        buf[:n].copy_(src, non_blocking=src.is_pinned() if dev.type == "cuda" else False)
     bufs = [torch.empty_like(buf) for _ in range(world)] if rank == dst else None
     dist.gather(buf, bufs, dst=dst)
     if rank != dst:
         return None
     total = sum(counts)
-    allrows = np.empty(total, dtype=rows.dtype)
-    raw = allrows.view(np.uint8).reshape(total, item) if total else None
+    allrows, raw = _recv_table(rows.dtype, total)
+    if raw is None and total:
+        raw = torch.from_numpy(allrows.view(np.uint8).reshape(total, item))
     pos = 0
     for b, c in zip(bufs, counts):
         if c:
-            torch.from_numpy(raw[pos:pos + c]).copy_(b[:c])   # device -> the final table, no intermediate host copy
+            raw[pos:pos + c].copy_(b[:c], non_blocking=dev.type == "cuda")   # device -> the final table, no intermediate host copy
             pos += c
+    if dev.type == "cuda":
+        torch.cuda.synchronize(dev)
     in_order = all(int(m[2]) == 1 for m in metas)
     prev = None
     for m in metas:     # ordered blocks in rank order, boundaries in order => sorted

@@ -56,6 +56,19 @@ def _worker(rank, world, port, mode, out_path):
             np.save(out_path + ".compact.npy", np.column_stack([rec, ch, smp, outs.astype(np.float64)]))
         else:
             assert call is None
+        # the same rows appended recording by recording to an EventTable (in place, order tracked on the way), gathered twice: the
+        # destination's table is reused between gathers
+        table = sh.EventTable(1, capacity=4)
+        for rep in range(2):
+            table.clear()
+            for r in rows:
+                if r.shape[0]:
+                    table.append(int(r[0, 0]), r[:, 1].astype(np.int64), r[:, 2].astype(np.int64), r[:, 3:])
+            assert table.in_order and np.array_equal(table.rows, compact)
+            tall = sh.gather_events(table, dist, dst=0)
+            assert (tall is None) == (rank != 0)
+            if rank == 0:
+                assert np.array_equal(tall, call)
     allrows = sh.gather_events(local, dist, dst=0)
     if rank == 0:
         np.save(out_path, allrows)
@@ -103,6 +116,11 @@ def test_two_rank_recording_shards_match_single_process(tmp_path, oracle_mod, sy
     c = sh.pack_events_compact(3, want[:5, 1].astype(np.int64), want[:5, 2].astype(np.int64), want[:5, 3:])
     assert c.dtype.itemsize == 16 and sh.rows_in_order(c) and not sh.rows_in_order(c[::-1])
     assert sh.gather_events(c, None).shape[0] == 5
+    t = sh.EventTable(want.shape[1] - 3, capacity=2)
+    t.append(3, want[:5, 1].astype(np.int64), want[:5, 2].astype(np.int64), want[:5, 3:])
+    assert t.in_order and t.n == 5 and np.array_equal(t.rows, c) and np.array_equal(sh.gather_events(t, None), c)
+    t.append(2, want[:5, 1].astype(np.int64), want[:5, 2].astype(np.int64), want[:5, 3:])     # an earlier recording after a later one
+    assert not t.in_order and sh.rows_in_order(sh.gather_events(t, None)) and sh.gather_events(t, None).shape[0] == 10
 
 
 def test_two_rank_time_slices_match_sequential_run(tmp_path, oracle_mod, synth):

@@ -621,7 +621,7 @@ def test_stream_group_resident_kernel(sd, cfg, orc, synth, monkeypatch, rate_in)
             total += int(new_a[0])
         if t == 300:
             time.sleep(0.05)          # ten idle limits: the kernel has left; the next tick starts it again
-        if t == 600:
+        if t == 601:                  # one buffer is waiting in the staging area: the meter read sends it through the resident kernel first
             la, lb = ref_group.read_levels(), g.read_levels()
             assert np.allclose(la[0], lb[0], rtol=1e-6, equal_nan=True) and np.array_equal(la[1], lb[1], equal_nan=True)
     assert total > 0 and g.resident_tick_count > 0 and g.resident_tick_count >= g.launch_count
@@ -629,6 +629,31 @@ def test_stream_group_resident_kernel(sd, cfg, orc, synth, monkeypatch, rate_in)
     if not rate_in:
         ref, _, _ = orc.run(x[3])
         assert np.abs(g.last_outputs[3] - ref[total - 1]).max() <= TOL_OUT
+
+
+def test_stream_group_resident_kernel_ragged_buffers(sd, cfg, synth, monkeypatch):
+    """Ragged buffers on a resident group: ticks of up to four columns stay on the resident kernel (several staged buffers per message),
+    longer buffers stop it, go through the per-phase launches and the next short tick starts it again - every output bit for bit what a
+    launched group gives."""
+    nch, n = 5, 120000
+    x = synth.make_audio(nch, n, seed=29)
+    ref_group = sd.StreamGroup(cfg, nch, max_buffer=4000)
+    monkeypatch.setenv("SYLDET_STREAM_RESIDENT", "1")
+    g = sd.StreamGroup(cfg, nch, max_buffer=4000)
+    monkeypatch.delenv("SYLDET_STREAM_RESIDENT")
+    rng = np.random.default_rng(31)
+    pos, done = 0, 0
+    while pos < n:
+        m = min(int(rng.choice([1, 7, 32, 32, 32, 64, 132, 257, 500, 700, 4000])), n - pos)
+        buf = x[:, pos:pos + m]
+        seen_a, new_a = ref_group.submit(buf)
+        seen_b, new_b = g.submit(buf)
+        pos += m
+        assert np.array_equal(new_a, new_b) and np.array_equal(seen_a, seen_b)
+        if new_a[0]:
+            assert np.array_equal(ref_group.last_outputs, g.last_outputs)
+            done += int(new_a[0])
+    assert done == cfg.num_evals(n) and g.resident_tick_count > 100 and g.launch_count > 10
 
 
 def test_stream_level_meters_and_pulses(sd, cfg, orc, synth):

@@ -675,10 +675,22 @@ syldet_status Batch::launch_tc_range(const float *d_planar, int n_channels, int6
     // a unit covers whole tiles: chunk = n_tiles * tile_frames - (T - 1) evaluations (the first T-1 columns of a unit only warm
     // the window up); long enough that the warm-up is noise, short enough that every CTA gets many units
     const int64_t tf = tc_tile_frames(), warm = c.time_range - 1;
+    // Units go to the CTAs round-robin, so the launch takes ceil(units / CTAs) units on the busiest CTA: pick the (even: tiles are
+    // contracted in pairs) unit length that minimises that, one tile charged per unit for the pipeline fill and the warm-up columns.
+    // 1 h x 8 ch: 32 tiles per unit leaves 4 800 units = 32.4 per CTA, i.e. 33 on some (2.3 % over the ideal); 74 gives 2 072 = 14 each.
     int64_t tiles_per_unit = 32;
-    const int64_t total_tiles = (int64_t)n_channels * ((eval_count + warm + tf - 1) / tf);
-    while (tiles_per_unit > 4 && total_tiles / tiles_per_unit < (int64_t)resident * 16) tiles_per_unit /= 2;
-    while (tiles_per_unit * tf <= 4 * warm) tiles_per_unit *= 2;
+    {
+        static const int forced = [] { const char *e = std::getenv("SYLDET_TC_UNIT_TILES"); return e ? std::atoi(e) : 0; }();
+        double best = 1e300;
+        for (int64_t tpu = 4; tpu <= 96; tpu += 2) {
+            if (tpu * tf <= 4 * warm) continue;
+            const int64_t ch = tpu * tf - warm;
+            const int64_t units = (int64_t)n_channels * ((eval_count + ch - 1) / ch);
+            const double cost = (double)((units + resident - 1) / resident) * (double)(tpu + 1);
+            if (cost < best) { best = cost; tiles_per_unit = tpu; }
+        }
+        if (forced > 0 && forced * tf > 4 * warm) tiles_per_unit = forced;
+    }
     const int64_t chunk = tiles_per_unit * tf - warm;
     w.chunk_evals = chunk;
     w.chunks_per_channel = (int)((eval_count + chunk - 1) / chunk);

@@ -174,7 +174,7 @@ def stream_latency(args, channels, buffer, seconds, paced, resident=False):
         if resident:   # the tick blocks stay on their SMs and poll a message in pinned memory
             env["SYLDET_STREAM_RESIDENT"] = "1"
         r = subprocess.run([exe, "-n", SAMPLE_TXT, "-c", str(channels), "-b", str(buffer), "-s", str(seconds), "-p", str(paced),
-                            "-d", os.environ.get("LOCAL_RANK", "0")], capture_output=True, text=True, timeout=600, env=env)
+                            "-d", os.environ.get("LOCAL_RANK", "0")], capture_output=True, text=True, timeout=120 if resident else 600, env=env)
         if r.returncode != 0:
             return {"error": (r.stderr or r.stdout)[-300:]}
         return json.loads(r.stdout)

@@ -23,6 +23,10 @@ namespace syldet {
 
 // ---------------------------------------------------------------------------------------------------------------
 namespace {
+// Resident tick kernels of this process, in blocks per device: their blocks wait for each other through memory, so all of them - of
+// every group - have to fit on the device's SMs at once. A group that would not fit keeps to launched ticks.
+std::atomic<int> g_resident_blocks[64];
+
 int64_t pow2_at_least(int64_t v) {
     int64_t p = 1;
     while (p < v) p <<= 1;
@@ -95,8 +99,14 @@ syldet_status StreamGroup::init(const Config &cfg, int n_channels, int max_buffe
     // Resident tick kernel (opt-in, SYLDET_STREAM_RESIDENT=1): one polling block per channel, all co-resident
     if (const char *e = std::getenv("SYLDET_STREAM_RESIDENT"); e && e[0] == '1') {
         const FusedPlan &fp = model_.fused();
-        if (fp.ok && stream_tick_fast_supported(c.fourier_length, fp.params) && n_channels + 1 <= model_.sm_count() &&
-            stream_tick_resident_plan(c.fourier_length, fp.launch.hp, fp.params, stage_cap_, &resident_geom_)) {
+        std::atomic<int> &in_use = g_resident_blocks[device & 63];
+        const bool room = in_use.fetch_add(n_channels + 1) + n_channels + 1 <= model_.sm_count();
+        if (!room) in_use.fetch_sub(n_channels + 1);
+        if (room && !(fp.ok && stream_tick_fast_supported(c.fourier_length, fp.params) &&
+                      stream_tick_resident_plan(c.fourier_length, fp.launch.hp, fp.params, stage_cap_, &resident_geom_))) {
+            in_use.fetch_sub(n_channels + 1);
+        } else if (room) {
+            resident_blocks_ = n_channels + 1;
             SYLDET_CUDA(cudaMallocHost(&h_post_, stream_tick_post_bytes()));
             std::memset(h_post_, 0, stream_tick_post_bytes());
             SYLDET_CUDA(cudaMallocHost(&h_ctl_, 32 * sizeof(unsigned)));
@@ -162,6 +172,11 @@ syldet_status StreamGroup::wait_for_resident_tick(const StreamTick &t) {
             } else if ((spins & 0xffff) == 0xffff) {
                 cudaError_t e = cudaStreamQuery(stream_);
                 if (e != cudaSuccess && e != cudaErrorNotReady) return cuda_fail(e, "resident live tick");
+                if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t_submit_).count() > 5.0) {
+                    // e.g. another process holds the SMs its blocks need: fail loudly rather than spin
+                    stop_resident();
+                    return set_error(SYLDET_ERR_CUDA, "the resident tick kernel did not answer within 5 s");
+                }
             }
         }
     }
@@ -172,6 +187,7 @@ StreamGroup::~StreamGroup() {
         cudaSetDevice(model_.device());
         stop_resident();
     }
+    if (resident_blocks_ > 0) g_resident_blocks[model_.device() & 63].fetch_sub(resident_blocks_);
     if (h_post_) cudaFreeHost(h_post_);
     if (h_ctl_) cudaFreeHost(h_ctl_);
     if (h_stamps_ && t_ticks_ > 0) {

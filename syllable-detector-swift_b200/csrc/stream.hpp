@@ -71,6 +71,7 @@ private:
     double t_phase_[4] = {0, 0, 0, 0}, t_eval_[6] = {0, 0, 0, 0, 0, 0}, t_host_[3] = {0, 0, 0}, t_sub_[6] = {0, 0, 0, 0, 0, 0};
     int64_t fast_ticks_ = 0;
     bool resident_ok_ = false, resident_running_ = false;
+    int resident_blocks_ = 0;         // this group's share of the device's resident blocks (0: launched ticks)
     TickGeom resident_geom_{};
     long long resident_idle_cycles_ = 0;
     void *h_post_ = nullptr;          // pinned: the tick message

@@ -418,16 +418,21 @@ def run_ours(args):
             sharding.gather_events(table, dist)
         barrier()
         te0 = time.perf_counter()
-        if world > 1:
+        if world > 1:   # the detections go straight into this rank's gather table (run_into), then ONE gather for the job
             table.clear()
-        for step in range(e2e_steps):
-            ev_h = det.run(h_np)
-            if world > 1:
-                table.append(rank * e2e_steps + step, ev_h.channel, ev_h.sample, ev_h.outputs)
-        if world > 1:
+            for step in range(e2e_steps):
+                n_last = det.run_into(table, rank * e2e_steps + step, h_np)
             sharding.gather_events(table, dist)
+        else:
+            for step in range(e2e_steps):
+                ev_h = det.run(h_np)
         barrier()
-        return time.perf_counter() - te0, ev_h
+        wall = time.perf_counter() - te0
+        if world > 1:   # the last step's rows, as the caller's checks want them
+            _, ch_l, smp_l, out_l = sharding.unpack_events(table.rows[table.n - n_last:])
+            assert table.in_order and len(ev_h) == n_last and np.array_equal(ev_h.sample, smp_l) and np.array_equal(ev_h.channel, ch_l) \
+                and np.array_equal(ev_h.outputs, out_l)
+        return wall, ev_h
 
     # 16-bit PCM (what a WAV corpus holds; converted on the device as x/32768): the e2e headline
     q = torch.clamp(torch.round(x * 32768.0), -32768, 32767).to(torch.int16)

@@ -193,6 +193,10 @@ const float *syldet_events_outputs(const syldet_events *ev); /* [count][O] */
 /* The same rows as separate columns, copied in one pass into caller arrays of syldet_events_count() entries (outputs: [count][O]);
  * any of the three pointers may be NULL. For bindings that want column arrays (numpy, Swift [Int64]). */
 void syldet_events_copy_columns(const syldet_events *ev, int32_t *channel, int64_t *sample, float *outputs);
+/* The same rows in the packed layout a multi-GPU job gathers (no padding, 12 + 4 O bytes per row): uint32 key = recording << 16 | channel,
+ * int64 sample, float outputs[O]; `rows` holds syldet_events_count() of them. Returns 1 when the rows are in (key, sample) order - they
+ * are after syldet_batch_run_host / _collect -, 0 otherwise. Recording and channels below 65 536. */
+int syldet_events_copy_compact(const syldet_events *ev, uint32_t recording, void *rows);
 void syldet_events_free(syldet_events *ev);
 
 /* ---- one stream: class SyllableDetector (Common/SyllableDetector.swift:13-231) ------------------------------------ */

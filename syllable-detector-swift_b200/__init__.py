@@ -100,7 +100,7 @@ def _load():
         "syldet_events_count": (i64, [vp]), "syldet_events_outputs_per_event": (i32, [vp]),
         "syldet_events_data": (C.POINTER(Event), [vp]), "syldet_events_outputs": (C.POINTER(C.c_float), [vp]),
         "syldet_events_free": (None, [vp]),
-        "syldet_events_copy_columns": (None, [vp, vp, vp, vp]),
+        "syldet_events_copy_columns": (None, [vp, vp, vp, vp]), "syldet_events_copy_compact": (i32, [vp, C.c_uint32, vp]),
         "syldet_detector_create": (i32, [vp, i32, pvp]), "syldet_detector_destroy": (None, [vp]),
         "syldet_detector_append": (i32, [vp, vp, i64]), "syldet_detector_process_new_value": (i32, [vp]),
         "syldet_detector_last_outputs": (i32, [vp, vp, i32]), "syldet_detector_last_detected": (i32, [vp]),
@@ -328,6 +328,29 @@ class BatchDetector:
                                          outs.ctypes.data if want_outputs else None, C.byref(ev)))
         events = Events(ev, self.config.sampling_rate)
         return (events, outs) if want_outputs else events
+
+    def run_into(self, table, recording, pcm, debounce_frames=0, detect_rule=DETECT_ANY_OUTPUT, layout=LAYOUT_PLANAR):
+        """run(), with the detections appended to a sharding.EventTable as compact gather rows of `recording` - written by the library
+        straight from its event list into the table's page-locked memory (no column arrays in between). -> number of detections"""
+        a = np.asarray(pcm)
+        if a.ndim == 1:
+            a = a[None, :] if layout == LAYOUT_PLANAR else a[:, None]
+        fmt = PCM_S16 if a.dtype == np.int16 else PCM_F32
+        a = np.ascontiguousarray(a, dtype=np.int16 if fmt == PCM_S16 else np.float32)
+        nch, n = (a.shape if layout == LAYOUT_PLANAR else a.shape[::-1])
+        if not (0 <= int(recording) < 65536) or nch > 65536:
+            raise ValueError("compact event rows hold recordings and channels below 65 536")
+        ev = C.c_void_p()
+        _check(lib.syldet_batch_run_host(self._h, a.ctypes.data, fmt, nch, n, n, layout, int(debounce_frames), detect_rule, None, C.byref(ev)))
+        try:
+            m = int(lib.syldet_events_count(ev))
+            if lib.syldet_events_outputs_per_event(ev) != table.dtype["out"].shape[0]:
+                raise ValueError("the table's rows hold a different number of outputs")
+            addr, _ = table.claim(m)
+            table.commit(m, lib.syldet_events_copy_compact(ev, int(recording), addr) if m else 1)
+        finally:
+            lib.syldet_events_free(ev)
+        return m
 
     def simulate(self, pcm, s16=False, layout=LAYOUT_PLANAR):
         """Simulator trace (ViewControllerSimulator.swift:251-254, 308-344): clamp(out0 / thr0, 0, 1) held per hop, one value per

@@ -243,6 +243,29 @@ void syldet_events_copy_columns(const syldet_events *ev, int32_t *channel, int64
     }
     if (outputs && n) std::memcpy(outputs, ev->e.outputs.data(), ev->e.outputs.size() * sizeof(float));
 }
+int syldet_events_copy_compact(const syldet_events *ev, uint32_t recording, void *rows) {
+    if (!ev || !rows) return 1;
+    const size_t n = ev->e.rows.size();
+    const int O = ev->e.outputs_per_event;
+    const size_t item = 12 + 4 * (size_t)O;
+    const syldet_event *r = ev->e.rows.data();
+    const float *o = ev->e.outputs.data();
+    unsigned char *dst = static_cast<unsigned char *>(rows);
+    int ordered = 1;
+    uint32_t prev_key = 0;
+    int64_t prev_sample = 0;
+    for (size_t i = 0; i < n; ++i, dst += item) {
+        const uint32_t key = (recording << 16) | (uint32_t)(r[i].channel & 0xffff);
+        const int64_t smp = r[i].sample;
+        if (i && (key < prev_key || (key == prev_key && smp < prev_sample))) ordered = 0;
+        prev_key = key;
+        prev_sample = smp;
+        std::memcpy(dst, &key, 4);
+        std::memcpy(dst + 4, &smp, 8);
+        std::memcpy(dst + 12, o + i * (size_t)O, 4 * (size_t)O);
+    }
+    return ordered;
+}
 void syldet_events_free(syldet_events *ev) { delete ev; }
 
 // ---- batched resampling -------------------------------------------------------------------------------------------------

@@ -62,10 +62,18 @@ def debounce_rows(samples, debounce_frames):
     return keep
 
 
+def _as_rows(outputs, n, dtype):
+    """outputs as [n, O]; an empty [0, O] array keeps its O (reshape(0, -1) cannot infer it)"""
+    outputs = np.asarray(outputs, dtype=dtype)
+    if n == 0:
+        return outputs.reshape(0, outputs.shape[-1] if outputs.ndim > 1 else 1)
+    return outputs.reshape(n, -1)
+
+
 def pack_events(recording, channel, sample, outputs):
     """-> float64 [n, 3 + O] rows (recording, channel, sample, out...) ready for gather; exact for |sample| < 2^53."""
     sample = np.asarray(sample, dtype=np.int64)
-    outputs = np.asarray(outputs, dtype=np.float64).reshape(sample.size, -1)
+    outputs = _as_rows(outputs, sample.size, np.float64)
     rows = np.empty((sample.size, 3 + outputs.shape[1]), dtype=np.float64)
     rows[:, 0] = recording
     rows[:, 1] = channel
@@ -83,7 +91,7 @@ def event_dtype(n_outputs):
 def pack_events_compact(recording, channel, sample, outputs):
     """-> structured array (event_dtype) of the rows of one recording; recording and channels below 65 536."""
     sample = np.asarray(sample, dtype=np.int64)
-    outputs = np.asarray(outputs, dtype=np.float32).reshape(sample.size, -1)
+    outputs = _as_rows(outputs, sample.size, np.float32)
     channel = np.asarray(channel)
     if not (0 <= int(recording) < 65536) or (channel.size and (int(channel.min()) < 0 or int(channel.max()) >= 65536)):
         raise ValueError("compact event rows hold recordings and channels below 65 536")
@@ -172,6 +180,25 @@ class EventTable:
             return None
         return self._pin[:self.n * self.dtype.itemsize].view(self.n, self.dtype.itemsize)
 
+    def claim(self, m):
+        """room for m more rows -> (address of the first, view of the m rows); commit(m, ordered) makes them part of the table. For
+        producers that write rows themselves (BatchDetector.run_into: the library fills them straight from its event list)."""
+        self._reserve(self.n + int(m))
+        it = self.dtype.itemsize
+        blk = self._raw[self.n * it:(self.n + int(m)) * it]
+        return blk.ctypes.data, blk.view(self.dtype)
+
+    def commit(self, m, ordered):
+        m = int(m)
+        if m:
+            it = self.dtype.itemsize
+            if self.in_order:
+                ok = bool(ordered)
+                if ok and self.n:   # the pair across the boundary
+                    ok = rows_in_order(self._raw[(self.n - 1) * it:(self.n + 1) * it].view(self.dtype))
+                self.in_order = ok
+            self.n += m
+
     def append(self, recording, channel, sample, outputs):
         """one recording's detections (as Events gives them: ordered by channel, sample)"""
         sample = np.asarray(sample)
@@ -184,7 +211,7 @@ class EventTable:
         blk = self._raw[self.n * it:(self.n + m) * it].view(self.dtype)
         blk["key"] = (np.uint32(int(recording)) << np.uint32(16)) | channel.astype(np.uint32)
         blk["sample"] = sample
-        blk["out"] = np.asarray(outputs, dtype=np.float32).reshape(m, -1)
+        blk["out"] = _as_rows(outputs, m, np.float32)
         if self.in_order and m:
             lo = max(self.n - 1, 0)   # with the last row of what was there: the boundary pair is checked too
             self.in_order = rows_in_order(self._raw[lo * it:(self.n + m) * it].view(self.dtype))

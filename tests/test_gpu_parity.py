@@ -6,6 +6,8 @@ frame whose output lies within tolerance of the threshold reported separately"):
     detections        identical evaluation indices / sample numbers, except evaluations whose oracle output lies
                       within TOL_OUT of the threshold, which are counted and must be rare
 """
+import importlib
+
 import numpy as np
 import pytest
 
@@ -443,6 +445,25 @@ def test_event_buffer_overflow_replay(sd, cw):
     assert det.active_kernel == sd.KERNEL_TENSOR
     assert len(ev) == 12 * c.num_evals(x.shape[1]) > (1 << 20)
     assert np.array_equal(ev.sample[:3], [1444, 1576, 1708]) and np.all(np.diff(ev.channel) >= 0)
+
+
+def test_run_into_event_table_matches_run(sd, cfg, synth):
+    """BatchDetector.run_into: the library writes a recording's detections straight into a sharding.EventTable as compact gather rows -
+    the same rows pack_events_compact builds from run()'s columns, order tracked across recordings."""
+    sh = importlib.import_module("syllable-detector-swift_b200.sharding")
+    det = sd.BatchDetector(cfg)
+    table = sh.EventTable(cfg.net_outputs, capacity=8)
+    want = []
+    for rec, (nch, n, seed) in enumerate([(3, 44100 * 4, 41), (1, 44100 * 2, 42), (2, 5000, 43), (4, 44100 * 3, 44)]):
+        x = synth.make_audio(nch, n, seed=seed)
+        ev = det.run(x)
+        assert det.run_into(table, rec, x) == len(ev)
+        want.append(sh.pack_events_compact(rec, ev.channel, ev.sample, ev.outputs))
+    want = np.concatenate(want)
+    assert table.n == want.shape[0] > 20 and table.in_order and np.array_equal(table.rows, want)
+    x = synth.make_audio(2, 44100 * 2, seed=45)
+    det.run_into(table, 1, x)                      # an earlier recording after a later one: the table notices
+    assert not table.in_order and sh.rows_in_order(sh.gather_events(table, None))
 
 
 def test_pcm16_and_interleaved_ingest(sd, cfg, synth):

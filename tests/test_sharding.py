@@ -116,7 +116,12 @@ def test_two_rank_recording_shards_match_single_process(tmp_path, oracle_mod, sy
     c = sh.pack_events_compact(3, want[:5, 1].astype(np.int64), want[:5, 2].astype(np.int64), want[:5, 3:])
     assert c.dtype.itemsize == 16 and sh.rows_in_order(c) and not sh.rows_in_order(c[::-1])
     assert sh.gather_events(c, None).shape[0] == 5
+    # a recording without detections packs to zero rows of the right layout (reshape(0, -1) cannot infer the width)
+    empty = sh.pack_events_compact(7, np.zeros(0, np.int32), np.zeros(0, np.int64), np.zeros((0, 1), np.float32))
+    assert empty.shape == (0,) and empty.dtype == c.dtype and sh.pack_events(7, [], [], np.zeros((0, 2))).shape == (0, 5)
     t = sh.EventTable(want.shape[1] - 3, capacity=2)
+    t.append(1, np.zeros(0, np.int32), np.zeros(0, np.int64), np.zeros((0, 1), np.float32))
+    assert t.n == 0 and t.in_order
     t.append(3, want[:5, 1].astype(np.int64), want[:5, 2].astype(np.int64), want[:5, 3:])
     assert t.in_order and t.n == 5 and np.array_equal(t.rows, c) and np.array_equal(sh.gather_events(t, None), c)
     t.append(2, want[:5, 1].astype(np.int64), want[:5, 2].astype(np.int64), want[:5, 3:])     # an earlier recording after a later one

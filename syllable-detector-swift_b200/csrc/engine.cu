@@ -690,6 +690,7 @@ syldet_status Batch::launch_tc_range(const float *d_planar, int n_channels, int6
             if (cost < best) { best = cost; tiles_per_unit = tpu; }
         }
         if (forced > 0 && forced * tf > 4 * warm) tiles_per_unit = forced;
+        while (tiles_per_unit * tf <= 4 * warm) tiles_per_unit *= 2;   // very long windows: no candidate above qualified
     }
     const int64_t chunk = tiles_per_unit * tf - warm;
     w.chunk_evals = chunk;

@@ -409,7 +409,7 @@ def run_ours(args):
 
     def timed_e2e(h_np):
         """e2e_steps recordings per rank through the host API, then the job's one gather of every rank's detections on rank 0"""
-        for _ in range(min(args.warmup, 2)):
+        for _ in range(max(1 if world > 1 else 0, min(args.warmup, 2))):   # (N > 1: the gather warm-up and the final check need one)
             ev_h = det.run(h_np)
         if world > 1:   # warm-up of the gather as well: the first point-to-point gather sets up NCCL's peer connections (~0.4 s, once per job)
             table.clear()

@@ -168,6 +168,10 @@ syldet_status syldet_batch_launch_device(syldet_batch *b, const float *d_pcm, in
 syldet_status syldet_batch_collect(syldet_batch *b, int64_t debounce_frames, syldet_events **events);
 /* Kernels launched by this handle since creation (for bench.py's gpu_launches). */
 int64_t syldet_batch_launch_count(const syldet_batch *b);
+/* Planning helper (no device needed): tiles per unit the tensor kernel would use for `evals_per_channel` evaluations of each of
+ * `n_channels` channels on `sm_count` persistent CTAs with a window of `time_range` columns - the even length that leaves the fewest
+ * tiles on the busiest CTA. */
+int syldet_plan_tensor_unit_tiles(int64_t evals_per_channel, int n_channels, int sm_count, int time_range);
 /* 1 once this handle has switched its tensor kernel to the all-TF32 variant because audio left the fp16 window (see above), else 0. */
 int64_t syldet_batch_range_fallbacks(const syldet_batch *b);
 /* Device time (ms) of the two kernels of the last SYLDET_KERNEL_WIDE launch, summed over its time segments: the high-overlap STFT

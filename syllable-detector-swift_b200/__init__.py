@@ -92,7 +92,7 @@ def _load():
         "syldet_batch_run_host": (i32, [vp, vp, i32, i32, i64, i64, i32, i64, i32, vp, pvp]),
         "syldet_batch_simulate_host": (i32, [vp, vp, i32, i32, i64, i64, i32, i32, vp]),
         "syldet_batch_launch_device": (i32, [vp, vp, i32, i64, i64, i32, i32, vp, vp]),
-        "syldet_batch_collect": (i32, [vp, i64, pvp]), "syldet_batch_launch_count": (i64, [vp]),
+        "syldet_batch_collect": (i32, [vp, i64, pvp]), "syldet_batch_launch_count": (i64, [vp]), "syldet_plan_tensor_unit_tiles": (i32, [i64, i32, i32, i32]),
         "syldet_batch_last_detection_count": (i32, [vp, C.POINTER(i64)]),
         "syldet_batch_range_fallbacks": (i64, [vp]),
         "syldet_batch_wide_phase_ms": (i32, [vp, C.POINTER(dbl), C.POINTER(dbl)]),

@@ -209,6 +209,10 @@ syldet_status syldet_batch_collect(syldet_batch *b, int64_t debounce_frames, syl
     });
 }
 int64_t syldet_batch_launch_count(const syldet_batch *b) { return b ? b->b.launch_count() : 0; }
+int syldet_plan_tensor_unit_tiles(int64_t evals_per_channel, int n_channels, int sm_count, int time_range) {
+    if (evals_per_channel < 0 || n_channels <= 0 || sm_count <= 0 || time_range <= 0) return 0;
+    return tc_plan_unit_tiles(evals_per_channel, n_channels, sm_count, tc_tile_frames(), time_range - 1);
+}
 int64_t syldet_batch_range_fallbacks(const syldet_batch *b) { return b ? b->b.range_fallbacks() : 0; }
 syldet_status syldet_batch_wide_phase_ms(syldet_batch *b, double *stft_ms, double *contraction_ms) {
     if (!b) return set_error(SYLDET_ERR_ARG, "null argument");

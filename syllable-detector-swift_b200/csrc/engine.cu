@@ -588,6 +588,25 @@ syldet_status Batch::ensure_sink(unsigned long long capacity) {
     return SYLDET_OK;
 }
 
+// Unit length of the tensor kernel in tiles. Units go to the CTAs round-robin, so the launch takes ceil(units / CTAs) units on the busiest
+// CTA: pick the (even: tiles are contracted in pairs) length that minimises that, one tile charged per unit for the pipeline fill and
+// the warm-up columns; a unit must be longer than four warm-ups. 1 h x 8 ch on 148 CTAs: 32 tiles per unit leaves 4 800 units = 32.4 per
+// CTA, i.e. 33 on some (2.3 % over the ideal); 74 gives 2 072 = 14 each.
+int tc_plan_unit_tiles(int64_t eval_count, int n_channels, int resident, int tile_frames, int warm) {
+    const int64_t tf = tile_frames;
+    int64_t best_tpu = 32;
+    double best = 1e300;
+    for (int64_t tpu = 4; tpu <= 96; tpu += 2) {
+        if (tpu * tf <= 4 * (int64_t)warm) continue;
+        const int64_t ch = tpu * tf - warm;
+        const int64_t units = (int64_t)n_channels * ((std::max<int64_t>(eval_count, 1) + ch - 1) / ch);
+        const double cost = (double)((units + resident - 1) / resident) * (double)(tpu + 1);
+        if (cost < best) { best = cost; best_tpu = tpu; }
+    }
+    while (best_tpu * tf <= 4 * (int64_t)warm) best_tpu *= 2;   // very long windows: no candidate above qualified
+    return (int)best_tpu;
+}
+
 namespace {
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -675,23 +694,9 @@ syldet_status Batch::launch_tc_range(const float *d_planar, int n_channels, int6
     // a unit covers whole tiles: chunk = n_tiles * tile_frames - (T - 1) evaluations (the first T-1 columns of a unit only warm
     // the window up); long enough that the warm-up is noise, short enough that every CTA gets many units
     const int64_t tf = tc_tile_frames(), warm = c.time_range - 1;
-    // Units go to the CTAs round-robin, so the launch takes ceil(units / CTAs) units on the busiest CTA: pick the (even: tiles are
-    // contracted in pairs) unit length that minimises that, one tile charged per unit for the pipeline fill and the warm-up columns.
-    // 1 h x 8 ch: 32 tiles per unit leaves 4 800 units = 32.4 per CTA, i.e. 33 on some (2.3 % over the ideal); 74 gives 2 072 = 14 each.
-    int64_t tiles_per_unit = 32;
-    {
-        static const int forced = [] { const char *e = std::getenv("SYLDET_TC_UNIT_TILES"); return e ? std::atoi(e) : 0; }();
-        double best = 1e300;
-        for (int64_t tpu = 4; tpu <= 96; tpu += 2) {
-            if (tpu * tf <= 4 * warm) continue;
-            const int64_t ch = tpu * tf - warm;
-            const int64_t units = (int64_t)n_channels * ((eval_count + ch - 1) / ch);
-            const double cost = (double)((units + resident - 1) / resident) * (double)(tpu + 1);
-            if (cost < best) { best = cost; tiles_per_unit = tpu; }
-        }
-        if (forced > 0 && forced * tf > 4 * warm) tiles_per_unit = forced;
-        while (tiles_per_unit * tf <= 4 * warm) tiles_per_unit *= 2;   // very long windows: no candidate above qualified
-    }
+    static const int forced = [] { const char *e = std::getenv("SYLDET_TC_UNIT_TILES"); return e ? std::atoi(e) : 0; }();
+    int64_t tiles_per_unit = tc_plan_unit_tiles(eval_count, n_channels, resident, (int)tf, (int)warm);
+    if (forced > 0 && forced * tf > 4 * warm) tiles_per_unit = forced;
     const int64_t chunk = tiles_per_unit * tf - warm;
     w.chunk_evals = chunk;
     w.chunks_per_channel = (int)((eval_count + chunk - 1) / chunk);

@@ -166,6 +166,7 @@ struct TcWork {
 size_t tc_smem_bytes(const FusedParams &p, int hp);
 int tc_lo_stages(const FusedParams &p, int hp);
 int tc_tile_frames();
+int tc_plan_unit_tiles(int64_t eval_count, int n_channels, int resident, int tile_frames, int warm);   // engine.cu: tiles per unit of a launch
 bool tc_direct_s16_supported(int hp, const FusedParams &p);
 int tc_k_pad();
 int tc_a16_cols();                  // 32-bit words per row of the fp16 A operand (TcWork::dft16)

@@ -186,6 +186,28 @@ def test_config_writer_round_trip(sd, cw):
     assert [p[0] for p in c.input_processing] == ["normalize", "mapstd"] and c.input_processing[1][3] == 0.25
 
 
+def test_tensor_unit_length_planner(sd):
+    """launch_tc_range's choice of the unit length (host logic, no device): even, longer than four warm-ups, and never more tiles on the
+    busiest of the round-robin CTAs than the former fixed 32 tiles per unit."""
+    import math
+    lib = sd.lib
+    tf = 63   # frames per tile (64 hop rows)
+
+    def busiest(tpu, evals, nch, sms, T):
+        chunk = tpu * tf - (T - 1)
+        return math.ceil(nch * math.ceil(max(evals, 1) / chunk) / sms) * (tpu + 1)
+
+    assert lib.syldet_plan_tensor_unit_tiles(1202717, 8, 148, 10) == 74          # 1 h x 8 ch: 2 072 units = 14 on every CTA
+    for evals, nch, sms, T in [(1202717, 8, 148, 10), (75169, 8, 148, 10), (20035, 1, 148, 10), (300, 2, 148, 10), (1202717, 1, 148, 10),
+                               (5_000_000, 64, 148, 10), (20035, 3, 132, 30), (100000, 5, 148, 120), (0, 1, 148, 10)]:
+        tpu = lib.syldet_plan_tensor_unit_tiles(evals, nch, sms, T)
+        assert tpu >= 4 and tpu % 2 == 0 and tpu * tf > 4 * (T - 1)
+        if 32 * tf > 4 * (T - 1):
+            assert busiest(tpu, evals, nch, sms, T) <= busiest(32, evals, nch, sms, T)
+    assert lib.syldet_plan_tensor_unit_tiles(1000, 1, 148, 3000) * tf > 4 * 2999   # very long window: the warm-up bound still holds
+    assert lib.syldet_plan_tensor_unit_tiles(-1, 1, 148, 10) == 0
+
+
 def test_resample_output_lengths(sd):
     """n_out of the two converters: Int(Float(n) / Float(rate_in / rate_out)) (Resampler.swift:32,40) and ceil(n up / down)."""
     assert sd.lib.syldet_resample_output_length(sd.RESAMPLE_LINEAR, 32, 48000.0, 44100.0) == int(np.float32(32) / np.float32(48000.0 / 44100.0))

@@ -262,7 +262,15 @@ class Events:
             self.sample = np.zeros(0, dtype=np.int64)
             self.outputs = np.zeros((0, o), dtype=np.float32)
         lib.syldet_events_free(handle)
-        self.seconds = self.sample / sampling_rate
+        self._sampling_rate = sampling_rate
+        self._seconds = None
+
+    @property
+    def seconds(self):
+        """sample / samplingRate (TrackDetector.swift:88-89 for a contiguous 0-based track); computed on first use"""
+        if self._seconds is None:
+            self._seconds = self.sample / self._sampling_rate
+        return self._seconds
 
     def __len__(self):
         return self.sample.size
